@@ -1,0 +1,101 @@
+"""ctypes binding of ``libgpode_b200.so`` (C ABI declared in ``include/gpode_b200.h``).
+
+There is no CPU or PyTorch fallback: if the shared library is missing or a call fails, an exception is raised.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgpode_b200.so")
+
+c_float_p = ctypes.c_void_p  # device pointers travel as plain addresses
+c_stream = ctypes.c_void_p
+
+
+class GpodeCache(ctypes.Structure):
+    """``gpode_cache_t`` of include/gpode_b200.h."""
+    _fields_ = [("D", ctypes.c_int32), ("M", ctypes.c_int32), ("S", ctypes.c_int32),
+                ("omega", ctypes.c_void_p), ("phase", ctypes.c_void_p), ("w", ctypes.c_void_p),
+                ("Z", ctypes.c_void_p), ("nu", ctypes.c_void_p), ("ell", ctypes.c_void_p), ("var", ctypes.c_void_p)]
+
+
+_I, _L, _P, _D, _F = ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_double, ctypes.c_float
+_CP = ctypes.POINTER(GpodeCache)
+
+# name -> (restype, argtypes); every symbol include/gpode_b200.h declares
+SIGNATURES = {
+    "gpode_abi_version": (_I, []),
+    "gpode_last_error": (ctypes.c_char_p, []),
+    "gpode_packed_floats": (_L, [_I, _I, _I]),
+    "gpode_pack_cache": (_I, [_CP, _P, _P]),
+    "gpode_vf_fwd": (_I, [_P, _I, _I, _I, _P, _P, _L, _P]),
+    "gpode_vf_bwd": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _L, _P]),
+    "gpode_rk4_fwd": (_I, [_P, _I, _I, _I, _P, _P, _I, _L, _P, _P, _P]),
+    "gpode_rk4_bwd": (_I, [_P, _I, _I, _I, _P, _I, _L, _P, _P, _P, _P, _P, _P, _P]),
+    "gpode_acc_floats": (_L, [_I, _I]),
+    "gpode_vrow_floats": (_L, [_I, _L]),
+    "gpode_grads_finalize": (_I, [_CP, _P, _P, _P, _P, _P, _P]),
+    "gpode_whiten_fwd": (_I, [_CP, _P, _F, _P, _P, _P, _P]),
+    "gpode_whiten_bwd": (_I, [_CP, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gpode_kl_fwd": (_I, [_P, _P, _I, _I, _P, _P]),
+    "gpode_kl_bwd": (_I, [_P, _P, _I, _I, _P, _P, _P, _P]),
+    # "gpode_dopri5_work_floats": (_L, [_I, _L]),
+    # "gpode_dopri5_fwd": (_I, [_P, _I, _I, _I, _P, _P, _I, _L, _D, _D, _P, _P, _P, _P]),
+}
+
+_lib = None
+
+
+class GpodeError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once). Raises if it has not been built -- no fallback exists."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GpodeError(
+            "%s is missing: build it with `python -m gaussian_process_odes_b200.build` "
+            "(or __graft_entry__.build()). The GPODE hot path has no CPU / PyTorch fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = header/library mismatch, fail loudly
+        fn.restype, fn.argtypes = res, args
+    if lib.gpode_abi_version() != 1:
+        raise GpodeError("libgpode_b200.so ABI version %d, expected 1" % lib.gpode_abi_version())
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().gpode_last_error().decode("utf-8", "replace")
+        raise GpodeError("gpode_b200 call failed (rc=%d): %s" % (rc, msg))
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device address of a contiguous float32/float64/int32 CUDA tensor (or NULL for None)."""
+    if t is None:
+        return ctypes.c_void_p(0)
+    if not t.is_cuda:
+        raise GpodeError("gpode_b200 needs CUDA tensors, got device %s (there is no CPU path)" % t.device)
+    if not t.is_contiguous():
+        raise GpodeError("gpode_b200 needs contiguous tensors")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def f32(t, name="tensor"):
+    """Detached contiguous float32 CUDA view of ``t`` (raises instead of silently moving/casting)."""
+    if t.dtype != torch.float32:
+        raise GpodeError("%s must be float32, got %s" % (name, t.dtype))
+    if not t.is_cuda:
+        raise GpodeError("%s must live on a CUDA device, got %s (there is no CPU path)" % (name, t.device))
+    return t.detach().contiguous()

@@ -1,0 +1,28 @@
+// One translation unit per state dimension (compiled with -DGPODE_D=<1..8>) so the eight sets of register-resident
+// kernels build in parallel.
+#include "integrate_impl.cuh"
+
+#ifndef GPODE_D
+#error "compile with -DGPODE_D=<state dimension>"
+#endif
+
+#define GPODE_CAT_(a, b) a##b
+#define GPODE_CAT(a, b) GPODE_CAT_(a, b)
+
+int GPODE_CAT(gpode_vf_fwd_d, GPODE_D)(const float* packed, int M, int S, const float* x, float* f, int64_t B,
+                                       cudaStream_t st) {
+    return launch_vf_fwd<GPODE_D>(packed, M, S, x, f, B, st);
+}
+int GPODE_CAT(gpode_rk4_fwd_d, GPODE_D)(const float* packed, int M, int S, const float* x0, const float* t, int Tg,
+                                        int64_t B, float* xs, float* kst, cudaStream_t st) {
+    return launch_rk4_fwd<GPODE_D>(packed, M, S, x0, t, Tg, B, xs, kst, st);
+}
+int GPODE_CAT(gpode_rk4_bwd_d, GPODE_D)(const float* packed, int M, int S, const float* t, int Tg, int64_t B,
+                                        const float* xs, const float* kst, const float* gxs, float* gx0, float* vy,
+                                        float* vk, float* acc, cudaStream_t st) {
+    return launch_rk4_bwd<GPODE_D>(packed, M, S, t, Tg, B, xs, kst, gxs, gx0, vy, vk, acc, st);
+}
+int GPODE_CAT(gpode_vf_bwd_d, GPODE_D)(const float* packed, int M, int S, const float* x, const float* f,
+                                       const float* gf, float* gx, int64_t B, float* acc, cudaStream_t st) {
+    return launch_vf_bwd<GPODE_D>(packed, M, S, x, f, gf, gx, B, acc, st);
+}

@@ -1,0 +1,415 @@
+// Vector-field evaluation, fixed-grid RK4 (3/8 rule) forward and its discrete adjoint.
+//
+// Replaces (reference paths): DSVGP_Layer.forward src/core/dsvgp.py:172-197; torchdiffeq 0.2.0
+// odeint(method='rk4') as called from Flow.forward src/core/flow.py:84-90 (step function rk4_alt_step_func, restated
+// in oracle/torchdiffeq_shim); autograd through the unrolled solver (use_adjoint=False, train_vdp_gpode.py:52).
+//
+// Mapping: one thread owns R trajectories; their state, stage derivatives and adjoints live in registers for the
+// whole time grid; the sampled function (RFF weights, Z, nu, lengthscales) lives in shared memory, staged once per
+// CTA with a bulk async copy. Global traffic is only x0 in, xs (and stage checkpoints) out, all coalesced in the
+// [time][row][dim] layout torchdiffeq itself returns.
+#pragma once
+#include "vf.cuh"
+
+namespace {
+
+constexpr int kThreads = 128;
+
+// rows (trajectories) per thread: as many as the register file allows without spills (ptxas -v)
+template <int D>
+struct RowsFwd {
+    static constexpr int value = D <= 2 ? 4 : (D <= 5 ? 2 : 1);
+};
+template <int D>
+struct RowsBwd {
+    static constexpr int value = D <= 2 ? 4 : (D <= 4 ? 2 : 1);
+};
+
+template <int D, int R>
+__device__ __forceinline__ void load_rows(float (&v)[R][D], const float* __restrict__ base, const int64_t row0,
+                                          const int64_t B, const int stride) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int64_t row = row0 + (int64_t)r * stride;
+#pragma unroll
+        for (int j = 0; j < D; ++j) v[r][j] = row < B ? __ldg(base + row * D + j) : 0.f;
+    }
+}
+
+template <int D, int R>
+__device__ __forceinline__ void store_rows(const float (&v)[R][D], float* __restrict__ base, const int64_t row0,
+                                           const int64_t B, const int stride) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int64_t row = row0 + (int64_t)r * stride;
+        if (row < B) {
+#pragma unroll
+            for (int j = 0; j < D; ++j) base[row * D + j] = v[r][j];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// f = vf(x)
+// ------------------------------------------------------------------------------------------------------------------
+template <int D, int R>
+__global__ void __launch_bounds__(kThreads)
+vf_fwd_kernel(const float* __restrict__ packed, const int M, const int S, const int total,
+              const float* __restrict__ x, float* __restrict__ f, const int64_t B) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const float* sp = stage_params(smem_raw, packed, total);
+    const int64_t tile_rows = (int64_t)blockDim.x * R;
+    const int64_t ntiles = (B + tile_rows - 1) / tile_rows;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t row0 = tile * tile_rows + threadIdx.x;
+        float xr[R][D], fr[R][D];
+        load_rows<D, R>(xr, x, row0, B, blockDim.x);
+        vf_eval<D, R>(sp, M, S, xr, fr);
+        store_rows<D, R>(fr, f, row0, B, blockDim.x);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// RK4 3/8 rule, operation order of torchdiffeq 0.2.0 rk4_alt_step_func (no FMA contraction in the stage algebra so
+// that, given identical stage derivatives, the step is bit-identical to the float32 torch ops):
+//   k2 = f(y + dt*k1*(1/3)); k3 = f(y + dt*(k2 - k1*(1/3))); k4 = f(y + dt*(k1 - k2 + k3));
+//   y1 = y + (k1 + 3*(k2 + k3) + k4) * dt * 0.125
+// ------------------------------------------------------------------------------------------------------------------
+#define GPODE_THIRD 0.3333333432674407958984375f  // float32(1/3), what torch multiplies by
+
+template <int D, int R>
+__device__ __forceinline__ void stage2(float (&o)[R][D], const float (&y)[R][D], const float (&k1)[R][D], float dt) {
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int j = 0; j < D; ++j)
+            o[r][j] = __fadd_rn(y[r][j], __fmul_rn(__fmul_rn(dt, k1[r][j]), GPODE_THIRD));
+}
+template <int D, int R>
+__device__ __forceinline__ void stage3(float (&o)[R][D], const float (&y)[R][D], const float (&k1)[R][D],
+                                       const float (&k2)[R][D], float dt) {
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int j = 0; j < D; ++j)
+            o[r][j] = __fadd_rn(y[r][j], __fmul_rn(dt, __fsub_rn(k2[r][j], __fmul_rn(k1[r][j], GPODE_THIRD))));
+}
+template <int D, int R>
+__device__ __forceinline__ void stage4(float (&o)[R][D], const float (&y)[R][D], const float (&k1)[R][D],
+                                       const float (&k2)[R][D], const float (&k3)[R][D], float dt) {
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int j = 0; j < D; ++j)
+            o[r][j] = __fadd_rn(y[r][j], __fmul_rn(dt, __fadd_rn(__fsub_rn(k1[r][j], k2[r][j]), k3[r][j])));
+}
+
+template <int D, int R>
+__global__ void __launch_bounds__(kThreads)
+rk4_fwd_kernel(const float* __restrict__ packed, const int M, const int S, const int total,
+               const float* __restrict__ x0, const float* __restrict__ ts, const int Tg, const int64_t B,
+               float* __restrict__ xs, float* __restrict__ kst) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const float* sp = stage_params(smem_raw, packed, total);
+    const int64_t tile_rows = (int64_t)blockDim.x * R;
+    const int64_t ntiles = (B + tile_rows - 1) / tile_rows;
+    const int64_t plane = B * D;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t row0 = tile * tile_rows + threadIdx.x;
+        float y[R][D];
+        load_rows<D, R>(y, x0, row0, B, blockDim.x);
+        store_rows<D, R>(y, xs, row0, B, blockDim.x);
+        for (int i = 0; i + 1 < Tg; ++i) {
+            const float dt = __fsub_rn(__ldg(ts + i + 1), __ldg(ts + i));
+            float k1[R][D], k2[R][D], k3[R][D], k4[R][D], ys[R][D];
+            vf_eval<D, R>(sp, M, S, y, k1);
+            stage2<D, R>(ys, y, k1, dt);
+            vf_eval<D, R>(sp, M, S, ys, k2);
+            stage3<D, R>(ys, y, k1, k2, dt);
+            vf_eval<D, R>(sp, M, S, ys, k3);
+            stage4<D, R>(ys, y, k1, k2, k3, dt);
+            vf_eval<D, R>(sp, M, S, ys, k4);
+            if (kst != nullptr) {
+                float* kb = kst + (int64_t)i * 4 * plane;
+                store_rows<D, R>(k1, kb, row0, B, blockDim.x);
+                store_rows<D, R>(k2, kb + plane, row0, B, blockDim.x);
+                store_rows<D, R>(k3, kb + 2 * plane, row0, B, blockDim.x);
+                store_rows<D, R>(k4, kb + 3 * plane, row0, B, blockDim.x);
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    const float sum = __fadd_rn(
+                        __fadd_rn(k1[r][j], __fmul_rn(3.0f, __fadd_rn(k2[r][j], k3[r][j]))), k4[r][j]);
+                    y[r][j] = __fadd_rn(y[r][j], __fmul_rn(__fmul_rn(sum, dt), 0.125f));
+                }
+            store_rows<D, R>(y, xs + (int64_t)(i + 1) * plane, row0, B, blockDim.x);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Discrete adjoint of the kernel above. For every step, walking backwards:
+//   kb4 = h/8 lam;                          yb4 = J(y4)^T kb4
+//   kb3 = 3h/8 lam + h yb4;                 yb3 = J(y3)^T kb3
+//   kb2 = 3h/8 lam + h yb3 - h yb4;         yb2 = J(y2)^T kb2
+//   kb1 = h/8 lam + (h/3)(yb2 - yb3) + h yb4; yb1 = J(y1)^T kb1
+//   lam <- grad_xs[i] + lam + yb1 + yb2 + yb3 + yb4
+// Stage inputs are rebuilt bit-exactly from the checkpointed stage derivatives; (stage input, cotangent) pairs are
+// written out as "virtual rows" for the per-inducing-point gradient kernel (param_grad.cu).
+// ------------------------------------------------------------------------------------------------------------------
+template <int D, int R>
+__global__ void __launch_bounds__(kThreads)
+rk4_bwd_kernel(const float* __restrict__ packed, const int M, const int S, const int total,
+               const float* __restrict__ ts, const int Tg, const int64_t B, const float* __restrict__ xs,
+               const float* __restrict__ kst, const float* __restrict__ gxs, float* __restrict__ gx0,
+               float* __restrict__ vy, float* __restrict__ vk, float* __restrict__ acc) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const float* sp = stage_params(smem_raw, packed, total);
+    float* red = reinterpret_cast<float*>(smem_raw + 16) + total;
+    for (int i = threadIdx.x; i < D * D + D; i += blockDim.x) red[i] = 0.f;
+
+    float A[D][D], V[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        V[k] = 0.f;
+#pragma unroll
+        for (int j = 0; j < D; ++j) A[k][j] = 0.f;
+    }
+
+    const int64_t tile_rows = (int64_t)blockDim.x * R;
+    const int64_t ntiles = (B + tile_rows - 1) / tile_rows;
+    const int64_t plane = B * D;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t row0 = tile * tile_rows + threadIdx.x;
+        float lam[R][D];
+        load_rows<D, R>(lam, gxs + (int64_t)(Tg - 1) * plane, row0, B, blockDim.x);
+        for (int i = Tg - 2; i >= 0; --i) {
+            const float h = __fsub_rn(__ldg(ts + i + 1), __ldg(ts + i));
+            const float* kb = kst + (int64_t)i * 4 * plane;
+            float* vyi = vy + (int64_t)i * 4 * plane;
+            float* vki = vk + (int64_t)i * 4 * plane;
+            float y[R][D], k1[R][D], k2[R][D], ks[R][D], ys[R][D], kbar[R][D], yb[R][D];
+            float sumyb[R][D], yb4[R][D], yb23[R][D];
+            load_rows<D, R>(y, xs + (int64_t)i * plane, row0, B, blockDim.x);
+            load_rows<D, R>(k1, kb, row0, B, blockDim.x);
+            load_rows<D, R>(k2, kb + plane, row0, B, blockDim.x);
+
+            // ---- stage 4 ----
+            load_rows<D, R>(ks, kb + 2 * plane, row0, B, blockDim.x);  // k3
+            stage4<D, R>(ys, y, k1, k2, ks, h);
+            load_rows<D, R>(ks, kb + 3 * plane, row0, B, blockDim.x);  // k4 = f(y4)
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int j = 0; j < D; ++j) kbar[r][j] = 0.125f * h * lam[r][j];
+            store_rows<D, R>(ys, vyi + 3 * plane, row0, B, blockDim.x);
+            store_rows<D, R>(kbar, vki + 3 * plane, row0, B, blockDim.x);
+            vf_vjp<D, R>(sp, M, S, ys, kbar, ks, yb4, A, V);
+
+            // ---- stage 3 ----
+            stage3<D, R>(ys, y, k1, k2, h);
+            load_rows<D, R>(ks, kb + 2 * plane, row0, B, blockDim.x);  // k3 = f(y3)
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int j = 0; j < D; ++j) kbar[r][j] = fmaf(0.375f * h, lam[r][j], h * yb4[r][j]);
+            store_rows<D, R>(ys, vyi + 2 * plane, row0, B, blockDim.x);
+            store_rows<D, R>(kbar, vki + 2 * plane, row0, B, blockDim.x);
+            vf_vjp<D, R>(sp, M, S, ys, kbar, ks, yb, A, V);
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    sumyb[r][j] = yb4[r][j] + yb[r][j];
+                    kbar[r][j] = fmaf(0.375f * h, lam[r][j], h * (yb[r][j] - yb4[r][j]));  // kb2
+                    yb23[r][j] = -yb[r][j];
+                }
+
+            // ---- stage 2 ----
+            stage2<D, R>(ys, y, k1, h);
+            store_rows<D, R>(ys, vyi + plane, row0, B, blockDim.x);
+            store_rows<D, R>(kbar, vki + plane, row0, B, blockDim.x);
+            vf_vjp<D, R>(sp, M, S, ys, kbar, k2, yb, A, V);
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    sumyb[r][j] += yb[r][j];
+                    yb23[r][j] += yb[r][j];  // yb2 - yb3
+                    kbar[r][j] = fmaf(0.125f * h, lam[r][j], fmaf(h * GPODE_THIRD, yb23[r][j], h * yb4[r][j]));
+                }
+
+            // ---- stage 1 ----
+            store_rows<D, R>(y, vyi, row0, B, blockDim.x);
+            store_rows<D, R>(kbar, vki, row0, B, blockDim.x);
+            vf_vjp<D, R>(sp, M, S, y, kbar, k1, yb, A, V);
+
+            float gi[R][D];
+            load_rows<D, R>(gi, gxs + (int64_t)i * plane, row0, B, blockDim.x);
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int j = 0; j < D; ++j) lam[r][j] = gi[r][j] + lam[r][j] + (sumyb[r][j] + yb[r][j]);
+        }
+        store_rows<D, R>(lam, gx0, row0, B, blockDim.x);
+    }
+    __syncthreads();
+    reduce_AV<D>(A, V, acc, red);
+}
+
+// VJP of a single vector-field evaluation (autograd through DSVGP_Layer.forward)
+template <int D, int R>
+__global__ void __launch_bounds__(kThreads)
+vf_bwd_kernel(const float* __restrict__ packed, const int M, const int S, const int total,
+              const float* __restrict__ x, const float* __restrict__ f, const float* __restrict__ gf,
+              float* __restrict__ gx, const int64_t B, float* __restrict__ acc) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const float* sp = stage_params(smem_raw, packed, total);
+    float* red = reinterpret_cast<float*>(smem_raw + 16) + total;
+    for (int i = threadIdx.x; i < D * D + D; i += blockDim.x) red[i] = 0.f;
+    float A[D][D], V[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        V[k] = 0.f;
+#pragma unroll
+        for (int j = 0; j < D; ++j) A[k][j] = 0.f;
+    }
+    const int64_t tile_rows = (int64_t)blockDim.x * R;
+    const int64_t ntiles = (B + tile_rows - 1) / tile_rows;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t row0 = tile * tile_rows + threadIdx.x;
+        float xr[R][D], fr[R][D], kb[R][D], xb[R][D];
+        load_rows<D, R>(xr, x, row0, B, blockDim.x);
+        load_rows<D, R>(fr, f, row0, B, blockDim.x);
+        load_rows<D, R>(kb, gf, row0, B, blockDim.x);
+        vf_vjp<D, R>(sp, M, S, xr, kb, fr, xb, A, V);
+        store_rows<D, R>(xb, gx, row0, B, blockDim.x);
+    }
+    __syncthreads();
+    reduce_AV<D>(A, V, acc, red);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host-side launch helpers
+// ------------------------------------------------------------------------------------------------------------------
+struct LaunchShape {
+    int threads, grid;
+    size_t smem;
+};
+
+inline int num_sms() {
+    static int g_num_sms = 0;
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+template <typename K>
+inline int shape_for(K kernel, int R, int64_t B, size_t smem, LaunchShape* out) {
+    // small batches: narrow CTAs so the rows spread over more SMs; large: 128 threads, grid = SMs x resident CTAs
+    int threads = (B <= (int64_t)num_sms() * 32 * R) ? 32 : kThreads;
+    GPODE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    GPODE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
+    if (occ < 1) {
+        gpode_set_error("kernel does not fit on an SM (smem %zu bytes)", smem);
+        return -2;
+    }
+    const int64_t tile_rows = (int64_t)threads * R;
+    const int64_t ntiles = (B + tile_rows - 1) / tile_rows;
+    const int64_t cap = (int64_t)num_sms() * occ;
+    out->threads = threads;
+    out->grid = (int)(ntiles < cap ? ntiles : cap);
+    out->smem = smem;
+    return 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------------
+// per-D launchers: wide tiles (R rows per thread) when the batch fills the machine twice over, else one row per thread
+// ------------------------------------------------------------------------------------------------------------------
+template <int D, int R>
+inline bool use_wide(int64_t B) {
+    return R > 1 && B >= (int64_t)num_sms() * 2 * kThreads * R;
+}
+
+template <int D>
+int launch_vf_fwd(const float* packed, int M, int S, const float* x, float* f, int64_t B, cudaStream_t st) {
+    const GpodeLayout L = gpode_layout(D, M, S);
+    const size_t smem = 16 + (size_t)L.total * 4;
+    LaunchShape ls;
+    constexpr int RW = RowsFwd<D>::value;
+    if (use_wide<D, RW>(B)) {
+        if (int rc = shape_for(vf_fwd_kernel<D, RW>, RW, B, smem, &ls)) return rc;
+        vf_fwd_kernel<D, RW><<<ls.grid, ls.threads, ls.smem, st>>>(packed, M, S, L.total, x, f, B);
+    } else {
+        if (int rc = shape_for(vf_fwd_kernel<D, 1>, 1, B, smem, &ls)) return rc;
+        vf_fwd_kernel<D, 1><<<ls.grid, ls.threads, ls.smem, st>>>(packed, M, S, L.total, x, f, B);
+    }
+    GPODE_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int D>
+int launch_rk4_fwd(const float* packed, int M, int S, const float* x0, const float* t, int Tg, int64_t B, float* xs,
+                   float* kst, cudaStream_t st) {
+    const GpodeLayout L = gpode_layout(D, M, S);
+    const size_t smem = 16 + (size_t)L.total * 4;
+    LaunchShape ls;
+    constexpr int RW = RowsFwd<D>::value;
+    if (use_wide<D, RW>(B)) {
+        if (int rc = shape_for(rk4_fwd_kernel<D, RW>, RW, B, smem, &ls)) return rc;
+        rk4_fwd_kernel<D, RW><<<ls.grid, ls.threads, ls.smem, st>>>(packed, M, S, L.total, x0, t, Tg, B, xs, kst);
+    } else {
+        if (int rc = shape_for(rk4_fwd_kernel<D, 1>, 1, B, smem, &ls)) return rc;
+        rk4_fwd_kernel<D, 1><<<ls.grid, ls.threads, ls.smem, st>>>(packed, M, S, L.total, x0, t, Tg, B, xs, kst);
+    }
+    GPODE_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int D>
+int launch_rk4_bwd(const float* packed, int M, int S, const float* t, int Tg, int64_t B, const float* xs,
+                   const float* kst, const float* gxs, float* gx0, float* vy, float* vk, float* acc,
+                   cudaStream_t st) {
+    const GpodeLayout L = gpode_layout(D, M, S);
+    const size_t smem = 16 + (size_t)(L.total + D * D + D) * 4;
+    LaunchShape ls;
+    constexpr int RW = RowsBwd<D>::value;
+    if (use_wide<D, RW>(B)) {
+        if (int rc = shape_for(rk4_bwd_kernel<D, RW>, RW, B, smem, &ls)) return rc;
+        rk4_bwd_kernel<D, RW><<<ls.grid, ls.threads, ls.smem, st>>>(packed, M, S, L.total, t, Tg, B, xs, kst, gxs, gx0,
+                                                                     vy, vk, acc);
+    } else {
+        if (int rc = shape_for(rk4_bwd_kernel<D, 1>, 1, B, smem, &ls)) return rc;
+        rk4_bwd_kernel<D, 1><<<ls.grid, ls.threads, ls.smem, st>>>(packed, M, S, L.total, t, Tg, B, xs, kst, gxs, gx0,
+                                                                    vy, vk, acc);
+    }
+    GPODE_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int D>
+int launch_vf_bwd(const float* packed, int M, int S, const float* x, const float* f, const float* gf, float* gx,
+                  int64_t B, float* acc, cudaStream_t st) {
+    const GpodeLayout L = gpode_layout(D, M, S);
+    const size_t smem = 16 + (size_t)(L.total + D * D + D) * 4;
+    LaunchShape ls;
+    constexpr int RW = RowsBwd<D>::value;
+    if (use_wide<D, RW>(B)) {
+        if (int rc = shape_for(vf_bwd_kernel<D, RW>, RW, B, smem, &ls)) return rc;
+        vf_bwd_kernel<D, RW><<<ls.grid, ls.threads, ls.smem, st>>>(packed, M, S, L.total, x, f, gf, gx, B, acc);
+    } else {
+        if (int rc = shape_for(vf_bwd_kernel<D, 1>, 1, B, smem, &ls)) return rc;
+        vf_bwd_kernel<D, 1><<<ls.grid, ls.threads, ls.smem, st>>>(packed, M, S, L.total, x, f, gf, gx, B, acc);
+    }
+    GPODE_LAUNCH_CHECK();
+    return 0;
+}

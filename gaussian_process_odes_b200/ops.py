@@ -1,0 +1,204 @@
+"""torch.autograd bindings of the CUDA hot path (one ``Function`` per C-ABI op pair).
+
+Tensor conventions follow the reference's cache attributes (``DSVGP_Layer.build_cache``, reference
+``src/core/dsvgp.py:92-122``): ``omega (D,S,D)``, ``phase (1,S,D)`` or ``(S,D)``, ``w (S,D)``, ``Z (M,D)``,
+``nu (D,M,1)`` or ``(D,M)``, ``ell (D,D)``, ``var (D,)``. Gradients flow to ``x / x0``, ``Z``, ``ell``, ``var``, ``nu``
+(and ``u`` for the whitening); ``omega`` is treated as ``eps/ell`` -- its gradient arrives folded into ``ell``
+(reference ``src/core/kernels.py:110-112``), ``w`` and ``phase`` carry no gradient in the reference either.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import GpodeCache, check, f32, ptr, stream_ptr
+
+
+def _cache_struct(D, M, S, omega, phase, w, Z, nu, ell, var):
+    c = GpodeCache()
+    c.D, c.M, c.S = D, M, S
+    c.omega, c.phase, c.w = ptr(omega).value, ptr(phase).value, ptr(w).value
+    c.Z, c.nu = ptr(Z).value, (ptr(nu).value if nu is not None else None)
+    c.ell, c.var = ptr(ell).value, ptr(var).value
+    return c
+
+
+class PackedCache:
+    """One sampled GP function repacked for the integrator kernels (``gpode_pack_cache``)."""
+
+    def __init__(self, Z, ell, var, nu, omega, phase, w):
+        lib = _lib.load()
+        self.Z, self.ell, self.var = f32(Z, "Z"), f32(ell, "ell"), f32(var, "var")
+        self.omega, self.w = f32(omega, "omega"), f32(w, "w")
+        self.M, self.D = self.Z.shape
+        self.S = self.w.shape[0]
+        self.phase = f32(phase, "phase").reshape(self.S, self.D)
+        self.nu = f32(nu, "nu").reshape(self.D, self.M)
+        if tuple(self.omega.shape) != (self.D, self.S, self.D) or tuple(self.ell.shape) != (self.D, self.D) \
+                or tuple(self.var.shape) != (self.D,) or tuple(self.w.shape) != (self.S, self.D):
+            raise _lib.GpodeError("inconsistent cache shapes: omega %s ell %s var %s w %s Z %s" % (
+                tuple(self.omega.shape), tuple(self.ell.shape), tuple(self.var.shape), tuple(self.w.shape),
+                tuple(self.Z.shape)))
+        n = lib.gpode_packed_floats(self.D, self.M, self.S)
+        self.packed = torch.empty(n, dtype=torch.float32, device=self.Z.device)
+        self.struct = _cache_struct(self.D, self.M, self.S, self.omega, self.phase, self.w, self.Z, self.nu,
+                                    self.ell, self.var)
+        check(lib.gpode_pack_cache(ctypes.byref(self.struct), ptr(self.packed), stream_ptr()))
+
+    def new_acc(self):
+        n = _lib.load().gpode_acc_floats(self.D, self.M)
+        return torch.zeros(n, dtype=torch.float32, device=self.Z.device)
+
+    def finalize(self, acc):
+        """acc -> (grad_Z, grad_ell, grad_var, grad_nu)"""
+        dev = self.Z.device
+        g_ell = torch.empty(self.D, self.D, dtype=torch.float32, device=dev)
+        g_var = torch.empty(self.D, dtype=torch.float32, device=dev)
+        g_Z = torch.empty(self.M, self.D, dtype=torch.float32, device=dev)
+        g_nu = torch.empty(self.D, self.M, dtype=torch.float32, device=dev)
+        check(_lib.load().gpode_grads_finalize(ctypes.byref(self.struct), ptr(acc), ptr(g_ell), ptr(g_var), ptr(g_Z),
+                                               ptr(g_nu), stream_ptr()))
+        return g_Z, g_ell, g_var, g_nu
+
+
+class _VectorField(torch.autograd.Function):
+    """f = DSVGP_Layer.forward(t, x) (reference src/core/dsvgp.py:172-197) via gpode_vf_fwd / gpode_vf_bwd."""
+
+    @staticmethod
+    def forward(ctx, x, Z, ell, var, nu, omega, phase, w):
+        pc = PackedCache(Z, ell, var, nu, omega, phase, w)
+        xc = f32(x, "x")
+        if xc.ndim != 2 or xc.shape[1] != pc.D:
+            raise _lib.GpodeError("x must be (B,%d), got %s" % (pc.D, tuple(xc.shape)))
+        f = torch.empty_like(xc)
+        check(_lib.load().gpode_vf_fwd(ptr(pc.packed), pc.D, pc.M, pc.S, ptr(xc), ptr(f), xc.shape[0], stream_ptr()))
+        ctx.pc, ctx.nu_shape = pc, nu.shape
+        ctx.save_for_backward(xc, f)
+        return f
+
+    @staticmethod
+    def backward(ctx, gf):
+        pc = ctx.pc
+        xc, f = ctx.saved_tensors
+        gf = f32(gf, "grad_f")
+        gx = torch.empty_like(xc)
+        acc = pc.new_acc()
+        check(_lib.load().gpode_vf_bwd(ptr(pc.packed), pc.D, pc.M, pc.S, ptr(xc), ptr(f), ptr(gf), ptr(gx), ptr(acc),
+                                       xc.shape[0], stream_ptr()))
+        g_Z, g_ell, g_var, g_nu = pc.finalize(acc)
+        return gx, g_Z, g_ell, g_var, g_nu.reshape(ctx.nu_shape), None, None, None
+
+
+class _RK4(torch.autograd.Function):
+    """xs = odeint(f, x0, t, method='rk4') (torchdiffeq 0.2.0 3/8 rule) via gpode_rk4_fwd / gpode_rk4_bwd."""
+
+    @staticmethod
+    def forward(ctx, x0, t, Z, ell, var, nu, omega, phase, w):
+        pc = PackedCache(Z, ell, var, nu, omega, phase, w)
+        xc, tc = f32(x0, "x0"), f32(t, "t")
+        if xc.ndim != 2 or xc.shape[1] != pc.D:
+            raise _lib.GpodeError("x0 must be (B,%d), got %s" % (pc.D, tuple(xc.shape)))
+        B, Tg = xc.shape[0], tc.shape[0]
+        need_grad = any(ctx.needs_input_grad)
+        xs = torch.empty(Tg, B, pc.D, dtype=torch.float32, device=xc.device)
+        kst = torch.empty(max(Tg - 1, 0), 4, B, pc.D, dtype=torch.float32, device=xc.device) if need_grad else None
+        check(_lib.load().gpode_rk4_fwd(ptr(pc.packed), pc.D, pc.M, pc.S, ptr(xc), ptr(tc), Tg, B, ptr(xs),
+                                        ptr(kst), stream_ptr()))
+        ctx.pc, ctx.nu_shape = pc, nu.shape
+        if need_grad:
+            ctx.save_for_backward(tc, xs, kst)
+        return xs
+
+    @staticmethod
+    def backward(ctx, gxs):
+        pc = ctx.pc
+        tc, xs, kst = ctx.saved_tensors
+        lib = _lib.load()
+        Tg, B, D = xs.shape
+        gxs = f32(gxs, "grad_xs")
+        gx0 = torch.empty(B, D, dtype=torch.float32, device=xs.device)
+        acc = pc.new_acc()
+        vrows = torch.empty(lib.gpode_vrow_floats(D, max(Tg - 1, 0) * 4 * B), dtype=torch.float32, device=xs.device)
+        check(lib.gpode_rk4_bwd(ptr(pc.packed), pc.D, pc.M, pc.S, ptr(tc), Tg, B, ptr(xs), ptr(kst), ptr(gxs),
+                                ptr(gx0), ptr(vrows), ptr(acc), stream_ptr()))
+        g_Z, g_ell, g_var, g_nu = pc.finalize(acc)
+        return gx0, None, g_Z, g_ell, g_var, g_nu.reshape(ctx.nu_shape), None, None, None
+
+
+class _Whiten(torch.autograd.Function):
+    """nu = Kzz^-1-whitening of build_cache (reference src/core/dsvgp.py:110-122) via gpode_whiten_fwd / _bwd."""
+
+    @staticmethod
+    def forward(ctx, Z, ell, var, u, omega, phase, w, jitter):
+        lib = _lib.load()
+        Zc, ec, vc, uc = f32(Z, "Z"), f32(ell, "ell"), f32(var, "var"), f32(u, "u")
+        oc, wc = f32(omega, "omega"), f32(w, "w")
+        M, D = Zc.shape
+        S = wc.shape[0]
+        pc_ = f32(phase, "phase").reshape(S, D)
+        st = _cache_struct(D, M, S, oc, pc_, wc, Zc, None, ec, vc)
+        nu = torch.empty(D, M, dtype=torch.float32, device=Zc.device)
+        L = torch.empty(D, M, M, dtype=torch.float64, device=Zc.device)
+        sp = torch.empty(D, 2, M, dtype=torch.float64, device=Zc.device)
+        check(lib.gpode_whiten_fwd(ctypes.byref(st), ptr(uc), float(jitter), ptr(nu), ptr(L), ptr(sp), stream_ptr()))
+        ctx.keep = (st, Zc, ec, vc, uc, oc, pc_, wc)
+        ctx.save_for_backward(L, sp)
+        return nu
+
+    @staticmethod
+    def backward(ctx, gnu):
+        lib = _lib.load()
+        st, Zc, ec, vc, uc, oc, pc_, wc = ctx.keep
+        L, sp = ctx.saved_tensors
+        M, D = Zc.shape
+        gnu = f32(gnu, "grad_nu").reshape(D, M)
+        g_u = torch.empty(M, D, dtype=torch.float32, device=Zc.device)
+        g_Z = torch.empty(M, D, dtype=torch.float32, device=Zc.device)
+        g_ell = torch.empty(D, D, dtype=torch.float32, device=Zc.device)
+        g_var = torch.empty(D, dtype=torch.float32, device=Zc.device)
+        check(lib.gpode_whiten_bwd(ctypes.byref(st), ptr(uc), ptr(L), ptr(sp), ptr(gnu), ptr(g_u), ptr(g_Z),
+                                   ptr(g_ell), ptr(g_var), stream_ptr()))
+        return g_Z, g_ell, g_var, g_u, None, None, None, None
+
+
+class _WhitenedKL(torch.autograd.Function):
+    """DSVGP_Layer.kl (reference src/core/dsvgp.py:199-230) on the PACKED lower-triangular optvar."""
+
+    @staticmethod
+    def forward(ctx, Um, Ls_packed):
+        Uc, Lc = f32(Um, "Um"), f32(Ls_packed, "Us_sqrt optvar")
+        M, D = Uc.shape
+        if tuple(Lc.shape) != (D, M * (M + 1) // 2):
+            raise _lib.GpodeError("Us_sqrt optvar must be (%d,%d), got %s" % (D, M * (M + 1) // 2, tuple(Lc.shape)))
+        out = torch.empty((), dtype=torch.float32, device=Uc.device)
+        check(_lib.load().gpode_kl_fwd(ptr(Uc), ptr(Lc), D, M, ptr(out), stream_ptr()))
+        ctx.save_for_backward(Uc, Lc)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        Uc, Lc = ctx.saved_tensors
+        M, D = Uc.shape
+        gU, gL = torch.empty_like(Uc), torch.empty_like(Lc)
+        check(_lib.load().gpode_kl_bwd(ptr(Uc), ptr(Lc), D, M, ptr(f32(g, "grad_kl")), ptr(gU), ptr(gL),
+                                       stream_ptr()))
+        return gU, gL
+
+
+def vector_field(x, Z, ell, var, nu, omega, phase, w):
+    """f(x) of one sampled GP function; differentiable in x, Z, ell, var, nu."""
+    return _VectorField.apply(x, Z, ell, var, nu, omega, phase, w)
+
+
+def rk4_integrate(x0, t, Z, ell, var, nu, omega, phase, w):
+    """Fixed-grid RK4 (3/8 rule) over the float32 grid ``t``; returns ``(len(t), B, D)`` like torchdiffeq."""
+    return _RK4.apply(x0, t, Z, ell, var, nu, omega, phase, w)
+
+
+def whiten(Z, ell, var, u, omega, phase, w, jitter=1e-5):
+    """nu (D,M) = L^-T (u - L^-1 rff_forward(Z)), L = chol(K(Z,Z) + jitter I), per output dimension."""
+    return _Whiten.apply(Z, ell, var, u, omega, phase, w, jitter)
+
+
+def whitened_kl(Um, Us_sqrt_packed):
+    return _WhitenedKL.apply(Um, Us_sqrt_packed)

@@ -1,0 +1,120 @@
+/*
+ * gpode_b200 -- C ABI of the B200-native (sm_100a) GPODE hot path.
+ *
+ * The reference (hegdepashupati/gaussian-process-odes) is pure Python/PyTorch and has no FFI layer; the seams this
+ * library replaces are Python call signatures. Each entry point below cites the reference code whose arithmetic it
+ * replaces (paths relative to the reference repo root). INTEGRATION.md shows the ctypes binding a maintainer of the
+ * reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to float32 (row-major, contiguous) unless it is named *_f64 or says "host";
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*) and never synchronises the host;
+ *   - return value: 0 = ok, <0 = argument/shape error, >0 = cudaError_t; gpode_last_error() gives the text;
+ *   - no global mutable state except the per-thread last-error string; float32 arithmetic on the path
+ *     (the Kzz factorisation accumulates in float64 in shared memory).
+ *
+ * Symbols: D = state dim (D_in == D_out), M = inducing points, S = Fourier features, B = rows of the integrated
+ * batch, Tg = length of the time grid.
+ */
+#ifndef GPODE_B200_H
+#define GPODE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPODE_B200_ABI_VERSION 1
+#define GPODE_MAX_D 8          /* register-resident state kernels are instantiated for 1 <= D <= 8 */
+#define GPODE_MAX_M_F64 112    /* whitening backward keeps two MxM float64 tiles in shared memory */
+#define GPODE_MAX_M 160        /* ... and falls back to float32 tiles up to this M */
+
+/* One sampled GP function = the reference's "cache" (DSVGP_Layer.build_cache, src/core/dsvgp.py:92-122) plus the
+ * kernel hyper-parameters it closes over (RBF, src/core/kernels.py:33-51). */
+typedef struct gpode_cache {
+    int32_t D, M, S;
+    const float* omega;   /* [D,S,D]  rff_omega = eps/lengthscale, index (j,s,k)        dsvgp.py:101, kernels.py:101-112 */
+    const float* phase;   /* [S,D]    rff_phase in radians                              dsvgp.py:102-103 */
+    const float* w;       /* [S,D]    rff_weights                                       dsvgp.py:100 */
+    const float* Z;       /* [M,D]    inducing locations                                dsvgp.py:66 */
+    const float* nu;      /* [D,M]    nu = Kzz^-1 (u - f_prior(Z))                      dsvgp.py:119-122 */
+    const float* ell;     /* [D,D]    lengthscales (k = output dim, j = input dim)      kernels.py:45-47 */
+    const float* var;     /* [D]      signal variances                                  kernels.py:49-51 */
+} gpode_cache_t;
+
+int         gpode_abi_version(void);
+const char* gpode_last_error(void);
+
+/* Number of floats of the packed, kernel-friendly parameter block for (D,M,S). */
+int64_t gpode_packed_floats(int D, int M, int S);
+
+/* Repack one cache into the layout the integrator kernels stage into shared memory with one bulk (TMA) copy:
+ * per (k,s) [Omega_0sk..Omega_{D-1}sk, phase_sk, w_sk*sqrt(var_k/S)], per m [Z_m, var_k*nu_km], scaled inverse
+ * lengthscales. Replaces the per-call tensor prep of DSVGP_Layer.forward (src/core/dsvgp.py:172-197). */
+int gpode_pack_cache(const gpode_cache_t* cache, float* packed, void* stream);
+
+/* f = vector field at x. Replaces DSVGP_Layer.forward(t, x) (src/core/dsvgp.py:172-197 = rff_forward :124-137 +
+ * RBF.K src/core/kernels.py:87-99 + einsum :192).  x, f: [B,D]. */
+int gpode_vf_fwd(const float* packed, int D, int M, int S, const float* x, float* f, int64_t B, void* stream);
+
+/* Vector-Jacobian product of the above (what autograd does through dsvgp.py:172-197).
+ *   grad_x [B,D]; shared-parameter gradients ACCUMULATE into `acc` (gpode_acc_floats floats, zero it first);
+ *   f [B,D] is the forward output (saved by the caller); scratch: gpode_vrow_floats(B*1) floats. */
+int gpode_vf_bwd(const float* packed, int D, int M, int S, const float* x, const float* f, const float* grad_f,
+                 float* grad_x, float* acc, int64_t B, void* stream);
+
+/* Fixed-grid RK4 (3/8 rule) over the user's grid t[Tg] (float32, device), i.e. torchdiffeq 0.2.0
+ * odeint(func, y0, t, method='rk4') as called by Flow.forward (src/core/flow.py:84-90) with func = ODEfunc
+ * (flow.py:29-37). xs: [Tg,B,D] with xs[0] = x0 (torchdiffeq's own layout; Flow permutes it to [B,Tg,D]).
+ * kstages: NULL, or [Tg-1,4,B,D] receiving the four stage derivatives of every step (the backward's checkpoints). */
+int gpode_rk4_fwd(const float* packed, int D, int M, int S, const float* x0, const float* t, int Tg, int64_t B,
+                  float* xs, float* kstages, void* stream);
+
+/* Discrete adjoint of gpode_rk4_fwd == autograd through the unrolled solver (use_adjoint=False, the reference
+ * default, train_vdp_gpode.py:52). grad_xs [Tg,B,D] -> grad_x0 [B,D]; shared-parameter gradients accumulate into
+ * `acc`. vrows: scratch of gpode_vrow_floats((Tg-1)*4*B) floats. */
+int gpode_rk4_bwd(const float* packed, int D, int M, int S, const float* t, int Tg, int64_t B, const float* xs,
+                  const float* kstages, const float* grad_xs, float* grad_x0, float* vrows, float* acc,
+                  void* stream);
+
+/* Accumulator block shared by the *_bwd entry points and its conversion to parameter gradients.
+ *   acc layout (floats): A[D,D] | V[D] | T[D,M] | W[D,M,D]
+ *   gpode_grads_finalize: grad_ell[D,D], grad_var[D], grad_Z[M,D], grad_nu[D,M] (overwritten). grad_ell already
+ *   contains the path through omega = eps/ell (kernels.py:110-112). */
+int64_t gpode_acc_floats(int D, int M);
+int64_t gpode_vrow_floats(int D, int64_t n_virtual_rows);
+int gpode_grads_finalize(const gpode_cache_t* cache, const float* acc, float* grad_ell, float* grad_var,
+                         float* grad_Z, float* grad_nu, void* stream);
+
+/* Kzz whitening of build_cache (src/core/dsvgp.py:110-122): L = chol(K(Z,Z) + jitter I), nu = L^-T (u - L^-1 p),
+ * p = rff_forward(Z) (dsvgp.py:112,124-137), batched over the D output dimensions (one CTA each, matrices in shared
+ * memory).  u: [M,D]; nu_out: [D,M]; L_f64: [D,M,M] float64 and s_f64: [D,M] float64 are saved for the backward. */
+int gpode_whiten_fwd(const gpode_cache_t* cache_without_nu, const float* u, float jitter, float* nu_out,
+                     double* L_f64, double* s_f64, void* stream);
+/* Backward of the above: grad_nu [D,M] -> grad_u [M,D], grad_Z [M,D], grad_ell [D,D], grad_var [D] (overwritten). */
+int gpode_whiten_bwd(const gpode_cache_t* cache_with_nu, const float* u, const double* L_f64, const double* s_f64,
+                     const float* grad_nu, float* grad_u, float* grad_Z, float* grad_ell, float* grad_var,
+                     void* stream);
+
+/* Whitened KL of DSVGP_Layer.kl (src/core/dsvgp.py:199-230), q_diag=False:
+ *   kl = 0.5 * sum_k [ |Um_k|^2 + |tril(Ls_k)|_F^2 - sum_i log Ls_k,ii^2 - M ],  Ls given PACKED as the optvar of
+ *   transforms.LowerTriangular (src/misc/transforms.py:70-76): [D, M(M+1)/2], row-major np.tril_indices order. */
+int gpode_kl_fwd(const float* Um, const float* Ls_packed, int D, int M, float* kl_out, void* stream);
+int gpode_kl_bwd(const float* Um, const float* Ls_packed, int D, int M, const float* grad_kl, float* grad_Um,
+                 float* grad_Ls_packed, void* stream);
+
+/* Adaptive Dormand-Prince 5(4) with torchdiffeq 0.2.0's controller (rtol/atol, whole-batch RMS norm, float64 time,
+ * 4th-order dense output) -- odeint(..., method='dopri5'), the reference's default solver (src/core/flow.py:41).
+ * Runs as ONE cooperative persistent kernel (accept/reject decided on the device). t_host: the Tg output times on the
+ * HOST (float64). work: gpode_dopri5_work_floats(B,D) floats. stats_out (device, 4 int32): nfe, accepted, rejected,
+ * status. */
+int64_t gpode_dopri5_work_floats(int D, int64_t B);
+int gpode_dopri5_fwd(const float* packed, int D, int M, int S, const float* x0, const double* t_host, int Tg,
+                     int64_t B, double rtol, double atol, float* xs, float* work, int32_t* stats_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPODE_B200_H */
