@@ -41,8 +41,8 @@ SIGNATURES = {
     "gpode_whiten_bwd": (_I, [_CP, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gpode_kl_fwd": (_I, [_P, _P, _I, _I, _P, _P]),
     "gpode_kl_bwd": (_I, [_P, _P, _I, _I, _P, _P, _P, _P]),
-    # "gpode_dopri5_work_floats": (_L, [_I, _L]),
-    # "gpode_dopri5_fwd": (_I, [_P, _I, _I, _I, _P, _P, _I, _L, _D, _D, _P, _P, _P, _P]),
+    "gpode_dopri5_work_floats": (_L, [_I, _L]),
+    "gpode_dopri5_fwd": (_I, [_P, _I, _I, _I, _P, _P, _I, _L, _D, _D, _P, _P, _P, _P]),
 }
 
 _lib = None

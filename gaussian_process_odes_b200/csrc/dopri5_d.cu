@@ -1,0 +1,14 @@
+// One translation unit per state dimension (compiled with -DGPODE_D=<1..8>).
+#include "dopri5_impl.cuh"
+
+#ifndef GPODE_D
+#error "compile with -DGPODE_D=<state dimension>"
+#endif
+#define GPODE_CAT_(a, b) a##b
+#define GPODE_CAT(a, b) GPODE_CAT_(a, b)
+
+int GPODE_CAT(gpode_dopri5_fwd_d, GPODE_D)(const float* packed, int M, int S, const float* x0, const double* t, int Tg,
+                                           int64_t B, double rtol, double atol, float* xs, float* work,
+                                           int32_t* stats, cudaStream_t st) {
+    return launch_dopri5<GPODE_D>(packed, M, S, x0, t, Tg, B, rtol, atol, xs, work, stats, st);
+}

@@ -1,0 +1,317 @@
+// Adaptive Dormand-Prince 5(4) with torchdiffeq 0.2.0's controller, as ONE cooperative persistent kernel.
+//
+// Replaces odeint(func, y0, t, rtol, atol, method='dopri5') (the reference's default solver, src/core/flow.py:41,84-90;
+// algorithm restated in oracle/torchdiffeq_shim from torchdiffeq 0.2.0: rk_common._runge_kutta_step / _adaptive_step,
+// misc._select_initial_step / _optimal_step_size / _compute_error_ratio, interp._interp_fit / _interp_evaluate).
+//
+// The reference decides accept/reject on the HOST after every attempt (one device->host sync per attempt, ~40 tiny
+// kernels in between). Here every thread owns rows of the batch, keeps the controller state (t, dt in float64,
+// pending output index) replicated in registers, and the only cross-thread quantity -- the whole-batch RMS error
+// norm -- is reduced through a float64 atomic accumulator and ONE grid-wide barrier per attempt.
+#pragma once
+#include <cooperative_groups.h>
+#include "vf.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int kDpThreads = 128;
+
+// Dormand-Prince / Shampine tableau (float32 copies, like torchdiffeq's tableau cast to the state dtype)
+__device__ __constant__ float kBeta[6][6] = {
+    {1.f / 5, 0, 0, 0, 0, 0},
+    {3.f / 40, 9.f / 40, 0, 0, 0, 0},
+    {44.f / 45, -56.f / 15, 32.f / 9, 0, 0, 0},
+    {(float)(19372.0 / 6561), (float)(-25360.0 / 2187), (float)(64448.0 / 6561), (float)(-212.0 / 729), 0, 0},
+    {(float)(9017.0 / 3168), (float)(-355.0 / 33), (float)(46732.0 / 5247), (float)(49.0 / 176),
+     (float)(-5103.0 / 18656), 0},
+    {(float)(35.0 / 384), 0.f, (float)(500.0 / 1113), (float)(125.0 / 192), (float)(-2187.0 / 6784),
+     (float)(11.0 / 84)}};
+__device__ __constant__ float kCErr[7] = {
+    (float)(35.0 / 384 - 1951.0 / 21600), 0.f, (float)(500.0 / 1113 - 22642.0 / 50085),
+    (float)(125.0 / 192 - 451.0 / 720), (float)(-2187.0 / 6784 + 12231.0 / 42400), (float)(11.0 / 84 - 649.0 / 6300),
+    (float)(-1.0 / 60)};
+__device__ __constant__ float kCMid[7] = {
+    (float)(6025192743.0 / 30085553152.0 / 2), 0.f, (float)(51252292925.0 / 65400821598.0 / 2),
+    (float)(-2691868925.0 / 45128329728.0 / 2), (float)(187940372067.0 / 1594534317056.0 / 2),
+    (float)(-1776094331.0 / 19743644256.0 / 2), (float)(11237099.0 / 235043384.0 / 2)};
+
+struct Dopri5Args {
+    const float* packed;
+    int M, S, total;
+    const float* x0;
+    const double* t;  // [Tg] device, float64 ("all time-like objects use float64")
+    int Tg;
+    int64_t B;
+    double rtol, atol;
+    float* xs;        // [Tg,B,D]
+    float* work;      // y | f | y1 | f1 | ymid  (5 x [B,D])
+    double* red;      // 4 accumulators (3 rotating for the error norm + 1 spare), zeroed by the host
+    int32_t* stats;   // nfe, accepted, rejected, status
+    int max_attempts;
+};
+
+__device__ __forceinline__ double block_sum_to(double v, double* smem_red) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) smem_red[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0)
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += smem_red[i];
+    return t;  // valid on thread 0
+}
+
+template <int D>
+__device__ __forceinline__ void ldrow(float (&v)[1][D], const float* p, int64_t row) {
+#pragma unroll
+    for (int j = 0; j < D; ++j) v[0][j] = p[row * D + j];
+}
+template <int D>
+__device__ __forceinline__ void strow(const float (&v)[1][D], float* p, int64_t row) {
+#pragma unroll
+    for (int j = 0; j < D; ++j) p[row * D + j] = v[0][j];
+}
+
+template <int D>
+__device__ __forceinline__ void vf_signed(const float* sp, int M, int S, float sgn, const float (&x)[1][D],
+                                          float (&f)[1][D]) {
+    vf_eval<D, 1>(sp, M, S, x, f);
+#pragma unroll
+    for (int j = 0; j < D; ++j) f[0][j] *= sgn;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kDpThreads) dopri5_kernel(const Dopri5Args a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double sred[kDpThreads / 32];
+    cg::grid_group grid = cg::this_grid();
+    const float* sp = stage_params(smem_raw, a.packed, a.total);
+    const int M = a.M, S = a.S;
+    const int64_t B = a.B, plane = B * D;
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
+    float* Y = a.work;
+    float* F = a.work + plane;
+    float* Y1 = a.work + 2 * plane;
+    float* F1 = a.work + 3 * plane;
+    float* YM = a.work + 4 * plane;
+    const float rtol = (float)a.rtol, atol = (float)a.atol;
+    const double n_elem = (double)B * (double)D;
+    // a decreasing grid is integrated as -f over -t, exactly what torchdiffeq's odeint does
+    const double dir = (a.Tg > 1 && a.t[a.Tg - 1] < a.t[0]) ? -1.0 : 1.0;
+    const float fsign = (float)dir;
+
+    // ---- y = x0, f0 = f(t0, y0); d0, d1 of _select_initial_step ----
+    double s0 = 0.0, s1 = 0.0;
+    for (int64_t row = gtid; row < B; row += gstride) {
+        float y[1][D], f[1][D];
+        ldrow<D>(y, a.x0, row);
+        vf_signed<D>(sp, M, S, fsign, y, f);
+        strow<D>(y, Y, row);
+        strow<D>(f, F, row);
+        strow<D>(y, a.xs, row);
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            const float sc = atol + fabsf(y[0][j]) * rtol;
+            const float q0 = y[0][j] / sc, q1 = f[0][j] / sc;
+            s0 += (double)(q0 * q0);
+            s1 += (double)(q1 * q1);
+        }
+    }
+    {
+        const double b0 = block_sum_to(s0, sred);
+        const double b1 = block_sum_to(s1, sred);
+        if (threadIdx.x == 0) {
+            atomicAdd(a.red + 0, b0);
+            atomicAdd(a.red + 1, b1);
+        }
+    }
+    grid.sync();
+    const float d0 = (float)sqrt(a.red[0] / n_elem), d1 = (float)sqrt(a.red[1] / n_elem);
+    float h0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6f : 0.01f * d0 / d1;
+    double s2 = 0.0;
+    for (int64_t row = gtid; row < B; row += gstride) {
+        float y[1][D], f[1][D], y1[1][D], f1[1][D];
+        ldrow<D>(y, Y, row);
+        ldrow<D>(f, F, row);
+#pragma unroll
+        for (int j = 0; j < D; ++j) y1[0][j] = y[0][j] + h0 * f[0][j];
+        vf_signed<D>(sp, M, S, fsign, y1, f1);
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            const float sc = atol + fabsf(y[0][j]) * rtol;
+            const float q = (f1[0][j] - f[0][j]) / sc;
+            s2 += (double)(q * q);
+        }
+    }
+    {
+        const double b2 = block_sum_to(s2, sred);
+        if (threadIdx.x == 0) atomicAdd(a.red + 2, b2);
+    }
+    grid.sync();
+    double dt;
+    {
+        const float d2 = (float)sqrt(a.red[2] / n_elem) / h0;
+        float h1;
+        if (d1 <= 1e-15f && d2 <= 1e-15f) h1 = fmaxf(1e-6f, h0 * 1e-3f);
+        else h1 = powf(0.01f / fmaxf(d1, d2), 1.0f / 5.0f);
+        dt = (double)fminf(100.f * h0, h1);
+    }
+    grid.sync();  // everyone has read red[0..2] before they are recycled as the rotating error accumulators
+    if (gtid == 0) a.red[0] = a.red[1] = a.red[2] = 0.0;
+    grid.sync();
+
+    // ---- main loop: controller state replicated in every thread ----
+    double t0 = dir * a.t[0], t1 = dir * a.t[0];
+    int jout = 1, nfe = 2, n_acc = 0, n_rej = 0, status = 0;
+    int attempt = 0;
+    while (jout < a.Tg) {
+        if (!(dir * a.t[jout] > t1)) {  // output time already covered by the last accepted step (handled at accept time)
+            ++jout;
+            continue;
+        }
+        if (attempt >= a.max_attempts || !(t1 + dt > t1)) {
+            status = attempt >= a.max_attempts ? 1 : 2;  // too many attempts / step-size underflow
+            break;
+        }
+        const float dts = (float)dt;
+        double se = 0.0;
+        for (int64_t row = gtid; row < B; row += gstride) {
+            float y[1][D], k[7][1][D], yi[1][D];
+            ldrow<D>(y, Y, row);
+            ldrow<D>(k[0], F, row);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    float s = 0.f;
+#pragma unroll
+                    for (int l = 0; l <= i; ++l) s = fmaf(k[l][0][j], __fmul_rn(kBeta[i][l], dts), s);
+                    yi[0][j] = y[0][j] + s;
+                }
+                vf_signed<D>(sp, M, S, fsign, yi, k[i + 1]);
+            }
+            float ym[1][D];
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                float e = 0.f, m = 0.f;
+#pragma unroll
+                for (int l = 0; l < 7; ++l) {
+                    e = fmaf(k[l][0][j], __fmul_rn(dts, kCErr[l]), e);
+                    m = fmaf(k[l][0][j], __fmul_rn(dts, kCMid[l]), m);
+                }
+                ym[0][j] = y[0][j] + m;
+                const float tol = atol + rtol * fmaxf(fabsf(y[0][j]), fabsf(yi[0][j]));
+                const float q = e / tol;
+                se += (double)(q * q);
+            }
+            strow<D>(yi, Y1, row);
+            strow<D>(k[6], F1, row);
+            strow<D>(ym, YM, row);
+        }
+        {
+            const double be = block_sum_to(se, sred);
+            if (threadIdx.x == 0) atomicAdd(a.red + (attempt % 3), be);
+        }
+        grid.sync();
+        const float ratio = (float)sqrt(a.red[attempt % 3] / n_elem);
+        if (gtid == 0) a.red[(attempt + 2) % 3] = 0.0;
+        const bool accept = ratio <= 1.0f;
+        nfe += 6;
+        if (accept) {
+            const double t1n = t1 + dt;
+            // outputs that fall inside (t1, t1n]
+            int jend = jout;
+            while (jend < a.Tg && !(dir * a.t[jend] > t1n)) ++jend;
+            for (int64_t row = gtid; row < B; row += gstride) {
+                float y[1][D], f[1][D], y1[1][D], f1[1][D], ym[1][D];
+                ldrow<D>(y1, Y1, row);
+                ldrow<D>(f1, F1, row);
+                if (jend > jout) {
+                    ldrow<D>(y, Y, row);
+                    ldrow<D>(f, F, row);
+                    ldrow<D>(ym, YM, row);
+#pragma unroll
+                    for (int j = 0; j < D; ++j) {
+                        const float y0 = y[0][j], yn = y1[0][j], f0 = f[0][j], fn = f1[0][j], ymj = ym[0][j];
+                        const float ca = 2 * dts * (fn - f0) - 8 * (yn + y0) + 16 * ymj;
+                        const float cb = dts * (5 * f0 - 3 * fn) + 18 * y0 + 14 * yn - 32 * ymj;
+                        const float cc = dts * (fn - 4 * f0) - 11 * y0 - 5 * yn + 16 * ymj;
+                        const float cd = dts * f0;
+                        for (int jo = jout; jo < jend; ++jo) {
+                            const float x = (float)((dir * a.t[jo] - t1) / (t1n - t1));
+                            float total = y0 + x * cd;
+                            float xp = x * x;
+                            total = total + xp * cc;
+                            xp = xp * x;
+                            total = total + xp * cb;
+                            xp = xp * x;
+                            total = total + xp * ca;
+                            a.xs[(int64_t)jo * plane + row * D + j] = total;
+                        }
+                    }
+                }
+                strow<D>(y1, Y, row);
+                strow<D>(f1, F, row);
+            }
+            jout = jend;
+            t0 = t1;
+            t1 = t1n;
+            ++n_acc;
+        } else {
+            ++n_rej;
+        }
+        // _optimal_step_size (safety 0.9, ifactor 10, dfactor 0.2, order 5)
+        if (ratio == 0.f) {
+            dt = dt * 10.0;
+        } else {
+            const double dfac = ratio < 1.f ? 1.0 : 0.2;
+            const double fac = fmin(10.0, fmax(0.9 / pow((double)ratio, 0.2), dfac));
+            dt = dt * fac;
+        }
+        ++attempt;
+    }
+    (void)t0;
+    if (gtid == 0) {
+        a.stats[0] = nfe;
+        a.stats[1] = n_acc;
+        a.stats[2] = n_rej;
+        a.stats[3] = status;
+    }
+}
+
+}  // namespace
+
+template <int D>
+int launch_dopri5(const float* packed, int M, int S, const float* x0, const double* t, int Tg, int64_t B, double rtol,
+                  double atol, float* xs, float* work, int32_t* stats, cudaStream_t st) {
+    const GpodeLayout L = gpode_layout(D, M, S);
+    const size_t smem = 16 + (size_t)L.total * 4;
+    GPODE_CUDA(cudaFuncSetAttribute(dopri5_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0, sms = 148, dev = 0;
+    GPODE_CUDA(cudaGetDevice(&dev));
+    GPODE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    GPODE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dopri5_kernel<D>, kDpThreads, smem));
+    if (occ < 1) {
+        gpode_set_error("dopri5 kernel does not fit on an SM (smem %zu bytes)", smem);
+        return -2;
+    }
+    const int64_t want = (B + kDpThreads - 1) / kDpThreads;
+    const int64_t cap = (int64_t)sms * occ;
+    const int grid = (int)(want < cap ? want : cap);
+    Dopri5Args a;
+    a.packed = packed; a.M = M; a.S = S; a.total = L.total; a.x0 = x0; a.t = t; a.Tg = Tg; a.B = B;
+    a.rtol = rtol; a.atol = atol; a.xs = xs;
+    const int64_t plane = B * D;
+    a.work = work;
+    a.red = reinterpret_cast<double*>(work + 5 * plane + ((5 * plane) & 1));
+    a.stats = stats;
+    a.max_attempts = 1 << 20;
+    GPODE_CUDA(cudaMemsetAsync(a.red, 0, 4 * sizeof(double), st));
+    void* params[] = {(void*)&a};
+    GPODE_CUDA(cudaLaunchCooperativeKernel((const void*)dopri5_kernel<D>, dim3(grid), dim3(kDpThreads), params, smem, st));
+    return 0;
+}

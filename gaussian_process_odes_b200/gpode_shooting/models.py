@@ -1,0 +1,69 @@
+"""Multiple-shooting GPODE (mirror of reference ``src/gpode_shooting/models.py``): every one-interval segment of every
+sampled state sequence is one row of a single wide batch that the fused integrator advances in one launch."""
+from torch import nn
+
+from ..misc.torch_utils import compute_ts_dense
+
+
+def stack_segments(unstacked):
+    return unstacked.reshape(-1, unstacked.shape[-1])
+
+
+def unstack_segments(stacked, unstacked_shape):
+    return stacked.reshape(unstacked_shape)
+
+
+class BaseSequenceModel(nn.Module):
+    def __init__(self, flow, num_observations, state_distribution, likelihood, constraint, ts_dense_scale=2):
+        super().__init__()
+        self.flow = flow
+        self.num_observations = num_observations
+        self.state_distribution = state_distribution
+        self.likelihood = likelihood
+        self.constraint = constraint
+        self.ts_dense_scale = ts_dense_scale
+
+    def build_flow(self, x0, ts):
+        if self.ts_dense_scale < 2:
+            raise ValueError("ts_dense_scale must be >= 2")
+        dense = compute_ts_dense(ts, self.ts_dense_scale)
+        ys = self.flow(x0, dense, return_divergence=False)
+        return ys[:, ::self.ts_dense_scale - 1, :]
+
+    def build_lowerbound_terms(self, ys, ts, **kwargs):
+        raise NotImplementedError
+
+    def build_objective(self, ys, ts):
+        observ_loglik, state_constraint_loglik, state_entropy, initial_state_kl = self.build_lowerbound_terms(ys, ts)
+        inducing_kl = self.build_inducing_kl()
+        return -(observ_loglik + state_constraint_loglik + state_entropy - initial_state_kl - inducing_kl)
+
+    def build_inducing_kl(self):
+        return self.flow.kl() / self.num_observations
+
+    def forward(self, x0, ts):
+        return self.build_flow(x0, ts)
+
+
+class UniformSequenceModel(BaseSequenceModel):
+    """Observations on a uniform time grid: every segment spans ``ts[:2]`` (reference ``models.py:88-146``)."""
+
+    def build_lowerbound_terms(self, ys, ts, num_samples=1, **kwargs):
+        """-> (observation log-lik mean, constraint log-lik, state entropy, initial-state KL), the last three scaled
+        by ``1/num_observations`` (reference ``models.py:108-146``)."""
+        ss_samples = self.state_distribution.sample(num_samples=num_samples)  # (S,N,T,D)
+        (S, N, T, D) = ss_samples.shape
+        # one launch: S*N*T independent one-interval IVPs sharing one GP function draw
+        predicted_xs = self.flow(x0=stack_segments(ss_samples), ts=ts[:2])  # (S*N*T, 2, D)
+        predicted_xs = unstack_segments(predicted_xs[:, -1], (S, N, T, D))
+        observation_loglik = self.likelihood.log_prob(predicted_xs, ys.unsqueeze(0))
+        state_entropy = self.state_distribution.entropy()  # (N,T-1)
+        state_constraint_logprob = self.constraint.log_prob(ss_samples[:, :, 1:, :],
+                                                            predicted_xs[:, :, :-1, :]).sum(3)  # (S,N,T-1)
+        initial_state_kl = self.state_distribution.x0.kl()
+        assert state_entropy.shape == (N, T - 1)
+        assert state_constraint_logprob.shape == (S, N, T - 1)
+        scaled_state_constraint_loglik = state_constraint_logprob.mean(0).sum() / self.num_observations
+        scaled_state_entropy = state_entropy.sum() / self.num_observations
+        scaled_initial_state_kl = initial_state_kl / self.num_observations
+        return observation_loglik.mean(), scaled_state_constraint_loglik, scaled_state_entropy, scaled_initial_state_kl

@@ -1,0 +1,79 @@
+"""Step-grid helpers and small utilities (mirror of reference ``src/misc/torch_utils.py``).
+
+``insert_zero_t0`` / ``compute_ts_dense`` define the RK4 step grid and must match the reference to the bit, so they
+run the very same float32 CPU ops (``torch.linspace`` per interval); the result is cached per time tensor so that a
+training loop pays the (tiny) host work and the device->host read of ``ts`` once, not every ELBO evaluation."""
+import os
+import random
+import weakref
+
+import numpy as np
+import torch
+
+from .settings import settings
+
+dtype = settings.torch_float
+
+
+def numpy2torch(x):
+    dev = settings.device
+    return torch.tensor(x, dtype=dtype).to(dev) if type(x) is np.ndarray else x.to(dev)
+
+
+def torch2numpy(x):
+    return x if type(x) is np.ndarray else x.detach().cpu().numpy()
+
+
+def restore_model(model, filename):
+    checkpt = torch.load(filename, map_location=lambda storage, loc: storage)
+    model.load_state_dict(checkpt['state_dict'])
+    return model
+
+
+def save_model(model, filename):
+    torch.save({'state_dict': model.state_dict()}, filename)
+
+
+def save_model_optimizer(model, optimizer, filename):
+    torch.save({'state_dict': model.state_dict(), 'optimizer_state_dict': optimizer.state_dict()}, filename)
+
+
+_GRID_CACHE = {}
+
+
+def _cached(kind, ts, extra, build):
+    # valid only while the very same tensor object is alive and unmodified (weakref + version counter)
+    key = (kind, id(ts), extra)
+    hit = _GRID_CACHE.get(key)
+    if hit is not None and hit[0]() is ts and hit[1] == ts._version:
+        return hit[2]
+    if len(_GRID_CACHE) > 64:
+        _GRID_CACHE.clear()
+    out = build(ts.detach().to("cpu", torch.float32)).to(ts.device)
+    _GRID_CACHE[key] = (weakref.ref(ts), ts._version, out)
+    return out
+
+
+def insert_zero_t0(ts):
+    """Prepend t=0 and shift the rest by one sampling interval (reference ``torch_utils.py:36-38``)."""
+    return _cached("zero", ts, None, lambda t: torch.cat([torch.tensor([0.0]), t + t[1] - t[0]]))
+
+
+def compute_ts_dense(ts, ts_dense_scale):
+    """(ts_dense_scale - 1) equal sub-steps per interval (reference ``torch_utils.py:41-48``)."""
+    if ts_dense_scale <= 1:
+        return ts
+
+    def build(t):
+        return torch.cat([torch.linspace(t1, t2, ts_dense_scale)[:-1] for (t1, t2) in zip(t[:-1], t[1:])] + [t[-1:]])
+
+    return _cached("dense", ts, int(ts_dense_scale), build)
+
+
+def seed_everything(seed):
+    random.seed(seed)
+    os.environ['PYTHONHASHSEED'] = str(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed(seed)

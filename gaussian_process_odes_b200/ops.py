@@ -195,6 +195,29 @@ def rk4_integrate(x0, t, Z, ell, var, nu, omega, phase, w):
     return _RK4.apply(x0, t, Z, ell, var, nu, omega, phase, w)
 
 
+def dopri5_integrate(x0, t, Z, ell, var, nu, omega, phase, w, rtol=1e-6, atol=1e-6):
+    """Adaptive dopri5 with torchdiffeq 0.2.0's controller in one cooperative kernel (``gpode_dopri5_fwd``).
+    Returns ``(xs (len(t),B,D), stats)`` where ``stats`` is a device int32 tensor [nfe, accepted, rejected, status];
+    ``xs`` carries no autograd graph (the adaptive solver's backward is not built yet -- train with 'rk4')."""
+    tensors = (x0, Z, ell, var, nu)
+    if torch.is_grad_enabled() and any(a.requires_grad for a in tensors):
+        raise _lib.GpodeError("dopri5: the discrete adjoint of the adaptive solver is not implemented; use "
+                              "solver='rk4' for training or call under torch.no_grad() for prediction")
+    lib = _lib.load()
+    pc = PackedCache(Z, ell, var, nu, omega, phase, w)
+    xc = f32(x0, "x0")
+    if xc.ndim != 2 or xc.shape[1] != pc.D:
+        raise _lib.GpodeError("x0 must be (B,%d), got %s" % (pc.D, tuple(xc.shape)))
+    B, Tg = xc.shape[0], t.shape[0]
+    t64 = t.detach().to(device=xc.device, dtype=torch.float64).contiguous()
+    xs = torch.empty(Tg, B, pc.D, dtype=torch.float32, device=xc.device)
+    work = torch.empty(lib.gpode_dopri5_work_floats(pc.D, B), dtype=torch.float32, device=xc.device)
+    stats = torch.zeros(4, dtype=torch.int32, device=xc.device)
+    check(lib.gpode_dopri5_fwd(ptr(pc.packed), pc.D, pc.M, pc.S, ptr(xc), ptr(t64), Tg, B, float(rtol), float(atol),
+                               ptr(xs), ptr(work), ptr(stats), stream_ptr()))
+    return xs, stats
+
+
 def whiten(Z, ell, var, u, omega, phase, w, jitter=1e-5):
     """nu (D,M) = L^-T (u - L^-1 rff_forward(Z)), L = chol(K(Z,Z) + jitter I), per output dimension."""
     return _Whiten.apply(Z, ell, var, u, omega, phase, w, jitter)

@@ -107,12 +107,13 @@ int gpode_kl_bwd(const float* Um, const float* Ls_packed, int D, int M, const fl
 
 /* Adaptive Dormand-Prince 5(4) with torchdiffeq 0.2.0's controller (rtol/atol, whole-batch RMS norm, float64 time,
  * 4th-order dense output) -- odeint(..., method='dopri5'), the reference's default solver (src/core/flow.py:41).
- * Runs as ONE cooperative persistent kernel (accept/reject decided on the device). t_host: the Tg output times on the
- * HOST (float64). work: gpode_dopri5_work_floats(B,D) floats. stats_out (device, 4 int32): nfe, accepted, rejected,
- * status. */
+ * Runs as ONE cooperative persistent kernel: accept/reject is decided on the device, one grid barrier per attempt.
+ * t: the Tg output times, DEVICE float64, strictly monotone in either direction (a decreasing grid is integrated as
+ * -f over -t, which is what torchdiffeq does). work: gpode_dopri5_work_floats(D,B) floats.
+ * stats_out (device, 4 int32): nfe, accepted steps, rejected steps, status (0 ok, 1 attempt limit, 2 dt underflow). */
 int64_t gpode_dopri5_work_floats(int D, int64_t B);
-int gpode_dopri5_fwd(const float* packed, int D, int M, int S, const float* x0, const double* t_host, int Tg,
-                     int64_t B, double rtol, double atol, float* xs, float* work, int32_t* stats_out, void* stream);
+int gpode_dopri5_fwd(const float* packed, int D, int M, int S, const float* x0, const double* t, int Tg, int64_t B,
+                     double rtol, double atol, float* xs, float* work, int32_t* stats_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,116 @@
+"""-m gpu: the product models (reference API) against the committed golden fixtures, which hold the outputs of the
+UNMODIFIED reference run in the build container (oracle/pin_against_reference.py) plus a float64 arbiter."""
+import ast
+
+import pytest
+import torch
+
+from util import (TOL_GRAD, TOL_TRAJ, TOL_VF, assert_parity, build_product_model, injected_draws, load_golden,
+                  product_grads, relerr)
+
+pytestmark = pytest.mark.gpu
+
+RK4_CASES = ["vdp_gpode_rk4", "vdp_shooting_rk4", "mocap_gpode_rk4", "mocap_shooting_rk4", "d3_shooting_rk4"]
+DOPRI5_CASES = ["vdp_gpode_dopri5", "vdp_shooting_dopri5"]
+
+
+def _model(g):
+    kind, solver, kw, extra = g['meta'][0], g['meta'][1], ast.literal_eval(g['meta'][2]), ast.literal_eval(g['meta'][3])
+    model = build_product_model(kind, g['p'], g['ys'], kw['S'], solver, ts_dense_scale=extra.get('ts_dense_scale', 4),
+                                proj=g['proj'])
+    return kind, solver, kw, model
+
+
+def _loss(kind, model, g, S_mc):
+    from gaussian_process_odes_b200 import builders
+    ys, ts = g['ys'].cuda(), g['ts'].cuda()
+    if kind == "gpode":
+        with injected_draws(g['draws'], mvn_order=("eps_x0",)):
+            loss, nll, k0, kl = builders.compute_loss_gpode(model, ys, ts)
+        terms = dict(observ_loglik=-nll, init_state_kl=k0, inducing_kl=kl)
+    else:
+        with injected_draws(g['draws'], mvn_order=("eps_x0", "eps_states")):
+            ll, c, e, k0 = model.build_lowerbound_terms(ys, ts, num_samples=S_mc)
+            kl = model.build_inducing_kl()
+            loss = -(ll + c + e - k0 - kl)
+        terms = dict(observ_loglik=ll, constraint_loglik=c, state_entropy=e, init_state_kl=k0, inducing_kl=kl)
+    return loss, terms
+
+
+@pytest.mark.parametrize("name", RK4_CASES)
+def test_elbo_and_gradients_match_reference(name):
+    g = load_golden(name)
+    kind, solver, kw, model = _model(g)
+    loss, terms = _loss(kind, model, g, kw.get('S_mc', 1))
+    loss.backward()
+    ref, f64 = g['ref'], g['f64']
+    assert_parity(name + " loss", loss, ref['loss'], f64['loss'], TOL_GRAD)
+    for k, v in terms.items():
+        assert_parity(name + " term " + k, v.reshape(()), ref['term_' + k].reshape(()), f64['term_' + k].reshape(()),
+                      TOL_GRAD)
+    grads = product_grads(model, kind)
+    for k, v in grads.items():
+        assert v is not None, k
+        assert_parity(name + " grad " + k, v.cpu(), ref['grad_' + k], f64['grad_' + k], TOL_GRAD)
+    assert model.flow.num_evals() == float(ref['nfe'])
+    # the cache of that ELBO evaluation
+    gp = model.flow.odefunc.diffeq
+    assert relerr(gp.rff_omega.cpu(), ref['cache_omega']) <= 1e-6
+    assert relerr(gp.rff_phase.cpu(), ref['cache_phase']) <= 1e-6
+    assert torch.equal(gp.rff_weights.cpu(), ref['cache_w'])
+    with torch.no_grad():
+        f = gp(None, ref['probe_x'].cuda()).cpu()
+    assert_parity(name + " probe f", f, ref['probe_f'], f64['probe_f_closed'], TOL_VF)
+
+
+@pytest.mark.parametrize("name", RK4_CASES + DOPRI5_CASES)
+def test_flow_forward_matches_reference(name):
+    g = load_golden(name)
+    kind, solver, kw, model = _model(g)
+    with torch.no_grad(), injected_draws(g['draws']):
+        xs = model.flow(g['ref']['traj_in'].cuda(), g['ref']['traj_grid'].cuda()).cpu()
+    assert xs.shape == g['ref']['traj_out'].shape
+    assert_parity(name + " Flow.forward", xs, g['ref']['traj_out'], g['f64']['traj_out'], TOL_TRAJ)
+
+
+@pytest.mark.parametrize("name", DOPRI5_CASES)
+def test_dopri5_elbo_value_matches_reference(name):
+    g = load_golden(name)
+    kind, solver, kw, model = _model(g)
+    with torch.no_grad():
+        loss, terms = _loss(kind, model, g, kw.get('S_mc', 1))
+    assert_parity(name + " loss", loss, g['ref']['loss'], g['f64']['loss'], TOL_GRAD)
+    # accept/reject decisions may differ by one attempt through float32 round-off of the error ratio
+    assert abs(model.flow.num_evals() - float(g['ref']['nfe'])) <= 12
+
+
+def test_state_dict_keys_and_reload():
+    g = load_golden("vdp_shooting_rk4")
+    kind, solver, kw, model = _model(g)
+    keys = set(model.state_dict().keys())
+    assert {'flow.odefunc.diffeq.kern.unconstrained_lengthscales', 'flow.odefunc.diffeq.kern.unconstrained_variance',
+            'flow.odefunc.diffeq.inducing_loc.optvar', 'flow.odefunc.diffeq.Um.optvar',
+            'flow.odefunc.diffeq.Us_sqrt.optvar', 'state_distribution.param_mean.optvar',
+            'state_distribution.param_lchol.optvar', 'state_distribution.x0.param_mean.optvar',
+            'state_distribution.x0.param_lchol.optvar', 'likelihood.unconstrained_variance',
+            'constraint.unconstrained_scale', 'flow.odefunc._num_evals'} == keys
+
+
+def test_training_step_decreases_loss():
+    """A few Adam steps through the full stack (whitening + RK4 adjoint) on the VDP shooting problem."""
+    from gaussian_process_odes_b200 import builders
+    from gaussian_process_odes_b200.misc.torch_utils import seed_everything
+    g = load_golden("vdp_shooting_rk4")
+    kind, solver, kw, model = _model(g)
+    seed_everything(3)
+    opt = torch.optim.Adam(model.parameters(), lr=5e-3)
+    ys, ts = g['ys'].cuda(), g['ts'].cuda()
+    losses = []
+    for _ in range(12):
+        opt.zero_grad()
+        loss = builders.compute_loss_shooting(model, ys, ts, num_samples=5)[0]
+        loss.backward()
+        opt.step()
+        losses.append(float(loss.detach()))
+    assert all(l == l for l in losses)
+    assert min(losses[-3:]) < losses[0]

@@ -63,3 +63,92 @@ def oracle_cache(p, draws, dtype=torch.float32):
     c = O.build_cache(gp['Z'], gp['Um'], gp['Us_sqrt'], gp['ell'], gp['var'], d['w'], d['eps_omega'], d['phase_u'],
                       d['eps_u'])
     return gp, c
+
+
+# ---- building the product model from the shared unconstrained-parameter dict, and injecting random draws ----------
+class _Queue:
+    def __init__(self, items, what):
+        self.items, self.what = list(items), what
+
+    def __call__(self, shape, *a, **k):
+        assert self.items, "more %s draws requested than injected" % self.what
+        x = self.items.pop(0)
+        assert tuple(x.shape) == tuple(shape), (self.what, tuple(x.shape), tuple(shape))
+        return x.clone()
+
+
+class injected_draws:
+    """The next build_cache / rsample calls of the product modules consume ``draws`` (same protocol as
+    oracle/reference_harness.injected_draws uses on the reference's modules)."""
+
+    def __init__(self, draws, n_caches=1, mvn_order=()):
+        self.d, self.n, self.mvn_order = draws, n_caches, mvn_order
+
+    def __enter__(self):
+        from gaussian_process_odes_b200.core import dsvgp, kernels, states
+        d = {k: v.cpu() for k, v in self.d.items()}
+        self.mods = (dsvgp, kernels, states)
+        self.saved = (dsvgp.sample_normal, dsvgp.sample_uniform, kernels.sample_normal, states._standard_normal)
+        dsvgp.sample_normal = _Queue([d['w'], d['eps_u']] * self.n, "dsvgp.normal")
+        dsvgp.sample_uniform = _Queue([d['phase_u']] * self.n, "dsvgp.uniform")
+        kernels.sample_normal = _Queue([d['eps_omega']] * self.n, "kernels.normal")
+        q = _Queue([d[k] for k in self.mvn_order], "states.standard_normal")
+        states._standard_normal = lambda shape, dtype, device: q(shape).to(device=device, dtype=dtype)
+        return self
+
+    def __exit__(self, *exc):
+        dsvgp, kernels, states = self.mods
+        dsvgp.sample_normal, dsvgp.sample_uniform, kernels.sample_normal, states._standard_normal = self.saved
+        return False
+
+
+def _set(param, value):
+    with torch.no_grad():
+        param.copy_(value.to(param))
+
+
+def build_product_model(kind, p, ys, S, solver, ts_dense_scale=4, proj=None):
+    from gaussian_process_odes_b200 import builders
+    N, T, Dobs = ys.shape
+    M, D = p['inducing_loc'].shape
+    projection = None
+    if proj is not None:
+        comp = proj.cuda()
+        projection = lambda x: torch.einsum('ntl,ld->ntd', x, comp)
+    if kind == "gpode":
+        model = builders.build_gpode(N, T, D, num_inducing=M, num_features=S, solver=solver,
+                                     ts_dense_scale=ts_dense_scale, D_obs=Dobs, projection=projection)
+        x0d = model.x0_distribution
+    else:
+        model = builders.build_gpode_shooting(N, T, D, num_inducing=M, num_features=S, solver=solver, D_obs=Dobs,
+                                              projection=projection)
+        x0d = model.state_distribution.x0
+        _set(model.state_distribution.param_mean.optvar, p['state_mean'])
+        _set(model.state_distribution.param_lchol.optvar, p['state_lchol_packed'])
+        _set(model.constraint.unconstrained_scale, p['constraint_unconstrained_scale'])
+    gp = model.flow.odefunc.diffeq
+    _set(gp.inducing_loc.optvar, p['inducing_loc'])
+    _set(gp.Um.optvar, p['Um'])
+    _set(gp.Us_sqrt.optvar, p['Us_sqrt_packed'])
+    _set(gp.kern.unconstrained_lengthscales, p['unconstrained_lengthscales'])
+    _set(gp.kern.unconstrained_variance, p['unconstrained_variance'])
+    _set(x0d.param_mean.optvar, p['x0_mean'])
+    _set(x0d.param_lchol.optvar, p['x0_lchol_packed'])
+    _set(model.likelihood.unconstrained_variance, p['lik_unconstrained_variance'])
+    return model
+
+
+def product_grads(model, kind):
+    gp = model.flow.odefunc.diffeq
+    g = dict(inducing_loc=gp.inducing_loc.optvar.grad, Um=gp.Um.optvar.grad, Us_sqrt_packed=gp.Us_sqrt.optvar.grad,
+             unconstrained_lengthscales=gp.kern.unconstrained_lengthscales.grad,
+             unconstrained_variance=gp.kern.unconstrained_variance.grad,
+             lik_unconstrained_variance=model.likelihood.unconstrained_variance.grad)
+    if kind == "gpode":
+        g.update(x0_mean=model.x0_distribution.param_mean.optvar.grad,
+                 x0_lchol_packed=model.x0_distribution.param_lchol.optvar.grad)
+    else:
+        sd = model.state_distribution
+        g.update(x0_mean=sd.x0.param_mean.optvar.grad, x0_lchol_packed=sd.x0.param_lchol.optvar.grad,
+                 state_mean=sd.param_mean.optvar.grad, state_lchol_packed=sd.param_lchol.optvar.grad)
+    return g
