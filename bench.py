@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- GP vector-field evals/s of the multiple-shooting ELBO forward+backward step (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--rows-scale F]
+
+Workload (``config.workload``): BASELINE.json configs[3], "MoCap GPODE shooting variant on long synthetic
+MoCap-shaped trajectories": latent D=5 -> D_obs=50 through a fixed orthonormal decoder, M=100 inducing points, S=256
+Fourier features, S_mc=5 Monte-Carlo samples, N=16 sequences of T=12500 points per GPU -> 1,000,000 one-interval
+shooting segments per GPU, one RK4 (3/8 rule) step of h=0.01 each. It is the largest single-GPU configuration, and
+the one that shards (sequences across GPUs, weak scaling: N grows with the GPU count).
+
+One "step" = one ELBO forward + backward (``build_lowerbound_terms`` + ``build_inducing_kl`` + ``loss.backward()``,
+plus the shared-gradient all-reduce when N > 1) through the reference-facing API: GP cache build (whitening kernel),
+fused RK4 forward kernel over all segments, the ELBO side terms, the discrete-adjoint kernel, the per-inducing-point
+gradient kernel, whitening backward. The optimiser step is not part of the metric.
+
+value = segments x 4 vector-field evaluations (the reference's own NFE count for this step) / step time, aggregated
+over all GPUs. ``e2e`` repeats the measurement with the observations copied from pinned host memory and the loss
+read back to the host inside every timed step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOAD = dict(name="mocap_shooting_long", D=5, D_obs=50, M=100, S=256, S_mc=5, N_per_gpu=16, T=12500, dt=0.01,
+                solver="rk4")
+METRIC = "gp_vector_field_evals_per_sec_elbo_fwd_bwd"
+UNIT = "evals/s"
+
+
+def f_vf(D, S, M):
+    """Algorithmic flops of one vector-field evaluation of one row."""
+    return D * (S * (2 * D + 4) + M * (3 * D + 4))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# synthetic problem of the workload's shape
+# ----------------------------------------------------------------------------------------------------------------------
+def synthetic_sequences(N, T, D, D_obs, seed):
+    """Smooth latent sequences (re-standardised cumulative sums) and their noisy decoded observations."""
+    rng = np.random.default_rng(seed)
+    lat = np.cumsum(rng.normal(size=(N, T, D)) * 0.05, axis=1)
+    lat = (lat - lat.mean(axis=(0, 1), keepdims=True)) / (lat.std(axis=(0, 1), keepdims=True) + 1e-8)
+    q, _ = np.linalg.qr(np.random.default_rng(1234).normal(size=(D_obs, D)))  # same decoder on every rank
+    comp = q.T.astype(np.float32)  # (D, D_obs)
+    ys = lat @ comp + rng.normal(size=(N, T, D_obs)) * 0.1
+    return lat.astype(np.float32), ys.astype(np.float32), comp
+
+
+def build_ours(w, rank, world, rows_scale):
+    from gaussian_process_odes_b200 import builders, distributed
+    T = max(3, int(round(w["T"] * rows_scale)))
+    N_loc, N_glob = w["N_per_gpu"], w["N_per_gpu"] * world
+    lat, ys, comp = synthetic_sequences(N_loc, T, w["D"], w["D_obs"], seed=121 + rank)
+    comp_d = torch.tensor(comp, device="cuda")
+    projection = lambda x: torch.einsum('ntl,ld->ntd', x, comp_d)
+    np.random.seed(121)  # identical GP initialisation on every rank
+    model = builders.build_gpode_shooting(N_loc, T, w["D"], num_inducing=w["M"], num_features=w["S"],
+                                          solver=w["solver"], D_obs=w["D_obs"], projection=projection)
+    model.num_observations = N_glob * T * w["D_obs"]
+    gp = model.flow.odefunc.diffeq
+    with torch.no_grad():
+        gp.inducing_loc.optvar.copy_(torch.tensor(np.random.default_rng(5).normal(size=(w["M"], w["D"])),
+                                                  dtype=torch.float32))
+        model.state_distribution.x0.param_mean.optvar.copy_(torch.tensor(lat[:, 0]))
+        model.state_distribution.param_mean.optvar.copy_(torch.tensor(lat[:, 1:]))
+    distributed.broadcast_shared_parameters(model)
+    ts = torch.arange(T, dtype=torch.float32) * w["dt"]
+    return model, torch.tensor(ys), ts, N_glob, T
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ----------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smmax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smmax.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(smmax) if smmax else None,
+                    power_w_max=max(power) if power else None, samples=len(sm), reasons=sorted(reasons))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port (reference algorithm restated op-for-op on torch CPU) on a bounded sample
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_elbo_timing(w, steps, warmup, T_sample=6000, N_sample=1):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import gpode_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    p, ys, ts, draws, proj = O.make_problem(D=w["D"], M=w["M"], S=w["S"], N=N_sample, T=T_sample, S_mc=w["S_mc"],
+                                            D_obs=w["D_obs"], dt=w["dt"], ell0=1.25, seed=121)
+    rows = w["S_mc"] * N_sample * T_sample
+    times = []
+    for i in range(warmup + steps):
+        pp = {k: v.detach().clone().requires_grad_(True) for k, v in p.items()}
+        t0 = time.perf_counter()
+        r = O.elbo_shooting(pp, ys, ts, draws, method=w["solver"], project=proj)
+        r["loss"].backward()
+        t1 = time.perf_counter()
+        if i >= warmup:
+            times.append(t1 - t0)
+    sec = float(np.median(times))
+    return dict(value=rows * 4 / sec, unit=UNIT, cores=torch.get_num_threads(), kind="port",
+                sample="%d segments (S_mc=%d x N=%d x T=%d) of the same D=%d,M=%d,S=%d,D_obs=%d workload, median of %d "
+                       "ELBO fwd+bwd steps of the oracle port (torch CPU float32, %d threads)" % (
+                           rows, w["S_mc"], N_sample, T_sample, w["D"], w["M"], w["S"], w["D_obs"], steps,
+                           torch.get_num_threads()),
+                ms_per_step=sec * 1e3, rows=rows)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = WORKLOAD
+    cb = cpu_elbo_timing(w, steps=max(args.steps, 3), warmup=max(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["name"], "D": w["D"], "D_obs": w["D_obs"], "M": w["M"], "S": w["S"],
+                       "S_mc": w["S_mc"], "solver": w["solver"], "segments_per_step": cb["rows"],
+                       "note": "reference algorithm (oracle port; the Python reference and torchdiffeq cannot travel "
+                               "to the GPU box) on the host cores, bounded sample of the workload"},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    from gaussian_process_odes_b200 import _lib, distributed
+    rank, world, local_rank = distributed.init_from_env()
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU path exists)"
+    if world != args.gpus:
+        if rank == 0:
+            print("warning: --gpus %d but WORLD_SIZE=%d" % (args.gpus, world), file=sys.stderr)
+    w = WORKLOAD
+    dev = torch.device("cuda", local_rank)
+    _lib.load()
+    distributed.seed_ranks(121, rank)
+    model, ys_host, ts_host, N_glob, T = build_ours(w, rank, world, args.rows_scale)
+    ys_pinned = ys_host.pin_memory()
+    ts_dev = ts_host.to(dev)
+    ys_dev = ys_pinned.to(dev, non_blocking=True)
+    rows_local = w["S_mc"] * w["N_per_gpu"] * T
+    rows_total = rows_local * world
+    evals_per_step = rows_total * 4
+
+    def step(ys):
+        model.zero_grad(set_to_none=True)
+        loss = distributed.sharded_shooting_loss(model, ys, ts_dev, w["S_mc"], N_glob, world)
+        loss.backward()
+        distributed.allreduce_shared_grads(model)
+        return loss
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(nsteps, body):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(nsteps):
+            body()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        step(ys_dev)
+
+    # ---- device-resident measurement ----
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    _lib.reset_launch_count()
+    ms_total = timed(args.steps, lambda: step(ys_dev))
+    launches = _lib.total_launches()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms_total / args.steps
+    value = evals_per_step / (ms_per_step * 1e-3)
+
+    # ---- end to end: pinned host observations in, loss out, every step ----
+    def e2e_body():
+        y = ys_pinned.to(dev, non_blocking=True)
+        t = ts_host.to(dev, non_blocking=True)
+        model.zero_grad(set_to_none=True)
+        loss = distributed.sharded_shooting_loss(model, y, t, w["S_mc"], N_glob, world)
+        loss.backward()
+        distributed.allreduce_shared_grads(model)
+        e2e_body.last = float(loss.detach().item())
+    for _ in range(2):
+        e2e_body()
+    ms_e2e = timed(args.steps, e2e_body) / args.steps
+    e2e = {"value": evals_per_step / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+           "h2d_bytes_per_step": int((ys_pinned.numel() + ts_host.numel()) * 4 * world), "d2h_bytes_per_step": 4 * world}
+
+    # ---- per-kernel breakdown (separate pass, CUDA events around every C-ABI call) and the roofline ----
+    _lib.profile_start()
+    n_prof = 3
+    for _ in range(n_prof):
+        step(ys_dev)
+    prof = _lib.profile_stop()
+    kern = {k: {"calls_per_step": c / n_prof, "ms_per_step": ms / n_prof} for k, (c, ms) in prof.items()}
+    ours_ms = sum(v["ms_per_step"] for v in kern.values())
+
+    roof = None
+    if rank == 0:
+        import ctypes
+        tf, ms_probe = ctypes.c_double(), ctypes.c_double()
+        scratch = torch.zeros(4, device=dev)
+        _lib.check(_lib.load().gpode_probe_fp32_fma(ctypes.byref(tf), ctypes.byref(ms_probe),
+                                                    _lib.ptr(scratch), _lib.stream_ptr()))
+        fv = f_vf(w["D"], w["S"], w["M"])
+        flops = {"gpode_rk4_fwd": rows_local * (4 * fv + 14 * w["D"]),   # 4 F_vf + 14 D per row-step
+                 "gpode_rk4_bwd": rows_local * 8 * fv}                     # 4 VJPs ~ 2 F_vf each; nothing is recomputed
+        dom = max(flops, key=lambda k: kern.get(k, {"ms_per_step": 0})["ms_per_step"])
+        ms_dom = kern[dom]["ms_per_step"] / max(kern[dom]["calls_per_step"], 1)
+        achieved = flops[dom] / (ms_dom * 1e-3) / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(dom)
+            except Exception:
+                traffic = None
+        other = "gpode_rk4_fwd" if dom == "gpode_rk4_bwd" else "gpode_rk4_bwd"
+        roof = {"bound": "fp32_fma", "kernel": dom, "achieved": achieved, "peak": tf.value, "unit": "TFLOP/s",
+                "frac": achieved / tf.value, "traffic": traffic,
+                "peak_source": "measured here: gpode_probe_fp32_fma (register-only FMA loop, best of 5); "
+                               "MEASURED_PEAKS.json has no FP32 entry",
+                "algorithmic_flops_per_launch": flops[dom], "kernel_ms": ms_dom,
+                "also": {other: {"achieved": flops[other] / (kern[other]["ms_per_step"] * 1e-3) / 1e12,
+                                 "frac": flops[other] / (kern[other]["ms_per_step"] * 1e-3) / 1e12 / tf.value,
+                                 "kernel_ms": kern[other]["ms_per_step"]}},
+                "hbm_note": "FMA-bound path: algorithmic HBM bytes are %d per row forward (arithmetic intensity > 1e3 "
+                            "flop/byte), so the HBM roofline (MEASURED_PEAKS.json hbm_gbs) is not the binding one" % (
+                                4 * w["D"] * 3)}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_elbo_timing(w, steps=8, warmup=2)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": w["name"], "D": w["D"], "D_obs": w["D_obs"], "M": w["M"], "S": w["S"],
+                           "S_mc": w["S_mc"], "N_sequences_per_gpu": w["N_per_gpu"], "T": T, "solver": w["solver"],
+                           "segments_per_gpu": rows_local, "segments_total": rows_total,
+                           "evals_per_step": evals_per_step, "parallelism": "sequences sharded x%d" % world,
+                           "l2": "working set per step (>= 0.6 GB of segment states, stage checkpoints and decoded "
+                                 "predictions) exceeds the 126 MB L2; no explicit flush"},
+                "elbo_fwd_bwd_ms": ms_per_step, "e2e": e2e, "gpu_launches": launches,
+                "kernels_ms_per_step": kern, "own_kernels_share_of_step": ours_ms / ms_per_step,
+                "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "loss": getattr(e2e_body, "last", None)}
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows-scale", type=float, default=1.0, help="scale T (segments per GPU) for quick runs")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -34,6 +34,7 @@ SIGNATURES = {
     "gpode_vf_bwd": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _L, _P]),
     "gpode_rk4_fwd": (_I, [_P, _I, _I, _I, _P, _P, _I, _L, _P, _P, _P]),
     "gpode_rk4_bwd": (_I, [_P, _I, _I, _I, _P, _I, _L, _P, _P, _P, _P, _P, _P, _P]),
+    "gpode_param_grad": (_I, [_P, _I, _I, _I, _P, _P, _L, _P, _P]),
     "gpode_acc_floats": (_L, [_I, _I]),
     "gpode_vrow_floats": (_L, [_I, _L]),
     "gpode_grads_finalize": (_I, [_CP, _P, _P, _P, _P, _P, _P]),
@@ -42,6 +43,7 @@ SIGNATURES = {
     "gpode_kl_fwd": (_I, [_P, _P, _I, _I, _P, _P]),
     "gpode_kl_bwd": (_I, [_P, _P, _I, _I, _P, _P, _P, _P]),
     "gpode_dopri5_work_floats": (_L, [_I, _L]),
+    "gpode_probe_fp32_fma": (_I, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), _P, _P]),
     "gpode_dopri5_fwd": (_I, [_P, _I, _I, _I, _P, _P, _I, _L, _D, _D, _P, _P, _P, _P]),
 }
 
@@ -99,3 +101,47 @@ def f32(t, name="tensor"):
     if not t.is_cuda:
         raise GpodeError("%s must live on a CUDA device, got %s (there is no CPU path)" % (name, t.device))
     return t.detach().contiguous()
+
+
+# ---- launch accounting and optional per-call CUDA-event timing (used by bench.py) --------------------------------
+# kernels enqueued by one C-ABI call (memsets / memcpys not counted)
+KERNELS_PER_CALL = {"gpode_pack_cache": 1, "gpode_vf_fwd": 1, "gpode_vf_bwd": 1, "gpode_rk4_fwd": 1,
+                    "gpode_rk4_bwd": 1, "gpode_param_grad": 1, "gpode_grads_finalize": 1, "gpode_whiten_fwd": 1, "gpode_whiten_bwd": 1,
+                    "gpode_kl_fwd": 1, "gpode_kl_bwd": 1, "gpode_dopri5_fwd": 1}
+LAUNCH_COUNT = {}
+_PROFILE = None  # None, or {name: [(start_event, end_event), ...]}
+
+
+def profile_start():
+    global _PROFILE
+    _PROFILE = {}
+
+
+def profile_stop():
+    """-> {name: (calls, total_ms)}; synchronises the device."""
+    global _PROFILE
+    rec, _PROFILE = _PROFILE, None
+    torch.cuda.synchronize()
+    return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in (rec or {}).items()}
+
+
+def reset_launch_count():
+    LAUNCH_COUNT.clear()
+
+
+def total_launches():
+    return sum(LAUNCH_COUNT.values())
+
+
+def call(name, *args):
+    """Invoke one C-ABI entry point on the current stream, check its return code, count its kernel launches."""
+    fn = getattr(load(), name)
+    LAUNCH_COUNT[name] = LAUNCH_COUNT.get(name, 0) + KERNELS_PER_CALL[name]
+    if _PROFILE is None:
+        check(fn(*args))
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    check(fn(*args))
+    e1.record()
+    _PROFILE.setdefault(name, []).append((e0, e1))

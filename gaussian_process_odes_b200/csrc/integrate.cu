@@ -85,10 +85,8 @@ extern "C" int gpode_rk4_bwd(const float* packed, int D, int M, int S, const flo
     const int64_t VR = (int64_t)(Tg - 1) * 4 * B;
     float* vy = vrows;
     float* vk = vrows + VR * D;
-    if (int rc = rk4_bwd_dispatch(packed, D, M, S, t, Tg, B, xs, kstages, grad_xs, grad_x0, vy, vk, acc,
-                                  (cudaStream_t)stream))
-        return rc;
-    return gpode_param_grad_launch(packed, D, M, S, vy, vk, VR, acc, (cudaStream_t)stream);
+    return rk4_bwd_dispatch(packed, D, M, S, t, Tg, B, xs, kstages, grad_xs, grad_x0, vy, vk, acc,
+                            (cudaStream_t)stream);
 }
 
 static int vf_bwd_dispatch(const float* packed, int D, int M, int S, const float* x, const float* f, const float* gf,
@@ -103,8 +101,15 @@ extern "C" int gpode_vf_bwd(const float* packed, int D, int M, int S, const floa
     if (int rc = check_common(packed, D, M, S, B)) return rc;
     if (B == 0) return 0;
     GPODE_CHECK_ARG(x && f && grad_f && grad_x && acc, "NULL argument");
-    if (int rc = vf_bwd_dispatch(packed, D, M, S, x, f, grad_f, grad_x, B, acc, (cudaStream_t)stream)) return rc;
-    return gpode_param_grad_launch(packed, D, M, S, x, grad_f, B, acc, (cudaStream_t)stream);
+    return vf_bwd_dispatch(packed, D, M, S, x, f, grad_f, grad_x, B, acc, (cudaStream_t)stream);
+}
+
+extern "C" int gpode_param_grad(const float* packed, int D, int M, int S, const float* ys, const float* kbs,
+                                int64_t n_rows, float* acc, void* stream) {
+    if (int rc = check_common(packed, D, M, S, n_rows)) return rc;
+    if (n_rows == 0) return 0;
+    GPODE_CHECK_ARG(ys && kbs && acc, "NULL argument");
+    return gpode_param_grad_launch(packed, D, M, S, ys, kbs, n_rows, acc, (cudaStream_t)stream);
 }
 
 extern "C" int64_t gpode_vrow_floats(int D, int64_t n_virtual_rows) { return 2 * n_virtual_rows * (int64_t)D; }

@@ -1,0 +1,108 @@
+"""Multi-GPU data parallelism over independent sequences / shooting segments.
+
+One process per GPU (``torch.distributed``, NCCL over NVLink). The multiple-shooting ELBO is a sum over sequences
+(reference ``src/gpode_shooting/models.py:119-146``): each rank owns a contiguous block of sequences together with
+their variational state parameters, every rank holds the same GP / likelihood parameters and draws the SAME GP
+function sample (the reference draws it with numpy's global generator, so seeding numpy identically on all ranks is
+enough), and the only exchange per step is ONE all-reduce(sum) of the small flattened shared-parameter gradient.
+There is no data-path collective: segment rows never leave their GPU.
+"""
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend=None):
+    """Initialise the default process group from torchrun's environment; returns (rank, world, local_rank)."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local_rank)
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kw = {}
+        if backend == "nccl":
+            kw["device_id"] = torch.device("cuda", local_rank)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
+    return rank, world, local_rank
+
+
+def shard_range(n_total, rank, world):
+    """Contiguous, balanced block ``[lo, hi)`` of ``n_total`` sequences for ``rank`` (first ranks get the remainder)."""
+    base, rem = divmod(n_total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def seed_ranks(seed, rank):
+    """numpy (GP function draws: identical on every rank) vs torch (state samples: different per rank)."""
+    np.random.seed(seed)
+    torch.manual_seed(seed + 1000003 * (rank + 1))
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed(seed + 1000003 * (rank + 1))
+
+
+def shared_parameters(model):
+    """Parameters replicated on every rank (GP, likelihood, constraint) -- everything but the per-sequence states."""
+    local = set()
+    for name in ("state_distribution", "x0_distribution"):
+        mod = getattr(model, name, None)
+        if mod is not None:
+            local.update(id(p) for p in mod.parameters())
+    return [p for p in model.parameters() if id(p) not in local]
+
+
+def broadcast_shared_parameters(model, src=0):
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    params = shared_parameters(model)
+    flat = torch.cat([p.data.reshape(-1) for p in params])
+    dist.broadcast(flat, src=src)
+    off = 0
+    for p in params:
+        n = p.numel()
+        p.data.copy_(flat[off:off + n].view_as(p))
+        off += n
+
+
+def allreduce_shared_grads(model):
+    """ONE all-reduce(sum) over the flattened gradients of the shared parameters (a few thousand floats)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return 0
+    params = [p for p in shared_parameters(model) if p.requires_grad]
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    off = 0
+    for p in params:
+        n = p.numel()
+        g = flat[off:off + n].view_as(p)
+        if p.grad is None:
+            p.grad = g.clone()
+        else:
+            p.grad.copy_(g)
+        off += n
+    return flat.numel()
+
+
+def combine_shard_terms(observ_loglik_mean_local, scaled_constraint, scaled_entropy, scaled_init_kl, scaled_inducing_kl,
+                        n_local, n_global, world):
+    """Rank-local loss whose SUM over ranks is the global negative ELBO.
+
+    The model on each rank is built with the GLOBAL ``num_observations``, so the constraint / entropy / initial-KL
+    terms (sums over local sequences divided by the global count) just add up; the observation term is a mean over
+    local observations and is re-weighted by ``n_local / n_global``; the inducing KL is counted once."""
+    w = float(n_local) / float(n_global)
+    return -(w * observ_loglik_mean_local + scaled_constraint + scaled_entropy - scaled_init_kl
+             - scaled_inducing_kl / float(world))
+
+
+def sharded_shooting_loss(model, ys_local, ts, num_samples, n_global, world):
+    ll, cons, ent, k0 = model.build_lowerbound_terms(ys_local, ts, num_samples=num_samples)
+    kl = model.build_inducing_kl()
+    return combine_shard_terms(ll, cons, ent, k0, kl, ys_local.shape[0], n_global, world)

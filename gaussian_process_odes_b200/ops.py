@@ -43,7 +43,7 @@ class PackedCache:
         self.packed = torch.empty(n, dtype=torch.float32, device=self.Z.device)
         self.struct = _cache_struct(self.D, self.M, self.S, self.omega, self.phase, self.w, self.Z, self.nu,
                                     self.ell, self.var)
-        check(lib.gpode_pack_cache(ctypes.byref(self.struct), ptr(self.packed), stream_ptr()))
+        _lib.call("gpode_pack_cache", ctypes.byref(self.struct), ptr(self.packed), stream_ptr())
 
     def new_acc(self):
         n = _lib.load().gpode_acc_floats(self.D, self.M)
@@ -56,8 +56,8 @@ class PackedCache:
         g_var = torch.empty(self.D, dtype=torch.float32, device=dev)
         g_Z = torch.empty(self.M, self.D, dtype=torch.float32, device=dev)
         g_nu = torch.empty(self.D, self.M, dtype=torch.float32, device=dev)
-        check(_lib.load().gpode_grads_finalize(ctypes.byref(self.struct), ptr(acc), ptr(g_ell), ptr(g_var), ptr(g_Z),
-                                               ptr(g_nu), stream_ptr()))
+        _lib.call("gpode_grads_finalize", ctypes.byref(self.struct), ptr(acc), ptr(g_ell), ptr(g_var), ptr(g_Z),
+                                               ptr(g_nu), stream_ptr())
         return g_Z, g_ell, g_var, g_nu
 
 
@@ -71,7 +71,7 @@ class _VectorField(torch.autograd.Function):
         if xc.ndim != 2 or xc.shape[1] != pc.D:
             raise _lib.GpodeError("x must be (B,%d), got %s" % (pc.D, tuple(xc.shape)))
         f = torch.empty_like(xc)
-        check(_lib.load().gpode_vf_fwd(ptr(pc.packed), pc.D, pc.M, pc.S, ptr(xc), ptr(f), xc.shape[0], stream_ptr()))
+        _lib.call("gpode_vf_fwd", ptr(pc.packed), pc.D, pc.M, pc.S, ptr(xc), ptr(f), xc.shape[0], stream_ptr())
         ctx.pc, ctx.nu_shape = pc, nu.shape
         ctx.save_for_backward(xc, f)
         return f
@@ -83,8 +83,10 @@ class _VectorField(torch.autograd.Function):
         gf = f32(gf, "grad_f")
         gx = torch.empty_like(xc)
         acc = pc.new_acc()
-        check(_lib.load().gpode_vf_bwd(ptr(pc.packed), pc.D, pc.M, pc.S, ptr(xc), ptr(f), ptr(gf), ptr(gx), ptr(acc),
-                                       xc.shape[0], stream_ptr()))
+        _lib.call("gpode_vf_bwd", ptr(pc.packed), pc.D, pc.M, pc.S, ptr(xc), ptr(f), ptr(gf), ptr(gx), ptr(acc),
+                                       xc.shape[0], stream_ptr())
+        _lib.call("gpode_param_grad", ptr(pc.packed), pc.D, pc.M, pc.S, ptr(xc), ptr(gf), xc.shape[0], ptr(acc),
+                  stream_ptr())
         g_Z, g_ell, g_var, g_nu = pc.finalize(acc)
         return gx, g_Z, g_ell, g_var, g_nu.reshape(ctx.nu_shape), None, None, None
 
@@ -102,8 +104,8 @@ class _RK4(torch.autograd.Function):
         need_grad = any(ctx.needs_input_grad)
         xs = torch.empty(Tg, B, pc.D, dtype=torch.float32, device=xc.device)
         kst = torch.empty(max(Tg - 1, 0), 4, B, pc.D, dtype=torch.float32, device=xc.device) if need_grad else None
-        check(_lib.load().gpode_rk4_fwd(ptr(pc.packed), pc.D, pc.M, pc.S, ptr(xc), ptr(tc), Tg, B, ptr(xs),
-                                        ptr(kst), stream_ptr()))
+        _lib.call("gpode_rk4_fwd", ptr(pc.packed), pc.D, pc.M, pc.S, ptr(xc), ptr(tc), Tg, B, ptr(xs),
+                                        ptr(kst), stream_ptr())
         ctx.pc, ctx.nu_shape = pc, nu.shape
         if need_grad:
             ctx.save_for_backward(tc, xs, kst)
@@ -118,9 +120,13 @@ class _RK4(torch.autograd.Function):
         gxs = f32(gxs, "grad_xs")
         gx0 = torch.empty(B, D, dtype=torch.float32, device=xs.device)
         acc = pc.new_acc()
-        vrows = torch.empty(lib.gpode_vrow_floats(D, max(Tg - 1, 0) * 4 * B), dtype=torch.float32, device=xs.device)
-        check(lib.gpode_rk4_bwd(ptr(pc.packed), pc.D, pc.M, pc.S, ptr(tc), Tg, B, ptr(xs), ptr(kst), ptr(gxs),
-                                ptr(gx0), ptr(vrows), ptr(acc), stream_ptr()))
+        n_vr = max(Tg - 1, 0) * 4 * B
+        vrows = torch.empty(lib.gpode_vrow_floats(D, n_vr), dtype=torch.float32, device=xs.device)
+        _lib.call("gpode_rk4_bwd", ptr(pc.packed), pc.D, pc.M, pc.S, ptr(tc), Tg, B, ptr(xs), ptr(kst), ptr(gxs),
+                                ptr(gx0), ptr(vrows), ptr(acc), stream_ptr())
+        if n_vr:
+            _lib.call("gpode_param_grad", ptr(pc.packed), pc.D, pc.M, pc.S, ptr(vrows), ptr(vrows[n_vr * D:]), n_vr,
+                      ptr(acc), stream_ptr())
         g_Z, g_ell, g_var, g_nu = pc.finalize(acc)
         return gx0, None, g_Z, g_ell, g_var, g_nu.reshape(ctx.nu_shape), None, None, None
 
@@ -140,7 +146,7 @@ class _Whiten(torch.autograd.Function):
         nu = torch.empty(D, M, dtype=torch.float32, device=Zc.device)
         L = torch.empty(D, M, M, dtype=torch.float64, device=Zc.device)
         sp = torch.empty(D, 2, M, dtype=torch.float64, device=Zc.device)
-        check(lib.gpode_whiten_fwd(ctypes.byref(st), ptr(uc), float(jitter), ptr(nu), ptr(L), ptr(sp), stream_ptr()))
+        _lib.call("gpode_whiten_fwd", ctypes.byref(st), ptr(uc), float(jitter), ptr(nu), ptr(L), ptr(sp), stream_ptr())
         ctx.keep = (st, Zc, ec, vc, uc, oc, pc_, wc)
         ctx.save_for_backward(L, sp)
         return nu
@@ -156,8 +162,8 @@ class _Whiten(torch.autograd.Function):
         g_Z = torch.empty(M, D, dtype=torch.float32, device=Zc.device)
         g_ell = torch.empty(D, D, dtype=torch.float32, device=Zc.device)
         g_var = torch.empty(D, dtype=torch.float32, device=Zc.device)
-        check(lib.gpode_whiten_bwd(ctypes.byref(st), ptr(uc), ptr(L), ptr(sp), ptr(gnu), ptr(g_u), ptr(g_Z),
-                                   ptr(g_ell), ptr(g_var), stream_ptr()))
+        _lib.call("gpode_whiten_bwd", ctypes.byref(st), ptr(uc), ptr(L), ptr(sp), ptr(gnu), ptr(g_u), ptr(g_Z),
+                                   ptr(g_ell), ptr(g_var), stream_ptr())
         return g_Z, g_ell, g_var, g_u, None, None, None, None
 
 
@@ -171,7 +177,7 @@ class _WhitenedKL(torch.autograd.Function):
         if tuple(Lc.shape) != (D, M * (M + 1) // 2):
             raise _lib.GpodeError("Us_sqrt optvar must be (%d,%d), got %s" % (D, M * (M + 1) // 2, tuple(Lc.shape)))
         out = torch.empty((), dtype=torch.float32, device=Uc.device)
-        check(_lib.load().gpode_kl_fwd(ptr(Uc), ptr(Lc), D, M, ptr(out), stream_ptr()))
+        _lib.call("gpode_kl_fwd", ptr(Uc), ptr(Lc), D, M, ptr(out), stream_ptr())
         ctx.save_for_backward(Uc, Lc)
         return out
 
@@ -180,8 +186,8 @@ class _WhitenedKL(torch.autograd.Function):
         Uc, Lc = ctx.saved_tensors
         M, D = Uc.shape
         gU, gL = torch.empty_like(Uc), torch.empty_like(Lc)
-        check(_lib.load().gpode_kl_bwd(ptr(Uc), ptr(Lc), D, M, ptr(f32(g, "grad_kl")), ptr(gU), ptr(gL),
-                                       stream_ptr()))
+        _lib.call("gpode_kl_bwd", ptr(Uc), ptr(Lc), D, M, ptr(f32(g, "grad_kl")), ptr(gU), ptr(gL),
+                                       stream_ptr())
         return gU, gL
 
 
@@ -213,8 +219,8 @@ def dopri5_integrate(x0, t, Z, ell, var, nu, omega, phase, w, rtol=1e-6, atol=1e
     xs = torch.empty(Tg, B, pc.D, dtype=torch.float32, device=xc.device)
     work = torch.empty(lib.gpode_dopri5_work_floats(pc.D, B), dtype=torch.float32, device=xc.device)
     stats = torch.zeros(4, dtype=torch.int32, device=xc.device)
-    check(lib.gpode_dopri5_fwd(ptr(pc.packed), pc.D, pc.M, pc.S, ptr(xc), ptr(t64), Tg, B, float(rtol), float(atol),
-                               ptr(xs), ptr(work), ptr(stats), stream_ptr()))
+    _lib.call("gpode_dopri5_fwd", ptr(pc.packed), pc.D, pc.M, pc.S, ptr(xc), ptr(t64), Tg, B, float(rtol), float(atol),
+                               ptr(xs), ptr(work), ptr(stats), stream_ptr())
     return xs, stats
 
 

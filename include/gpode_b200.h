@@ -59,9 +59,10 @@ int gpode_pack_cache(const gpode_cache_t* cache, float* packed, void* stream);
  * RBF.K src/core/kernels.py:87-99 + einsum :192).  x, f: [B,D]. */
 int gpode_vf_fwd(const float* packed, int D, int M, int S, const float* x, float* f, int64_t B, void* stream);
 
-/* Vector-Jacobian product of the above (what autograd does through dsvgp.py:172-197).
- *   grad_x [B,D]; shared-parameter gradients ACCUMULATE into `acc` (gpode_acc_floats floats, zero it first);
- *   f [B,D] is the forward output (saved by the caller); scratch: gpode_vrow_floats(B*1) floats. */
+/* Vector-Jacobian product of the above (what autograd does through dsvgp.py:172-197), row part:
+ *   grad_x [B,D]; the lengthscale / variance partial sums ACCUMULATE into `acc` (gpode_acc_floats floats, zero it
+ *   first); f [B,D] is the forward output (saved by the caller). Follow with gpode_param_grad(x, grad_f, B) for the
+ *   per-inducing-point part and gpode_grads_finalize. */
 int gpode_vf_bwd(const float* packed, int D, int M, int S, const float* x, const float* f, const float* grad_f,
                  float* grad_x, float* acc, int64_t B, void* stream);
 
@@ -73,11 +74,19 @@ int gpode_rk4_fwd(const float* packed, int D, int M, int S, const float* x0, con
                   float* xs, float* kstages, void* stream);
 
 /* Discrete adjoint of gpode_rk4_fwd == autograd through the unrolled solver (use_adjoint=False, the reference
- * default, train_vdp_gpode.py:52). grad_xs [Tg,B,D] -> grad_x0 [B,D]; shared-parameter gradients accumulate into
- * `acc`. vrows: scratch of gpode_vrow_floats((Tg-1)*4*B) floats. */
+ * default, train_vdp_gpode.py:52). grad_xs [Tg,B,D] -> grad_x0 [B,D]; lengthscale / variance partial sums accumulate
+ * into `acc`. vrows (gpode_vrow_floats(D, (Tg-1)*4*B) floats) receives, for every step and stage, the stage input
+ * and its cotangent: rows [0, n) hold the stage inputs, rows [n, 2n) the cotangents, n = (Tg-1)*4*B. Follow with
+ * gpode_param_grad(vrows, vrows + n*D, n) and gpode_grads_finalize. */
 int gpode_rk4_bwd(const float* packed, int D, int M, int S, const float* t, int Tg, int64_t B, const float* xs,
                   const float* kstages, const float* grad_xs, float* grad_x0, float* vrows, float* acc,
                   void* stream);
+
+/* Per-inducing-point gradient contraction over n_rows (point y, cotangent kb) pairs: accumulates
+ * T[k,m] += kb_k K_km(y) and W[k,m,j] += kb_k K_km(y) (y_j - Z_mj) into `acc` (autograd through
+ * src/core/kernels.py:53-99 and the einsum of src/core/dsvgp.py:192 w.r.t. nu and Z).  ys, kbs: [n_rows,D]. */
+int gpode_param_grad(const float* packed, int D, int M, int S, const float* ys, const float* kbs, int64_t n_rows,
+                     float* acc, void* stream);
 
 /* Accumulator block shared by the *_bwd entry points and its conversion to parameter gradients.
  *   acc layout (floats): A[D,D] | V[D] | T[D,M] | W[D,M,D]
@@ -114,6 +123,10 @@ int gpode_kl_bwd(const float* Um, const float* Ls_packed, int D, int M, const fl
 int64_t gpode_dopri5_work_floats(int D, int64_t B);
 int gpode_dopri5_fwd(const float* packed, int D, int M, int S, const float* x0, const double* t, int Tg, int64_t B,
                      double rtol, double atol, float* xs, float* work, int32_t* stats_out, void* stream);
+
+/* Measurement utility (no reference counterpart): sustained FP32 FMA throughput of the current device in TFLOP/s
+ * (best of 5 launches of a register-only FMA loop; synchronises the stream). scratch: >= 1 float (device). */
+int gpode_probe_fp32_fma(double* tflops_out_host, double* ms_out_host, float* scratch, void* stream);
 
 #ifdef __cplusplus
 }
