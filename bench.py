@@ -28,6 +28,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout and would break the one-JSON-line contract
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -307,7 +309,7 @@ def run_ours(args):
                            "evals_per_step": evals_per_step, "parallelism": "sequences sharded x%d" % world,
                            "l2": "working set per step (>= 0.6 GB of segment states, stage checkpoints and decoded "
                                  "predictions) exceeds the 126 MB L2; no explicit flush"},
-                "elbo_fwd_bwd_ms": ms_per_step, "e2e": e2e, "gpu_launches": launches,
+                "elbo_fwd_bwd_ms": ms_per_step, "e2e": e2e, "gpu_launches": launches * world,
                 "kernels_ms_per_step": kern, "own_kernels_share_of_step": ours_ms / ms_per_step,
                 "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "loss": getattr(e2e_body, "last", None)}
         print(json.dumps(line))
