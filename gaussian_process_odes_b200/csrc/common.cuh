@@ -42,7 +42,7 @@ void gpode_set_error(const char* fmt, ...);
 // packed parameter block (what every integrator CTA stages into shared memory with one bulk copy)
 //   rff  : [k][s][RS]  = Omega_{0,s,k} .. Omega_{D-1,s,k}, phase_{s,k}, a_{s,k} = w_{s,k} sqrt(var_k/S), pad
 //   kern : [m][KS]     = Z_{m,0..D-1}, c_{0,m} .. c_{D-1,m} (c_{k,m} = var_k nu_{k,m}), pad
-//   il   : [k][DP]     = sqrt(0.5 log2 e) / ell_{k,j}   (so that exp(-0.5 r^2) = 2^(-sum (d_j il_kj)^2))
+//   il   : [k][DP]     = w_{k,j} = 0.5 log2(e) / ell_{k,j}^2   (so that exp(-0.5 r^2) = 2^(-sum d_j^2 w_kj))
 // ------------------------------------------------------------------------------------------------------------------
 struct GpodeLayout {
     int D, M, S, RS, KS, DP;
@@ -78,7 +78,7 @@ __host__ __device__ inline GpodeAcc gpode_acc_layout(int D, int M) {
     return a;
 }
 
-#define GPODE_SQRT_HALF_LOG2E 0.84932180028801904272f  // sqrt(0.5 * log2(e))
+#define GPODE_HALF_LOG2E 0.72134752044448170368f  // 0.5 * log2(e)
 #define GPODE_NEG_2LN2 (-1.3862943611198906f)          // -2 ln 2
 
 // ------------------------------------------------------------------------------------------------------------------

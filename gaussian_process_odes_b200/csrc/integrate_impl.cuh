@@ -292,6 +292,216 @@ vf_bwd_kernel(const float* __restrict__ packed, const int M, const int S, const 
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Warp-per-row variants for small batches (the reference's own training shapes: N = 1 / 6 trajectories over 75-100
+// sequential steps, or a few thousand shooting segments). One warp owns one trajectory: its 32 lanes split the S
+// Fourier features and the M inducing points of every evaluation and combine the partial sums with an xor-shuffle
+// all-reduce, so the state stays replicated in registers and one evaluation costs ~(S+M)/32 feature visits instead
+// of S+M. Same arithmetic per term; only the summation order differs from the row-per-thread kernels.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kWarpsPerCta = 4;
+
+template <int D>
+__device__ __forceinline__ void warp_allreduce(float (&v)[1][D]) {
+#pragma unroll
+    for (int j = 0; j < D; ++j) v[0][j] = gpode_warp_sum(v[0][j]);
+}
+
+template <int D>
+__device__ __forceinline__ void vf_eval_warp(const float* sp, int M, int S, const float (&x)[1][D], float (&f)[1][D],
+                                             int lane) {
+    vf_eval<D, 1>(sp, M, S, x, f, lane, 32);
+    warp_allreduce<D>(f);
+}
+
+template <int D>
+__device__ __forceinline__ void vf_vjp_warp(const float* sp, int M, int S, const float (&x)[1][D],
+                                            const float (&kb)[1][D], const float (&fst)[1][D], float (&xb)[1][D],
+                                            float (&A)[D][D], float (&V)[D], int lane) {
+    float fm[1][D];  // f(x) enters the variance partial sum once per row, not once per lane
+#pragma unroll
+    for (int j = 0; j < D; ++j) fm[0][j] = lane == 0 ? fst[0][j] : 0.f;
+    vf_vjp<D, 1>(sp, M, S, x, kb, fm, xb, A, V, lane, 32);
+    warp_allreduce<D>(xb);
+}
+
+template <int D>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+vf_fwd_warp_kernel(const float* __restrict__ packed, const int M, const int S, const int total,
+                   const float* __restrict__ x, float* __restrict__ f, const int64_t B) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const float* sp = stage_params(smem_raw, packed, total);
+    const int lane = threadIdx.x & 31;
+    for (int64_t row = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); row < B;
+         row += (int64_t)gridDim.x * kWarpsPerCta) {
+        float xr[1][D], fr[1][D];
+        load_rows<D, 1>(xr, x, row, B, 0);
+        vf_eval_warp<D>(sp, M, S, xr, fr, lane);
+        if (lane == 0) store_rows<D, 1>(fr, f, row, B, 0);
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+rk4_fwd_warp_kernel(const float* __restrict__ packed, const int M, const int S, const int total,
+                    const float* __restrict__ x0, const float* __restrict__ ts, const int Tg, const int64_t B,
+                    float* __restrict__ xs, float* __restrict__ kst) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const float* sp = stage_params(smem_raw, packed, total);
+    const int lane = threadIdx.x & 31;
+    const int64_t plane = B * D;
+    for (int64_t row = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); row < B;
+         row += (int64_t)gridDim.x * kWarpsPerCta) {
+        float y[1][D];
+        load_rows<D, 1>(y, x0, row, B, 0);
+        if (lane == 0) store_rows<D, 1>(y, xs, row, B, 0);
+        for (int i = 0; i + 1 < Tg; ++i) {
+            const float dt = __fsub_rn(__ldg(ts + i + 1), __ldg(ts + i));
+            float k1[1][D], k2[1][D], k3[1][D], k4[1][D], ys[1][D];
+            vf_eval_warp<D>(sp, M, S, y, k1, lane);
+            stage2<D, 1>(ys, y, k1, dt);
+            vf_eval_warp<D>(sp, M, S, ys, k2, lane);
+            stage3<D, 1>(ys, y, k1, k2, dt);
+            vf_eval_warp<D>(sp, M, S, ys, k3, lane);
+            stage4<D, 1>(ys, y, k1, k2, k3, dt);
+            vf_eval_warp<D>(sp, M, S, ys, k4, lane);
+            if (kst != nullptr && lane == 0) {
+                float* kb = kst + (int64_t)i * 4 * plane;
+                store_rows<D, 1>(k1, kb, row, B, 0);
+                store_rows<D, 1>(k2, kb + plane, row, B, 0);
+                store_rows<D, 1>(k3, kb + 2 * plane, row, B, 0);
+                store_rows<D, 1>(k4, kb + 3 * plane, row, B, 0);
+            }
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                const float sum = __fadd_rn(__fadd_rn(k1[0][j], __fmul_rn(3.0f, __fadd_rn(k2[0][j], k3[0][j]))),
+                                            k4[0][j]);
+                y[0][j] = __fadd_rn(y[0][j], __fmul_rn(__fmul_rn(sum, dt), 0.125f));
+            }
+            if (lane == 0) store_rows<D, 1>(y, xs + (int64_t)(i + 1) * plane, row, B, 0);
+        }
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+rk4_bwd_warp_kernel(const float* __restrict__ packed, const int M, const int S, const int total,
+                    const float* __restrict__ ts, const int Tg, const int64_t B, const float* __restrict__ xs,
+                    const float* __restrict__ kst, const float* __restrict__ gxs, float* __restrict__ gx0,
+                    float* __restrict__ vy, float* __restrict__ vk, float* __restrict__ acc) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const float* sp = stage_params(smem_raw, packed, total);
+    float* red = reinterpret_cast<float*>(smem_raw + 16) + total;
+    for (int i = threadIdx.x; i < D * D + D; i += blockDim.x) red[i] = 0.f;
+    float A[D][D], V[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        V[k] = 0.f;
+#pragma unroll
+        for (int j = 0; j < D; ++j) A[k][j] = 0.f;
+    }
+    const int lane = threadIdx.x & 31;
+    const int64_t plane = B * D;
+    for (int64_t row = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); row < B;
+         row += (int64_t)gridDim.x * kWarpsPerCta) {
+        float lam[1][D];
+        load_rows<D, 1>(lam, gxs + (int64_t)(Tg - 1) * plane, row, B, 0);
+        for (int i = Tg - 2; i >= 0; --i) {
+            const float h = __fsub_rn(__ldg(ts + i + 1), __ldg(ts + i));
+            const float* kb = kst + (int64_t)i * 4 * plane;
+            float* vyi = vy + (int64_t)i * 4 * plane;
+            float* vki = vk + (int64_t)i * 4 * plane;
+            float y[1][D], k1[1][D], k2[1][D], k3[1][D], k4[1][D], ys[1][D], kbar[1][D], yb[1][D];
+            float sumyb[1][D], yb4[1][D], yb23[1][D];
+            load_rows<D, 1>(y, xs + (int64_t)i * plane, row, B, 0);
+            load_rows<D, 1>(k1, kb, row, B, 0);
+            load_rows<D, 1>(k2, kb + plane, row, B, 0);
+            load_rows<D, 1>(k3, kb + 2 * plane, row, B, 0);
+            load_rows<D, 1>(k4, kb + 3 * plane, row, B, 0);
+            // stage 4
+            stage4<D, 1>(ys, y, k1, k2, k3, h);
+#pragma unroll
+            for (int j = 0; j < D; ++j) kbar[0][j] = 0.125f * h * lam[0][j];
+            if (lane == 0) {
+                store_rows<D, 1>(ys, vyi + 3 * plane, row, B, 0);
+                store_rows<D, 1>(kbar, vki + 3 * plane, row, B, 0);
+            }
+            vf_vjp_warp<D>(sp, M, S, ys, kbar, k4, yb4, A, V, lane);
+            // stage 3
+            stage3<D, 1>(ys, y, k1, k2, h);
+#pragma unroll
+            for (int j = 0; j < D; ++j) kbar[0][j] = fmaf(0.375f * h, lam[0][j], h * yb4[0][j]);
+            if (lane == 0) {
+                store_rows<D, 1>(ys, vyi + 2 * plane, row, B, 0);
+                store_rows<D, 1>(kbar, vki + 2 * plane, row, B, 0);
+            }
+            vf_vjp_warp<D>(sp, M, S, ys, kbar, k3, yb, A, V, lane);
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                sumyb[0][j] = yb4[0][j] + yb[0][j];
+                kbar[0][j] = fmaf(0.375f * h, lam[0][j], h * (yb[0][j] - yb4[0][j]));
+                yb23[0][j] = -yb[0][j];
+            }
+            // stage 2
+            stage2<D, 1>(ys, y, k1, h);
+            if (lane == 0) {
+                store_rows<D, 1>(ys, vyi + plane, row, B, 0);
+                store_rows<D, 1>(kbar, vki + plane, row, B, 0);
+            }
+            vf_vjp_warp<D>(sp, M, S, ys, kbar, k2, yb, A, V, lane);
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                sumyb[0][j] += yb[0][j];
+                yb23[0][j] += yb[0][j];
+                kbar[0][j] = fmaf(0.125f * h, lam[0][j], fmaf(h * GPODE_THIRD, yb23[0][j], h * yb4[0][j]));
+            }
+            // stage 1
+            if (lane == 0) {
+                store_rows<D, 1>(y, vyi, row, B, 0);
+                store_rows<D, 1>(kbar, vki, row, B, 0);
+            }
+            vf_vjp_warp<D>(sp, M, S, y, kbar, k1, yb, A, V, lane);
+            float gi[1][D];
+            load_rows<D, 1>(gi, gxs + (int64_t)i * plane, row, B, 0);
+#pragma unroll
+            for (int j = 0; j < D; ++j) lam[0][j] = gi[0][j] + lam[0][j] + (sumyb[0][j] + yb[0][j]);
+        }
+        if (lane == 0) store_rows<D, 1>(lam, gx0, row, B, 0);
+    }
+    __syncthreads();
+    reduce_AV<D>(A, V, acc, red);
+}
+
+template <int D>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+vf_bwd_warp_kernel(const float* __restrict__ packed, const int M, const int S, const int total,
+                   const float* __restrict__ x, const float* __restrict__ f, const float* __restrict__ gf,
+                   float* __restrict__ gx, const int64_t B, float* __restrict__ acc) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const float* sp = stage_params(smem_raw, packed, total);
+    float* red = reinterpret_cast<float*>(smem_raw + 16) + total;
+    for (int i = threadIdx.x; i < D * D + D; i += blockDim.x) red[i] = 0.f;
+    float A[D][D], V[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        V[k] = 0.f;
+#pragma unroll
+        for (int j = 0; j < D; ++j) A[k][j] = 0.f;
+    }
+    const int lane = threadIdx.x & 31;
+    for (int64_t row = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); row < B;
+         row += (int64_t)gridDim.x * kWarpsPerCta) {
+        float xr[1][D], fr[1][D], kb[1][D], xb[1][D];
+        load_rows<D, 1>(xr, x, row, B, 0);
+        load_rows<D, 1>(fr, f, row, B, 0);
+        load_rows<D, 1>(kb, gf, row, B, 0);
+        vf_vjp_warp<D>(sp, M, S, xr, kb, fr, xb, A, V, lane);
+        if (lane == 0) store_rows<D, 1>(xb, gx, row, B, 0);
+    }
+    __syncthreads();
+    reduce_AV<D>(A, V, acc, red);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // host-side launch helpers
 // ------------------------------------------------------------------------------------------------------------------
 struct LaunchShape {
@@ -335,6 +545,26 @@ inline int shape_for(K kernel, int R, int64_t B, size_t smem, LaunchShape* out) 
 // ------------------------------------------------------------------------------------------------------------------
 // per-D launchers: wide tiles (R rows per thread) when the batch fills the machine twice over, else one row per thread
 // ------------------------------------------------------------------------------------------------------------------
+// batches up to this many rows go to the warp-per-row kernels (above it, row-per-thread fills the machine)
+constexpr int64_t kWarpPathMaxRows = 16384;
+
+template <typename K>
+inline int warp_shape_for(K kernel, int64_t B, size_t smem, LaunchShape* out) {
+    GPODE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    GPODE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kWarpsPerCta * 32, smem));
+    if (occ < 1) {
+        gpode_set_error("kernel does not fit on an SM (smem %zu bytes)", smem);
+        return -2;
+    }
+    const int64_t want = (B + kWarpsPerCta - 1) / kWarpsPerCta;
+    const int64_t cap = (int64_t)num_sms() * occ;
+    out->threads = kWarpsPerCta * 32;
+    out->grid = (int)(want < cap ? want : cap);
+    out->smem = smem;
+    return 0;
+}
+
 template <int D, int R>
 inline bool use_wide(int64_t B) {
     return R > 1 && B >= (int64_t)num_sms() * 2 * kThreads * R;
@@ -346,7 +576,10 @@ int launch_vf_fwd(const float* packed, int M, int S, const float* x, float* f, i
     const size_t smem = 16 + (size_t)L.total * 4;
     LaunchShape ls;
     constexpr int RW = RowsFwd<D>::value;
-    if (use_wide<D, RW>(B)) {
+    if (B <= kWarpPathMaxRows) {
+        if (int rc = warp_shape_for(vf_fwd_warp_kernel<D>, B, smem, &ls)) return rc;
+        vf_fwd_warp_kernel<D><<<ls.grid, ls.threads, ls.smem, st>>>(packed, M, S, L.total, x, f, B);
+    } else if (use_wide<D, RW>(B)) {
         if (int rc = shape_for(vf_fwd_kernel<D, RW>, RW, B, smem, &ls)) return rc;
         vf_fwd_kernel<D, RW><<<ls.grid, ls.threads, ls.smem, st>>>(packed, M, S, L.total, x, f, B);
     } else {
@@ -364,7 +597,10 @@ int launch_rk4_fwd(const float* packed, int M, int S, const float* x0, const flo
     const size_t smem = 16 + (size_t)L.total * 4;
     LaunchShape ls;
     constexpr int RW = RowsFwd<D>::value;
-    if (use_wide<D, RW>(B)) {
+    if (B <= kWarpPathMaxRows) {
+        if (int rc = warp_shape_for(rk4_fwd_warp_kernel<D>, B, smem, &ls)) return rc;
+        rk4_fwd_warp_kernel<D><<<ls.grid, ls.threads, ls.smem, st>>>(packed, M, S, L.total, x0, t, Tg, B, xs, kst);
+    } else if (use_wide<D, RW>(B)) {
         if (int rc = shape_for(rk4_fwd_kernel<D, RW>, RW, B, smem, &ls)) return rc;
         rk4_fwd_kernel<D, RW><<<ls.grid, ls.threads, ls.smem, st>>>(packed, M, S, L.total, x0, t, Tg, B, xs, kst);
     } else {
@@ -383,7 +619,11 @@ int launch_rk4_bwd(const float* packed, int M, int S, const float* t, int Tg, in
     const size_t smem = 16 + (size_t)(L.total + D * D + D) * 4;
     LaunchShape ls;
     constexpr int RW = RowsBwd<D>::value;
-    if (use_wide<D, RW>(B)) {
+    if (B <= kWarpPathMaxRows) {
+        if (int rc = warp_shape_for(rk4_bwd_warp_kernel<D>, B, smem, &ls)) return rc;
+        rk4_bwd_warp_kernel<D><<<ls.grid, ls.threads, ls.smem, st>>>(packed, M, S, L.total, t, Tg, B, xs, kst, gxs,
+                                                                     gx0, vy, vk, acc);
+    } else if (use_wide<D, RW>(B)) {
         if (int rc = shape_for(rk4_bwd_kernel<D, RW>, RW, B, smem, &ls)) return rc;
         rk4_bwd_kernel<D, RW><<<ls.grid, ls.threads, ls.smem, st>>>(packed, M, S, L.total, t, Tg, B, xs, kst, gxs, gx0,
                                                                      vy, vk, acc);
@@ -403,7 +643,10 @@ int launch_vf_bwd(const float* packed, int M, int S, const float* x, const float
     const size_t smem = 16 + (size_t)(L.total + D * D + D) * 4;
     LaunchShape ls;
     constexpr int RW = RowsBwd<D>::value;
-    if (use_wide<D, RW>(B)) {
+    if (B <= kWarpPathMaxRows) {
+        if (int rc = warp_shape_for(vf_bwd_warp_kernel<D>, B, smem, &ls)) return rc;
+        vf_bwd_warp_kernel<D><<<ls.grid, ls.threads, ls.smem, st>>>(packed, M, S, L.total, x, f, gf, gx, B, acc);
+    } else if (use_wide<D, RW>(B)) {
         if (int rc = shape_for(vf_bwd_kernel<D, RW>, RW, B, smem, &ls)) return rc;
         vf_bwd_kernel<D, RW><<<ls.grid, ls.threads, ls.smem, st>>>(packed, M, S, L.total, x, f, gf, gx, B, acc);
     } else {

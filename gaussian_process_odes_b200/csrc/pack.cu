@@ -45,7 +45,7 @@ __global__ void pack_kernel(const GpodeLayout L, const float* __restrict__ omega
         } else {
             const int k = i - n_rff - n_kern;
             float* o = out + L.off_il + (size_t)k * L.DP;
-            for (int j = 0; j < D; ++j) o[j] = GPODE_SQRT_HALF_LOG2E / ell[k * D + j];
+            for (int j = 0; j < D; ++j) o[j] = GPODE_HALF_LOG2E / (ell[k * D + j] * ell[k * D + j]);
             for (int j = D; j < L.DP; ++j) o[j] = 0.f;
         }
     }

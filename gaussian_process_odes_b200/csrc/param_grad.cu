@@ -72,8 +72,7 @@ param_grad_kernel(const float* __restrict__ packed, const int M, const int S, co
 #pragma unroll
                 for (int j = 0; j < D; ++j) {
                     d[j] = sy[r * D + j] - z[j];
-                    const float t = d[j] * il[j];
-                    e = fmaf(t, t, e);
+                    e = fmaf(d[j] * d[j], il[j], e);
                 }
                 const float p = sk[r * D + k] * gpode_ex2(-e);
                 T += p;

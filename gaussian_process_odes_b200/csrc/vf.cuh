@@ -25,10 +25,14 @@ __device__ __forceinline__ void lds_vec(float (&dst)[N], const float* __restrict
     }
 }
 
-// f[r][k] = sum_s a_sk cos(sum_j x_j Omega_jsk + phase_sk) + sum_m c_km 2^(-sum_j ((x_j - Z_mj) il_kj)^2)
+// f[r][k] = sum_s a_sk cos(sum_j x_j Omega_jsk + phase_sk) + sum_m c_km 2^(-sum_j (x_j - Z_mj)^2 w_kj)
+// with w_kj = 0.5 log2(e) / ell_kj^2 (the `il` block of the packed cache)
+// (i0, istep): which features / inducing points this thread sums -- (0,1) when the thread owns whole rows, (lane,32) in
+// the warp-per-row kernels, where the partial sums are then combined with a warp all-reduce.
 template <int D, int R>
 __device__ __forceinline__ void vf_eval(const float* __restrict__ sp, const int M, const int S,
-                                        const float (&x)[R][D], float (&f)[R][D]) {
+                                        const float (&x)[R][D], float (&f)[R][D], const int i0 = 0,
+                                        const int istep = 1) {
     constexpr int RS = VfShape<D>::RS, KS = VfShape<D>::KS, DP = VfShape<D>::DP;
     const float* __restrict__ rff = sp;
     const float* __restrict__ kern = sp + D * S * RS;
@@ -41,7 +45,7 @@ __device__ __forceinline__ void vf_eval(const float* __restrict__ sp, const int 
 
     // ---- random-Fourier-feature prior sample: feature s outer, output k inner (D*R independent chains) ----
 #pragma unroll 2
-    for (int s = 0; s < S; ++s) {
+    for (int s = i0; s < S; s += istep) {
 #pragma unroll
         for (int k = 0; k < D; ++k) {
             float prm[RS];
@@ -62,22 +66,22 @@ __device__ __forceinline__ void vf_eval(const float* __restrict__ sp, const int 
     for (int k = 0; k < D; ++k) lds_vec<DP>(il[k], ilp + k * DP);
 
 #pragma unroll 2
-    for (int m = 0; m < M; ++m) {
+    for (int m = i0; m < M; m += istep) {
         float kp[KS];
         lds_vec<KS>(kp, kern + m * KS);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            float d[D];
+            float dd[D];
 #pragma unroll
-            for (int j = 0; j < D; ++j) d[j] = x[r][j] - kp[j];
+            for (int j = 0; j < D; ++j) {
+                const float d = x[r][j] - kp[j];
+                dd[j] = d * d;
+            }
 #pragma unroll
             for (int k = 0; k < D; ++k) {
                 float e = 0.f;
 #pragma unroll
-                for (int j = 0; j < D; ++j) {
-                    const float t = d[j] * il[k][j];
-                    e = fmaf(t, t, e);
-                }
+                for (int j = 0; j < D; ++j) e = fmaf(dd[j], il[k][j], e);
                 f[r][k] = fmaf(kp[D + k], gpode_ex2(-e), f[r][k]);
             }
         }
@@ -86,13 +90,14 @@ __device__ __forceinline__ void vf_eval(const float* __restrict__ sp, const int 
 
 // VJP at x with cotangent kb: xb = J(x)^T kb, and the per-thread partial sums of the shared-parameter gradients that
 // do not need a cross-row contraction per inducing point:
-//   A[k][j] += x_j G_kj + sum_m q' t_j^2     (lengthscale gradient = -A/ell, RFF path through omega = eps/ell + RBF)
+//   A[k][j] += x_j G_kj + sum_m q' w_kj d_j^2    (lengthscale gradient = -A/ell, RFF path through omega = eps/ell + RBF)
 //   V[k]    += kb_k (f_k + f_upd_k)          (variance gradient = V / (2 var))
 // fst = f(x) from the forward pass (so f_rff = fst - f_upd needs no cosine here).
 template <int D, int R>
 __device__ __forceinline__ void vf_vjp(const float* __restrict__ sp, const int M, const int S,
                                        const float (&x)[R][D], const float (&kb)[R][D], const float (&fst)[R][D],
-                                       float (&xb)[R][D], float (&A)[D][D], float (&V)[D]) {
+                                       float (&xb)[R][D], float (&A)[D][D], float (&V)[D], const int i0 = 0,
+                                       const int istep = 1) {
     constexpr int RS = VfShape<D>::RS, KS = VfShape<D>::KS, DP = VfShape<D>::DP;
     const float* __restrict__ rff = sp;
     const float* __restrict__ kern = sp + D * S * RS;
@@ -112,7 +117,7 @@ __device__ __forceinline__ void vf_vjp(const float* __restrict__ sp, const int M
 #pragma unroll
             for (int j = 0; j < D; ++j) G[r][j] = 0.f;
 #pragma unroll 4
-        for (int s = 0; s < S; ++s) {
+        for (int s = i0; s < S; s += istep) {
             float prm[RS];
             lds_vec<RS>(prm, rff + (k * S + s) * RS);
 #pragma unroll
@@ -145,31 +150,30 @@ __device__ __forceinline__ void vf_vjp(const float* __restrict__ sp, const int M
         for (int k = 0; k < D; ++k) fu[r][k] = 0.f;
 
 #pragma unroll 2
-    for (int m = 0; m < M; ++m) {
+    for (int m = i0; m < M; m += istep) {
         float kp[KS];
         lds_vec<KS>(kp, kern + m * KS);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            float d[D];
+            float d[D], dd[D];
 #pragma unroll
-            for (int j = 0; j < D; ++j) d[j] = x[r][j] - kp[j];
+            for (int j = 0; j < D; ++j) {
+                d[j] = x[r][j] - kp[j];
+                dd[j] = d[j] * d[j];
+            }
 #pragma unroll
             for (int k = 0; k < D; ++k) {
-                float t[D];
                 float e = 0.f;
 #pragma unroll
-                for (int j = 0; j < D; ++j) {
-                    t[j] = d[j] * il[k][j];
-                    e = fmaf(t[j], t[j], e);
-                }
+                for (int j = 0; j < D; ++j) e = fmaf(dd[j], il[k][j], e);
                 const float cK = kp[D + k] * gpode_ex2(-e);
                 fu[r][k] += cK;
                 const float q = kb[r][k] * cK * GPODE_NEG_2LN2;
 #pragma unroll
                 for (int j = 0; j < D; ++j) {
-                    const float tmp = q * t[j];
-                    xb[r][j] = fmaf(tmp, il[k][j], xb[r][j]);
-                    A[k][j] = fmaf(tmp, t[j], A[k][j]);
+                    const float u = q * il[k][j];
+                    xb[r][j] = fmaf(u, d[j], xb[r][j]);
+                    A[k][j] = fmaf(u, dd[j], A[k][j]);
                 }
             }
         }

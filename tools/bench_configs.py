@@ -1,0 +1,165 @@
+#!/usr/bin/env python
+"""ELBO fwd+bwd step time of the four BASELINE.json model configs and vector-field evals/s of the scaling sweep
+(SURVEY.md section 8d), CUDA path next to the oracle port on the host cores.
+
+    python tools/bench_configs.py [--no-cpu] [--out profiles/xyz.json]
+
+Timing: CUDA events, 5 warm-ups, median of 20 (GPU); perf_counter, 2 warm-ups, median of 5 (CPU oracle port)."""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import gpode_oracle as O  # noqa: E402
+from util import build_product_model  # noqa: E402
+
+CONFIGS = {
+    "vdp_gpode":       dict(kind="gpode", D=2, M=16, S=256, N=1, T=25, S_mc=1, ts_dense_scale=4),
+    "vdp_shooting":    dict(kind="shooting", D=2, M=16, S=256, N=1, T=25, S_mc=5),
+    "mocap_gpode":     dict(kind="gpode", D=5, M=100, S=256, N=6, T=100, S_mc=1, D_obs=50, dt=0.01, ell0=1.25,
+                            ts_dense_scale=2),
+    "mocap_shooting":  dict(kind="shooting", D=5, M=100, S=256, N=6, T=100, S_mc=5, D_obs=50, dt=0.01, ell0=1.25),
+}
+
+
+def gpu_time(fn, warm=5, reps=20):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts))
+
+
+def wall_time(fn, warm=5, reps=20):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fn()
+        torch.cuda.synchronize()
+        ts.append((time.perf_counter() - t0) * 1e3)
+    return float(np.median(ts))
+
+
+def cpu_time(fn, warm=2, reps=5):
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fn()
+        ts.append((time.perf_counter() - t0) * 1e3)
+    return float(np.median(ts))
+
+
+def run_config(name, c, solver, do_cpu):
+    from gaussian_process_odes_b200 import builders
+    kw = {k: v for k, v in c.items() if k not in ("kind", "ts_dense_scale")}
+    p, ys, ts, draws, proj = O.make_problem(seed=121, **kw)
+    comp = proj.components if proj is not None else None
+    model = build_product_model(c["kind"], p, ys, c["S"], solver, ts_dense_scale=c.get("ts_dense_scale", 4), proj=comp)
+    ysd, tsd = ys.cuda(), ts.cuda()
+
+    def step():
+        model.zero_grad(set_to_none=True)
+        if c["kind"] == "gpode":
+            loss = builders.compute_loss_gpode(model, ysd, tsd)[0]
+        else:
+            loss = builders.compute_loss_shooting(model, ysd, tsd, num_samples=c["S_mc"])[0]
+        loss.backward()
+
+    def fwd():
+        with torch.no_grad():
+            if c["kind"] == "gpode":
+                builders.compute_loss_gpode(model, ysd, tsd)
+            else:
+                builders.compute_loss_shooting(model, ysd, tsd, num_samples=c["S_mc"])
+
+    out = dict(config=name, solver=solver, rows=(c["S_mc"] * c["N"] * c["T"] if c["kind"] == "shooting" else c["N"]))
+    if solver == "rk4":
+        out["gpu_fwd_bwd_ms"] = gpu_time(step)
+        out["gpu_fwd_bwd_wall_ms"] = wall_time(step)
+    out["gpu_fwd_ms"] = gpu_time(fwd)
+    out["nfe"] = model.flow.num_evals()
+    if do_cpu:
+        def cpu_step():
+            pp = {k: v.detach().clone().requires_grad_(True) for k, v in p.items()}
+            if c["kind"] == "gpode":
+                r = O.elbo_gpode(pp, ys, ts, draws, method=solver, project=proj, ts_dense_scale=c["ts_dense_scale"])
+            else:
+                r = O.elbo_shooting(pp, ys, ts, draws, method=solver, project=proj)
+            r["loss"].backward()
+        out["cpu_port_fwd_bwd_ms"] = cpu_time(cpu_step)
+        out["cpu_threads"] = torch.get_num_threads()
+    return out
+
+
+def run_sweep(D, M, S, B, K, do_cpu):
+    from gaussian_process_odes_b200 import ops
+    p, ys, ts, draws, _ = O.make_problem(D=D, M=M, S=S, N=1, T=4, seed=5)
+    gp = O.gp_params(p)
+    d = draws
+    omega = d['eps_omega'] / gp['ell'].T.unsqueeze(1)
+    nu = torch.tensor(np.random.default_rng(1).normal(size=(D, M)) * 0.1, dtype=torch.float32)
+    args = [a.cuda().contiguous() for a in (gp['Z'], gp['ell'], gp['var'], nu, omega, d['phase_u'] * 2 * np.pi, d['w'])]
+    x = torch.randn(B, D, device="cuda")
+    tg = (torch.arange(K + 1, dtype=torch.float32) * 0.01).cuda()
+    with torch.no_grad():
+        ms = gpu_time(lambda: ops.rk4_integrate(x, tg, *args), warm=3, reps=10)
+    fv = D * (S * (2 * D + 4) + M * (3 * D + 4))
+    evals = B * 4 * K
+    out = dict(sweep=True, D=D, M=M, S=S, B=B, rk4_steps=K, ms=ms, evals_per_s=evals / (ms * 1e-3),
+               algorithmic_tflops=evals * fv / (ms * 1e-3) / 1e12)
+    if do_cpu and B <= 100000:
+        c = dict(rff_omega=omega, rff_phase=d['phase_u'] * 2 * np.pi, rff_weights=d['w'], nu=nu.unsqueeze(2))
+        xc = x.cpu()
+        with torch.no_grad():
+            t = cpu_time(lambda: O.vf_forward(xc, gp['Z'], gp['ell'], gp['var'], c), warm=1, reps=3)
+        out["cpu_port_vf_evals_per_s"] = B / (t * 1e-3)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--out", default=None)
+    ap.add_argument("--only", default=None)
+    args = ap.parse_args()
+    torch.set_num_threads(os.cpu_count())
+    res = []
+    for name, c in CONFIGS.items():
+        if args.only and args.only not in name:
+            continue
+        for solver in ("rk4", "dopri5"):
+            r = run_config(name, c, solver, not args.no_cpu and solver == "rk4")
+            print(json.dumps(r), flush=True)
+            res.append(r)
+    if not args.only or args.only == "sweep":
+        for D, M in ((2, 16), (4, 100), (5, 100), (8, 100)):
+            for B, K in ((10000, 32), (100000, 32), (1000000, 1), (1000000, 32)):
+                r = run_sweep(D, M, 256, B, K, not args.no_cpu)
+                print(json.dumps(r), flush=True)
+                res.append(r)
+    if args.out:
+        json.dump(res, open(args.out, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
