@@ -64,8 +64,8 @@ def build_ours(w, rank, world, rows_scale):
     T = max(3, int(round(w["T"] * rows_scale)))
     N_loc, N_glob = w["N_per_gpu"], w["N_per_gpu"] * world
     lat, ys, comp = synthetic_sequences(N_loc, T, w["D"], w["D_obs"], seed=121 + rank)
-    comp_d = torch.tensor(comp, device="cuda")
-    projection = lambda x: torch.einsum('ntl,ld->ntd', x, comp_d)
+    from gaussian_process_odes_b200.misc.mocap_utils import LinearProjection
+    projection = LinearProjection(comp)
     np.random.seed(121)  # identical GP initialisation on every rank
     model = builders.build_gpode_shooting(N_loc, T, w["D"], num_inducing=w["M"], num_features=w["S"],
                                           solver=w["solver"], D_obs=w["D_obs"], projection=projection)

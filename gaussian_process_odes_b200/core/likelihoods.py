@@ -27,6 +27,29 @@ class Gaussian(nn.Module):
         var = self.variance
         return -0.5 * (np.log(2.0 * np.pi) + torch.log(var) + torch.pow(F - Y, 2) / var)
 
+    # ---- fused mean log-likelihood (what both ELBOs reduce log_prob to: models.py:56-58 / shooting models.py:128,143) ----
+    def _affine(self, F):
+        """(W (D,D_obs), bias or None) of the latent -> observation map, or None if it is not a known affine map."""
+        d = F.shape[-1]
+        eye = getattr(self, "_eye", None)
+        if eye is None or eye.shape[0] != d or eye.device != F.device:
+            eye = torch.eye(d, dtype=F.dtype, device=F.device)
+            self._eye = eye
+        return eye, None
+
+    def log_prob_mean(self, F, Y):
+        """``log_prob(F, Y).mean()`` in one kernel (value + gradients) when the shapes allow it."""
+        aff = self._affine(F) if F.is_cuda else None
+        if aff is not None:
+            W, b = aff
+            lead = tuple(F.shape[:-1])
+            ylead = tuple(Y.shape[:-1])
+            if Y.shape[-1] == W.shape[1] and W.shape[0] <= 8 and W.shape[1] <= 128 and (
+                    ylead == lead or (len(ylead) == len(lead) and ylead[0] == 1 and ylead[1:] == lead[1:])):
+                from .. import ops
+                return ops.loglik_mean(F, Y, W, b, self.variance)
+        return self.log_prob(F, Y).mean()
+
 
 class ProjectedGaussian(Gaussian):
     """Gaussian likelihood behind a fixed latent->data projection (reference ``likelihoods.py:31-45``)."""
@@ -41,3 +64,7 @@ class ProjectedGaussian(Gaussian):
         else:
             F = self.projection(F)
         return super().log_prob(F, Y)
+
+    def _affine(self, F):
+        as_affine = getattr(self.projection, "as_affine", None)
+        return as_affine() if as_affine is not None else None

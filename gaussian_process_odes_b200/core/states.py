@@ -10,6 +10,7 @@ import numpy as np
 import torch
 from torch import nn
 
+from .. import ops
 from ..misc import transforms
 from ..misc.param import Param
 
@@ -29,30 +30,48 @@ def _standard_normal(shape, dtype, device):
 
 
 class _FullRankGaussian:
-    """N(mean, lchol lchol^T + jitter I) over the last axis, batched over the leading axes."""
+    """N(mean, lchol lchol^T + jitter I) over the last axis, batched over the leading axes.
 
-    def __init__(self, mean, lchol):
-        d = mean.shape[-1]
-        cov = lchol @ lchol.transpose(-1, -2) + torch.eye(d, dtype=mean.dtype, device=mean.device) * jitter
+    On a CUDA device sampling and entropy run in the fused kernels of ``gpode_state_fwd/_bwd`` straight from the
+    PACKED lower-triangular parameter (one thread per D x D matrix: Cholesky, matrix-vector product, log-determinant
+    and their backward in registers); elsewhere the same algebra is spelled out with torch ops."""
+
+    def __init__(self, mean, lchol_fn, packed):
         self.loc = mean
-        self.scale_tril = torch.linalg.cholesky(cov)
+        self._lchol_fn = lchol_fn
+        self._packed = packed
+        self._fused = mean.is_cuda and mean.shape[-1] <= 8
+        self._scale_tril = None
+
+    @property
+    def scale_tril(self):
+        if self._scale_tril is None:
+            lchol = self._lchol_fn()
+            d = self.loc.shape[-1]
+            cov = lchol @ lchol.transpose(-1, -2) + torch.eye(d, dtype=lchol.dtype, device=lchol.device) * jitter
+            self._scale_tril = torch.linalg.cholesky(cov)
+        return self._scale_tril
 
     def rsample(self, sample_shape):
         shape = tuple(sample_shape) + tuple(self.loc.shape)
         eps = _standard_normal(shape, self.loc.dtype, self.loc.device)
+        if self._fused:
+            return ops.state_sample(self.loc, self._packed, eps, jitter)
         return self.loc + (self.scale_tril @ eps.unsqueeze(-1)).squeeze(-1)
 
     def entropy(self):
         d = self.loc.shape[-1]
+        if self._fused:
+            return ops.state_entropy(self._packed, d, jitter)
         half_log_det = self.scale_tril.diagonal(dim1=-2, dim2=-1).log().sum(-1)
         return 0.5 * d * (1.0 + math.log(2 * math.pi)) + half_log_det
 
     def log_prob(self, x):
         d = self.loc.shape[-1]
         diff = (x - self.loc).unsqueeze(-1)
-        z = torch.linalg.solve_triangular(self.scale_tril.expand(diff.shape[:-2] + self.scale_tril.shape[-2:]), diff,
-                                          upper=False).squeeze(-1)
-        half_log_det = self.scale_tril.diagonal(dim1=-2, dim2=-1).log().sum(-1)
+        tril = self.scale_tril
+        z = torch.linalg.solve_triangular(tril.expand(diff.shape[:-2] + tril.shape[-2:]), diff, upper=False).squeeze(-1)
+        half_log_det = tril.diagonal(dim1=-2, dim2=-1).log().sum(-1)
         return -0.5 * (d * math.log(2 * math.pi) + z.pow(2).sum(-1)) - half_log_det
 
 
@@ -95,7 +114,7 @@ class StateInitialVariationalGaussian(StateInitialDistribution):
         return self.param_lchol()
 
     def distribution(self):
-        return _FullRankGaussian(self.mean(), self.lchol())
+        return _FullRankGaussian(self.mean(), self.lchol, self.param_lchol.optvar)
 
     def sample_numpy(self, num_samples=1, seed=None):
         eps = sample_normal(shape=(num_samples, self.dim_n, self.dim_d), seed=seed).to(self.param_mean.optvar.device)
@@ -162,7 +181,7 @@ class StateSequenceVariationalFactorizedGaussian(StateSequenceVariationalDistrib
         return self.param_lchol()
 
     def distribution(self):
-        return _FullRankGaussian(self.mean(), self.lchol())
+        return _FullRankGaussian(self.mean(), self.lchol, self.param_lchol.optvar)
 
     def sample_numpy(self, num_samples=1, seed=None):
         dev = self.param_mean.optvar.device

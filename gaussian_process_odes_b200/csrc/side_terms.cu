@@ -1,0 +1,351 @@
+// ELBO side terms either side of the integrator: the full-rank Gaussian state
+// posteriors and the (projected) Gaussian observation log-likelihood.
+//
+// Reference arithmetic replaced:
+//  * src/core/states.py:69-74,91-92,177-182,199-204 -- MultivariateNormal(mean, L L^T + 1e-5 I).rsample / .entropy
+//    with L scattered from its packed lower triangle by src/misc/transforms.py:70-76,105-112: per matrix a D x D
+//    Cholesky, a matrix-vector product per sample, a log-determinant; autograd through all of it. In PyTorch that is
+//    ~50 batched-library launches per ELBO step (magma gemm, potrf_batch, trsm_batch, ...); here one thread owns one
+//    D x D matrix in registers.
+//  * src/core/likelihoods.py:27-28,38-45 -- mean over all elements of the Gaussian log-density of the decoded
+//    prediction, decoder = fixed affine map (src/misc/mocap_utils.py:24-34). One warp per observation row, lanes over
+//    observed dimensions; value and gradient in one pass (the mean is a scalar, so backward is a scale).
+#include "common.cuh"
+#include <math.h>
+
+namespace {
+
+// ---- D x D helpers (fully unrolled, registers) -------------------------------------------------------------------
+template <int D>
+struct Tri {
+    static constexpr int P = D * (D + 1) / 2;
+    __device__ static __forceinline__ int idx(int i, int j) { return i * (i + 1) / 2 + j; }  // row-major tril packing
+};
+
+// C = chol(L L^T + jitter I), L given packed
+template <int D>
+__device__ __forceinline__ void chol_from_packed(const float (&Lp)[Tri<D>::P], const float jitter, float (&C)[D][D]) {
+    float A[D][D];
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            float s = (i == j) ? jitter : 0.f;
+#pragma unroll
+            for (int k = 0; k <= j; ++k) s = fmaf(Lp[Tri<D>::idx(i, k)], Lp[Tri<D>::idx(j, k)], s);
+            A[i][j] = s;
+        }
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        float s = A[j][j];
+#pragma unroll
+        for (int k = 0; k < j; ++k) s = fmaf(-C[j][k], C[j][k], s);
+        const float cjj = sqrtf(s);
+        C[j][j] = cjj;
+        const float inv = 1.0f / cjj;
+#pragma unroll
+        for (int i = j + 1; i < D; ++i) {
+            float t = A[i][j];
+#pragma unroll
+            for (int k = 0; k < j; ++k) t = fmaf(-C[i][k], C[j][k], t);
+            C[i][j] = t * inv;
+        }
+#pragma unroll
+        for (int i = 0; i < j; ++i) C[i][j] = 0.f;
+    }
+}
+
+// Cb (lower) -> gradient w.r.t. the packed L:  Ab = sym(C^-T Phi(C^T Cb) C^-1),  Lb = tril(2 Ab L)
+template <int D>
+__device__ __forceinline__ void chol_backward_to_packed(const float (&Lp)[Tri<D>::P], const float (&C)[D][D],
+                                                        const float (&Cb)[D][D], float (&gLp)[Tri<D>::P]) {
+    float Pm[D][D];
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            float s = 0.f;
+            if (j <= i) {
+#pragma unroll
+                for (int l = i; l < D; ++l) s = fmaf(C[l][i], Cb[l][j], s);  // (C^T Cb)_ij, Cb lower => l >= i >= j
+                if (i == j) s *= 0.5f;
+            }
+            Pm[i][j] = s;
+        }
+    // X = C^-T P : back substitution over rows
+#pragma unroll
+    for (int i = D - 1; i >= 0; --i) {
+        const float inv = 1.0f / C[i][i];
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            float s = Pm[i][j];
+#pragma unroll
+            for (int l = i + 1; l < D; ++l) s = fmaf(-C[l][i], Pm[l][j], s);
+            Pm[i][j] = s * inv;
+        }
+    }
+    // Y = X C^-1 : columns from the right
+#pragma unroll
+    for (int c = D - 1; c >= 0; --c) {
+        const float inv = 1.0f / C[c][c];
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            float s = Pm[i][c];
+#pragma unroll
+            for (int l = c + 1; l < D; ++l) s = fmaf(-Pm[i][l], C[l][c], s);
+            Pm[i][c] = s * inv;
+        }
+    }
+    // Lb_ij = sum_k (Y + Y^T)_ik L_kj, i >= j
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            float s = 0.f;
+#pragma unroll
+            for (int k = j; k < D; ++k) s = fmaf(Pm[i][k] + Pm[k][i], Lp[Tri<D>::idx(k, j)], s);
+            gLp[Tri<D>::idx(i, j)] = s;
+        }
+}
+
+// mode bit 0: samples, bit 1: entropy
+template <int D>
+__global__ void __launch_bounds__(128)
+state_fwd_kernel(const float* __restrict__ mean, const float* __restrict__ Lpk, const float* __restrict__ eps,
+                 const int S, const int64_t R, const float jitter, float* __restrict__ samples,
+                 float* __restrict__ entropy) {
+    constexpr int P = Tri<D>::P;
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    float Lp[P], C[D][D];
+#pragma unroll
+    for (int i = 0; i < P; ++i) Lp[i] = __ldg(Lpk + r * P + i);
+    chol_from_packed<D>(Lp, jitter, C);
+    if (entropy != nullptr) {
+        float h = 0.5f * D * (1.0f + 1.8378770664093453f);  // D/2 (1 + log 2 pi)
+#pragma unroll
+        for (int i = 0; i < D; ++i) h += logf(C[i][i]);
+        entropy[r] = h;
+    }
+    if (samples != nullptr) {
+        float m[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) m[i] = __ldg(mean + r * D + i);
+        for (int s = 0; s < S; ++s) {
+            float e[D];
+#pragma unroll
+            for (int i = 0; i < D; ++i) e[i] = __ldg(eps + ((int64_t)s * R + r) * D + i);
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                float y = m[i];
+#pragma unroll
+                for (int j = 0; j <= i; ++j) y = fmaf(C[i][j], e[j], y);
+                samples[((int64_t)s * R + r) * D + i] = y;
+            }
+        }
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(128)
+state_bwd_kernel(const float* __restrict__ Lpk, const float* __restrict__ eps, const int S, const int64_t R,
+                 const float jitter, const float* __restrict__ g_samples, const float* __restrict__ g_entropy,
+                 float* __restrict__ g_mean, float* __restrict__ g_Lpk) {
+    constexpr int P = Tri<D>::P;
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    float Lp[P], C[D][D], Cb[D][D], gm[D];
+#pragma unroll
+    for (int i = 0; i < P; ++i) Lp[i] = __ldg(Lpk + r * P + i);
+    chol_from_packed<D>(Lp, jitter, C);
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        gm[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < D; ++j) Cb[i][j] = 0.f;
+    }
+    if (g_samples != nullptr) {
+        for (int s = 0; s < S; ++s) {
+            float e[D], gy[D];
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                e[i] = __ldg(eps + ((int64_t)s * R + r) * D + i);
+                gy[i] = __ldg(g_samples + ((int64_t)s * R + r) * D + i);
+                gm[i] += gy[i];
+            }
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+#pragma unroll
+                for (int j = 0; j <= i; ++j) Cb[i][j] = fmaf(gy[i], e[j], Cb[i][j]);
+        }
+    }
+    if (g_entropy != nullptr) {
+        const float gh = __ldg(g_entropy + r);
+#pragma unroll
+        for (int i = 0; i < D; ++i) Cb[i][i] += gh / C[i][i];
+    }
+    float gL[P];
+    chol_backward_to_packed<D>(Lp, C, Cb, gL);
+#pragma unroll
+    for (int i = 0; i < P; ++i) g_Lpk[r * P + i] = gL[i];
+    if (g_mean != nullptr) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) g_mean[r * D + i] = gm[i];
+    }
+}
+
+// ---- mean Gaussian log-likelihood of decoded predictions, value + gradients in one pass ------------------------------
+// pred [S, R, D], ys [R, Dobs], W [D, Dobs], bias [Dobs] (may be NULL), var [Dobs].
+// out[0] += sum log N(y | pred W + b, var);  g_pred [S,R,D] = d(sum)/d pred;  g_var [Dobs] += d(sum)/d var.
+constexpr int kLlMaxD = GPODE_MAX_D;
+constexpr int kLlPasses = 4;  // Dobs <= 128
+
+__global__ void __launch_bounds__(256)
+loglik_kernel(const float* __restrict__ pred, const float* __restrict__ ys, const float* __restrict__ W,
+              const float* __restrict__ bias, const float* __restrict__ var, const int S, const int64_t R, const int D,
+              const int Dobs, double* __restrict__ out, float* __restrict__ g_pred, float* __restrict__ g_var) {
+    __shared__ double s_sum[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    float w[kLlPasses][kLlMaxD], b[kLlPasses], iv[kLlPasses], lv[kLlPasses], gv[kLlPasses];
+#pragma unroll
+    for (int p = 0; p < kLlPasses; ++p) {
+        const int d = p * 32 + lane;
+        const bool ok = d < Dobs;
+        b[p] = (ok && bias) ? bias[d] : 0.f;
+        const float v = ok ? var[d] : 1.f;
+        iv[p] = 1.0f / v;
+        lv[p] = ok ? (1.8378770664093453f + logf(v)) : 0.f;  // log(2 pi) + log var
+        gv[p] = 0.f;
+#pragma unroll
+        for (int l = 0; l < kLlMaxD; ++l) w[p][l] = (ok && l < D) ? W[l * Dobs + d] : 0.f;
+    }
+    double acc = 0.0;
+    for (int64_t r = (int64_t)blockIdx.x * nwarps + warp; r < R; r += (int64_t)gridDim.x * nwarps) {
+        float y[kLlPasses];
+#pragma unroll
+        for (int p = 0; p < kLlPasses; ++p) {
+            const int d = p * 32 + lane;
+            y[p] = d < Dobs ? __ldg(ys + r * Dobs + d) : 0.f;
+        }
+        float local = 0.f;
+        for (int s = 0; s < S; ++s) {
+            const float* xr = pred + ((int64_t)s * R + r) * D;
+            float x[kLlMaxD];
+#pragma unroll
+            for (int l = 0; l < kLlMaxD; ++l) x[l] = l < D ? __ldg(xr + l) : 0.f;
+            float gx[kLlMaxD];
+#pragma unroll
+            for (int l = 0; l < kLlMaxD; ++l) gx[l] = 0.f;
+#pragma unroll
+            for (int p = 0; p < kLlPasses; ++p) {
+                if (p * 32 < Dobs) {
+                    float f = b[p];
+#pragma unroll
+                    for (int l = 0; l < kLlMaxD; ++l) f = fmaf(x[l], w[p][l], f);
+                    const bool ok = p * 32 + lane < Dobs;
+                    const float diff = ok ? f - y[p] : 0.f;
+                    const float q = diff * iv[p];
+                    local += ok ? -0.5f * (lv[p] + diff * q) : 0.f;
+                    gv[p] += ok ? -0.5f * (iv[p] - q * q) : 0.f;
+#pragma unroll
+                    for (int l = 0; l < kLlMaxD; ++l) gx[l] = fmaf(-q, w[p][l], gx[l]);
+                }
+            }
+            if (g_pred != nullptr) {
+#pragma unroll
+                for (int l = 0; l < kLlMaxD; ++l) {
+                    if (l < D) {
+                        const float v = gpode_warp_sum(gx[l]);
+                        if (lane == 0) g_pred[((int64_t)s * R + r) * D + l] = v;
+                    }
+                }
+            }
+        }
+        acc += (double)local;
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) s_sum[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < nwarps; ++i) t += s_sum[i];
+        atomicAdd(out, t);
+    }
+    if (g_var != nullptr) {
+#pragma unroll
+        for (int p = 0; p < kLlPasses; ++p) {
+            const int d = p * 32 + lane;
+            if (d < Dobs) atomicAdd(g_var + d, gv[p]);
+        }
+    }
+}
+
+int check_states(int D, int S, int64_t R) {
+    GPODE_CHECK_ARG(D >= 1 && D <= GPODE_MAX_D, "state dimension D=%d outside 1..%d", D, GPODE_MAX_D);
+    GPODE_CHECK_ARG(S >= 0 && R >= 0, "negative sizes S=%d R=%lld", S, (long long)R);
+    return 0;
+}
+
+}  // namespace
+
+#define GPODE_STATE_SWITCH(D_, KERNEL, ...)                                      \
+    switch (D_) {                                                                \
+        case 1: KERNEL<1><<<grid, 128, 0, st>>>(__VA_ARGS__); break;             \
+        case 2: KERNEL<2><<<grid, 128, 0, st>>>(__VA_ARGS__); break;             \
+        case 3: KERNEL<3><<<grid, 128, 0, st>>>(__VA_ARGS__); break;             \
+        case 4: KERNEL<4><<<grid, 128, 0, st>>>(__VA_ARGS__); break;             \
+        case 5: KERNEL<5><<<grid, 128, 0, st>>>(__VA_ARGS__); break;             \
+        case 6: KERNEL<6><<<grid, 128, 0, st>>>(__VA_ARGS__); break;             \
+        case 7: KERNEL<7><<<grid, 128, 0, st>>>(__VA_ARGS__); break;             \
+        case 8: KERNEL<8><<<grid, 128, 0, st>>>(__VA_ARGS__); break;             \
+    }
+
+extern "C" int gpode_state_fwd(const float* mean, const float* L_packed, const float* eps, int S, int64_t R, int D,
+                               float jitter, float* samples_out, float* entropy_out, void* stream) {
+    if (int rc = check_states(D, S, R)) return rc;
+    if (R == 0) return 0;
+    GPODE_CHECK_ARG(L_packed != nullptr, "L_packed is NULL");
+    GPODE_CHECK_ARG(samples_out == nullptr || (mean && eps), "sampling needs mean and eps");
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)((R + 127) / 128);
+    GPODE_STATE_SWITCH(D, state_fwd_kernel, mean, L_packed, eps, S, R, jitter, samples_out, entropy_out)
+    GPODE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gpode_state_bwd(const float* L_packed, const float* eps, int S, int64_t R, int D, float jitter,
+                               const float* grad_samples, const float* grad_entropy, float* grad_mean,
+                               float* grad_L_packed, void* stream) {
+    if (int rc = check_states(D, S, R)) return rc;
+    if (R == 0) return 0;
+    GPODE_CHECK_ARG(L_packed && grad_L_packed, "NULL argument");
+    GPODE_CHECK_ARG(grad_samples == nullptr || eps != nullptr, "sample gradient needs eps");
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)((R + 127) / 128);
+    GPODE_STATE_SWITCH(D, state_bwd_kernel, L_packed, eps, S, R, jitter, grad_samples, grad_entropy, grad_mean,
+                       grad_L_packed)
+    GPODE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gpode_loglik_sum(const float* pred, const float* ys, const float* W, const float* bias,
+                                const float* var, int S, int64_t R, int D, int D_obs, double* sum_out,
+                                float* grad_pred, float* grad_var, void* stream) {
+    GPODE_CHECK_ARG(D >= 1 && D <= GPODE_MAX_D, "latent dimension D=%d outside 1..%d", D, GPODE_MAX_D);
+    GPODE_CHECK_ARG(D_obs >= 1 && D_obs <= 32 * kLlPasses, "observed dimension %d outside 1..%d", D_obs, 32 * kLlPasses);
+    GPODE_CHECK_ARG(S >= 1 && R >= 0, "bad sizes S=%d R=%lld", S, (long long)R);
+    GPODE_CHECK_ARG(pred && ys && W && var && sum_out, "NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    GPODE_CUDA(cudaMemsetAsync(sum_out, 0, sizeof(double), st));
+    if (grad_var) GPODE_CUDA(cudaMemsetAsync(grad_var, 0, sizeof(float) * D_obs, st));
+    if (R == 0) return 0;
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int64_t want = (R + 7) / 8;
+    const int64_t cap = (int64_t)sms * 8;
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
+    loglik_kernel<<<grid, 256, 0, st>>>(pred, ys, W, bias, var, S, R, D, D_obs, sum_out, grad_pred, grad_var);
+    GPODE_LAUNCH_CHECK();
+    return 0;
+}

@@ -29,8 +29,9 @@ class SequenceModel(nn.Module):
         x0_samples = self.x0_distribution.sample(num_samples=1)[0]
         x0_kl = self.x0_distribution.kl()
         xs = self.build_flow(x0_samples, ts)[:, 1:]
-        loglik = self.likelihood.log_prob(xs, ys)
-        return loglik.mean(), x0_kl.mean() / self.num_observations
+        mean_fn = getattr(self.likelihood, "log_prob_mean", None)
+        loglik_mean = mean_fn(xs, ys) if mean_fn is not None else self.likelihood.log_prob(xs, ys).mean()
+        return loglik_mean, x0_kl.mean() / self.num_observations
 
     def build_kl(self):
         return self.flow.kl() / self.num_observations

@@ -56,7 +56,12 @@ class UniformSequenceModel(BaseSequenceModel):
         # one launch: S*N*T independent one-interval IVPs sharing one GP function draw
         predicted_xs = self.flow(x0=stack_segments(ss_samples), ts=ts[:2])  # (S*N*T, 2, D)
         predicted_xs = unstack_segments(predicted_xs[:, -1], (S, N, T, D))
-        observation_loglik = self.likelihood.log_prob(predicted_xs, ys.unsqueeze(0))
+        # mean log-likelihood: one fused decode + log-density kernel when the likelihood offers it
+        mean_fn = getattr(self.likelihood, "log_prob_mean", None)
+        if mean_fn is not None:
+            observation_loglik_mean = mean_fn(predicted_xs, ys.unsqueeze(0))
+        else:
+            observation_loglik_mean = self.likelihood.log_prob(predicted_xs, ys.unsqueeze(0)).mean()
         state_entropy = self.state_distribution.entropy()  # (N,T-1)
         state_constraint_logprob = self.constraint.log_prob(ss_samples[:, :, 1:, :],
                                                             predicted_xs[:, :, :-1, :]).sum(3)  # (S,N,T-1)
@@ -66,4 +71,4 @@ class UniformSequenceModel(BaseSequenceModel):
         scaled_state_constraint_loglik = state_constraint_logprob.mean(0).sum() / self.num_observations
         scaled_state_entropy = state_entropy.sum() / self.num_observations
         scaled_initial_state_kl = initial_state_kl / self.num_observations
-        return observation_loglik.mean(), scaled_state_constraint_loglik, scaled_state_entropy, scaled_initial_state_kl
+        return observation_loglik_mean, scaled_state_constraint_loglik, scaled_state_entropy, scaled_initial_state_kl

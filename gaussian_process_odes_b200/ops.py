@@ -191,6 +191,103 @@ class _WhitenedKL(torch.autograd.Function):
         return gU, gL
 
 
+class _StateSample(torch.autograd.Function):
+    """mean + chol(L L^T + jitter I) eps for a batch of packed lower-triangular factors (gpode_state_fwd/_bwd)."""
+
+    @staticmethod
+    def forward(ctx, mean, L_packed, eps, jitter):
+        mc, lc, ec = f32(mean, "mean"), f32(L_packed, "L_packed"), f32(eps, "eps")
+        D = mc.shape[-1]
+        R = mc.numel() // D
+        S = ec.numel() // (R * D) if R else 0
+        out = torch.empty_like(ec)
+        _lib.call("gpode_state_fwd", ptr(mc), ptr(lc), ptr(ec), S, R, D, float(jitter), ptr(out), ptr(None),
+                  stream_ptr())
+        ctx.save_for_backward(lc, ec)
+        ctx.dims = (S, R, D, float(jitter), mean.shape, L_packed.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lc, ec = ctx.saved_tensors
+        S, R, D, jitter, mshape, lshape = ctx.dims
+        gm = torch.empty(mshape, dtype=torch.float32, device=lc.device)
+        gl = torch.empty(lshape, dtype=torch.float32, device=lc.device)
+        _lib.call("gpode_state_bwd", ptr(lc), ptr(ec), S, R, D, jitter, ptr(f32(g, "grad_samples")), ptr(None),
+                  ptr(gm), ptr(gl), stream_ptr())
+        return gm, gl, None, None
+
+
+class _StateEntropy(torch.autograd.Function):
+    """Entropy of N(., L L^T + jitter I) per matrix (gpode_state_fwd/_bwd with only the entropy output)."""
+
+    @staticmethod
+    def forward(ctx, L_packed, D, jitter):
+        lc = f32(L_packed, "L_packed")
+        R = lc.numel() // (D * (D + 1) // 2)
+        out = torch.empty(L_packed.shape[:-1], dtype=torch.float32, device=lc.device)
+        _lib.call("gpode_state_fwd", ptr(None), ptr(lc), ptr(None), 0, R, D, float(jitter), ptr(None), ptr(out),
+                  stream_ptr())
+        ctx.save_for_backward(lc)
+        ctx.dims = (R, D, float(jitter), L_packed.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (lc,) = ctx.saved_tensors
+        R, D, jitter, lshape = ctx.dims
+        gl = torch.empty(lshape, dtype=torch.float32, device=lc.device)
+        _lib.call("gpode_state_bwd", ptr(lc), ptr(None), 0, R, D, jitter, ptr(None), ptr(f32(g, "grad_entropy")),
+                  ptr(None), ptr(gl), stream_ptr())
+        return gl, None, None
+
+
+class _LoglikMean(torch.autograd.Function):
+    """mean over all elements of log N(ys | pred W + b, var), value and gradients in one kernel (gpode_loglik_sum)."""
+
+    @staticmethod
+    def forward(ctx, pred, ys, W, bias, var):
+        pc, yc, wc, vc = f32(pred, "pred"), f32(ys, "ys"), f32(W, "W"), f32(var, "var")
+        bc = f32(bias, "bias") if bias is not None else None
+        D, Dobs = wc.shape
+        R = yc.numel() // Dobs
+        S = pc.numel() // (R * D) if R else 1
+        need_p, need_v = ctx.needs_input_grad[0], ctx.needs_input_grad[4]
+        total = torch.empty((), dtype=torch.float64, device=pc.device)
+        gp = torch.empty_like(pc) if need_p else None
+        gv = torch.empty_like(vc) if need_v else None
+        _lib.call("gpode_loglik_sum", ptr(pc), ptr(yc), ptr(wc), ptr(bc), ptr(vc), S, R, D, Dobs, ptr(total), ptr(gp),
+                  ptr(gv), stream_ptr())
+        count = float(S * R * Dobs)
+        ctx.count = count
+        ctx.save_for_backward(*(t for t in (gp, gv) if t is not None))
+        ctx.have = (need_p, need_v)
+        return (total / count).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        saved = list(ctx.saved_tensors)
+        need_p, need_v = ctx.have
+        scale = g / ctx.count
+        gp = saved.pop(0) * scale if need_p else None
+        gv = saved.pop(0) * scale if need_v else None
+        return gp, None, None, None, gv
+
+
+def state_sample(mean, L_packed, eps, jitter=1e-5):
+    """``eps (S, *batch, D)`` -> samples ``(S, *batch, D)`` of N(mean, L L^T + jitter I), L packed ``(*batch, P)``."""
+    return _StateSample.apply(mean, L_packed, eps, jitter)
+
+
+def state_entropy(L_packed, D, jitter=1e-5):
+    return _StateEntropy.apply(L_packed, D, jitter)
+
+
+def loglik_mean(pred, ys, W, bias, var):
+    """pred ``(S?, ..., D)``, ys ``(..., D_obs)``: mean Gaussian log-density of ``ys`` under ``pred @ W + bias``."""
+    return _LoglikMean.apply(pred, ys, W, bias, var)
+
+
 def vector_field(x, Z, ell, var, nu, omega, phase, w):
     """f(x) of one sampled GP function; differentiable in x, Z, ell, var, nu."""
     return _VectorField.apply(x, Z, ell, var, nu, omega, phase, w)

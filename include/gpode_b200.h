@@ -124,6 +124,26 @@ int64_t gpode_dopri5_work_floats(int D, int64_t B);
 int gpode_dopri5_fwd(const float* packed, int D, int M, int S, const float* x0, const double* t, int Tg, int64_t B,
                      double rtol, double atol, float* xs, float* work, int32_t* stats_out, void* stream);
 
+/* ---- ELBO side terms either side of the integrator -------------------------------
+ * Full-rank Gaussian state posteriors N(mean_r, L_r L_r^T + jitter I), r < R, L_r given as the PACKED lower triangle
+ * (the optvar of transforms.LowerTriangular / StackedLowerTriangular, src/misc/transforms.py:70-76,105-112).
+ * Replaces MultivariateNormal(...).rsample / .entropy of src/core/states.py:69-74,91-92,177-182,199-204:
+ *   samples_out [S,R,D] = mean + chol(L L^T + jitter I) eps,  eps [S,R,D];   entropy_out [R] (either may be NULL). */
+int gpode_state_fwd(const float* mean, const float* L_packed, const float* eps, int S, int64_t R, int D, float jitter,
+                    float* samples_out, float* entropy_out, void* stream);
+/* Backward: grad_samples [S,R,D] and/or grad_entropy [R] -> grad_mean [R,D] (may be NULL), grad_L_packed [R,D(D+1)/2]. */
+int gpode_state_bwd(const float* L_packed, const float* eps, int S, int64_t R, int D, float jitter,
+                    const float* grad_samples, const float* grad_entropy, float* grad_mean, float* grad_L_packed,
+                    void* stream);
+
+/* Sum over all elements of the Gaussian log-density of decoded predictions, with its gradients in the same pass
+ * (Gaussian / ProjectedGaussian.log_prob, src/core/likelihoods.py:27-28,38-45, decoder = affine map as in
+ * src/misc/mocap_utils.py:24-34): pred [S,R,D], ys [R,D_obs], W [D,D_obs], bias [D_obs] or NULL, var [D_obs].
+ * sum_out (device float64) = sum log N(ys | pred W + bias, var); grad_pred [S,R,D] / grad_var [D_obs] (may be NULL)
+ * are the derivatives of that SUM. */
+int gpode_loglik_sum(const float* pred, const float* ys, const float* W, const float* bias, const float* var, int S,
+                     int64_t R, int D, int D_obs, double* sum_out, float* grad_pred, float* grad_var, void* stream);
+
 /* Measurement utility (no reference counterpart): sustained FP32 FMA throughput of the current device in TFLOP/s
  * (best of 5 launches of a register-only FMA loop; synchronises the stream). scratch: >= 1 float (device). */
 int gpode_probe_fp32_fma(double* tflops_out_host, double* ms_out_host, float* scratch, void* stream);

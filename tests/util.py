@@ -117,8 +117,8 @@ def build_product_model(kind, p, ys, S, solver, ts_dense_scale=4, proj=None):
     M, D = p['inducing_loc'].shape
     projection = None
     if proj is not None:
-        comp = proj.cuda()
-        projection = lambda x: torch.einsum('ntl,ld->ntd', x, comp)
+        from gaussian_process_odes_b200.misc.mocap_utils import LinearProjection
+        projection = LinearProjection(proj.cpu().numpy())
     if kind == "gpode":
         model = builders.build_gpode(N, T, D, num_inducing=M, num_features=S, solver=solver,
                                      ts_dense_scale=ts_dense_scale, D_obs=Dobs, projection=projection)
