@@ -9,6 +9,12 @@
 
 int GPODE_CAT(gpode_dopri5_fwd_d, GPODE_D)(const float* packed, int M, int S, const float* x0, const double* t, int Tg,
                                            int64_t B, double rtol, double atol, float* xs, float* work,
-                                           int32_t* stats, cudaStream_t st) {
-    return launch_dopri5<GPODE_D>(packed, M, S, x0, t, Tg, B, rtol, atol, xs, work, stats, st);
+                                           int32_t* stats, float* ckpt, int cap, cudaStream_t st) {
+    return launch_dopri5<GPODE_D>(packed, M, S, x0, t, Tg, B, rtol, atol, xs, work, stats, ckpt, cap, st);
+}
+
+int GPODE_CAT(gpode_dopri5_bwd_d, GPODE_D)(const float* packed, int M, int S, const double* t, int Tg, int64_t B,
+                                           const float* gxs, const float* ckpt, int cap, int n_acc, float* gx0,
+                                           float* vrows, float* acc, cudaStream_t st) {
+    return launch_dopri5_bwd<GPODE_D>(packed, M, S, t, Tg, B, gxs, ckpt, cap, n_acc, gx0, vrows, acc, st);
 }

@@ -50,6 +50,13 @@ struct Dopri5Args {
     double* red;      // 4 accumulators (3 rotating for the error norm + 1 spare), zeroed by the host
     int32_t* stats;   // nfe, accepted, rejected, status
     int max_attempts;
+    // optional checkpoints of the ACCEPTED steps for the discrete adjoint (all NULL when not training)
+    float* ck_y;      // [cap][B][D]    state at the start of accepted step n
+    float* ck_k;      // [cap][7][B][D] the seven stage derivatives of accepted step n (as integrated: sign included)
+    float* ck_dt;     // [cap]          float32 step size used by the stage algebra
+    int32_t* out_step;  // [Tg] accepted-step index that produced output j (-1 for j = 0)
+    float* out_x;     // [Tg] interpolation abscissa of output j inside its step
+    int cap;
 };
 
 __device__ __forceinline__ double block_sum_to(double v, double* smem_red) {
@@ -177,6 +184,10 @@ __global__ void __launch_bounds__(kDpThreads) dopri5_kernel(const Dopri5Args a) 
             status = attempt >= a.max_attempts ? 1 : 2;  // too many attempts / step-size underflow
             break;
         }
+        if (a.ck_k != nullptr && n_acc >= a.cap) {
+            status = 3;  // checkpoint capacity exhausted: the caller retries with a larger one
+            break;
+        }
         const float dts = (float)dt;
         double se = 0.0;
         for (int64_t row = gtid; row < B; row += gstride) {
@@ -211,6 +222,11 @@ __global__ void __launch_bounds__(kDpThreads) dopri5_kernel(const Dopri5Args a) 
             strow<D>(yi, Y1, row);
             strow<D>(k[6], F1, row);
             strow<D>(ym, YM, row);
+            if (a.ck_k != nullptr && n_acc < a.cap) {  // slot n_acc is simply overwritten if this attempt is rejected
+                strow<D>(y, a.ck_y + (int64_t)n_acc * plane, row);
+#pragma unroll
+                for (int l = 0; l < 7; ++l) strow<D>(k[l], a.ck_k + ((int64_t)n_acc * 7 + l) * plane, row);
+            }
         }
         {
             const double be = block_sum_to(se, sred);
@@ -243,6 +259,10 @@ __global__ void __launch_bounds__(kDpThreads) dopri5_kernel(const Dopri5Args a) 
                         const float cd = dts * f0;
                         for (int jo = jout; jo < jend; ++jo) {
                             const float x = (float)((dir * a.t[jo] - t1) / (t1n - t1));
+                            if (a.out_x != nullptr && gtid == 0 && j == 0) {
+                                a.out_step[jo] = n_acc;
+                                a.out_x[jo] = x;
+                            }
                             float total = y0 + x * cd;
                             float xp = x * x;
                             total = total + xp * cc;
@@ -257,6 +277,7 @@ __global__ void __launch_bounds__(kDpThreads) dopri5_kernel(const Dopri5Args a) 
                 strow<D>(y1, Y, row);
                 strow<D>(f1, F, row);
             }
+            if (a.ck_dt != nullptr && gtid == 0) a.ck_dt[n_acc] = dts;
             jout = jend;
             t0 = t1;
             t1 = t1n;
@@ -276,6 +297,7 @@ __global__ void __launch_bounds__(kDpThreads) dopri5_kernel(const Dopri5Args a) 
     }
     (void)t0;
     if (gtid == 0) {
+        if (a.out_step != nullptr) a.out_step[0] = -1;
         a.stats[0] = nfe;
         a.stats[1] = n_acc;
         a.stats[2] = n_rej;
@@ -287,7 +309,7 @@ __global__ void __launch_bounds__(kDpThreads) dopri5_kernel(const Dopri5Args a) 
 
 template <int D>
 int launch_dopri5(const float* packed, int M, int S, const float* x0, const double* t, int Tg, int64_t B, double rtol,
-                  double atol, float* xs, float* work, int32_t* stats, cudaStream_t st) {
+                  double atol, float* xs, float* work, int32_t* stats, float* ckpt, int cap, cudaStream_t st) {
     const GpodeLayout L = gpode_layout(D, M, S);
     const size_t smem = 16 + (size_t)L.total * 4;
     GPODE_CUDA(cudaFuncSetAttribute(dopri5_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -300,8 +322,8 @@ int launch_dopri5(const float* packed, int M, int S, const float* x0, const doub
         return -2;
     }
     const int64_t want = (B + kDpThreads - 1) / kDpThreads;
-    const int64_t cap = (int64_t)sms * occ;
-    const int grid = (int)(want < cap ? want : cap);
+    const int64_t grid_cap = (int64_t)sms * occ;
+    const int grid = (int)(want < grid_cap ? want : grid_cap);
     Dopri5Args a;
     a.packed = packed; a.M = M; a.S = S; a.total = L.total; a.x0 = x0; a.t = t; a.Tg = Tg; a.B = B;
     a.rtol = rtol; a.atol = atol; a.xs = xs;
@@ -310,8 +332,205 @@ int launch_dopri5(const float* packed, int M, int S, const float* x0, const doub
     a.red = reinterpret_cast<double*>(work + 5 * plane + ((5 * plane) & 1));
     a.stats = stats;
     a.max_attempts = 1 << 20;
+    a.ck_y = a.ck_k = a.ck_dt = a.out_x = nullptr;
+    a.out_step = nullptr;
+    a.cap = 0;
+    if (ckpt != nullptr && cap > 0) {  // layout documented at gpode_dopri5_ckpt_floats
+        a.cap = cap;
+        a.ck_y = ckpt;
+        a.ck_k = a.ck_y + (int64_t)cap * plane;
+        a.ck_dt = a.ck_k + (int64_t)cap * 7 * plane;
+        a.out_x = a.ck_dt + cap;
+        a.out_step = reinterpret_cast<int32_t*>(a.out_x + Tg);
+    }
     GPODE_CUDA(cudaMemsetAsync(a.red, 0, 4 * sizeof(double), st));
     void* params[] = {(void*)&a};
     GPODE_CUDA(cudaLaunchCooperativeKernel((const void*)dopri5_kernel<D>, dim3(grid), dim3(kDpThreads), params, smem, st));
+    return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// Discrete adjoint of the accepted steps (step sizes are constants, exactly as torchdiffeq computes them under
+// no_grad): walking the accepted steps backwards, each is an explicit 7-stage RK step
+//     Y_i = y0 + dt sum_{l<i} beta_il k_l,  k_i = f(Y_i),  y1 = Y_7,  y_mid = y0 + dt sum c_mid_l k_l,  f1 = k_7 (FSAL)
+// and every requested output inside it is the quartic through (y0, y_mid, y1, f0, f1). Warp-per-row mapping (lanes
+// split features / inducing points), so it serves the small training batches dopri5 is used with.
+// ------------------------------------------------------------------------------------------------------------------
+struct Dopri5BwdArgs {
+    const float* packed;
+    int M, S, total;
+    const double* t;
+    int Tg;
+    int64_t B;
+    const float* gxs;     // [Tg,B,D]
+    const float* ckpt;    // forward checkpoints
+    int cap, n_acc;
+    float* gx0;           // [B,D]
+    float* vy;            // virtual rows: stage inputs  [(6 n_acc + 1)][B][D]
+    float* vk;            //               cotangents
+    float* acc;
+};
+
+template <int D>
+__global__ void __launch_bounds__(kDpThreads) dopri5_bwd_kernel(const Dopri5BwdArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const float* sp = stage_params(smem_raw, a.packed, a.total);
+    float* red = reinterpret_cast<float*>(smem_raw + 16) + a.total;
+    for (int i = threadIdx.x; i < D * D + D; i += blockDim.x) red[i] = 0.f;
+    float A[D][D], V[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        V[k] = 0.f;
+#pragma unroll
+        for (int j = 0; j < D; ++j) A[k][j] = 0.f;
+    }
+    const int M = a.M, S = a.S, Tg = a.Tg, cap = a.cap, n_acc = a.n_acc;
+    const int64_t B = a.B, plane = B * D;
+    const float* ck_y = a.ckpt;
+    const float* ck_k = ck_y + (int64_t)cap * plane;
+    const float* ck_dt = ck_k + (int64_t)cap * 7 * plane;
+    const float* out_x = ck_dt + cap;
+    const int32_t* out_step = reinterpret_cast<const int32_t*>(out_x + Tg);
+    const float fsign = (Tg > 1 && a.t[Tg - 1] < a.t[0]) ? -1.f : 1.f;
+    const int lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+
+    for (int64_t row = (int64_t)blockIdx.x * wpc + (threadIdx.x >> 5); row < B; row += (int64_t)gridDim.x * wpc) {
+        float lam[D], kap[D];  // adjoints of y (end of the current step) and of f1 = k7
+#pragma unroll
+        for (int j = 0; j < D; ++j) lam[j] = kap[j] = 0.f;
+        int jo = Tg - 1;
+        for (int n = n_acc - 1; n >= 0; --n) {
+            const float dt = ck_dt[n];
+            float y0[1][D], k[7][1][D];
+            ldrow<D>(y0, ck_y + (int64_t)n * plane, row);
+#pragma unroll
+            for (int l = 0; l < 7; ++l) ldrow<D>(k[l], ck_k + ((int64_t)n * 7 + l) * plane, row);
+            // cotangents of the outputs interpolated inside this step
+            float yb0[D], yb1[D], ybm[D], fb0[D], fb1[D];
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                yb0[j] = 0.f; yb1[j] = lam[j]; ybm[j] = 0.f; fb0[j] = 0.f; fb1[j] = kap[j];
+            }
+            while (jo >= 1 && out_step[jo] == n) {
+                const float x = out_x[jo], x2 = x * x, x3 = x2 * x, x4 = x2 * x2;
+                const float p0 = 1.f - 11.f * x2 + 18.f * x3 - 8.f * x4;
+                const float p1 = -5.f * x2 + 14.f * x3 - 8.f * x4;
+                const float pm = 16.f * x2 - 32.f * x3 + 16.f * x4;
+                const float q0 = dt * (x - 4.f * x2 + 5.f * x3 - 2.f * x4);
+                const float q1 = dt * (x2 - 3.f * x3 + 2.f * x4);
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    const float g = __ldg(a.gxs + (int64_t)jo * plane + row * D + j);
+                    yb0[j] = fmaf(g, p0, yb0[j]);
+                    yb1[j] = fmaf(g, p1, yb1[j]);
+                    ybm[j] = fmaf(g, pm, ybm[j]);
+                    fb0[j] = fmaf(g, q0, fb0[j]);
+                    fb1[j] = fmaf(g, q1, fb1[j]);
+                }
+                --jo;
+            }
+            float kb[7][D];
+#pragma unroll
+            for (int l = 0; l < 7; ++l)
+#pragma unroll
+                for (int j = 0; j < D; ++j)
+                    kb[l][j] = (l < 6 ? __fmul_rn(kBeta[5][l], dt) * yb1[j] : 0.f) + __fmul_rn(dt, kCMid[l]) * ybm[j];
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                kb[6][j] += fb1[j];
+                kb[0][j] += fb0[j];
+                yb0[j] += yb1[j] + ybm[j];
+            }
+            // stages 7 .. 2
+#pragma unroll
+            for (int i = 6; i >= 1; --i) {
+                float Yi[1][D], kbi[1][D], fst[1][D], Yb[1][D];
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    float s = 0.f;
+#pragma unroll
+                    for (int l = 0; l < i; ++l) s = fmaf(k[l][0][j], __fmul_rn(kBeta[i - 1][l], dt), s);
+                    Yi[0][j] = y0[0][j] + s;
+                    kbi[0][j] = fsign * kb[i][j];   // cotangent of f(Y_i); the integrated k is fsign * f
+                    fst[0][j] = lane == 0 ? fsign * k[i][0][j] : 0.f;  // f(Y_i) enters the variance sum once per row
+                }
+                const int64_t slot = (int64_t)n * 6 + (i - 1);
+                if (lane == 0) {
+                    strow<D>(Yi, a.vy + slot * plane, row);
+                    strow<D>(kbi, a.vk + slot * plane, row);
+                }
+                vf_vjp<D, 1>(sp, M, S, Yi, kbi, fst, Yb, A, V, lane, 32);
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    Yb[0][j] = gpode_warp_sum(Yb[0][j]);
+                    yb0[j] += Yb[0][j];
+                }
+#pragma unroll
+                for (int l = 0; l < i; ++l)
+#pragma unroll
+                    for (int j = 0; j < D; ++j) kb[l][j] = fmaf(__fmul_rn(kBeta[i - 1][l], dt), Yb[0][j], kb[l][j]);
+            }
+            if (n > 0) {
+#pragma unroll
+                for (int j = 0; j < D; ++j) kap[j] = kb[0][j];  // k1 of this step is k7 of the previous one (FSAL)
+            } else {
+                float kbi[1][D], fst[1][D], Yb[1][D];
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    kbi[0][j] = fsign * kb[0][j];
+                    fst[0][j] = lane == 0 ? fsign * k[0][0][j] : 0.f;
+                }
+                const int64_t slot = (int64_t)n_acc * 6;
+                if (lane == 0) {
+                    strow<D>(y0, a.vy + slot * plane, row);
+                    strow<D>(kbi, a.vk + slot * plane, row);
+                }
+                vf_vjp<D, 1>(sp, M, S, y0, kbi, fst, Yb, A, V, lane, 32);
+#pragma unroll
+                for (int j = 0; j < D; ++j) yb0[j] += gpode_warp_sum(Yb[0][j]);
+            }
+#pragma unroll
+            for (int j = 0; j < D; ++j) lam[j] = yb0[j];
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                float g = lam[j] + __ldg(a.gxs + row * D + j);  // output 0 is y0 itself
+                // outputs that were never reached by a step (status != 0) cannot occur for a successful forward
+                a.gx0[row * D + j] = g;
+            }
+        }
+    }
+    __syncthreads();
+    reduce_AV<D>(A, V, a.acc, red);
+}
+
+template <int D>
+int launch_dopri5_bwd(const float* packed, int M, int S, const double* t, int Tg, int64_t B, const float* gxs,
+                      const float* ckpt, int cap, int n_acc, float* gx0, float* vrows, float* acc, cudaStream_t st) {
+    const GpodeLayout L = gpode_layout(D, M, S);
+    const size_t smem = 16 + (size_t)(L.total + D * D + D) * 4;
+    GPODE_CUDA(cudaFuncSetAttribute(dopri5_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0, sms = 148, dev = 0;
+    GPODE_CUDA(cudaGetDevice(&dev));
+    GPODE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    GPODE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dopri5_bwd_kernel<D>, kDpThreads, smem));
+    if (occ < 1) {
+        gpode_set_error("dopri5 backward kernel does not fit on an SM (smem %zu bytes)", smem);
+        return -2;
+    }
+    const int wpc = kDpThreads / 32;
+    const int64_t want = (B + wpc - 1) / wpc;
+    const int64_t cap_grid = (int64_t)sms * occ;
+    Dopri5BwdArgs a;
+    a.packed = packed; a.M = M; a.S = S; a.total = L.total; a.t = t; a.Tg = Tg; a.B = B; a.gxs = gxs; a.ckpt = ckpt;
+    a.cap = cap; a.n_acc = n_acc; a.gx0 = gx0;
+    const int64_t VR = ((int64_t)6 * n_acc + 1) * B;
+    a.vy = vrows;
+    a.vk = vrows + VR * D;
+    a.acc = acc;
+    dopri5_bwd_kernel<D><<<(unsigned)(want < cap_grid ? want : cap_grid), kDpThreads, smem, st>>>(a);
+    GPODE_LAUNCH_CHECK();
     return 0;
 }

@@ -298,27 +298,71 @@ def rk4_integrate(x0, t, Z, ell, var, nu, omega, phase, w):
     return _RK4.apply(x0, t, Z, ell, var, nu, omega, phase, w)
 
 
+class _Dopri5(torch.autograd.Function):
+    """xs = odeint(f, x0, t, method='dopri5') (torchdiffeq 0.2.0 controller) via gpode_dopri5_fwd / gpode_dopri5_bwd."""
+
+    @staticmethod
+    def forward(ctx, x0, t, Z, ell, var, nu, omega, phase, w, rtol, atol):
+        lib = _lib.load()
+        pc = PackedCache(Z, ell, var, nu, omega, phase, w)
+        xc = f32(x0, "x0")
+        if xc.ndim != 2 or xc.shape[1] != pc.D:
+            raise _lib.GpodeError("x0 must be (B,%d), got %s" % (pc.D, tuple(xc.shape)))
+        B, Tg = xc.shape[0], t.shape[0]
+        t64 = t.detach().to(device=xc.device, dtype=torch.float64).contiguous()
+        need_grad = any(ctx.needs_input_grad[:6])
+        xs = torch.empty(Tg, B, pc.D, dtype=torch.float32, device=xc.device)
+        work = torch.empty(lib.gpode_dopri5_work_floats(pc.D, B), dtype=torch.float32, device=xc.device)
+        stats = torch.zeros(4, dtype=torch.int32, device=xc.device)
+        cap = max(32, 4 * Tg) if need_grad else 0
+        ckpt, n_acc = None, 0
+        while True:
+            if need_grad:
+                ckpt = torch.empty(lib.gpode_dopri5_ckpt_floats(pc.D, B, Tg, cap), dtype=torch.float32,
+                                   device=xc.device)
+            _lib.call("gpode_dopri5_fwd", ptr(pc.packed), pc.D, pc.M, pc.S, ptr(xc), ptr(t64), Tg, B, float(rtol),
+                      float(atol), ptr(xs), ptr(work), ptr(stats), ptr(ckpt), cap, stream_ptr())
+            if not need_grad:
+                break  # inference: no host synchronisation at all; `stats` stays on the device
+            st = [int(v) for v in stats.cpu()]  # training: one sync per integration (the reference syncs per attempt)
+            if st[3] == 3 and B > 0:
+                cap *= 2
+                continue
+            if st[3] != 0:
+                raise _lib.GpodeError("dopri5 failed: status %d (1 = attempt limit, 2 = step-size underflow)" % st[3])
+            n_acc = st[1]
+            break
+        ctx.pc, ctx.nu_shape, ctx.cap, ctx.n_acc = pc, nu.shape, cap, n_acc
+        if need_grad:
+            ctx.save_for_backward(t64, ckpt)
+        ctx.mark_non_differentiable(stats)
+        return xs, stats
+
+    @staticmethod
+    def backward(ctx, gxs, _gstats):
+        lib = _lib.load()
+        pc = ctx.pc
+        t64, ckpt = ctx.saved_tensors
+        gxs = f32(gxs, "grad_xs")
+        Tg, B, D = gxs.shape
+        gx0 = torch.empty(B, D, dtype=torch.float32, device=gxs.device)
+        acc = pc.new_acc()
+        n_vr = (6 * ctx.n_acc + 1) * B
+        vrows = torch.empty(lib.gpode_vrow_floats(D, n_vr), dtype=torch.float32, device=gxs.device)
+        _lib.call("gpode_dopri5_bwd", ptr(pc.packed), pc.D, pc.M, pc.S, ptr(t64), Tg, B, ptr(gxs), ptr(ckpt), ctx.cap,
+                  ctx.n_acc, ptr(gx0), ptr(vrows), ptr(acc), stream_ptr())
+        if n_vr:
+            _lib.call("gpode_param_grad", ptr(pc.packed), pc.D, pc.M, pc.S, ptr(vrows), ptr(vrows[n_vr * D:]), n_vr,
+                      ptr(acc), stream_ptr())
+        g_Z, g_ell, g_var, g_nu = pc.finalize(acc)
+        return gx0, None, g_Z, g_ell, g_var, g_nu.reshape(ctx.nu_shape), None, None, None, None, None
+
+
 def dopri5_integrate(x0, t, Z, ell, var, nu, omega, phase, w, rtol=1e-6, atol=1e-6):
-    """Adaptive dopri5 with torchdiffeq 0.2.0's controller in one cooperative kernel (``gpode_dopri5_fwd``).
-    Returns ``(xs (len(t),B,D), stats)`` where ``stats`` is a device int32 tensor [nfe, accepted, rejected, status];
-    ``xs`` carries no autograd graph (the adaptive solver's backward is not built yet -- train with 'rk4')."""
-    tensors = (x0, Z, ell, var, nu)
-    if torch.is_grad_enabled() and any(a.requires_grad for a in tensors):
-        raise _lib.GpodeError("dopri5: the discrete adjoint of the adaptive solver is not implemented; use "
-                              "solver='rk4' for training or call under torch.no_grad() for prediction")
-    lib = _lib.load()
-    pc = PackedCache(Z, ell, var, nu, omega, phase, w)
-    xc = f32(x0, "x0")
-    if xc.ndim != 2 or xc.shape[1] != pc.D:
-        raise _lib.GpodeError("x0 must be (B,%d), got %s" % (pc.D, tuple(xc.shape)))
-    B, Tg = xc.shape[0], t.shape[0]
-    t64 = t.detach().to(device=xc.device, dtype=torch.float64).contiguous()
-    xs = torch.empty(Tg, B, pc.D, dtype=torch.float32, device=xc.device)
-    work = torch.empty(lib.gpode_dopri5_work_floats(pc.D, B), dtype=torch.float32, device=xc.device)
-    stats = torch.zeros(4, dtype=torch.int32, device=xc.device)
-    _lib.call("gpode_dopri5_fwd", ptr(pc.packed), pc.D, pc.M, pc.S, ptr(xc), ptr(t64), Tg, B, float(rtol), float(atol),
-                               ptr(xs), ptr(work), ptr(stats), stream_ptr())
-    return xs, stats
+    """Adaptive dopri5 with torchdiffeq 0.2.0's controller in one cooperative kernel. Returns ``(xs (len(t),B,D),
+    stats)`` with ``stats`` a device int32 tensor [nfe, accepted, rejected, status]. Differentiable in x0, Z, ell,
+    var, nu through the discrete adjoint of the accepted steps (step sizes are constants, as in torchdiffeq)."""
+    return _Dopri5.apply(x0, t, Z, ell, var, nu, omega, phase, w, rtol, atol)
 
 
 def whiten(Z, ell, var, u, omega, phase, w, jitter=1e-5):

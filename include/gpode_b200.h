@@ -119,10 +119,23 @@ int gpode_kl_bwd(const float* Um, const float* Ls_packed, int D, int M, const fl
  * Runs as ONE cooperative persistent kernel: accept/reject is decided on the device, one grid barrier per attempt.
  * t: the Tg output times, DEVICE float64, strictly monotone in either direction (a decreasing grid is integrated as
  * -f over -t, which is what torchdiffeq does). work: gpode_dopri5_work_floats(D,B) floats.
- * stats_out (device, 4 int32): nfe, accepted steps, rejected steps, status (0 ok, 1 attempt limit, 2 dt underflow). */
+ * stats_out (device, 4 int32): nfe, accepted steps, rejected steps, status (0 ok, 1 attempt limit, 2 dt underflow,
+ * 3 checkpoint capacity). */
 int64_t gpode_dopri5_work_floats(int D, int64_t B);
+/* ckpt / cap: NULL / 0 for inference. For training pass gpode_dopri5_ckpt_floats(D,B,Tg,cap) floats: the kernel
+ * records, for every ACCEPTED step, the state at its start, its seven stage derivatives and its step size, and for
+ * every output the step and abscissa it was interpolated at. status 3 = more than `cap` accepted steps (retry). */
+int64_t gpode_dopri5_ckpt_floats(int D, int64_t B, int Tg, int cap);
 int gpode_dopri5_fwd(const float* packed, int D, int M, int S, const float* x0, const double* t, int Tg, int64_t B,
-                     double rtol, double atol, float* xs, float* work, int32_t* stats_out, void* stream);
+                     double rtol, double atol, float* xs, float* work, int32_t* stats_out, float* ckpt, int cap,
+                     void* stream);
+/* Discrete adjoint through the accepted steps and the dense-output interpolation (step sizes are constants, as in
+ * torchdiffeq where the controller runs under no_grad): grad_xs [Tg,B,D] -> grad_x0 [B,D]; lengthscale / variance
+ * partial sums accumulate into `acc`; vrows = gpode_vrow_floats(D, (6 n_accepted + 1) B) floats in the layout of
+ * gpode_rk4_bwd. Follow with gpode_param_grad over n = (6 n_accepted + 1) B rows and gpode_grads_finalize. */
+int gpode_dopri5_bwd(const float* packed, int D, int M, int S, const double* t, int Tg, int64_t B,
+                     const float* grad_xs, const float* ckpt, int cap, int n_accepted, float* grad_x0, float* vrows,
+                     float* acc, void* stream);
 
 /* ---- ELBO side terms either side of the integrator -------------------------------
  * Full-rank Gaussian state posteriors N(mean_r, L_r L_r^T + jitter I), r < R, L_r given as the PACKED lower triangle

@@ -74,12 +74,16 @@ def test_flow_forward_matches_reference(name):
 
 
 @pytest.mark.parametrize("name", DOPRI5_CASES)
-def test_dopri5_elbo_value_matches_reference(name):
+def test_dopri5_elbo_and_gradients_match_reference(name):
     g = load_golden(name)
     kind, solver, kw, model = _model(g)
-    with torch.no_grad():
-        loss, terms = _loss(kind, model, g, kw.get('S_mc', 1))
+    loss, terms = _loss(kind, model, g, kw.get('S_mc', 1))
+    loss.backward()
     assert_parity(name + " loss", loss, g['ref']['loss'], g['f64']['loss'], TOL_GRAD)
+    for k, v in product_grads(model, kind).items():
+        assert v is not None, k
+        # exact gradients of two discrete adaptive solves that may differ by one accept/reject decision
+        assert_parity(name + " grad " + k, v.cpu(), g['ref']['grad_' + k], g['f64']['grad_' + k], 3 * TOL_GRAD)
     # accept/reject decisions may differ by one attempt through float32 round-off of the error ratio
     assert abs(model.flow.num_evals() - float(g['ref']['nfe'])) <= 12
 
