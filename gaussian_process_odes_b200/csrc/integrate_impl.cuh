@@ -22,7 +22,7 @@ struct RowsFwd {
 };
 template <int D>
 struct RowsBwd {
-    static constexpr int value = D <= 2 ? 4 : (D <= 4 ? 2 : 1);
+    static constexpr int value = D <= 2 ? 4 : (D <= 5 ? 2 : 1);
 };
 
 template <int D, int R>

@@ -4,7 +4,8 @@
 // ROWS, not over inducing points, so they cannot be reduced inside the row-per-thread adjoint kernel without M*D
 // cross-thread reductions per row. Instead the adjoint kernel writes (stage input y, cotangent kb) pairs -- "virtual
 // rows" -- and this kernel maps one thread to one (output dim k, inducing point m) pair and streams the virtual rows
-// through shared memory (broadcast reads), accumulating in registers
+// through shared memory (broadcast reads; round-1 revision: one thread per inducing point m covering all D outputs,
+// so the squared differences are computed once per m instead of once per (k,m)), accumulating in registers
 //     T[k][m]    += kb_k K_km                      -> grad nu_km = var_k T
 //     W[k][m][j] += kb_k K_km (y_j - Z_mj)         -> grad Z_mj  = sum_k c_km W / ell_kj^2
 // ("kernel" VJP lines; reference arithmetic: autograd through src/core/kernels.py:53-99
@@ -16,44 +17,47 @@ namespace {
 constexpr int kPgThreads = 256;
 constexpr int kPgTile = 128;  // virtual rows staged per pass
 
+// thread = one inducing point m (all D outputs k: the squared differences (y_j - Z_mj)^2 are shared by the D kernels);
+// a CTA holds G = 256 / M row-groups that each take every G-th row of the staged tile.
 template <int D>
 __global__ void __launch_bounds__(kPgThreads)
 param_grad_kernel(const float* __restrict__ packed, const int M, const int S, const float* __restrict__ ys,
                   const float* __restrict__ kbs, const int64_t VR, const int64_t rows_per_cta,
                   float* __restrict__ acc) {
     constexpr int RS = VfShape<D>::RS, KS = VfShape<D>::KS, DP = VfShape<D>::DP;
-    __shared__ float sy[kPgTile * D];
-    __shared__ float sk[kPgTile * D];
+    constexpr int RW = 2 * DP;  // floats per staged row: y padded to DP, cotangent padded to DP
+    __shared__ __align__(16) float srow[kPgTile * RW];
 
     const float* __restrict__ kern = packed + D * S * RS;
     const float* __restrict__ ilp = kern + M * KS;
-    const int P = D * M;
-    // pair assignment: blockIdx.y selects a block of kPgThreads pairs; if the whole problem has fewer pairs than
-    // threads, the CTA is split into G row-groups that each take every G-th row of the tile.
-    int pair, group, G;
-    if (P >= kPgThreads) {
-        pair = blockIdx.y * kPgThreads + threadIdx.x;
+    int m, group, G;
+    if (M >= kPgThreads) {
+        m = blockIdx.y * kPgThreads + threadIdx.x;
         group = 0;
         G = 1;
     } else {
-        G = kPgThreads / P;
-        group = threadIdx.x / P;
-        pair = threadIdx.x - group * P;
-        if (group >= G) pair = P;  // idle tail threads
+        G = kPgThreads / M;
+        group = threadIdx.x / M;
+        m = threadIdx.x - group * M;
+        if (group >= G) m = M;  // idle tail threads
     }
-    const bool active = pair < P;
-    const int k = active ? pair / M : 0;
-    const int m = active ? pair - k * M : 0;
+    const bool active = m < M;
+    const int mm = active ? m : 0;
 
-    float z[D], il[D];
+    float z[D], w[D][DP];
 #pragma unroll
-    for (int j = 0; j < D; ++j) {
-        z[j] = __ldg(kern + m * KS + j);
-        il[j] = __ldg(ilp + k * DP + j);
+    for (int j = 0; j < D; ++j) z[j] = __ldg(kern + mm * KS + j);
+#pragma unroll
+    for (int k = 0; k < D; ++k)
+#pragma unroll
+        for (int j = 0; j < D; ++j) w[k][j] = __ldg(ilp + k * DP + j);
+    float T[D], W[D][D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        T[k] = 0.f;
+#pragma unroll
+        for (int j = 0; j < D; ++j) W[k][j] = 0.f;
     }
-    float T = 0.f, W[D];
-#pragma unroll
-    for (int j = 0; j < D; ++j) W[j] = 0.f;
 
     const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta;
     const int64_t r_end = r_begin + rows_per_cta < VR ? r_begin + rows_per_cta : VR;
@@ -61,31 +65,44 @@ param_grad_kernel(const float* __restrict__ packed, const int M, const int S, co
         const int n = (int)((r_end - base) < kPgTile ? (r_end - base) : kPgTile);
         __syncthreads();
         for (int i = threadIdx.x; i < n * D; i += kPgThreads) {
-            sy[i] = __ldg(ys + base * D + i);
-            sk[i] = __ldg(kbs + base * D + i);
+            const int r = i / D, j = i - r * D;
+            srow[r * RW + j] = __ldg(ys + base * D + i);
+            srow[r * RW + DP + j] = __ldg(kbs + base * D + i);
         }
         __syncthreads();
         if (active) {
-#pragma unroll 4
+#pragma unroll 2
             for (int r = group; r < n; r += G) {
-                float d[D], e = 0.f;
+                float y[DP], kb[DP];
+                lds_vec<DP>(y, srow + r * RW);
+                lds_vec<DP>(kb, srow + r * RW + DP);
+                float d[D], dd[D];
 #pragma unroll
                 for (int j = 0; j < D; ++j) {
-                    d[j] = sy[r * D + j] - z[j];
-                    e = fmaf(d[j] * d[j], il[j], e);
+                    d[j] = y[j] - z[j];
+                    dd[j] = d[j] * d[j];
                 }
-                const float p = sk[r * D + k] * gpode_ex2(-e);
-                T += p;
 #pragma unroll
-                for (int j = 0; j < D; ++j) W[j] = fmaf(p, d[j], W[j]);
+                for (int k = 0; k < D; ++k) {
+                    float e = 0.f;
+#pragma unroll
+                    for (int j = 0; j < D; ++j) e = fmaf(dd[j], w[k][j], e);
+                    const float p = kb[k] * gpode_ex2(-e);
+                    T[k] += p;
+#pragma unroll
+                    for (int j = 0; j < D; ++j) W[k][j] = fmaf(p, d[j], W[k][j]);
+                }
             }
         }
     }
     if (active) {
         const GpodeAcc a = gpode_acc_layout(D, M);
-        atomicAdd(acc + a.off_T + k * M + m, T);
 #pragma unroll
-        for (int j = 0; j < D; ++j) atomicAdd(acc + a.off_W + (k * M + m) * D + j, W[j]);
+        for (int k = 0; k < D; ++k) {
+            atomicAdd(acc + a.off_T + k * M + m, T[k]);
+#pragma unroll
+            for (int j = 0; j < D; ++j) atomicAdd(acc + a.off_W + (k * M + m) * D + j, W[k][j]);
+        }
     }
 }
 
@@ -118,8 +135,7 @@ int gpode_param_grad_launch(const float* packed, int D, int M, int S, const floa
     int sms = 148, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int P = D * M;
-    const int gy = P >= kPgThreads ? (P + kPgThreads - 1) / kPgThreads : 1;
+    const int gy = M >= kPgThreads ? (M + kPgThreads - 1) / kPgThreads : 1;
     // rows per CTA: enough CTAs to fill the machine (~4 per SM across gy), but at least one full tile each
     int64_t want_ctas = (int64_t)sms * 4 / gy;
     if (want_ctas < 1) want_ctas = 1;

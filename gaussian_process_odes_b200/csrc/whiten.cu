@@ -19,11 +19,11 @@ namespace {
 __device__ __forceinline__ int ld_for(int M) { return (M & 1) ? M : M + 1; }
 
 // K_k(Z_m, Z_n) in double from the float32 parameters (direct squared-distance form)
-__device__ __forceinline__ double rbf_entry(const float* __restrict__ Z, const float* __restrict__ ellk, double vark,
+__device__ __forceinline__ double rbf_entry(const float* __restrict__ Z, const double* __restrict__ inv_l, double vark,
                                             int D, int m, int n) {
     double e = 0.0;
     for (int j = 0; j < D; ++j) {
-        const double d = ((double)Z[m * D + j] - (double)Z[n * D + j]) / (double)ellk[j];
+        const double d = ((double)Z[m * D + j] - (double)Z[n * D + j]) * inv_l[j];
         e += d * d;
     }
     return vark * exp(-0.5 * e);
@@ -109,9 +109,11 @@ __global__ void whiten_fwd_kernel(const gpode_cache_t c, const float* __restrict
 
     const float* ellk = c.ell + k * D;
     const double vark = (double)c.var[k];
+    double inv_l[GPODE_MAX_D];
+    for (int j = 0; j < D; ++j) inv_l[j] = 1.0 / (double)ellk[j];
     for (int i = threadIdx.x; i < M * M; i += blockDim.x) {
         const int m = i / M, n = i - m * M;
-        if (n <= m) A[m * ld + n] = (Real)(rbf_entry(c.Z, ellk, vark, D, m, n) + (m == n ? (double)jitter : 0.0));
+        if (n <= m) A[m * ld + n] = (Real)(rbf_entry(c.Z, inv_l, vark, D, m, n) + (m == n ? (double)jitter : 0.0));
     }
     rff_at_Z(c, k, pvec);
     __syncthreads();
@@ -150,6 +152,8 @@ __global__ void whiten_bwd_kernel(const gpode_cache_t c, const float* __restrict
 
     const float* ellk = c.ell + k * D;
     const double vark = (double)c.var[k];
+    double inv_l[GPODE_MAX_D];
+    for (int j = 0; j < D; ++j) inv_l[j] = 1.0 / (double)ellk[j];
     for (int i = threadIdx.x; i < M * M; i += blockDim.x) {
         const int m = i / M, n = i - m * M;
         L[m * ld + n] = (Real)L_in[(size_t)k * M * M + i];
@@ -204,35 +208,45 @@ __global__ void whiten_bwd_kernel(const gpode_cache_t c, const float* __restrict
         }
         __syncthreads();
     }
-    // RBF backward with Kb = (X + X^T)/2: one thread per inducing point m
+    // RBF backward with Kb = (X + X^T)/2: thread = (inducing point m, slice of the partner points n)
     {
         double gvar = 0.0;
         double gl[GPODE_MAX_D];
         for (int j = 0; j < D; ++j) gl[j] = 0.0;
-        for (int m = threadIdx.x; m < M; m += blockDim.x) {
+        const int parts = blockDim.x / M;  // launches use 128 threads for M < 64 and 512 for M <= 160: parts >= 1
+        const int m = threadIdx.x % M, part = threadIdx.x / M;
+        if (part < parts) {
             double gz[GPODE_MAX_D];
             for (int j = 0; j < D; ++j) gz[j] = 0.0;
-            for (int n = 0; n < M; ++n) {
+            for (int n = part; n < M; n += parts) {
                 const double kb = 0.5 * ((double)P[m * ld + n] + (double)P[n * ld + m]);
-                const double E = kb * rbf_entry(c.Z, ellk, vark, D, m, n);
+                const double E = kb * rbf_entry(c.Z, inv_l, vark, D, m, n);
                 gvar += E;
                 for (int j = 0; j < D; ++j) {
-                    const double l = (double)ellk[j];
-                    const double d = (double)c.Z[m * D + j] - (double)c.Z[n * D + j];
-                    gz[j] -= 2.0 * E * d / (l * l);
-                    gl[j] += E * d * d / (l * l * l);
+                    const double d = ((double)c.Z[m * D + j] - (double)c.Z[n * D + j]) * inv_l[j];
+                    gz[j] -= 2.0 * E * d * inv_l[j];
+                    gl[j] += E * d * d * inv_l[j];
                 }
             }
             for (int j = 0; j < D; ++j) atomicAdd(g_Z + m * D + j, (float)gz[j]);
         }
-        atomicAdd(&red[D], gvar / vark);
-        for (int j = 0; j < D; ++j) atomicAdd(&red[j], gl[j]);
+        // warp-reduce first: shared-memory float64 atomics are CAS loops and serialise badly under contention
+        gvar /= vark;
+        for (int o = 16; o > 0; o >>= 1) gvar += __shfl_xor_sync(0xffffffffu, gvar, o);
+        for (int j = 0; j < D; ++j)
+            for (int o = 16; o > 0; o >>= 1) gl[j] += __shfl_xor_sync(0xffffffffu, gl[j], o);
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&red[D], gvar);
+            for (int j = 0; j < D; ++j) atomicAdd(&red[j], gl[j]);
+        }
     }
     // RFF VJP at x = Z with cotangent pb (only output dim k): one warp per inducing point, lanes over features
     {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
         const float ak = sqrtf(c.var[k] / (float)S);
         double gvar = 0.0;
+        double glw[GPODE_MAX_D];
+        for (int j = 0; j < D; ++j) glw[j] = 0.0;
         for (int m = warp; m < M; m += nwarps) {
             double G[GPODE_MAX_D];
             for (int j = 0; j < D; ++j) G[j] = 0.0;
@@ -248,12 +262,15 @@ __global__ void whiten_bwd_kernel(const gpode_cache_t c, const float* __restrict
                 for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
                 if (lane == 0) {
                     atomicAdd(g_Z + m * D + j, (float)v);
-                    atomicAdd(&red[j], -v * (double)c.Z[m * D + j] / (double)ellk[j]);
+                    glw[j] += -v * (double)c.Z[m * D + j] / (double)ellk[j];
                 }
             }
             if (lane == 0) gvar += pbm * sp_in[((size_t)k * 2 + 1) * M + m] / (2.0 * vark);
         }
-        if (lane == 0) atomicAdd(&red[D], gvar);
+        if (lane == 0) {
+            atomicAdd(&red[D], gvar);
+            for (int j = 0; j < D; ++j) atomicAdd(&red[j], glw[j]);
+        }
     }
     __syncthreads();
     for (int j = threadIdx.x; j < D; j += blockDim.x) g_ell[k * D + j] = (float)red[j];

@@ -1,0 +1,113 @@
+"""CUDA-graph capture of a whole ELBO forward+backward step.
+
+The reference's real training shapes are tiny (1-6 trajectories, 125-3000 shooting segments): after the integrator is
+one kernel, a step is ~100 small launches whose CPU dispatch cost (PyTorch op overhead, ctypes calls) dominates.
+Everything in the step is stream-ordered and shape-static, so it is captured once and replayed: the only per-step host
+work is drawing the GP cache's random numbers with numpy (same generator, same order as the reference,
+``src/core/dsvgp.py:100-103,83``) and copying them into static device buffers.
+
+    step = GraphedStep(model, lambda: compute_loss_shooting(model, ys, ts, num_samples=5)[0])
+    for it in range(n):
+        loss = step()          # parameters' .grad hold the new gradients; call optimizer.step() yourself
+
+Only solver='rk4' (and dopri5 under no_grad) can be captured: the adaptive solver's training path reads its step
+count on the host.
+"""
+import numpy as np
+import torch
+
+from .core import dsvgp as _dsvgp
+from .core import kernels as _kernels
+
+
+class _StaticDraws:
+    """Replaces the three host samplers by static device buffers that ``refresh()`` refills in call order."""
+
+    def __init__(self, device):
+        self.device = device
+        self.slots = []      # (kind, shape, pinned_host, device_buffer)
+        self.cursor = 0
+        self.recording = True
+        self._saved = None
+
+    def _provide(self, kind, shape):
+        shape = tuple(shape)
+        if self.recording:
+            host = torch.empty(shape, dtype=torch.float32).pin_memory()
+            dev = torch.empty(shape, dtype=torch.float32, device=self.device)
+            self.slots.append((kind, shape, host, dev))
+            self._fill(len(self.slots) - 1)
+            return dev
+        kind_, shape_, _, dev = self.slots[self.cursor]
+        assert (kind_, shape_) == (kind, shape), "sampler call sequence changed between capture and replay"
+        self.cursor += 1
+        return dev
+
+    def _fill(self, i):
+        kind, shape, host, dev = self.slots[i]
+        if kind == "uniform":
+            arr = np.random.uniform(low=0.0, high=1.0, size=shape)
+        else:
+            arr = np.random.normal(size=shape)
+        host.copy_(torch.from_numpy(arr.astype(np.float32)))
+        dev.copy_(host, non_blocking=True)
+
+    def refresh(self):
+        for i in range(len(self.slots)):
+            self._fill(i)
+
+    def install(self):
+        self._saved = (_dsvgp.sample_normal, _dsvgp.sample_uniform, _kernels.sample_normal)
+        _dsvgp.sample_normal = lambda shape, seed=None: self._provide("normal", shape)
+        _dsvgp.sample_uniform = lambda shape, seed=None: self._provide("uniform", shape)
+        _kernels.sample_normal = lambda shape, seed=None: self._provide("normal", shape)
+
+    def uninstall(self):
+        if self._saved is not None:
+            _dsvgp.sample_normal, _dsvgp.sample_uniform, _kernels.sample_normal = self._saved
+            self._saved = None
+
+
+class GraphedStep:
+    def __init__(self, model, loss_fn, warmup=3):
+        params = [p for p in model.parameters() if p.requires_grad]
+        if not params or not params[0].is_cuda:
+            raise RuntimeError("GraphedStep needs a model on a CUDA device")
+        self.model, self.loss_fn, self.params = model, loss_fn, params
+        # a cache left over from an eager step keeps that step's autograd graph -- and the parameters' AccumulateGrad
+        # nodes, bound to the eager stream -- alive, which would break capture on the graph's side stream
+        for mod in model.modules():
+            if isinstance(mod, _dsvgp.DSVGP_Layer):
+                for attr in ("nu", "rff_omega", "rff_phase", "rff_weights"):
+                    if isinstance(getattr(mod, attr, None), torch.Tensor):
+                        setattr(mod, attr, getattr(mod, attr).detach())
+        self.draws = _StaticDraws(params[0].device)
+        self.draws.install()
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for i in range(warmup):  # warm-up on a side stream (allocator, lazy inits, grid caches)
+                    if i == 1:
+                        self.draws.recording = False
+                    self.draws.cursor = 0
+                    for p in params:
+                        p.grad = None
+                    loss_fn().backward()
+            torch.cuda.current_stream().wait_stream(side)
+            self.draws.recording = False
+            for p in params:
+                p.grad = None
+            self.graph = torch.cuda.CUDAGraph()
+            self.draws.cursor = 0
+            with torch.cuda.graph(self.graph):
+                self.loss = loss_fn()
+                self.loss.backward()
+        finally:
+            self.draws.uninstall()
+
+    def __call__(self):
+        """New GP draw (host numpy -> static buffers), replay fwd+bwd; returns the static loss tensor."""
+        self.draws.refresh()
+        self.graph.replay()
+        return self.loss

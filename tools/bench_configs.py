@@ -96,6 +96,14 @@ def run_config(name, c, solver, do_cpu):
     if solver == "rk4":
         out["gpu_fwd_bwd_ms"] = gpu_time(step)
         out["gpu_fwd_bwd_wall_ms"] = wall_time(step)
+        from gaussian_process_odes_b200 import graphs
+        if c["kind"] == "gpode":
+            gstep = graphs.GraphedStep(model, lambda: builders.compute_loss_gpode(model, ysd, tsd)[0])
+        else:
+            gstep = graphs.GraphedStep(model, lambda: builders.compute_loss_shooting(model, ysd, tsd,
+                                                                                    num_samples=c["S_mc"])[0])
+        out["gpu_fwd_bwd_graphed_ms"] = gpu_time(gstep)
+        out["gpu_fwd_bwd_graphed_wall_ms"] = wall_time(gstep)
     out["gpu_fwd_ms"] = gpu_time(fwd)
     out["nfe"] = model.flow.num_evals()
     if do_cpu:
