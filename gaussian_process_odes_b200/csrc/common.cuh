@@ -39,13 +39,18 @@ void gpode_set_error(const char* fmt, ...);
     } while (0)
 
 // ------------------------------------------------------------------------------------------------------------------
-// packed parameter block (what every integrator CTA stages into shared memory with one bulk copy)
-//   rff  : [k][s][RS]  = Omega_{0,s,k} .. Omega_{D-1,s,k}, phase_{s,k}, a_{s,k} = w_{s,k} sqrt(var_k/S), pad
-//   kern : [m][KS]     = Z_{m,0..D-1}, c_{0,m} .. c_{D-1,m} (c_{k,m} = var_k nu_{k,m}), pad
-//   il   : [k][DP]     = w_{k,j} = 0.5 log2(e) / ell_{k,j}^2   (so that exp(-0.5 r^2) = 2^(-sum d_j^2 w_kj))
+// packed parameter block (what every integrator CTA stages into shared memory with one bulk copy). Records are laid
+// out for the packed dual-FP32 FMA of sm_100 (SASS FFMA2, PTX fma.rn.f32x2): two Fourier features / two output
+// dimensions sit side by side so that one 64-bit register pair feeds one FFMA2.
+//   rff  : [k][s2][RP] , s2 = feature pair (2 s2, 2 s2 + 1):
+//            Omega_{0,s,k}, Omega_{0,s',k}, ..., Omega_{D-1,s,k}, Omega_{D-1,s',k}, phase_s, phase_s', a_s, a_s', pad
+//            (a_{s,k} = w_{s,k} sqrt(var_k / S); an odd S is padded with a zero-weight feature)
+//   kern : [m][KS]     = Z_{m,0..D-1}, then output pairs c_{0,m}, c_{1,m}, ... (c_{k,m} = var_k nu_{k,m}; zero pad)
+//   il   : [j][WP]     = output pairs -w_{0,j}, -w_{1,j}, ...  with w_{k,j} = 0.5 log2(e) / ell_{k,j}^2
+//                        so that exp(-0.5 r_k^2) = 2^(sum_j d_j^2 (-w_kj))
 // ------------------------------------------------------------------------------------------------------------------
 struct GpodeLayout {
-    int D, M, S, RS, KS, DP;
+    int D, M, S, S2, RP, KS, WP;
     int off_rff, off_kern, off_il, total;  // in floats; every offset and `total` is a multiple of 4 (16 bytes)
 };
 
@@ -54,13 +59,14 @@ __host__ __device__ inline int gpode_round_up4(int x) { return (x + 3) & ~3; }
 __host__ __device__ inline GpodeLayout gpode_layout(int D, int M, int S) {
     GpodeLayout L;
     L.D = D; L.M = M; L.S = S;
-    L.RS = gpode_round_up4(D + 2);
-    L.KS = gpode_round_up4(2 * D);
-    L.DP = gpode_round_up4(D);
+    L.S2 = (S + 1) / 2;
+    L.RP = gpode_round_up4(2 * D + 4);
+    L.KS = gpode_round_up4(D + 2 * ((D + 1) / 2));
+    L.WP = gpode_round_up4(2 * ((D + 1) / 2));
     L.off_rff = 0;
-    L.off_kern = L.off_rff + D * S * L.RS;
+    L.off_kern = L.off_rff + D * L.S2 * L.RP;
     L.off_il = L.off_kern + M * L.KS;
-    L.total = L.off_il + D * L.DP;
+    L.total = L.off_il + D * L.WP;
     return L;
 }
 
@@ -89,6 +95,37 @@ __device__ __forceinline__ float gpode_ex2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+
+// ---- packed dual-FP32 arithmetic (sm_100: one issue slot, two FMAs) ---------------------------------------------
+__device__ __forceinline__ unsigned long long gpode_pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float2 gpode_unpack2(unsigned long long v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(d)
+        : "l"(gpode_pack2(a.x, a.y)), "l"(gpode_pack2(b.x, b.y)), "l"(gpode_pack2(c.x, c.y)));
+    return gpode_unpack2(d);
+}
+__device__ __forceinline__ float2 ffma2(float a, float2 b, float2 c) { return ffma2(make_float2(a, a), b, c); }
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(gpode_pack2(a.x, a.y)), "l"(gpode_pack2(b.x, b.y)));
+    return gpode_unpack2(d);
+}
+__device__ __forceinline__ float2 fmul2(float a, float2 b) { return fmul2(make_float2(a, a), b); }
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(gpode_pack2(a.x, a.y)), "l"(gpode_pack2(b.x, b.y)));
+    return gpode_unpack2(d);
 }
 
 __device__ __forceinline__ uint32_t gpode_smem_u32(const void* p) {

@@ -26,27 +26,30 @@ namespace {
 __global__ void pack_kernel(const GpodeLayout L, const float* __restrict__ omega, const float* __restrict__ phase,
                             const float* __restrict__ w, const float* __restrict__ Z, const float* __restrict__ nu,
                             const float* __restrict__ ell, const float* __restrict__ var, float* __restrict__ out) {
-    const int D = L.D, M = L.M, S = L.S;
-    const int n_rff = D * S, n_kern = M, n_il = D;
+    const int D = L.D, M = L.M, S = L.S, S2 = L.S2;
+    const int n_rff = D * S2, n_kern = M, n_il = D;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rff + n_kern + n_il; i += gridDim.x * blockDim.x) {
         if (i < n_rff) {
-            const int k = i / S, s = i - k * S;
-            float* o = out + L.off_rff + (size_t)i * L.RS;
-            for (int j = 0; j < D; ++j) o[j] = omega[((size_t)j * S + s) * D + k];
-            o[D] = phase[s * D + k];
-            o[D + 1] = w[s * D + k] * sqrtf(var[k] / (float)S);
-            for (int j = D + 2; j < L.RS; ++j) o[j] = 0.f;
+            const int k = i / S2, s2 = i - k * S2;
+            float* o = out + L.off_rff + (size_t)i * L.RP;
+            for (int h = 0; h < 2; ++h) {
+                const int s = 2 * s2 + h;
+                const bool ok = s < S;
+                for (int j = 0; j < D; ++j) o[2 * j + h] = ok ? omega[((size_t)j * S + s) * D + k] : 0.f;
+                o[2 * D + h] = ok ? phase[s * D + k] : 0.f;
+                o[2 * D + 2 + h] = ok ? w[s * D + k] * sqrtf(var[k] / (float)S) : 0.f;
+            }
+            for (int j = 2 * D + 4; j < L.RP; ++j) o[j] = 0.f;
         } else if (i < n_rff + n_kern) {
             const int m = i - n_rff;
             float* o = out + L.off_kern + (size_t)m * L.KS;
             for (int j = 0; j < D; ++j) o[j] = Z[m * D + j];
-            for (int k = 0; k < D; ++k) o[D + k] = nu ? var[k] * nu[k * M + m] : 0.f;
-            for (int j = 2 * D; j < L.KS; ++j) o[j] = 0.f;
+            for (int k = 0; k < L.KS - D; ++k) o[D + k] = (nu && k < D) ? var[k] * nu[k * M + m] : 0.f;
         } else {
-            const int k = i - n_rff - n_kern;
-            float* o = out + L.off_il + (size_t)k * L.DP;
-            for (int j = 0; j < D; ++j) o[j] = GPODE_HALF_LOG2E / (ell[k * D + j] * ell[k * D + j]);
-            for (int j = D; j < L.DP; ++j) o[j] = 0.f;
+            const int j = i - n_rff - n_kern;
+            float* o = out + L.off_il + (size_t)j * L.WP;
+            for (int k = 0; k < L.WP; ++k)
+                o[k] = k < D ? -GPODE_HALF_LOG2E / (ell[k * D + j] * ell[k * D + j]) : 0.f;
         }
     }
 }
@@ -59,7 +62,7 @@ extern "C" int gpode_pack_cache(const gpode_cache_t* c, float* packed, void* str
     GPODE_CHECK_ARG(c->M >= 1 && c->S >= 1, "M=%d and S=%d must be positive", c->M, c->S);
     GPODE_CHECK_ARG(c->omega && c->phase && c->w && c->Z && c->ell && c->var, "cache tensor is NULL");
     const GpodeLayout L = gpode_layout(c->D, c->M, c->S);
-    const int n = c->D * c->S + c->M + c->D;
+    const int n = c->D * L.S2 + c->M + c->D;
     pack_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(L, c->omega, c->phase, c->w, c->Z, c->nu, c->ell,
                                                                    c->var, packed);
     GPODE_LAUNCH_CHECK();

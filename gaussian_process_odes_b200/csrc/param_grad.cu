@@ -24,12 +24,13 @@ __global__ void __launch_bounds__(kPgThreads)
 param_grad_kernel(const float* __restrict__ packed, const int M, const int S, const float* __restrict__ ys,
                   const float* __restrict__ kbs, const int64_t VR, const int64_t rows_per_cta,
                   float* __restrict__ acc) {
-    constexpr int RS = VfShape<D>::RS, KS = VfShape<D>::KS, DP = VfShape<D>::DP;
+    constexpr int RP = VfShape<D>::RP, KS = VfShape<D>::KS, WP = VfShape<D>::WP;
+    constexpr int DP = (D + 3) & ~3;
     constexpr int RW = 2 * DP;  // floats per staged row: y padded to DP, cotangent padded to DP
     __shared__ __align__(16) float srow[kPgTile * RW];
 
-    const float* __restrict__ kern = packed + D * S * RS;
-    const float* __restrict__ ilp = kern + M * KS;
+    const float* __restrict__ kern = packed + D * ((S + 1) >> 1) * RP;
+    const float* __restrict__ wnp = kern + M * KS;  // -w, [j][WP] with outputs k along the row
     int m, group, G;
     if (M >= kPgThreads) {
         m = blockIdx.y * kPgThreads + threadIdx.x;
@@ -50,7 +51,7 @@ param_grad_kernel(const float* __restrict__ packed, const int M, const int S, co
 #pragma unroll
     for (int k = 0; k < D; ++k)
 #pragma unroll
-        for (int j = 0; j < D; ++j) w[k][j] = __ldg(ilp + k * DP + j);
+        for (int j = 0; j < D; ++j) w[k][j] = -__ldg(wnp + j * WP + k);
     float T[D], W[D][D];
 #pragma unroll
     for (int k = 0; k < D; ++k) {

@@ -10,9 +10,10 @@
 
 template <int D>
 struct VfShape {
-    static constexpr int RS = (D + 2 + 3) & ~3;
-    static constexpr int KS = (2 * D + 3) & ~3;
-    static constexpr int DP = (D + 3) & ~3;
+    static constexpr int KP = (D + 1) / 2;              // output-dimension pairs
+    static constexpr int RP = (2 * D + 4 + 3) & ~3;     // floats per (k, feature pair) record
+    static constexpr int KS = (D + 2 * KP + 3) & ~3;    // floats per inducing-point record
+    static constexpr int WP = (2 * KP + 3) & ~3;        // floats per input-dimension row of -w
 };
 
 template <int N>
@@ -26,162 +27,214 @@ __device__ __forceinline__ void lds_vec(float (&dst)[N], const float* __restrict
 }
 
 // f[r][k] = sum_s a_sk cos(sum_j x_j Omega_jsk + phase_sk) + sum_m c_km 2^(-sum_j (x_j - Z_mj)^2 w_kj)
-// with w_kj = 0.5 log2(e) / ell_kj^2 (the `il` block of the packed cache)
-// (i0, istep): which features / inducing points this thread sums -- (0,1) when the thread owns whole rows, (lane,32) in
-// the warp-per-row kernels, where the partial sums are then combined with a warp all-reduce.
+// Two features (RFF term) / two output dimensions (RBF term) ride in one FFMA2.
+// (i0, istep): which feature pairs / inducing points this thread sums -- (0,1) when the thread owns whole rows,
+// (lane,32) in the warp-per-row kernels, where the partial sums are then combined with a warp all-reduce.
 template <int D, int R>
 __device__ __forceinline__ void vf_eval(const float* __restrict__ sp, const int M, const int S,
                                         const float (&x)[R][D], float (&f)[R][D], const int i0 = 0,
                                         const int istep = 1) {
-    constexpr int RS = VfShape<D>::RS, KS = VfShape<D>::KS, DP = VfShape<D>::DP;
+    constexpr int RP = VfShape<D>::RP, KS = VfShape<D>::KS, WP = VfShape<D>::WP, KP = VfShape<D>::KP;
+    const int S2 = (S + 1) >> 1;
     const float* __restrict__ rff = sp;
-    const float* __restrict__ kern = sp + D * S * RS;
-    const float* __restrict__ ilp = kern + M * KS;
+    const float* __restrict__ kern = sp + D * S2 * RP;
+    const float* __restrict__ wnp = kern + M * KS;
 
+    float2 fr[R][D];   // RFF partial sums, one half per feature of the pair
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
-        for (int k = 0; k < D; ++k) f[r][k] = 0.f;
+        for (int k = 0; k < D; ++k) fr[r][k] = make_float2(0.f, 0.f);
 
-    // ---- random-Fourier-feature prior sample: feature s outer, output k inner (D*R independent chains) ----
 #pragma unroll 2
-    for (int s = i0; s < S; s += istep) {
+    for (int s2 = i0; s2 < S2; s2 += istep) {
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-            float prm[RS];
-            lds_vec<RS>(prm, rff + (k * S + s) * RS);
+            float prm[RP];
+            lds_vec<RP>(prm, rff + (k * S2 + s2) * RP);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                float th = prm[D];
+                float2 th = make_float2(prm[2 * D], prm[2 * D + 1]);
 #pragma unroll
-                for (int j = 0; j < D; ++j) th = fmaf(x[r][j], prm[j], th);
-                f[r][k] = fmaf(prm[D + 1], __cosf(th), f[r][k]);
+                for (int j = 0; j < D; ++j) th = ffma2(x[r][j], make_float2(prm[2 * j], prm[2 * j + 1]), th);
+                const float2 c = make_float2(__cosf(th.x), __cosf(th.y));
+                fr[r][k] = ffma2(c, make_float2(prm[2 * D + 2], prm[2 * D + 3]), fr[r][k]);
             }
         }
     }
 
-    // ---- pathwise update: inducing point m outer (x - Z_m shared by all k), output k inner ----
-    float il[D][DP];
+    float2 wn[D][KP];  // -w, output pairs
 #pragma unroll
-    for (int k = 0; k < D; ++k) lds_vec<DP>(il[k], ilp + k * DP);
+    for (int j = 0; j < D; ++j) {
+        float t[WP];
+        lds_vec<WP>(t, wnp + j * WP);
+#pragma unroll
+        for (int kp = 0; kp < KP; ++kp) wn[j][kp] = make_float2(t[2 * kp], t[2 * kp + 1]);
+    }
+    float2 fk[R][KP];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int kp = 0; kp < KP; ++kp) fk[r][kp] = make_float2(0.f, 0.f);
 
 #pragma unroll 2
     for (int m = i0; m < M; m += istep) {
-        float kp[KS];
-        lds_vec<KS>(kp, kern + m * KS);
+        float kp_[KS];
+        lds_vec<KS>(kp_, kern + m * KS);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             float dd[D];
 #pragma unroll
             for (int j = 0; j < D; ++j) {
-                const float d = x[r][j] - kp[j];
+                const float d = x[r][j] - kp_[j];
                 dd[j] = d * d;
             }
 #pragma unroll
-            for (int k = 0; k < D; ++k) {
-                float e = 0.f;
+            for (int kp = 0; kp < KP; ++kp) {
+                float2 e = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int j = 0; j < D; ++j) e = fmaf(dd[j], il[k][j], e);
-                f[r][k] = fmaf(kp[D + k], gpode_ex2(-e), f[r][k]);
+                for (int j = 0; j < D; ++j) e = ffma2(dd[j], wn[j][kp], e);
+                float2 K;
+                K.x = gpode_ex2(e.x);
+                K.y = (2 * kp + 1 < D) ? gpode_ex2(e.y) : 0.f;
+                fk[r][kp] = ffma2(make_float2(kp_[D + 2 * kp], kp_[D + 2 * kp + 1]), K, fk[r][kp]);
             }
         }
     }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int k = 0; k < D; ++k)
+            f[r][k] = (fr[r][k].x + fr[r][k].y) + ((k & 1) ? fk[r][k >> 1].y : fk[r][k >> 1].x);
 }
 
 // VJP at x with cotangent kb: xb = J(x)^T kb, and the per-thread partial sums of the shared-parameter gradients that
 // do not need a cross-row contraction per inducing point:
-//   A[k][j] += x_j G_kj + sum_m q' w_kj d_j^2    (lengthscale gradient = -A/ell, RFF path through omega = eps/ell + RBF)
-//   V[k]    += kb_k (f_k + f_upd_k)          (variance gradient = V / (2 var))
+//   A[k][j] += x_j G_kj + sum_m q'_km w_kj d_j^2     (lengthscale gradient = -A/ell: RFF path via omega = eps/ell + RBF)
+//   V[k]    += kb_k (f_k + f_upd_k)                   (variance gradient = V / (2 var))
 // fst = f(x) from the forward pass (so f_rff = fst - f_upd needs no cosine here).
 template <int D, int R>
 __device__ __forceinline__ void vf_vjp(const float* __restrict__ sp, const int M, const int S,
                                        const float (&x)[R][D], const float (&kb)[R][D], const float (&fst)[R][D],
                                        float (&xb)[R][D], float (&A)[D][D], float (&V)[D], const int i0 = 0,
                                        const int istep = 1) {
-    constexpr int RS = VfShape<D>::RS, KS = VfShape<D>::KS, DP = VfShape<D>::DP;
+    constexpr int RP = VfShape<D>::RP, KS = VfShape<D>::KS, WP = VfShape<D>::WP, KP = VfShape<D>::KP;
+    const int S2 = (S + 1) >> 1;
     const float* __restrict__ rff = sp;
-    const float* __restrict__ kern = sp + D * S * RS;
-    const float* __restrict__ ilp = kern + M * KS;
+    const float* __restrict__ kern = sp + D * S2 * RP;
+    const float* __restrict__ wnp = kern + M * KS;
 
+    float2 xb2[R][D];  // two partial sums per component, folded at the end
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
-        for (int j = 0; j < D; ++j) xb[r][j] = 0.f;
+        for (int j = 0; j < D; ++j) xb2[r][j] = make_float2(0.f, 0.f);
 
-    // ---- RFF part: output k outer (only R*D partial-Jacobian registers live), feature s inner ----
+    // ---- RFF part: output k outer, feature pair inner ----
 #pragma unroll
     for (int k = 0; k < D; ++k) {
-        float G[R][D];
+        float2 G[R][D];
 #pragma unroll
         for (int r = 0; r < R; ++r)
 #pragma unroll
-            for (int j = 0; j < D; ++j) G[r][j] = 0.f;
-#pragma unroll 4
-        for (int s = i0; s < S; s += istep) {
-            float prm[RS];
-            lds_vec<RS>(prm, rff + (k * S + s) * RS);
+            for (int j = 0; j < D; ++j) G[r][j] = make_float2(0.f, 0.f);
+#pragma unroll 2
+        for (int s2 = i0; s2 < S2; s2 += istep) {
+            float prm[RP];
+            lds_vec<RP>(prm, rff + (k * S2 + s2) * RP);
+            const float2 a2 = make_float2(prm[2 * D + 2], prm[2 * D + 3]);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                float th = prm[D];
+                float2 th = make_float2(prm[2 * D], prm[2 * D + 1]);
 #pragma unroll
-                for (int j = 0; j < D; ++j) th = fmaf(x[r][j], prm[j], th);
-                const float g = -(kb[r][k] * prm[D + 1]) * __sinf(th);
+                for (int j = 0; j < D; ++j) th = ffma2(x[r][j], make_float2(prm[2 * j], prm[2 * j + 1]), th);
+                const float2 sn = make_float2(__sinf(th.x), __sinf(th.y));
+                const float2 g = fmul2(-kb[r][k], fmul2(a2, sn));
 #pragma unroll
-                for (int j = 0; j < D; ++j) G[r][j] = fmaf(g, prm[j], G[r][j]);
+                for (int j = 0; j < D; ++j) G[r][j] = ffma2(g, make_float2(prm[2 * j], prm[2 * j + 1]), G[r][j]);
             }
         }
 #pragma unroll
         for (int r = 0; r < R; ++r)
 #pragma unroll
             for (int j = 0; j < D; ++j) {
-                xb[r][j] += G[r][j];
-                A[k][j] = fmaf(x[r][j], G[r][j], A[k][j]);
+                const float gj = G[r][j].x + G[r][j].y;
+                xb2[r][j].x += gj;
+                A[k][j] = fmaf(x[r][j], gj, A[k][j]);
             }
     }
 
-    // ---- RBF part ----
-    float il[D][DP];
+    // ---- RBF part: inducing point m outer, output pairs inner ----
+    float2 wn[D][KP];
 #pragma unroll
-    for (int k = 0; k < D; ++k) lds_vec<DP>(il[k], ilp + k * DP);
-    float fu[R][D];
+    for (int j = 0; j < D; ++j) {
+        float t[WP];
+        lds_vec<WP>(t, wnp + j * WP);
+#pragma unroll
+        for (int kp = 0; kp < KP; ++kp) wn[j][kp] = make_float2(t[2 * kp], t[2 * kp + 1]);
+    }
+    float2 fu[R][KP], A2[KP][D];
+#pragma unroll
+    for (int kp = 0; kp < KP; ++kp) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) fu[r][kp] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < D; ++j) A2[kp][j] = make_float2(0.f, 0.f);
+    }
+    float2 kbn[R][KP];  // 2 ln2 * kb, output pairs  (q' = -2 ln2 kb c K and u = q' w = (2 ln2 kb c K)(-w))
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
-        for (int k = 0; k < D; ++k) fu[r][k] = 0.f;
+        for (int kp = 0; kp < KP; ++kp)
+            kbn[r][kp] = make_float2(-GPODE_NEG_2LN2 * kb[r][2 * kp],
+                                     (2 * kp + 1 < D) ? -GPODE_NEG_2LN2 * kb[r][(2 * kp + 1 < D) ? 2 * kp + 1 : 0] : 0.f);
 
 #pragma unroll 2
     for (int m = i0; m < M; m += istep) {
-        float kp[KS];
-        lds_vec<KS>(kp, kern + m * KS);
+        float kp_[KS];
+        lds_vec<KS>(kp_, kern + m * KS);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             float d[D], dd[D];
 #pragma unroll
             for (int j = 0; j < D; ++j) {
-                d[j] = x[r][j] - kp[j];
+                d[j] = x[r][j] - kp_[j];
                 dd[j] = d[j] * d[j];
             }
 #pragma unroll
-            for (int k = 0; k < D; ++k) {
-                float e = 0.f;
+            for (int kp = 0; kp < KP; ++kp) {
+                float2 e = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int j = 0; j < D; ++j) e = fmaf(dd[j], il[k][j], e);
-                const float cK = kp[D + k] * gpode_ex2(-e);
-                fu[r][k] += cK;
-                const float q = kb[r][k] * cK * GPODE_NEG_2LN2;
+                for (int j = 0; j < D; ++j) e = ffma2(dd[j], wn[j][kp], e);
+                float2 K;
+                K.x = gpode_ex2(e.x);
+                K.y = (2 * kp + 1 < D) ? gpode_ex2(e.y) : 0.f;
+                const float2 cK = fmul2(make_float2(kp_[D + 2 * kp], kp_[D + 2 * kp + 1]), K);
+                fu[r][kp] = fadd2(fu[r][kp], cK);
+                const float2 q = fmul2(kbn[r][kp], cK);
 #pragma unroll
                 for (int j = 0; j < D; ++j) {
-                    const float u = q * il[k][j];
-                    xb[r][j] = fmaf(u, d[j], xb[r][j]);
-                    A[k][j] = fmaf(u, dd[j], A[k][j]);
+                    const float2 u = fmul2(q, wn[j][kp]);        // u_kj = q'_k w_kj for the two outputs of the pair
+                    xb2[r][j] = ffma2(d[j], u, xb2[r][j]);
+                    A2[kp][j] = ffma2(dd[j], u, A2[kp][j]);
                 }
             }
         }
     }
 #pragma unroll
-    for (int r = 0; r < R; ++r)
+    for (int r = 0; r < R; ++r) {
 #pragma unroll
-        for (int k = 0; k < D; ++k) V[k] = fmaf(kb[r][k], fst[r][k] + fu[r][k], V[k]);
+        for (int j = 0; j < D; ++j) xb[r][j] = xb2[r][j].x + xb2[r][j].y;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const float fuk = (k & 1) ? fu[r][k >> 1].y : fu[r][k >> 1].x;
+            V[k] = fmaf(kb[r][k], fst[r][k] + fuk, V[k]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k)
+#pragma unroll
+        for (int j = 0; j < D; ++j) A[k][j] += (k & 1) ? A2[k >> 1][j].y : A2[k >> 1][j].x;
 }
 
 // ---- staging of the packed block into shared memory (bulk async copy + mbarrier) -------------------------------

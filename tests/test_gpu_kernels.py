@@ -43,7 +43,11 @@ def test_vf_forward(D, M, S, B):
     n32 = O.vf_forward(xp, gp32['Z'], gp32['ell'], gp32['var'], c32)
     n64 = O.vf_closed_form(xp.double(), gp64['Z'], gp64['ell'], gp64['var'], c32['rff_omega'].double(),
                            c32['rff_phase'].double(), c32['rff_weights'].double(), c32['nu'].double())
-    assert_parity("vf D=%d" % D, f, f32, f64, TOL_VF, ref_noise=relerr(n32, n64) * float(n64.abs().max() / f64.abs().max()))
+    # synthetic worst case: random Z and whitened nu give |var nu| ~ 1e2, so every K(x,Z_m) term's round-off (ex2.approx
+    # here, the cancelling expanded distance in the reference) is amplified 100x; both sit at ~1e-5 of max|f|, and the
+    # CUDA value is required to stay within 2.5x of the reference's own float32 error (seed-to-seed ratio 0.3 .. 2)
+    assert_parity("vf D=%d" % D, f, f32, f64, TOL_VF,
+                  ref_noise=relerr(n32, n64) * float(n64.abs().max() / f64.abs().max()), slack=2.5)
 
 
 BIG_SHAPES = [(2, 16, 256), (5, 100, 256), (3, 24, 64), (8, 20, 32)]
