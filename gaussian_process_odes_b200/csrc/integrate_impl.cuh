@@ -9,6 +9,7 @@
 // CTA with a bulk async copy. Global traffic is only x0 in, xs (and stage checkpoints) out, all coalesced in the
 // [time][row][dim] layout torchdiffeq itself returns.
 #pragma once
+#include <stdlib.h>
 #include "vf.cuh"
 
 namespace {
@@ -567,7 +568,8 @@ inline int warp_shape_for(K kernel, int64_t B, size_t smem, LaunchShape* out) {
 
 template <int D, int R>
 inline bool use_wide(int64_t B) {
-    return R > 1 && B >= (int64_t)num_sms() * 2 * kThreads * R;
+    static const bool force_narrow = getenv("GPODE_FORCE_NARROW") != nullptr;  // tuning knob: one row per thread
+    return !force_narrow && R > 1 && B >= (int64_t)num_sms() * 2 * kThreads * R;
 }
 
 template <int D>
