@@ -288,13 +288,43 @@ def loglik_mean(pred, ys, W, bias, var):
     return _LoglikMean.apply(pred, ys, W, bias, var)
 
 
+MAX_D_REGISTER = 8    # GPODE_MAX_D: differentiable register-resident kernels
+MAX_D_LARGE = 64      # GPODE_MAX_D_LARGE: forward-only tiled kernels
+
+
+def _large_d_call(name, x, t, Z, ell, var, nu, omega, phase, w):
+    """Forward-only evaluation / integration for 8 < D <= 64 on the raw cache tensors."""
+    tensors = (x, Z, ell, var, nu)
+    if torch.is_grad_enabled() and any(a.requires_grad for a in tensors):
+        raise _lib.GpodeError("state dimension %d > %d: only the forward (no_grad) path exists for large D"
+                              % (Z.shape[1], MAX_D_REGISTER))
+    Zc, ec, vc, oc, wc, xc = f32(Z, "Z"), f32(ell, "ell"), f32(var, "var"), f32(omega, "omega"), f32(w, "w"), f32(x, "x")
+    M, D = Zc.shape
+    S = wc.shape[0]
+    pc_, nc = f32(phase, "phase").reshape(S, D), f32(nu, "nu").reshape(D, M)
+    st = _cache_struct(D, M, S, oc, pc_, wc, Zc, nc, ec, vc)
+    B = xc.shape[0]
+    if name == "gpode_vf_fwd_large":
+        out = torch.empty_like(xc)
+        _lib.call(name, ctypes.byref(st), ptr(xc), ptr(out), B, stream_ptr())
+    else:
+        tc = f32(t, "t")
+        out = torch.empty(tc.shape[0], B, D, dtype=torch.float32, device=xc.device)
+        _lib.call(name, ctypes.byref(st), ptr(xc), ptr(tc), tc.shape[0], B, ptr(out), stream_ptr())
+    return out
+
+
 def vector_field(x, Z, ell, var, nu, omega, phase, w):
-    """f(x) of one sampled GP function; differentiable in x, Z, ell, var, nu."""
+    """f(x) of one sampled GP function; differentiable in x, Z, ell, var, nu (forward only for D > 8)."""
+    if Z.shape[1] > MAX_D_REGISTER:
+        return _large_d_call("gpode_vf_fwd_large", x, None, Z, ell, var, nu, omega, phase, w)
     return _VectorField.apply(x, Z, ell, var, nu, omega, phase, w)
 
 
 def rk4_integrate(x0, t, Z, ell, var, nu, omega, phase, w):
     """Fixed-grid RK4 (3/8 rule) over the float32 grid ``t``; returns ``(len(t), B, D)`` like torchdiffeq."""
+    if Z.shape[1] > MAX_D_REGISTER:
+        return _large_d_call("gpode_rk4_fwd_large", x0, t, Z, ell, var, nu, omega, phase, w)
     return _RK4.apply(x0, t, Z, ell, var, nu, omega, phase, w)
 
 

@@ -28,6 +28,7 @@ extern "C" {
 
 #define GPODE_B200_ABI_VERSION 1
 #define GPODE_MAX_D 8          /* register-resident state kernels are instantiated for 1 <= D <= 8 */
+#define GPODE_MAX_D_LARGE 64   /* forward-only shared-memory-tile kernels cover 8 < D <= 64 */
 #define GPODE_MAX_M_F64 112    /* whitening backward keeps two MxM float64 tiles in shared memory */
 #define GPODE_MAX_M 160        /* ... and falls back to float32 tiles up to this M */
 
@@ -136,6 +137,12 @@ int gpode_dopri5_fwd(const float* packed, int D, int M, int S, const float* x0, 
 int gpode_dopri5_bwd(const float* packed, int D, int M, int S, const double* t, int Tg, int64_t B,
                      const float* grad_xs, const float* ckpt, int cap, int n_accepted, float* grad_x0, float* vrows,
                      float* acc, void* stream);
+
+/* Forward-only paths for 8 < D <= GPODE_MAX_D_LARGE (the upper half of the scaling sweep): same arithmetic as
+ * gpode_vf_fwd / gpode_rk4_fwd, state tiles in shared memory, Omega streamed from L2; they take the RAW cache. */
+int gpode_vf_fwd_large(const gpode_cache_t* cache, const float* x, float* f, int64_t B, void* stream);
+int gpode_rk4_fwd_large(const gpode_cache_t* cache, const float* x0, const float* t, int Tg, int64_t B, float* xs,
+                        void* stream);
 
 /* ---- ELBO side terms either side of the integrator -------------------------------
  * Full-rank Gaussian state posteriors N(mean_r, L_r L_r^T + jitter I), r < R, L_r given as the PACKED lower triangle

@@ -155,6 +155,28 @@ def test_rk4_forward(D, M, S, B, Tg, h):
     assert_parity("rk4 D=%d" % D, xs, ref32, ref64, TOL_TRAJ)
 
 
+@pytest.mark.parametrize("D,M,S,B", [(16, 100, 256, 1000), (32, 40, 64, 77), (64, 100, 256, 300), (9, 10, 17, 5),
+                                      (24, 7, 33, 64)])
+def test_large_state_dimension_forward(D, M, S, B):
+    """8 < D <= 64 (upper half of the scaling sweep): forward-only tiled kernels, same parity bars."""
+    from gaussian_process_odes_b200 import ops, _lib
+    gp32, c32, gp64, c64, x = _setup(D, M, S, B, seed=D, nu_scale=0.1)
+    args = _cuda_args(gp32, c32)
+    with torch.no_grad():
+        f = ops.vector_field(x.cuda(), *args).cpu()
+        ts = _grid(4, 0.02, 2)
+        xs = ops.rk4_integrate(x.cuda(), ts.cuda(), *args).cpu()
+    f32 = O.vf_forward(x, gp32['Z'], gp32['ell'], gp32['var'], c32)
+    c64n = dict(c64, nu=c32['nu'].double())
+    f64 = O.vf_forward(x.double(), gp64['Z'], gp64['ell'], gp64['var'], c64n)
+    assert_parity("large-D vf", f, f32, f64, TOL_VF)
+    ref32 = O.odeint(lambda t, y: O.vf_forward(y, gp32['Z'], gp32['ell'], gp32['var'], c32), x, ts, method='rk4')
+    assert relerr(xs, ref32) <= TOL_TRAJ
+    xg = x.cuda().requires_grad_(True)
+    with pytest.raises(_lib.GpodeError):
+        ops.vector_field(xg, *args)
+
+
 def test_rk4_decreasing_grid():
     """odeint accepts a decreasing grid (used by initialize_latents_with_data, model_initialization.py:70-73)."""
     from gaussian_process_odes_b200 import ops
