@@ -42,15 +42,19 @@ void gpode_set_error(const char* fmt, ...);
 // packed parameter block (what every integrator CTA stages into shared memory with one bulk copy). Records are laid
 // out for the packed dual-FP32 FMA of sm_100 (SASS FFMA2, PTX fma.rn.f32x2): two Fourier features / two output
 // dimensions sit side by side so that one 64-bit register pair feeds one FFMA2.
-//   rff  : [k][s2][RP] , s2 = feature pair (2 s2, 2 s2 + 1):
+//   rff  : one record of RP floats per (k, feature pair s2 = (2 s2, 2 s2 + 1)):
 //            Omega_{0,s,k}, Omega_{0,s',k}, ..., Omega_{D-1,s,k}, Omega_{D-1,s',k}, phase_s, phase_s', a_s, a_s', pad
-//            (a_{s,k} = w_{s,k} sqrt(var_k / S); an odd S is padded with a zero-weight feature)
+//            (a_{s,k} = w_{s,k} sqrt(var_k / S); an odd S is padded with a zero-weight feature).
+//            Records are stored in groups of 32, 16-byte chunk-major inside a group: float offset
+//              (k S2P + (s2 & ~31)) RP + c 128 + (s2 & 31) 4 + i     for chunk c, element i of the chunk,
+//            so a warp whose lanes read 32 consecutive records (warp-per-row kernels) touches 512 contiguous bytes
+//            per LDS.128 (conflict-free), while the row-per-thread kernels read one record by broadcast.
 //   kern : [m][KS]     = Z_{m,0..D-1}, then output pairs c_{0,m}, c_{1,m}, ... (c_{k,m} = var_k nu_{k,m}; zero pad)
 //   il   : [j][WP]     = output pairs -w_{0,j}, -w_{1,j}, ...  with w_{k,j} = 0.5 log2(e) / ell_{k,j}^2
 //                        so that exp(-0.5 r_k^2) = 2^(sum_j d_j^2 (-w_kj))
 // ------------------------------------------------------------------------------------------------------------------
 struct GpodeLayout {
-    int D, M, S, S2, RP, KS, WP;
+    int D, M, S, S2, S2P, RP, KS, WP;
     int off_rff, off_kern, off_il, total;  // in floats; every offset and `total` is a multiple of 4 (16 bytes)
 };
 
@@ -60,11 +64,12 @@ __host__ __device__ inline GpodeLayout gpode_layout(int D, int M, int S) {
     GpodeLayout L;
     L.D = D; L.M = M; L.S = S;
     L.S2 = (S + 1) / 2;
+    L.S2P = (L.S2 + 31) & ~31;
     L.RP = gpode_round_up4(2 * D + 4);
     L.KS = gpode_round_up4(D + 2 * ((D + 1) / 2));
     L.WP = gpode_round_up4(2 * ((D + 1) / 2));
     L.off_rff = 0;
-    L.off_kern = L.off_rff + D * L.S2 * L.RP;
+    L.off_kern = L.off_rff + D * L.S2P * L.RP;
     L.off_il = L.off_kern + M * L.KS;
     L.total = L.off_il + D * L.WP;
     return L;

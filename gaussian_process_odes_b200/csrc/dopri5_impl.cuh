@@ -460,7 +460,7 @@ __global__ void __launch_bounds__(kDpThreads) dopri5_bwd_kernel(const Dopri5BwdA
                     strow<D>(Yi, a.vy + slot * plane, row);
                     strow<D>(kbi, a.vk + slot * plane, row);
                 }
-                vf_vjp<D, 1>(sp, M, S, Yi, kbi, fst, Yb, A, V, lane, 32);
+                vf_vjp<D, 1, true>(sp, M, S, Yi, kbi, fst, Yb, A, V, lane, 32);
 #pragma unroll
                 for (int j = 0; j < D; ++j) {
                     Yb[0][j] = gpode_warp_sum(Yb[0][j]);
@@ -486,7 +486,7 @@ __global__ void __launch_bounds__(kDpThreads) dopri5_bwd_kernel(const Dopri5BwdA
                     strow<D>(y0, a.vy + slot * plane, row);
                     strow<D>(kbi, a.vk + slot * plane, row);
                 }
-                vf_vjp<D, 1>(sp, M, S, y0, kbi, fst, Yb, A, V, lane, 32);
+                vf_vjp<D, 1, true>(sp, M, S, y0, kbi, fst, Yb, A, V, lane, 32);
 #pragma unroll
                 for (int j = 0; j < D; ++j) yb0[j] += gpode_warp_sum(Yb[0][j]);
             }

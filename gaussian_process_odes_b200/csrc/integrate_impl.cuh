@@ -310,7 +310,7 @@ __device__ __forceinline__ void warp_allreduce(float (&v)[1][D]) {
 template <int D>
 __device__ __forceinline__ void vf_eval_warp(const float* sp, int M, int S, const float (&x)[1][D], float (&f)[1][D],
                                              int lane) {
-    vf_eval<D, 1>(sp, M, S, x, f, lane, 32);
+    vf_eval<D, 1, true>(sp, M, S, x, f, lane, 32);
     warp_allreduce<D>(f);
 }
 
@@ -321,7 +321,7 @@ __device__ __forceinline__ void vf_vjp_warp(const float* sp, int M, int S, const
     float fm[1][D];  // f(x) enters the variance partial sum once per row, not once per lane
 #pragma unroll
     for (int j = 0; j < D; ++j) fm[0][j] = lane == 0 ? fst[0][j] : 0.f;
-    vf_vjp<D, 1>(sp, M, S, x, kb, fm, xb, A, V, lane, 32);
+    vf_vjp<D, 1, true>(sp, M, S, x, kb, fm, xb, A, V, lane, 32);
     warp_allreduce<D>(xb);
 }
 

@@ -31,15 +31,18 @@ __global__ void pack_kernel(const GpodeLayout L, const float* __restrict__ omega
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rff + n_kern + n_il; i += gridDim.x * blockDim.x) {
         if (i < n_rff) {
             const int k = i / S2, s2 = i - k * S2;
-            float* o = out + L.off_rff + (size_t)i * L.RP;
+            // element e of the record lives at chunk e/4, slot e%4 of the chunk-major group layout
+            float* base = out + L.off_rff + ((size_t)k * L.S2P + (s2 & ~31)) * L.RP + (s2 & 31) * 4;
+#define GPODE_REC(e) base[((e) >> 2) * 128 + ((e) & 3)]
             for (int h = 0; h < 2; ++h) {
                 const int s = 2 * s2 + h;
                 const bool ok = s < S;
-                for (int j = 0; j < D; ++j) o[2 * j + h] = ok ? omega[((size_t)j * S + s) * D + k] : 0.f;
-                o[2 * D + h] = ok ? phase[s * D + k] : 0.f;
-                o[2 * D + 2 + h] = ok ? w[s * D + k] * sqrtf(var[k] / (float)S) : 0.f;
+                for (int j = 0; j < D; ++j) GPODE_REC(2 * j + h) = ok ? omega[((size_t)j * S + s) * D + k] : 0.f;
+                GPODE_REC(2 * D + h) = ok ? phase[s * D + k] : 0.f;
+                GPODE_REC(2 * D + 2 + h) = ok ? w[s * D + k] * sqrtf(var[k] / (float)S) : 0.f;
             }
-            for (int j = 2 * D + 4; j < L.RP; ++j) o[j] = 0.f;
+            for (int j = 2 * D + 4; j < L.RP; ++j) GPODE_REC(j) = 0.f;
+#undef GPODE_REC
         } else if (i < n_rff + n_kern) {
             const int m = i - n_rff;
             float* o = out + L.off_kern + (size_t)m * L.KS;

@@ -29,7 +29,7 @@ param_grad_kernel(const float* __restrict__ packed, const int M, const int S, co
     constexpr int RW = 2 * DP;  // floats per staged row: y padded to DP, cotangent padded to DP
     __shared__ __align__(16) float srow[kPgTile * RW];
 
-    const float* __restrict__ kern = packed + D * ((S + 1) >> 1) * RP;
+    const float* __restrict__ kern = packed + D * ((((S + 1) >> 1) + 31) & ~31) * RP;
     const float* __restrict__ wnp = kern + M * KS;  // -w, [j][WP] with outputs k along the row
     int m, group, G;
     if (M >= kPgThreads) {

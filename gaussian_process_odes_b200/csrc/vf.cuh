@@ -16,6 +16,16 @@ struct VfShape {
     static constexpr int WP = (2 * KP + 3) & ~3;        // floats per input-dimension row of -w
 };
 
+// one RFF record (see common.cuh: chunk-major inside groups of 32 records)
+template <int RP>
+__device__ __forceinline__ void lds_rff(float (&dst)[RP], const float* __restrict__ src) {
+#pragma unroll
+    for (int c = 0; c < RP / 4; ++c) {
+        const float4 v = *reinterpret_cast<const float4*>(src + c * 128);
+        dst[4 * c + 0] = v.x; dst[4 * c + 1] = v.y; dst[4 * c + 2] = v.z; dst[4 * c + 3] = v.w;
+    }
+}
+
 template <int N>
 __device__ __forceinline__ void lds_vec(float (&dst)[N], const float* __restrict__ src) {
     static_assert(N % 4 == 0, "packed records are padded to 16 bytes");
@@ -30,14 +40,14 @@ __device__ __forceinline__ void lds_vec(float (&dst)[N], const float* __restrict
 // Two features (RFF term) / two output dimensions (RBF term) ride in one FFMA2.
 // (i0, istep): which feature pairs / inducing points this thread sums -- (0,1) when the thread owns whole rows,
 // (lane,32) in the warp-per-row kernels, where the partial sums are then combined with a warp all-reduce.
-template <int D, int R>
+template <int D, int R, bool kWarp = false>
 __device__ __forceinline__ void vf_eval(const float* __restrict__ sp, const int M, const int S,
                                         const float (&x)[R][D], float (&f)[R][D], const int i0 = 0,
                                         const int istep = 1) {
     constexpr int RP = VfShape<D>::RP, KS = VfShape<D>::KS, WP = VfShape<D>::WP, KP = VfShape<D>::KP;
-    const int S2 = (S + 1) >> 1;
+    const int S2 = (S + 1) >> 1, S2P = (S2 + 31) & ~31;
     const float* __restrict__ rff = sp;
-    const float* __restrict__ kern = sp + D * S2 * RP;
+    const float* __restrict__ kern = sp + D * S2P * RP;
     const float* __restrict__ wnp = kern + M * KS;
 
     float2 fr[R][D];   // RFF partial sums, one half per feature of the pair
@@ -46,12 +56,12 @@ __device__ __forceinline__ void vf_eval(const float* __restrict__ sp, const int 
 #pragma unroll
         for (int k = 0; k < D; ++k) fr[r][k] = make_float2(0.f, 0.f);
 
-#pragma unroll 2
-    for (int s2 = i0; s2 < S2; s2 += istep) {
+    // records come in groups of 32 (chunk-major inside a group)
+    auto rff_body = [&](const float* __restrict__ rec) {   // rec: chunk 0 of the k = 0 record of one feature pair
 #pragma unroll
         for (int k = 0; k < D; ++k) {
             float prm[RP];
-            lds_vec<RP>(prm, rff + (k * S2 + s2) * RP);
+            lds_rff<RP>(prm, rec + k * S2P * RP);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 float2 th = make_float2(prm[2 * D], prm[2 * D + 1]);
@@ -60,6 +70,16 @@ __device__ __forceinline__ void vf_eval(const float* __restrict__ sp, const int 
                 const float2 c = make_float2(__cosf(th.x), __cosf(th.y));
                 fr[r][k] = ffma2(c, make_float2(prm[2 * D + 2], prm[2 * D + 3]), fr[r][k]);
             }
+        }
+    };
+    if constexpr (kWarp) {  // lane i0 owns slot i0 of every group: stride one whole group
+#pragma unroll 2
+        for (int s2 = i0; s2 < S2; s2 += 32) rff_body(rff + (s2 - i0) * RP + i0 * 4);
+    } else {                // walk the groups, then the slots of a group
+        for (int g0 = 0; g0 < S2; g0 += 32) {
+            const int lim = S2 - g0 < 32 ? S2 - g0 : 32;
+#pragma unroll 2
+            for (int i = i0; i < lim; i += istep) rff_body(rff + g0 * RP + i * 4);
         }
     }
 
@@ -113,15 +133,15 @@ __device__ __forceinline__ void vf_eval(const float* __restrict__ sp, const int 
 //   A[k][j] += x_j G_kj + sum_m q'_km w_kj d_j^2     (lengthscale gradient = -A/ell: RFF path via omega = eps/ell + RBF)
 //   V[k]    += kb_k (f_k + f_upd_k)                   (variance gradient = V / (2 var))
 // fst = f(x) from the forward pass (so f_rff = fst - f_upd needs no cosine here).
-template <int D, int R>
+template <int D, int R, bool kWarp = false>
 __device__ __forceinline__ void vf_vjp(const float* __restrict__ sp, const int M, const int S,
                                        const float (&x)[R][D], const float (&kb)[R][D], const float (&fst)[R][D],
                                        float (&xb)[R][D], float (&A)[D][D], float (&V)[D], const int i0 = 0,
                                        const int istep = 1) {
     constexpr int RP = VfShape<D>::RP, KS = VfShape<D>::KS, WP = VfShape<D>::WP, KP = VfShape<D>::KP;
-    const int S2 = (S + 1) >> 1;
+    const int S2 = (S + 1) >> 1, S2P = (S2 + 31) & ~31;
     const float* __restrict__ rff = sp;
-    const float* __restrict__ kern = sp + D * S2 * RP;
+    const float* __restrict__ kern = sp + D * S2P * RP;
     const float* __restrict__ wnp = kern + M * KS;
 
     float2 xb2[R][D];  // two partial sums per component, folded at the end
@@ -138,10 +158,9 @@ __device__ __forceinline__ void vf_vjp(const float* __restrict__ sp, const int M
         for (int r = 0; r < R; ++r)
 #pragma unroll
             for (int j = 0; j < D; ++j) G[r][j] = make_float2(0.f, 0.f);
-#pragma unroll 2
-        for (int s2 = i0; s2 < S2; s2 += istep) {
+        auto rff_body = [&](const float* __restrict__ rec) {
             float prm[RP];
-            lds_vec<RP>(prm, rff + (k * S2 + s2) * RP);
+            lds_rff<RP>(prm, rec);
             const float2 a2 = make_float2(prm[2 * D + 2], prm[2 * D + 3]);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
@@ -152,6 +171,17 @@ __device__ __forceinline__ void vf_vjp(const float* __restrict__ sp, const int M
                 const float2 g = fmul2(-kb[r][k], fmul2(a2, sn));
 #pragma unroll
                 for (int j = 0; j < D; ++j) G[r][j] = ffma2(g, make_float2(prm[2 * j], prm[2 * j + 1]), G[r][j]);
+            }
+        };
+        const float* __restrict__ rk = rff + k * S2P * RP;
+        if constexpr (kWarp) {
+#pragma unroll 2
+            for (int s2 = i0; s2 < S2; s2 += 32) rff_body(rk + (s2 - i0) * RP + i0 * 4);
+        } else {
+            for (int g0 = 0; g0 < S2; g0 += 32) {
+                const int lim = S2 - g0 < 32 ? S2 - g0 : 32;
+#pragma unroll 2
+                for (int i = i0; i < lim; i += istep) rff_body(rk + g0 * RP + i * 4);
             }
         }
 #pragma unroll
