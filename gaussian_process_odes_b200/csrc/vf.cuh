@@ -168,7 +168,7 @@ __device__ __forceinline__ void vf_vjp(const float* __restrict__ sp, const int M
 #pragma unroll
                 for (int j = 0; j < D; ++j) th = ffma2(x[r][j], make_float2(prm[2 * j], prm[2 * j + 1]), th);
                 const float2 sn = make_float2(__sinf(th.x), __sinf(th.y));
-                const float2 g = fmul2(-kb[r][k], fmul2(a2, sn));
+                const float2 g = fmul2(a2, sn);   // the row's factor -kb_k is applied once, after the feature loop
 #pragma unroll
                 for (int j = 0; j < D; ++j) G[r][j] = ffma2(g, make_float2(prm[2 * j], prm[2 * j + 1]), G[r][j]);
             }
@@ -188,7 +188,7 @@ __device__ __forceinline__ void vf_vjp(const float* __restrict__ sp, const int M
         for (int r = 0; r < R; ++r)
 #pragma unroll
             for (int j = 0; j < D; ++j) {
-                const float gj = G[r][j].x + G[r][j].y;
+                const float gj = -kb[r][k] * (G[r][j].x + G[r][j].y);
                 xb2[r][j].x += gj;
                 A[k][j] = fmaf(x[r][j], gj, A[k][j]);
             }
@@ -231,6 +231,9 @@ __device__ __forceinline__ void vf_vjp(const float* __restrict__ sp, const int M
                 d[j] = x[r][j] - kp_[j];
                 dd[j] = d[j] * d[j];
             }
+            float2 tq[D];  // t_j = sum_k q'_k (-w_kj), one partial per output of the pair
+#pragma unroll
+            for (int j = 0; j < D; ++j) tq[j] = make_float2(0.f, 0.f);
 #pragma unroll
             for (int kp = 0; kp < KP; ++kp) {
                 float2 e = make_float2(0.f, 0.f);
@@ -244,11 +247,12 @@ __device__ __forceinline__ void vf_vjp(const float* __restrict__ sp, const int M
                 const float2 q = fmul2(kbn[r][kp], cK);
 #pragma unroll
                 for (int j = 0; j < D; ++j) {
-                    const float2 u = fmul2(q, wn[j][kp]);        // u_kj = q'_k w_kj for the two outputs of the pair
-                    xb2[r][j] = ffma2(d[j], u, xb2[r][j]);
-                    A2[kp][j] = ffma2(dd[j], u, A2[kp][j]);
+                    tq[j] = ffma2(q, wn[j][kp], tq[j]);
+                    A2[kp][j] = ffma2(dd[j], q, A2[kp][j]);   // the factor -w_kj is applied once, at the very end
                 }
             }
+#pragma unroll
+            for (int j = 0; j < D; ++j) xb2[r][j].x = fmaf(d[j], tq[j].x + tq[j].y, xb2[r][j].x);
         }
     }
 #pragma unroll
@@ -264,7 +268,8 @@ __device__ __forceinline__ void vf_vjp(const float* __restrict__ sp, const int M
 #pragma unroll
     for (int k = 0; k < D; ++k)
 #pragma unroll
-        for (int j = 0; j < D; ++j) A[k][j] += (k & 1) ? A2[k >> 1][j].y : A2[k >> 1][j].x;
+        for (int j = 0; j < D; ++j)
+            A[k][j] = fmaf((k & 1) ? wn[j][k >> 1].y : wn[j][k >> 1].x, (k & 1) ? A2[k >> 1][j].y : A2[k >> 1][j].x, A[k][j]);
 }
 
 // ---- staging of the packed block into shared memory (bulk async copy + mbarrier) -------------------------------
