@@ -222,9 +222,16 @@ def normal_logprob(y, loc, scale):
 # the two ELBOs
 # ----------------------------------------------------------------------------------------------------------------
 def gp_params(p):
-    """Constrained GP parameters from the module-state layout of SURVEY.md section 8(a) (state_dict names)."""
+    """Constrained GP parameters from the module-state layout of SURVEY.md section 8(a) (state_dict names).
+    ``Us_sqrt_diag_unconstrained`` (M,D) instead of ``Us_sqrt_packed`` selects q_diag=True (src/core/dsvgp.py:69-72):
+    the diagonal scale is embedded as D diagonal (M,M) matrices, for which sample_inducing and kl give the q_diag
+    formulas of src/core/dsvgp.py:84-85,207-223."""
     M, D = p['inducing_loc'].shape
-    return dict(Z=p['inducing_loc'], Um=p['Um'], Us_sqrt=tril_from_packed(p['Us_sqrt_packed'], M),
+    if 'Us_sqrt_diag_unconstrained' in p:
+        Us = torch.diag_embed(softplus(p['Us_sqrt_diag_unconstrained']).t())  # (D,M,M)
+    else:
+        Us = tril_from_packed(p['Us_sqrt_packed'], M)
+    return dict(Z=p['inducing_loc'], Um=p['Um'], Us_sqrt=Us,
                 ell=softplus(p['unconstrained_lengthscales']), var=softplus(p['unconstrained_variance']))
 
 

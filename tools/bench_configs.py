@@ -119,6 +119,25 @@ def run_config(name, c, solver, do_cpu):
     return out
 
 
+def run_prediction(n_samples=64):
+    """the notebook's prediction rate (VDP GPODE, dopri5, ts_dense_scale=2, 51-point grid,
+    one new GP function draw per sample; reference: 3.54 it/s on an unknown CPU)."""
+    from gaussian_process_odes_b200 import builders
+    c = dict(D=2, M=16, S=256, N=1, T=51)
+    p, ys, ts, draws, _ = O.make_problem(seed=121, **c)
+    model = build_product_model("gpode", p, ys, c["S"], "dopri5", ts_dense_scale=2)
+    tsd = ts.cuda()
+    builders.compute_predictions(model, tsd, eval_sample_size=4)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = builders.compute_predictions(model, tsd, eval_sample_size=n_samples)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return dict(prediction=True, config="vdp_gpode_notebook", solver="dopri5", samples=n_samples,
+                it_per_s=n_samples / dt, ms_per_sample=dt / n_samples * 1e3, out_shape=list(out.shape),
+                reference_it_per_s=3.54)
+
+
 def run_sweep(D, M, S, B, K, do_cpu):
     from gaussian_process_odes_b200 import ops
     p, ys, ts, draws, _ = O.make_problem(D=D, M=M, S=S, N=1, T=4, seed=5)
@@ -159,6 +178,10 @@ def main():
             r = run_config(name, c, solver, not args.no_cpu and solver == "rk4")
             print(json.dumps(r), flush=True)
             res.append(r)
+    if not args.only or args.only == "prediction":
+        r = run_prediction()
+        print(json.dumps(r), flush=True)
+        res.append(r)
     if not args.only or args.only == "sweep":
         for D, M in ((2, 16), (4, 100), (5, 100), (8, 100)):
             for B, K in ((10000, 32), (100000, 32), (1000000, 1), (1000000, 32)):
