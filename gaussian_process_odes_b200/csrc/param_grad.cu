@@ -36,7 +36,7 @@ param_grad_kernel(const float* __restrict__ packed, const int M, const int S, co
         m = blockIdx.y * kPgThreads + threadIdx.x;
         group = 0;
         G = 1;
-    } else {
+    } else {  // the launch sizes the CTA to G*M threads rounded up to a warp: groups are packed back to back
         G = kPgThreads / M;
         group = threadIdx.x / M;
         m = threadIdx.x - group * M;
@@ -45,19 +45,22 @@ param_grad_kernel(const float* __restrict__ packed, const int M, const int S, co
     const bool active = m < M;
     const int mm = active ? m : 0;
 
-    float z[D], w[D][DP];
+    constexpr int KP = VfShape<D>::KP;
+    float z[D];
+    float2 wn[D][KP];  // -w, output pairs (same packing as the integrator kernels)
 #pragma unroll
-    for (int j = 0; j < D; ++j) z[j] = __ldg(kern + mm * KS + j);
+    for (int j = 0; j < D; ++j) {
+        z[j] = __ldg(kern + mm * KS + j);
 #pragma unroll
-    for (int k = 0; k < D; ++k)
+        for (int kp = 0; kp < KP; ++kp)
+            wn[j][kp] = make_float2(__ldg(wnp + j * WP + 2 * kp), __ldg(wnp + j * WP + 2 * kp + 1));
+    }
+    float2 T2[KP], W2[KP][D];
 #pragma unroll
-        for (int j = 0; j < D; ++j) w[k][j] = -__ldg(wnp + j * WP + k);
-    float T[D], W[D][D];
+    for (int kp = 0; kp < KP; ++kp) {
+        T2[kp] = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int k = 0; k < D; ++k) {
-        T[k] = 0.f;
-#pragma unroll
-        for (int j = 0; j < D; ++j) W[k][j] = 0.f;
+        for (int j = 0; j < D; ++j) W2[kp][j] = make_float2(0.f, 0.f);
     }
 
     const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta;
@@ -65,7 +68,7 @@ param_grad_kernel(const float* __restrict__ packed, const int M, const int S, co
     for (int64_t base = r_begin; base < r_end; base += kPgTile) {
         const int n = (int)((r_end - base) < kPgTile ? (r_end - base) : kPgTile);
         __syncthreads();
-        for (int i = threadIdx.x; i < n * D; i += kPgThreads) {
+        for (int i = threadIdx.x; i < n * D; i += blockDim.x) {
             const int r = i / D, j = i - r * D;
             srow[r * RW + j] = __ldg(ys + base * D + i);
             srow[r * RW + DP + j] = __ldg(kbs + base * D + i);
@@ -84,14 +87,17 @@ param_grad_kernel(const float* __restrict__ packed, const int M, const int S, co
                     dd[j] = d[j] * d[j];
                 }
 #pragma unroll
-                for (int k = 0; k < D; ++k) {
-                    float e = 0.f;
+                for (int kp = 0; kp < KP; ++kp) {
+                    float2 e = make_float2(0.f, 0.f);
 #pragma unroll
-                    for (int j = 0; j < D; ++j) e = fmaf(dd[j], w[k][j], e);
-                    const float p = kb[k] * gpode_ex2(-e);
-                    T[k] += p;
+                    for (int j = 0; j < D; ++j) e = ffma2(dd[j], wn[j][kp], e);
+                    float2 K;
+                    K.x = gpode_ex2(e.x);
+                    K.y = (2 * kp + 1 < D) ? gpode_ex2(e.y) : 0.f;
+                    const float2 p = fmul2(make_float2(kb[2 * kp], (2 * kp + 1 < D) ? kb[(2 * kp + 1 < DP) ? 2 * kp + 1 : 0] : 0.f), K);
+                    T2[kp] = fadd2(T2[kp], p);
 #pragma unroll
-                    for (int j = 0; j < D; ++j) W[k][j] = fmaf(p, d[j], W[k][j]);
+                    for (int j = 0; j < D; ++j) W2[kp][j] = ffma2(d[j], p, W2[kp][j]);
                 }
             }
         }
@@ -100,9 +106,10 @@ param_grad_kernel(const float* __restrict__ packed, const int M, const int S, co
         const GpodeAcc a = gpode_acc_layout(D, M);
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-            atomicAdd(acc + a.off_T + k * M + m, T[k]);
+            atomicAdd(acc + a.off_T + k * M + m, (k & 1) ? T2[k >> 1].y : T2[k >> 1].x);
 #pragma unroll
-            for (int j = 0; j < D; ++j) atomicAdd(acc + a.off_W + (k * M + m) * D + j, W[k][j]);
+            for (int j = 0; j < D; ++j)
+                atomicAdd(acc + a.off_W + (k * M + m) * D + j, (k & 1) ? W2[k >> 1][j].y : W2[k >> 1][j].x);
         }
     }
 }
@@ -144,10 +151,11 @@ int gpode_param_grad_launch(const float* packed, int D, int M, int S, const floa
     rows_per_cta = ((rows_per_cta + kPgTile - 1) / kPgTile) * kPgTile;
     const int64_t gx = (VR + rows_per_cta - 1) / rows_per_cta;
     dim3 grid((unsigned)gx, (unsigned)gy);
+    const int threads = M >= kPgThreads ? kPgThreads : (((kPgThreads / M) * M + 31) / 32) * 32;
     switch (D) {
 #define GPODE_PG_CASE(D_)                                                                                        \
     case D_:                                                                                                     \
-        param_grad_kernel<D_><<<grid, kPgThreads, 0, stream>>>(packed, M, S, ys, kbs, VR, rows_per_cta, acc);    \
+        param_grad_kernel<D_><<<grid, threads, 0, stream>>>(packed, M, S, ys, kbs, VR, rows_per_cta, acc);    \
         break;
         GPODE_PG_CASE(1) GPODE_PG_CASE(2) GPODE_PG_CASE(3) GPODE_PG_CASE(4)
         GPODE_PG_CASE(5) GPODE_PG_CASE(6) GPODE_PG_CASE(7) GPODE_PG_CASE(8)
