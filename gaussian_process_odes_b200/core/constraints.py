@@ -24,6 +24,18 @@ class _ScaleFamily(nn.Module):
         return softplus(self.unconstrained_scale)
 
 
+    _laplace = False
+
+    def shooting_sum(self, ss, pred):
+        """sum over everything of ``log_prob(ss[..., 1:, :], pred[..., :-1, :])`` -- the only way the multiple-shooting
+        ELBO uses this prior (reference ``src/gpode_shooting/models.py:134-135,143``). One fused kernel when the scale
+        is frozen (the reference default) and the tensors live on a GPU; plain tensor ops otherwise."""
+        if ss.is_cuda and not self.unconstrained_scale.requires_grad and self.unconstrained_scale.numel() == 1:
+            from .. import ops
+            return ops.constraint_sum(ss, pred, self.scale.detach(), laplace=self._laplace)
+        return self.log_prob(ss[..., 1:, :], pred[..., :-1, :]).sum()
+
+
 class Gaussian(_ScaleFamily):
     """N(y; f, scale^2) elementwise (reference ``constraints.py:9-36``)."""
 
@@ -40,6 +52,7 @@ class Gaussian(_ScaleFamily):
 
 class Laplace(_ScaleFamily):
     """Laplace(y; f, scale) elementwise (reference ``constraints.py:39-66``)."""
+    _laplace = True
 
     @property
     def variance(self):

@@ -280,6 +280,47 @@ loglik_kernel(const float* __restrict__ pred, const float* __restrict__ ys, cons
     }
 }
 
+// ---- shooting-constraint term: sum over (s, n, t < T-1, d) of log N(ss[s,n,t+1,d] | pred[s,n,t,d], scale) ----------
+// ss, pred: [SN, T, D] (SN = S*N sequences). One thread per element of the (SN, T-1, D) index space, grid-stride;
+// value and both gradients in one pass (the result is a scalar, so backward is a scale).
+__global__ void __launch_bounds__(256)
+constraint_kernel(const float* __restrict__ ss, const float* __restrict__ pred, const float* __restrict__ scale_p,
+                  const int64_t SN, const int T, const int D, const int laplace, double* __restrict__ out,
+                  float* __restrict__ g_ss, float* __restrict__ g_pred) {
+    __shared__ double s_sum[8];
+    const float scale = scale_p[0];
+    const float inv = 1.0f / scale, inv2 = inv * inv;
+    const float c0 = laplace ? -logf(2.0f * scale) : -logf(scale) - 0.9189385332046727f;  // -log s - 0.5 log 2 pi
+    const int64_t per_seq = (int64_t)(T - 1) * D;
+    const int64_t total = SN * per_seq;
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t seq = i / per_seq, rem = i - seq * per_seq;  // rem = t*D + d, t < T-1
+        const int64_t ip = seq * (int64_t)T * D + rem;             // pred[seq, t, d]
+        const int64_t is = ip + D;                                 // ss[seq, t+1, d]
+        const float diff = __ldg(ss + is) - __ldg(pred + ip);
+        float lp, g;
+        if (laplace) {
+            lp = c0 - fabsf(diff) * inv;
+            g = diff > 0.f ? -inv : (diff < 0.f ? inv : 0.f);      // d lp / d ss
+        } else {
+            lp = c0 - 0.5f * diff * diff * inv2;
+            g = -diff * inv2;
+        }
+        acc += (double)lp;
+        if (g_ss != nullptr) g_ss[is] = g;
+        if (g_pred != nullptr) g_pred[ip] = -g;
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s_sum[i];
+        atomicAdd(out, t);
+    }
+}
+
 int check_states(int D, int S, int64_t R) {
     GPODE_CHECK_ARG(D >= 1 && D <= GPODE_MAX_D, "state dimension D=%d outside 1..%d", D, GPODE_MAX_D);
     GPODE_CHECK_ARG(S >= 0 && R >= 0, "negative sizes S=%d R=%lld", S, (long long)R);
@@ -346,6 +387,28 @@ extern "C" int gpode_loglik_sum(const float* pred, const float* ys, const float*
     const int64_t cap = (int64_t)sms * 8;
     const unsigned grid = (unsigned)(want < cap ? want : cap);
     loglik_kernel<<<grid, 256, 0, st>>>(pred, ys, W, bias, var, S, R, D, D_obs, sum_out, grad_pred, grad_var);
+    GPODE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gpode_constraint_sum(const float* ss, const float* pred, const float* scale, int64_t SN, int T, int D,
+                                    int laplace, double* sum_out, float* grad_ss, float* grad_pred, void* stream) {
+    GPODE_CHECK_ARG(ss && pred && scale && sum_out, "NULL argument");
+    GPODE_CHECK_ARG(SN >= 0 && T >= 1 && D >= 1, "bad sizes SN=%lld T=%d D=%d", (long long)SN, T, D);
+    cudaStream_t st = (cudaStream_t)stream;
+    GPODE_CUDA(cudaMemsetAsync(sum_out, 0, sizeof(double), st));
+    const int64_t n_all = SN * (int64_t)T * D;
+    if (grad_ss) GPODE_CUDA(cudaMemsetAsync(grad_ss, 0, sizeof(float) * n_all, st));      // t = 0 slots stay zero
+    if (grad_pred) GPODE_CUDA(cudaMemsetAsync(grad_pred, 0, sizeof(float) * n_all, st));  // t = T-1 slots stay zero
+    const int64_t total = SN * (int64_t)(T - 1) * D;
+    if (total == 0) return 0;
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int64_t want = (total + 255) / 256;
+    const int64_t cap = (int64_t)sms * 8;
+    constraint_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(ss, pred, scale, SN, T, D, laplace, sum_out,
+                                                                          grad_ss, grad_pred);
     GPODE_LAUNCH_CHECK();
     return 0;
 }

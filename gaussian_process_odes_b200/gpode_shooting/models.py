@@ -63,12 +63,18 @@ class UniformSequenceModel(BaseSequenceModel):
         else:
             observation_loglik_mean = self.likelihood.log_prob(predicted_xs, ys.unsqueeze(0)).mean()
         state_entropy = self.state_distribution.entropy()  # (N,T-1)
-        state_constraint_logprob = self.constraint.log_prob(ss_samples[:, :, 1:, :],
-                                                            predicted_xs[:, :, :-1, :]).sum(3)  # (S,N,T-1)
+        shooting_sum = getattr(self.constraint, "shooting_sum", None)
+        if shooting_sum is not None:
+            # mean over samples of the sum over (n, t, d): one fused kernel instead of a chain of (S,N,T-1,D) ops
+            constraint_total = shooting_sum(ss_samples, predicted_xs) / S
+        else:
+            state_constraint_logprob = self.constraint.log_prob(ss_samples[:, :, 1:, :],
+                                                                predicted_xs[:, :, :-1, :]).sum(3)  # (S,N,T-1)
+            assert state_constraint_logprob.shape == (S, N, T - 1)
+            constraint_total = state_constraint_logprob.mean(0).sum()
         initial_state_kl = self.state_distribution.x0.kl()
         assert state_entropy.shape == (N, T - 1)
-        assert state_constraint_logprob.shape == (S, N, T - 1)
-        scaled_state_constraint_loglik = state_constraint_logprob.mean(0).sum() / self.num_observations
+        scaled_state_constraint_loglik = constraint_total / self.num_observations
         scaled_state_entropy = state_entropy.sum() / self.num_observations
         scaled_initial_state_kl = initial_state_kl / self.num_observations
         return observation_loglik_mean, scaled_state_constraint_loglik, scaled_state_entropy, scaled_initial_state_kl

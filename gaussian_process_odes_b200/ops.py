@@ -274,6 +274,40 @@ class _LoglikMean(torch.autograd.Function):
         return gp, None, None, None, gv
 
 
+class _ConstraintSum(torch.autograd.Function):
+    """sum_{s,n,t<T-1,d} log p(ss[s,n,t+1,d] | pred[s,n,t,d], scale) in one kernel (gpode_constraint_sum)."""
+
+    @staticmethod
+    def forward(ctx, ss, pred, scale, laplace):
+        sc, pc, kc = f32(ss, "ss"), f32(pred, "pred"), f32(scale, "scale")
+        T, D = sc.shape[-2], sc.shape[-1]
+        SN = sc.numel() // (T * D)
+        need_s, need_p = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if ctx.needs_input_grad[2]:
+            raise _lib.GpodeError("the fused constraint term treats the scale as a constant (requires_grad=False)")
+        total = torch.empty((), dtype=torch.float64, device=sc.device)
+        gs = torch.empty_like(sc) if need_s else None
+        gp = torch.empty_like(pc) if need_p else None
+        _lib.call("gpode_constraint_sum", ptr(sc), ptr(pc), ptr(kc), SN, T, D, int(bool(laplace)), ptr(total), ptr(gs),
+                  ptr(gp), stream_ptr())
+        ctx.save_for_backward(*(t for t in (gs, gp) if t is not None))
+        ctx.have = (need_s, need_p)
+        return total.to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        saved = list(ctx.saved_tensors)
+        need_s, need_p = ctx.have
+        gs = saved.pop(0) * g if need_s else None
+        gp = saved.pop(0) * g if need_p else None
+        return gs, gp, None, None
+
+
+def constraint_sum(ss, pred, scale, laplace=False):
+    """``ss``, ``pred``: (..., T, D). Sum over all leading axes, t < T-1 and D of log p(ss[t+1] | pred[t], scale)."""
+    return _ConstraintSum.apply(ss, pred, scale, laplace)
+
+
 def state_sample(mean, L_packed, eps, jitter=1e-5):
     """``eps (S, *batch, D)`` -> samples ``(S, *batch, D)`` of N(mean, L L^T + jitter I), L packed ``(*batch, P)``."""
     return _StateSample.apply(mean, L_packed, eps, jitter)

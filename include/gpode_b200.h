@@ -164,6 +164,13 @@ int gpode_state_bwd(const float* L_packed, const float* eps, int S, int64_t R, i
 int gpode_loglik_sum(const float* pred, const float* ys, const float* W, const float* bias, const float* var, int S,
                      int64_t R, int D, int D_obs, double* sum_out, float* grad_pred, float* grad_var, void* stream);
 
+/* Shooting-constraint term of UniformSequenceModel (src/gpode_shooting/models.py:134-135,143 with
+ * src/core/constraints.py:26-36 Gaussian / :56-66 Laplace): sum over sequences, t < T-1 and dims of
+ * log p(ss[.,t+1,.] | loc = pred[.,t,.], scale). ss, pred: [SN,T,D]; scale: 1 float (device). grad_ss / grad_pred
+ * ([SN,T,D], may be NULL) receive the derivatives of that SUM (untouched slots are zeroed). */
+int gpode_constraint_sum(const float* ss, const float* pred, const float* scale, int64_t SN, int T, int D, int laplace,
+                         double* sum_out, float* grad_ss, float* grad_pred, void* stream);
+
 /* Measurement utility (no reference counterpart): sustained FP32 FMA throughput of the current device in TFLOP/s
  * (best of 5 launches of a register-only FMA loop; synchronises the stream). scratch: >= 1 float (device). */
 int gpode_probe_fp32_fma(double* tflops_out_host, double* ms_out_host, float* scratch, void* stream);

@@ -81,3 +81,47 @@ def test_generic_projection_callable_still_works():
     assert relerr(out[0][0], out[1][0]) <= 1e-5
     assert relerr(out[0][1], out[1][1]) <= 1e-4
     assert relerr(out[0][2], out[1][2]) <= 1e-4
+
+
+@pytest.mark.parametrize("laplace", [False, True])
+@pytest.mark.parametrize("shape", [(3, 2, 7, 2), (5, 1, 25, 2), (2, 3, 4, 5), (1, 1, 2, 1)])
+def test_constraint_sum(laplace, shape):
+    """Fused shooting-constraint term against torch.distributions (reference src/core/constraints.py:26-36,56-66)."""
+    from gaussian_process_odes_b200 import ops
+    rng = np.random.default_rng(sum(shape))
+    ss = torch.tensor(rng.normal(size=shape), dtype=torch.float32)
+    pred = torch.tensor(rng.normal(size=shape), dtype=torch.float32)
+    scale = torch.tensor([0.37], dtype=torch.float32)
+    s64, p64 = ss.double().requires_grad_(True), pred.double().requires_grad_(True)
+    dist = (torch.distributions.Laplace if laplace else torch.distributions.Normal)(loc=p64[:, :, :-1], scale=scale.double())
+    ref = dist.log_prob(s64[:, :, 1:]).sum()
+    (ref * 0.3).backward()
+    sc, pc = ss.cuda().requires_grad_(True), pred.cuda().requires_grad_(True)
+    got = ops.constraint_sum(sc, pc, scale.cuda(), laplace=laplace)
+    (got * 0.3).backward()
+    assert relerr(got, ref) <= 2e-6
+    assert relerr(sc.grad, s64.grad) <= 2e-6
+    assert relerr(pc.grad, p64.grad) <= 2e-6
+
+
+def test_laplace_constraint_model_matches_tensor_path():
+    """UniformSequenceModel with the Laplace prior: fused term == the reference formulation on plain tensors."""
+    from gaussian_process_odes_b200 import builders
+    from util import injected_draws, load_golden, build_product_model
+    g = load_golden("vdp_shooting_rk4")
+    out = []
+    for fused in (True, False):
+        m = builders.build_gpode_shooting(1, 25, 2, num_inducing=16, num_features=256, solver="rk4",
+                                          constraint_type="laplace", constraint_initial_scale=1e-2)
+        ref_m = build_product_model("shooting", g['p'], g['ys'], 256, "rk4")
+        sd = ref_m.state_dict()
+        sd["constraint.unconstrained_scale"] = m.state_dict()["constraint.unconstrained_scale"]
+        m.load_state_dict(sd)
+        if not fused:
+            m.constraint.shooting_sum = None
+        with injected_draws(g['draws'], mvn_order=("eps_x0", "eps_states")):
+            loss = builders.compute_loss_shooting(m, g['ys'].cuda(), g['ts'].cuda(), num_samples=5)[0]
+        loss.backward()
+        out.append((loss.detach().cpu(), m.state_distribution.param_mean.optvar.grad.cpu()))
+    assert relerr(out[0][0], out[1][0]) <= 1e-5
+    assert relerr(out[0][1], out[1][1]) <= 1e-4
