@@ -228,35 +228,46 @@ loglik_kernel(const float* __restrict__ pred, const float* __restrict__ ys, cons
             y[p] = d < Dobs ? __ldg(ys + r * Dobs + d) : 0.f;
         }
         float local = 0.f;
-        for (int s = 0; s < S; ++s) {
-            const float* xr = pred + ((int64_t)s * R + r) * D;
-            float x[kLlMaxD];
+        constexpr int kSC = 4;  // samples per chunk: their (independent) loads are all issued before any use
+        for (int s0 = 0; s0 < S; s0 += kSC) {
+            float x[kSC][kLlMaxD];
 #pragma unroll
-            for (int l = 0; l < kLlMaxD; ++l) x[l] = l < D ? __ldg(xr + l) : 0.f;
-            float gx[kLlMaxD];
+            for (int c = 0; c < kSC; ++c) {
+                const int sc = s0 + c < S ? s0 + c : S - 1;
+                const float* xr = pred + ((int64_t)sc * R + r) * D;
 #pragma unroll
-            for (int l = 0; l < kLlMaxD; ++l) gx[l] = 0.f;
-#pragma unroll
-            for (int p = 0; p < kLlPasses; ++p) {
-                if (p * 32 < Dobs) {
-                    float f = b[p];
-#pragma unroll
-                    for (int l = 0; l < kLlMaxD; ++l) f = fmaf(x[l], w[p][l], f);
-                    const bool ok = p * 32 + lane < Dobs;
-                    const float diff = ok ? f - y[p] : 0.f;
-                    const float q = diff * iv[p];
-                    local += ok ? -0.5f * (lv[p] + diff * q) : 0.f;
-                    gv[p] += ok ? -0.5f * (iv[p] - q * q) : 0.f;
-#pragma unroll
-                    for (int l = 0; l < kLlMaxD; ++l) gx[l] = fmaf(-q, w[p][l], gx[l]);
-                }
+                for (int l = 0; l < kLlMaxD; ++l) x[c][l] = l < D ? __ldg(xr + l) : 0.f;
             }
-            if (g_pred != nullptr) {
 #pragma unroll
-                for (int l = 0; l < kLlMaxD; ++l) {
-                    if (l < D) {
-                        const float v = gpode_warp_sum(gx[l]);
-                        if (lane == 0) g_pred[((int64_t)s * R + r) * D + l] = v;
+            for (int c = 0; c < kSC; ++c) {
+                if (s0 + c < S) {
+                    const int s = s0 + c;
+                    float gx[kLlMaxD];
+#pragma unroll
+                    for (int l = 0; l < kLlMaxD; ++l) gx[l] = 0.f;
+#pragma unroll
+                    for (int p = 0; p < kLlPasses; ++p) {
+                        if (p * 32 < Dobs) {
+                            float f = b[p];
+#pragma unroll
+                            for (int l = 0; l < kLlMaxD; ++l) f = fmaf(x[c][l], w[p][l], f);
+                            const bool ok = p * 32 + lane < Dobs;
+                            const float diff = ok ? f - y[p] : 0.f;
+                            const float q = diff * iv[p];
+                            local += ok ? -0.5f * (lv[p] + diff * q) : 0.f;
+                            gv[p] += ok ? -0.5f * (iv[p] - q * q) : 0.f;
+#pragma unroll
+                            for (int l = 0; l < kLlMaxD; ++l) gx[l] = fmaf(-q, w[p][l], gx[l]);
+                        }
+                    }
+                    if (g_pred != nullptr) {
+#pragma unroll
+                        for (int l = 0; l < kLlMaxD; ++l) {
+                            if (l < D) {
+                                const float v = gpode_warp_sum(gx[l]);
+                                if (lane == 0) g_pred[((int64_t)s * R + r) * D + l] = v;
+                            }
+                        }
                     }
                 }
             }
