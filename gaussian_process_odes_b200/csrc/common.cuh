@@ -56,7 +56,13 @@ void gpode_set_error(const char* fmt, ...);
 struct GpodeLayout {
     int D, M, S, S2, S2P, RP, KS, WP;
     int off_rff, off_kern, off_il, total;  // in floats; every offset and `total` is a multiple of 4 (16 bytes)
+    // tensor-core (mma.sync m16n8k8 tf32) operand blocks, appended after `total`, one record per (output k, tile of
+    // 8 features):  mma  : 80 floats = 64 theta-B fragment (lane-major b0,b1) | 16 (phase, phase', a, a') per quad lane
+    //               mmag : 64 floats = G-B fragment (lane-major b0,b1), used by the adjoint only
+    int S8, off_mma, off_mmag, total_all;
 };
+#define GPODE_MMA_REC 80
+#define GPODE_MMAG_REC 64
 
 __host__ __device__ inline int gpode_round_up4(int x) { return (x + 3) & ~3; }
 
@@ -72,6 +78,10 @@ __host__ __device__ inline GpodeLayout gpode_layout(int D, int M, int S) {
     L.off_kern = L.off_rff + D * L.S2P * L.RP;
     L.off_il = L.off_kern + M * L.KS;
     L.total = L.off_il + D * L.WP;
+    L.S8 = (S + 7) / 8;
+    L.off_mma = L.total;
+    L.off_mmag = L.off_mma + D * L.S8 * GPODE_MMA_REC;
+    L.total_all = L.off_mmag + D * L.S8 * GPODE_MMAG_REC;
     return L;
 }
 
@@ -131,6 +141,20 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
     unsigned long long d;
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(gpode_pack2(a.x, a.y)), "l"(gpode_pack2(b.x, b.y)));
     return gpode_unpack2(d);
+}
+
+// ---- legacy tensor-core path: mma.sync m16n8k8, tf32 operands, fp32 accumulate (SASS HMMA.1688.F32.TF32) ----------
+// tf32 operands are passed as raw fp32 bit patterns: the tensor core ignores the 13 low mantissa bits, so
+// hi = v & 0xffffe000 is exactly what it sees and lo = v - hi is exact in fp32 (error-compensated "3xTF32" split).
+__device__ __forceinline__ void gpode_split_tf32(float v, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(v) & 0xffffe000u;
+    lo = __float_as_uint(v - __uint_as_float(hi));
+}
+__device__ __forceinline__ void gpode_mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t b0,
+                                               const uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
 __device__ __forceinline__ uint32_t gpode_smem_u32(const void* p) {

@@ -10,7 +10,7 @@
 // [time][row][dim] layout torchdiffeq itself returns.
 #pragma once
 #include <stdlib.h>
-#include "vf.cuh"
+#include "vf_mma.cuh"
 
 namespace {
 
@@ -503,6 +503,50 @@ vf_bwd_warp_kernel(const float* __restrict__ packed, const int M, const int S, c
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Tensor-core (quad layout) kernels: a warp owns 32 rows, see vf_mma.cuh
+// ------------------------------------------------------------------------------------------------------------------
+template <int D>
+__device__ __forceinline__ void load_rows_quad(float (&v)[4][D], const float* __restrict__ base, const int64_t row0,
+                                               const int64_t B) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int64_t row = row0 + 8 * r;
+#pragma unroll
+        for (int j = 0; j < D; ++j) v[r][j] = row < B ? __ldg(base + row * D + j) : 0.f;
+    }
+}
+// the four lanes of a quad hold identical values: lane t writes row slot t
+template <int D>
+__device__ __forceinline__ void store_rows_quad(const float (&v)[4][D], float* __restrict__ base, const int64_t row0,
+                                                const int64_t B, const int t) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int64_t row = row0 + 8 * r;
+        if (r == t && row < B) {
+#pragma unroll
+            for (int j = 0; j < D; ++j) base[row * D + j] = v[r][j];
+        }
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreads, 4)
+vf_fwd_mma_kernel(const float* __restrict__ packed, const int M, const int S, const int off_kern, const int total_all,
+                  const float* __restrict__ x, float* __restrict__ f, const int64_t B) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const float* sp = stage_params_mma(smem_raw, packed, off_kern, total_all);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    const int64_t nblocks = (B + 31) / 32;
+    for (int64_t blk = (int64_t)blockIdx.x * wpc + warp; blk < nblocks; blk += (int64_t)gridDim.x * wpc) {
+        const int64_t row0 = blk * 32 + (lane >> 2);
+        float xr[4][D], fr[4][D];
+        load_rows_quad<D>(xr, x, row0, B);
+        vf_eval_mma<D>(sp, M, S, xr, fr, lane);
+        store_rows_quad<D>(fr, f, row0, B, lane & 3);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // host-side launch helpers
 // ------------------------------------------------------------------------------------------------------------------
 struct LaunchShape {
@@ -578,7 +622,20 @@ int launch_vf_fwd(const float* packed, int M, int S, const float* x, float* f, i
     const size_t smem = 16 + (size_t)L.total * 4;
     LaunchShape ls;
     constexpr int RW = RowsFwd<D>::value;
-    if (B <= kWarpPathMaxRows) {
+    static const bool use_mma = getenv("GPODE_USE_MMA") != nullptr;
+    if (use_mma && B > kWarpPathMaxRows) {
+        const size_t smem_mma = 16 + (size_t)(L.off_mmag - L.off_kern) * 4;  // forward: no G fragments
+        GPODE_CUDA(cudaFuncSetAttribute(vf_fwd_mma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma));
+        int occ = 0;
+        GPODE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, vf_fwd_mma_kernel<D>, kThreads, smem_mma));
+        if (occ < 1) {
+            gpode_set_error("mma kernel does not fit on an SM (smem %zu bytes)", smem_mma);
+            return -2;
+        }
+        const int64_t want = (B + 127) / 128, cap = (int64_t)num_sms() * occ;
+        vf_fwd_mma_kernel<D><<<(unsigned)(want < cap ? want : cap), kThreads, smem_mma, st>>>(
+            packed, M, S, L.off_kern, L.off_mmag, x, f, B);
+    } else if (B <= kWarpPathMaxRows) {
         if (int rc = warp_shape_for(vf_fwd_warp_kernel<D>, B, smem, &ls)) return rc;
         vf_fwd_warp_kernel<D><<<ls.grid, ls.threads, ls.smem, st>>>(packed, M, S, L.total, x, f, B);
     } else if (use_wide<D, RW>(B)) {

@@ -16,7 +16,7 @@ extern "C" int gpode_abi_version(void) { return GPODE_B200_ABI_VERSION; }
 
 extern "C" int64_t gpode_packed_floats(int D, int M, int S) {
     if (D < 1 || M < 1 || S < 1) return -1;
-    return gpode_layout(D, M, S).total;
+    return gpode_layout(D, M, S).total_all;
 }
 
 namespace {
@@ -27,8 +27,9 @@ __global__ void pack_kernel(const GpodeLayout L, const float* __restrict__ omega
                             const float* __restrict__ w, const float* __restrict__ Z, const float* __restrict__ nu,
                             const float* __restrict__ ell, const float* __restrict__ var, float* __restrict__ out) {
     const int D = L.D, M = L.M, S = L.S, S2 = L.S2;
-    const int n_rff = D * S2, n_kern = M, n_il = D;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rff + n_kern + n_il; i += gridDim.x * blockDim.x) {
+    const int n_rff = D * S2, n_kern = M, n_il = D, n_mma = D * L.S8 * 32;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rff + n_kern + n_il + n_mma;
+         i += gridDim.x * blockDim.x) {
         if (i < n_rff) {
             const int k = i / S2, s2 = i - k * S2;
             // element e of the record lives at chunk e/4, slot e%4 of the chunk-major group layout
@@ -48,11 +49,37 @@ __global__ void pack_kernel(const GpodeLayout L, const float* __restrict__ omega
             float* o = out + L.off_kern + (size_t)m * L.KS;
             for (int j = 0; j < D; ++j) o[j] = Z[m * D + j];
             for (int k = 0; k < L.KS - D; ++k) o[D + k] = (nu && k < D) ? var[k] * nu[k * M + m] : 0.f;
-        } else {
+        } else if (i < n_rff + n_kern + n_il) {
             const int j = i - n_rff - n_kern;
             float* o = out + L.off_il + (size_t)j * L.WP;
             for (int k = 0; k < L.WP; ++k)
                 o[k] = k < D ? -GPODE_HALF_LOG2E / (ell[k * D + j] * ell[k * D + j]) : 0.f;
+        } else {
+            // tensor-core operand fragments of one (k, feature tile) for one lane (g = lane / 4, t = lane % 4)
+            const int q = i - n_rff - n_kern - n_il;
+            const int lane = q & 31, rec = q >> 5;          // rec = k * S8 + ft
+            const int k = rec / L.S8, ft = rec - k * L.S8;
+            const int g = lane >> 2, t = lane & 3;
+            float* o = out + L.off_mma + (size_t)rec * GPODE_MMA_REC;
+            float* og = out + L.off_mmag + (size_t)rec * GPODE_MMAG_REC;
+            auto om = [&](int j, int sidx) -> float {
+                return (j < D && sidx < S) ? omega[((size_t)j * S + sidx) * D + k] : 0.f;
+            };
+            // theta = x Omega: B is (j x feature), b0 = B[t][g], b1 = B[t+4][g]
+            o[lane * 2 + 0] = om(t, 8 * ft + g);
+            o[lane * 2 + 1] = om(t + 4, 8 * ft + g);
+            // G = g Omega^T: B is (feature x j) with the feature order of the theta accumulator fragment
+            // (A columns t, t+4 hold features 2t, 2t+1): b0 = Omega[j=g][2t], b1 = Omega[j=g][2t+1]
+            og[lane * 2 + 0] = om(g, 8 * ft + 2 * t);
+            og[lane * 2 + 1] = om(g, 8 * ft + 2 * t + 1);
+            if (g == 0) {
+                const float ak = sqrtf(var[k] / (float)S);
+                for (int h = 0; h < 2; ++h) {
+                    const int sidx = 8 * ft + 2 * t + h;
+                    o[64 + t * 4 + h] = sidx < S ? phase[sidx * D + k] : 0.f;
+                    o[64 + t * 4 + 2 + h] = sidx < S ? w[sidx * D + k] * ak : 0.f;
+                }
+            }
         }
     }
 }
@@ -65,7 +92,7 @@ extern "C" int gpode_pack_cache(const gpode_cache_t* c, float* packed, void* str
     GPODE_CHECK_ARG(c->M >= 1 && c->S >= 1, "M=%d and S=%d must be positive", c->M, c->S);
     GPODE_CHECK_ARG(c->omega && c->phase && c->w && c->Z && c->ell && c->var, "cache tensor is NULL");
     const GpodeLayout L = gpode_layout(c->D, c->M, c->S);
-    const int n = c->D * L.S2 + c->M + c->D;
+    const int n = c->D * L.S2 + c->M + c->D + c->D * L.S8 * 32;
     pack_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(L, c->omega, c->phase, c->w, c->Z, c->nu, c->ell,
                                                                    c->var, packed);
     GPODE_LAUNCH_CHECK();
