@@ -111,3 +111,50 @@ class GraphedStep:
         self.draws.refresh()
         self.graph.replay()
         return self.loss
+
+
+class GraphedPrediction:
+    """CUDA-graph replay of one posterior-predictive sample: new GP function draw (``build_cache``) + one integration
+    of ``x0_fn()`` over ``ts`` under ``torch.no_grad()`` -- the body of the reference's ``compute_predictions`` loop
+    (``src/gpode/model_builder.py:60-78``), which rebuilds the cache for each of its 128 samples.
+
+        pred = GraphedPrediction(model, ts)            # x0 ~ q(x0) each sample
+        samples = pred.sample_many(128)                # (128, N, T, D)
+    """
+
+    def __init__(self, model, ts, x0_fn=None, warmup=2):
+        from .misc.torch_utils import insert_zero_t0
+        dev = next(model.parameters()).device
+        self.model = model
+        dist = model.x0_distribution if hasattr(model, "x0_distribution") else model.state_distribution.x0
+        self.x0_fn = x0_fn if x0_fn is not None else (lambda: dist.sample().squeeze(0))
+        self.ts0 = insert_zero_t0(ts)
+        self.draws = _StaticDraws(dev)
+        self.draws.install()
+        try:
+            with torch.no_grad():
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for i in range(warmup):
+                        if i == 1:
+                            self.draws.recording = False
+                        self.draws.cursor = 0
+                        model(self.x0_fn(), self.ts0)
+                torch.cuda.current_stream().wait_stream(side)
+                self.draws.recording = False
+                self.draws.cursor = 0
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph):
+                    self.out = model(self.x0_fn(), self.ts0)[:, 1:]
+        finally:
+            self.draws.uninstall()
+
+    def sample(self):
+        """One predictive trajectory set ``(N, T, D)`` (a view of the static output buffer: clone to keep it)."""
+        self.draws.refresh()
+        self.graph.replay()
+        return self.out
+
+    def sample_many(self, n):
+        return torch.stack([self.sample().clone() for _ in range(n)], 0)

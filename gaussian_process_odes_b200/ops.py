@@ -95,13 +95,14 @@ class _RK4(torch.autograd.Function):
     """xs = odeint(f, x0, t, method='rk4') (torchdiffeq 0.2.0 3/8 rule) via gpode_rk4_fwd / gpode_rk4_bwd."""
 
     @staticmethod
-    def forward(ctx, x0, t, Z, ell, var, nu, omega, phase, w):
+    def forward(ctx, x0, t, Z, ell, var, nu, omega, phase, w, want_grad):
         pc = PackedCache(Z, ell, var, nu, omega, phase, w)
         xc, tc = f32(x0, "x0"), f32(t, "t")
         if xc.ndim != 2 or xc.shape[1] != pc.D:
             raise _lib.GpodeError("x0 must be (B,%d), got %s" % (pc.D, tuple(xc.shape)))
         B, Tg = xc.shape[0], tc.shape[0]
-        need_grad = any(ctx.needs_input_grad)
+        # ctx.needs_input_grad is True under torch.no_grad() too; the caller tells whether a graph is being recorded
+        need_grad = want_grad and any(ctx.needs_input_grad)
         xs = torch.empty(Tg, B, pc.D, dtype=torch.float32, device=xc.device)
         kst = torch.empty(max(Tg - 1, 0), 4, B, pc.D, dtype=torch.float32, device=xc.device) if need_grad else None
         _lib.call("gpode_rk4_fwd", ptr(pc.packed), pc.D, pc.M, pc.S, ptr(xc), ptr(tc), Tg, B, ptr(xs),
@@ -128,7 +129,7 @@ class _RK4(torch.autograd.Function):
             _lib.call("gpode_param_grad", ptr(pc.packed), pc.D, pc.M, pc.S, ptr(vrows), ptr(vrows[n_vr * D:]), n_vr,
                       ptr(acc), stream_ptr())
         g_Z, g_ell, g_var, g_nu = pc.finalize(acc)
-        return gx0, None, g_Z, g_ell, g_var, g_nu.reshape(ctx.nu_shape), None, None, None
+        return gx0, None, g_Z, g_ell, g_var, g_nu.reshape(ctx.nu_shape), None, None, None, None
 
 
 class _Whiten(torch.autograd.Function):
@@ -359,14 +360,14 @@ def rk4_integrate(x0, t, Z, ell, var, nu, omega, phase, w):
     """Fixed-grid RK4 (3/8 rule) over the float32 grid ``t``; returns ``(len(t), B, D)`` like torchdiffeq."""
     if Z.shape[1] > MAX_D_REGISTER:
         return _large_d_call("gpode_rk4_fwd_large", x0, t, Z, ell, var, nu, omega, phase, w)
-    return _RK4.apply(x0, t, Z, ell, var, nu, omega, phase, w)
+    return _RK4.apply(x0, t, Z, ell, var, nu, omega, phase, w, torch.is_grad_enabled())
 
 
 class _Dopri5(torch.autograd.Function):
     """xs = odeint(f, x0, t, method='dopri5') (torchdiffeq 0.2.0 controller) via gpode_dopri5_fwd / gpode_dopri5_bwd."""
 
     @staticmethod
-    def forward(ctx, x0, t, Z, ell, var, nu, omega, phase, w, rtol, atol):
+    def forward(ctx, x0, t, Z, ell, var, nu, omega, phase, w, rtol, atol, want_grad):
         lib = _lib.load()
         pc = PackedCache(Z, ell, var, nu, omega, phase, w)
         xc = f32(x0, "x0")
@@ -374,7 +375,7 @@ class _Dopri5(torch.autograd.Function):
             raise _lib.GpodeError("x0 must be (B,%d), got %s" % (pc.D, tuple(xc.shape)))
         B, Tg = xc.shape[0], t.shape[0]
         t64 = t.detach().to(device=xc.device, dtype=torch.float64).contiguous()
-        need_grad = any(ctx.needs_input_grad[:6])
+        need_grad = want_grad and any(ctx.needs_input_grad[:6])
         xs = torch.empty(Tg, B, pc.D, dtype=torch.float32, device=xc.device)
         work = torch.empty(lib.gpode_dopri5_work_floats(pc.D, B), dtype=torch.float32, device=xc.device)
         stats = torch.zeros(4, dtype=torch.int32, device=xc.device)
@@ -419,14 +420,14 @@ class _Dopri5(torch.autograd.Function):
             _lib.call("gpode_param_grad", ptr(pc.packed), pc.D, pc.M, pc.S, ptr(vrows), ptr(vrows[n_vr * D:]), n_vr,
                       ptr(acc), stream_ptr())
         g_Z, g_ell, g_var, g_nu = pc.finalize(acc)
-        return gx0, None, g_Z, g_ell, g_var, g_nu.reshape(ctx.nu_shape), None, None, None, None, None
+        return gx0, None, g_Z, g_ell, g_var, g_nu.reshape(ctx.nu_shape), None, None, None, None, None, None
 
 
 def dopri5_integrate(x0, t, Z, ell, var, nu, omega, phase, w, rtol=1e-6, atol=1e-6):
     """Adaptive dopri5 with torchdiffeq 0.2.0's controller in one cooperative kernel. Returns ``(xs (len(t),B,D),
     stats)`` with ``stats`` a device int32 tensor [nfe, accepted, rejected, status]. Differentiable in x0, Z, ell,
     var, nu through the discrete adjoint of the accepted steps (step sizes are constants, as in torchdiffeq)."""
-    return _Dopri5.apply(x0, t, Z, ell, var, nu, omega, phase, w, rtol, atol)
+    return _Dopri5.apply(x0, t, Z, ell, var, nu, omega, phase, w, rtol, atol, torch.is_grad_enabled())
 
 
 def whiten(Z, ell, var, u, omega, phase, w, jitter=1e-5):

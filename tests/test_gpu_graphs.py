@@ -91,3 +91,25 @@ def test_graphed_step_equals_eager_when_noise_is_fixed():
     for (n1, p1), (n2, p2) in zip(m1.named_parameters(), m2.named_parameters()):
         if p1.grad is not None:
             assert relerr(p2.grad, p1.grad) <= 1e-4, n1  # float32 atomics: summation order differs run to run
+
+
+@pytest.mark.parametrize("solver", ["rk4", "dopri5"])
+def test_graphed_prediction_matches_eager(solver):
+    """One replayed predictive sample == the eager compute_predictions body for the same host draws."""
+    from gaussian_process_odes_b200 import graphs
+    g = load_golden("vdp_gpode_rk4")
+    model = build_product_model("gpode", g['p'], g['ys'], 256, solver, ts_dense_scale=4)
+    ts = g['ts'].cuda()
+    x0 = g['ref']['traj_in'].cuda()
+    pred = graphs.GraphedPrediction(model, ts, x0_fn=lambda: x0)
+    np.random.seed(11)
+    a = pred.sample().clone()
+    from gaussian_process_odes_b200.misc.torch_utils import insert_zero_t0
+    np.random.seed(11)
+    with torch.no_grad():
+        b = model(x0, insert_zero_t0(ts))[:, 1:]
+    assert a.shape == b.shape == (1, 25, 2)
+    assert relerr(a, b) <= 1e-5
+    many = pred.sample_many(5)
+    assert many.shape == (5, 1, 25, 2) and torch.isfinite(many).all()
+    assert relerr(many[0], many[1]) > 1e-3  # different function draws

@@ -133,9 +133,23 @@ def run_prediction(n_samples=64):
     out = builders.compute_predictions(model, tsd, eval_sample_size=n_samples)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    return dict(prediction=True, config="vdp_gpode_notebook", solver="dopri5", samples=n_samples,
-                it_per_s=n_samples / dt, ms_per_sample=dt / n_samples * 1e3, out_shape=list(out.shape),
-                reference_it_per_s=3.54)
+    res = dict(prediction=True, config="vdp_gpode_notebook", solver="dopri5", samples=n_samples,
+               it_per_s=n_samples / dt, ms_per_sample=dt / n_samples * 1e3, out_shape=list(out.shape),
+               reference_it_per_s=3.54)
+    try:
+        from gaussian_process_odes_b200 import graphs
+        gp = graphs.GraphedPrediction(model, tsd)
+        gp.sample_many(4)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out2 = gp.sample_many(n_samples)
+        torch.cuda.synchronize()
+        dt2 = time.perf_counter() - t0
+        res.update(graphed_it_per_s=n_samples / dt2, graphed_ms_per_sample=dt2 / n_samples * 1e3,
+                   graphed_out_shape=list(out2.shape))
+    except Exception as e:  # cooperative launches may not be capturable on every driver
+        res["graphed_error"] = repr(e)[:200]
+    return res
 
 
 def run_sweep(D, M, S, B, K, do_cpu):
