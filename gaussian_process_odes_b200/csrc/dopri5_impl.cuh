@@ -82,15 +82,23 @@ __device__ __forceinline__ void strow(const float (&v)[1][D], float* p, int64_t 
     for (int j = 0; j < D; ++j) p[row * D + j] = v[0][j];
 }
 
-template <int D>
+// kWarp: one WARP per row (lanes split the features / inducing points, xor-shuffle all-reduce) for small batches;
+// otherwise one thread per row.
+template <int D, bool kWarp>
 __device__ __forceinline__ void vf_signed(const float* sp, int M, int S, float sgn, const float (&x)[1][D],
                                           float (&f)[1][D]) {
-    vf_eval<D, 1>(sp, M, S, x, f);
+    if constexpr (kWarp) {
+        vf_eval<D, 1, true>(sp, M, S, x, f, threadIdx.x & 31, 32);
 #pragma unroll
-    for (int j = 0; j < D; ++j) f[0][j] *= sgn;
+        for (int j = 0; j < D; ++j) f[0][j] = gpode_warp_sum(f[0][j]) * sgn;
+    } else {
+        vf_eval<D, 1>(sp, M, S, x, f);
+#pragma unroll
+        for (int j = 0; j < D; ++j) f[0][j] *= sgn;
+    }
 }
 
-template <int D>
+template <int D, bool kWarp>
 __global__ void __launch_bounds__(kDpThreads) dopri5_kernel(const Dopri5Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double sred[kDpThreads / 32];
@@ -98,8 +106,11 @@ __global__ void __launch_bounds__(kDpThreads) dopri5_kernel(const Dopri5Args a) 
     const float* sp = stage_params(smem_raw, a.packed, a.total);
     const int M = a.M, S = a.S;
     const int64_t B = a.B, plane = B * D;
-    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
+    // gtid / gstride index ROWS: threads in the row-per-thread mode, warps in the warp-per-row mode (where every lane
+    // of a warp carries the same row and only lane 0 stores and contributes to the error norm)
+    const int64_t gtid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / (kWarp ? 32 : 1);
+    const int64_t gstride = ((int64_t)gridDim.x * blockDim.x) / (kWarp ? 32 : 1);
+    const bool writer = !kWarp || (threadIdx.x & 31) == 0;
     float* Y = a.work;
     float* F = a.work + plane;
     float* Y1 = a.work + 2 * plane;
@@ -116,10 +127,12 @@ __global__ void __launch_bounds__(kDpThreads) dopri5_kernel(const Dopri5Args a) 
     for (int64_t row = gtid; row < B; row += gstride) {
         float y[1][D], f[1][D];
         ldrow<D>(y, a.x0, row);
-        vf_signed<D>(sp, M, S, fsign, y, f);
-        strow<D>(y, Y, row);
-        strow<D>(f, F, row);
-        strow<D>(y, a.xs, row);
+        vf_signed<D, kWarp>(sp, M, S, fsign, y, f);
+        if (writer) {
+            strow<D>(y, Y, row);
+            strow<D>(f, F, row);
+            strow<D>(y, a.xs, row);
+        }
 #pragma unroll
         for (int j = 0; j < D; ++j) {
             const float sc = atol + fabsf(y[0][j]) * rtol;
@@ -128,6 +141,7 @@ __global__ void __launch_bounds__(kDpThreads) dopri5_kernel(const Dopri5Args a) 
             s1 += (double)(q1 * q1);
         }
     }
+    if (!writer) s0 = s1 = 0.0;  // warp-per-row mode: a row counts once
     {
         const double b0 = block_sum_to(s0, sred);
         const double b1 = block_sum_to(s1, sred);
@@ -146,7 +160,7 @@ __global__ void __launch_bounds__(kDpThreads) dopri5_kernel(const Dopri5Args a) 
         ldrow<D>(f, F, row);
 #pragma unroll
         for (int j = 0; j < D; ++j) y1[0][j] = y[0][j] + h0 * f[0][j];
-        vf_signed<D>(sp, M, S, fsign, y1, f1);
+        vf_signed<D, kWarp>(sp, M, S, fsign, y1, f1);
 #pragma unroll
         for (int j = 0; j < D; ++j) {
             const float sc = atol + fabsf(y[0][j]) * rtol;
@@ -154,6 +168,7 @@ __global__ void __launch_bounds__(kDpThreads) dopri5_kernel(const Dopri5Args a) 
             s2 += (double)(q * q);
         }
     }
+    if (!writer) s2 = 0.0;
     {
         const double b2 = block_sum_to(s2, sred);
         if (threadIdx.x == 0) atomicAdd(a.red + 2, b2);
@@ -203,7 +218,7 @@ __global__ void __launch_bounds__(kDpThreads) dopri5_kernel(const Dopri5Args a) 
                     for (int l = 0; l <= i; ++l) s = fmaf(k[l][0][j], __fmul_rn(kBeta[i][l], dts), s);
                     yi[0][j] = y[0][j] + s;
                 }
-                vf_signed<D>(sp, M, S, fsign, yi, k[i + 1]);
+                vf_signed<D, kWarp>(sp, M, S, fsign, yi, k[i + 1]);
             }
             float ym[1][D];
 #pragma unroll
@@ -219,15 +234,18 @@ __global__ void __launch_bounds__(kDpThreads) dopri5_kernel(const Dopri5Args a) 
                 const float q = e / tol;
                 se += (double)(q * q);
             }
-            strow<D>(yi, Y1, row);
-            strow<D>(k[6], F1, row);
-            strow<D>(ym, YM, row);
-            if (a.ck_k != nullptr && n_acc < a.cap) {  // slot n_acc is simply overwritten if this attempt is rejected
+            if (writer) {
+                strow<D>(yi, Y1, row);
+                strow<D>(k[6], F1, row);
+                strow<D>(ym, YM, row);
+            }
+            if (writer && a.ck_k != nullptr && n_acc < a.cap) {  // slot n_acc is simply overwritten if this attempt is rejected
                 strow<D>(y, a.ck_y + (int64_t)n_acc * plane, row);
 #pragma unroll
                 for (int l = 0; l < 7; ++l) strow<D>(k[l], a.ck_k + ((int64_t)n_acc * 7 + l) * plane, row);
             }
         }
+        if (!writer) se = 0.0;
         {
             const double be = block_sum_to(se, sred);
             if (threadIdx.x == 0) atomicAdd(a.red + (attempt % 3), be);
@@ -270,12 +288,18 @@ __global__ void __launch_bounds__(kDpThreads) dopri5_kernel(const Dopri5Args a) 
                             total = total + xp * cb;
                             xp = xp * x;
                             total = total + xp * ca;
-                            a.xs[(int64_t)jo * plane + row * D + j] = total;
+                            if (writer) a.xs[(int64_t)jo * plane + row * D + j] = total;
                         }
                     }
                 }
-                strow<D>(y1, Y, row);
-                strow<D>(f1, F, row);
+                // warp-per-row mode: every lane has read the old state before lane 0 overwrites it, and the next
+                // attempt's loads see the new one (lanes of a warp are not guaranteed to run in lockstep)
+                if constexpr (kWarp) __syncwarp();
+                if (writer) {
+                    strow<D>(y1, Y, row);
+                    strow<D>(f1, F, row);
+                }
+                if constexpr (kWarp) __syncwarp();
             }
             if (a.ck_dt != nullptr && gtid == 0) a.ck_dt[n_acc] = dts;
             jout = jend;
@@ -312,16 +336,24 @@ int launch_dopri5(const float* packed, int M, int S, const float* x0, const doub
                   double atol, float* xs, float* work, int32_t* stats, float* ckpt, int cap, cudaStream_t st) {
     const GpodeLayout L = gpode_layout(D, M, S);
     const size_t smem = 16 + (size_t)L.total * 4;
-    GPODE_CUDA(cudaFuncSetAttribute(dopri5_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // small batches: one warp per row (the reference's N = 1 / 6 trajectories, a few thousand shooting segments)
+    const bool warp_mode = B <= 1024;
+    const void* kern = warp_mode ? (const void*)dopri5_kernel<D, true> : (const void*)dopri5_kernel<D, false>;
+    GPODE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0, sms = 148, dev = 0;
     GPODE_CUDA(cudaGetDevice(&dev));
     GPODE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    GPODE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dopri5_kernel<D>, kDpThreads, smem));
+    if (warp_mode) {
+        GPODE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dopri5_kernel<D, true>, kDpThreads, smem));
+    } else {
+        GPODE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dopri5_kernel<D, false>, kDpThreads, smem));
+    }
     if (occ < 1) {
         gpode_set_error("dopri5 kernel does not fit on an SM (smem %zu bytes)", smem);
         return -2;
     }
-    const int64_t want = (B + kDpThreads - 1) / kDpThreads;
+    const int64_t rows_per_cta = warp_mode ? kDpThreads / 32 : kDpThreads;
+    const int64_t want = (B + rows_per_cta - 1) / rows_per_cta;
     const int64_t grid_cap = (int64_t)sms * occ;
     const int grid = (int)(want < grid_cap ? want : grid_cap);
     Dopri5Args a;
@@ -345,7 +377,7 @@ int launch_dopri5(const float* packed, int M, int S, const float* x0, const doub
     }
     GPODE_CUDA(cudaMemsetAsync(a.red, 0, 4 * sizeof(double), st));
     void* params[] = {(void*)&a};
-    GPODE_CUDA(cudaLaunchCooperativeKernel((const void*)dopri5_kernel<D>, dim3(grid), dim3(kDpThreads), params, smem, st));
+    GPODE_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kDpThreads), params, smem, st));
     return 0;
 }
 
