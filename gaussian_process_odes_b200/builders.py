@@ -60,17 +60,36 @@ def compute_loss_shooting(model, ys, ts, **kwargs):
     return loss, -ll, -(cons + ent), k0, inducing_kl
 
 
-def compute_predictions(model, ts, eval_sample_size=10, x0_distribution=None):
-    """Posterior-predictive trajectories from the optimised initial-state posterior, one GP function draw per sample
-    (reference ``src/gpode/model_builder.py:60-78``, ``src/gpode_shooting/model_builder.py:75-93``)."""
+def _x0_posterior(model):
+    return model.x0_distribution if hasattr(model, "x0_distribution") else model.state_distribution.x0
+
+
+def compute_predictions(model, ts, eval_sample_size=10, x0_distribution=None, batched=True, rng="numpy"):
+    """Posterior-predictive trajectories ``(S,N,T,D)`` from the optimised initial-state posterior, one GP function
+    draw per sample (reference ``src/gpode/model_builder.py:60-78``, ``src/gpode_shooting/model_builder.py:75-93``).
+
+    ``batched=True`` (default): all ``eval_sample_size`` draws go through ONE whitening, one pack and one integrator
+    launch (``model.forward_sets``); the host generator is consumed in the reference's per-sample order
+    (``rng='numpy'``) or skipped (``rng='device'``). ``batched=False`` is the reference's loop, one launch set per
+    sample."""
     from .misc.torch_utils import insert_zero_t0
     model.eval()
-    dist = x0_distribution
-    if dist is None:
-        dist = model.x0_distribution if hasattr(model, "x0_distribution") else model.state_distribution.x0
+    dist = _x0_posterior(model) if x0_distribution is None else x0_distribution
     ts = insert_zero_t0(ts)
-    out = []
     with torch.no_grad():
-        for _ in range(eval_sample_size):
-            out.append(model(dist.sample().squeeze(0), ts))
+        if batched:
+            x0 = dist.sample(num_samples=eval_sample_size)  # (S,N,D), one draw of the initial state per sample
+            return model.forward_sets(x0, ts, rng=rng)[:, :, 1:]
+        out = [model(dist.sample().squeeze(0), ts) for _ in range(eval_sample_size)]
     return torch.stack(out, 0)[:, :, 1:]
+
+
+def compute_test_predictions(model, x0, ts, eval_sample_size=10, batched=True, rng="numpy"):
+    """Predictive trajectories ``(S,N,T,D)`` from a GIVEN initial state ``x0 (N,D)`` (reference
+    ``src/gpode/model_builder.py:81-96``, ``src/gpode_shooting/mocap_model_builder.py:104-119``)."""
+    model.eval()
+    with torch.no_grad():
+        if batched:
+            x0s = x0.unsqueeze(0).expand(eval_sample_size, *x0.shape).contiguous()
+            return model.forward_sets(x0s, ts, rng=rng)
+        return torch.stack([model(x0, ts) for _ in range(eval_sample_size)], 0)

@@ -88,6 +88,49 @@ class DSVGP_Layer(torch.nn.Module):
         # reference shapes: (D,M,1) dimwise, (M,D) otherwise
         self.nu = nu.unsqueeze(2) if self.dimwise else nu.t()
 
+    def build_cache_sets(self, n, rng="numpy"):
+        """``n`` independent function draws at once for batched Monte-Carlo prediction (no gradient): the tensors of
+        ``build_cache`` with a leading draw axis, in the dimwise layout of the kernels --
+        ``(nu (n,D,M), omega (n,D,S,D), phase (n,S,D), w (n,S,D))``.
+
+        ``rng='numpy'`` consumes the host generators draw by draw in the reference's order (weights, omega, phase,
+        epsilon -- ``dsvgp.py:100-103,83``), i.e. exactly the numbers ``n`` successive ``build_cache()`` calls would
+        use; ``rng='device'`` draws with torch's CUDA generator instead (same distributions, no host work)."""
+        dev, D, S, M = self._device, self.D_out, self.S, self.M
+        om_shape = (D, S, D) if self.dimwise else (D, S)
+        ph_shape = (1, S, D) if self.dimwise else (1, S)
+        if rng == "numpy":
+            from . import kernels as _kernels
+            ws, oms, phs, eps = [], [], [], []
+            for _ in range(n):  # host order per draw; module-level samplers so tests can inject
+                ws.append(sample_normal((S, D)))
+                oms.append(_kernels.sample_normal(om_shape))
+                phs.append(sample_uniform(ph_shape))
+                eps.append(sample_normal((M, D)))
+            w, om_eps, ph, ep = (torch.stack(v).to(dev, non_blocking=True) for v in (ws, oms, phs, eps))
+        elif rng == "device":
+            w = torch.randn(n, S, D, device=dev)
+            om_eps = torch.randn(n, *om_shape, device=dev)
+            ph = torch.rand(n, *ph_shape, device=dev)
+            ep = torch.randn(n, M, D, device=dev)
+        else:
+            raise ValueError("rng must be 'numpy' or 'device'")
+        with torch.no_grad():
+            ls = self.kern.lengthscales
+            omega = om_eps / (ls.T.unsqueeze(1) if self.dimwise else ls.unsqueeze(1))
+            phase = (ph * 2 * np.pi).reshape(n, S, -1)
+            if not self.dimwise:
+                omega = omega.unsqueeze(3).expand(n, D, S, D)
+                phase = phase.expand(n, S, D)
+            omega, phase = omega.contiguous(), phase.contiguous()
+            if self.q_diag:
+                u = self.Us_sqrt() * ep + self.Um()
+            else:
+                u = torch.einsum('dnm,smd->snd', self.Us_sqrt(), ep) + self.Um()
+            nu = ops.whiten_sets(self.inducing_loc(), self.kern.lengthscales_dimwise(), self.kern.variance_dimwise(),
+                                 u.contiguous(), omega, phase, w, jitter)
+        return nu, omega, phase, w
+
     def _nu_dimwise(self):
         return self.nu.squeeze(2) if self.dimwise else self.nu.t()
 

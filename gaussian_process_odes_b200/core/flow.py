@@ -57,6 +57,21 @@ class Flow(nn.Module):
         xs = odeint(self.odefunc, x0, ts, atol=self.atol, rtol=self.rtol, method=self.solver)
         return xs.permute(1, 0, 2)
 
+    def forward_sets(self, x0, ts, rng="numpy"):
+        """Batched Monte-Carlo prediction: ``x0 (n,N,D)`` -> ``(n,N,T,D)``, draw q of the GP integrating ``x0[q]``.
+        Equivalent to ``n`` calls of ``forward`` (cache rebuilt per call, ``flow.py:69``) under ``torch.no_grad()`` --
+        the body of the reference's ``compute_predictions`` loop -- but one whitening, one pack and ONE integrator
+        launch for all draws (dopri5 keeps one step-size controller per draw)."""
+        from .. import ops
+        layer = self.odefunc.diffeq
+        with torch.no_grad():
+            nu, omega, phase, w = layer.build_cache_sets(x0.shape[0], rng=rng)
+            xs, stats = ops.integrate_sets(x0, ts, layer.inducing_loc(), layer.kern.lengthscales_dimwise(),
+                                           layer.kern.variance_dimwise(), nu, omega, phase, w, method=self.solver,
+                                           rtol=self.rtol, atol=self.atol)
+        self.last_sets_stats = stats  # device int32 (n,4) for dopri5: nfe, accepted, rejected, status
+        return xs
+
     def inverse(self, x0, ts, return_divergence=False):
         """Backward-in-time solve on the flipped grid, re-using the current cache (reference ``flow.py:92-115``)."""
         if return_divergence:

@@ -5,7 +5,9 @@
     int gpode_dopri5_fwd_d##D_(const float*, int, int, const float*, const double*, int, int64_t, double, double, \
                                float*, float*, int32_t*, float*, int, cudaStream_t);                              \
     int gpode_dopri5_bwd_d##D_(const float*, int, int, const double*, int, int64_t, const float*, const float*,   \
-                               int, int, float*, float*, float*, cudaStream_t);
+                               int, int, float*, float*, float*, cudaStream_t);                                   \
+    int gpode_dopri5_sets_d##D_(const float*, int, int, int, int64_t, const float*, const double*, int, double,   \
+                                double, float*, float*, int32_t*, cudaStream_t);
 GPODE_DECL(1) GPODE_DECL(2) GPODE_DECL(3) GPODE_DECL(4) GPODE_DECL(5) GPODE_DECL(6) GPODE_DECL(7) GPODE_DECL(8)
 #undef GPODE_DECL
 
@@ -59,6 +61,25 @@ extern "C" int gpode_dopri5_bwd(const float* packed, int D, int M, int S, const 
 #define GPODE_CASE(D_) \
     case D_:           \
         return gpode_dopri5_bwd_d##D_(packed, M, S, t, Tg, B, grad_xs, ckpt, cap, n_accepted, grad_x0, vrows, acc, st);
+        GPODE_CASE(1) GPODE_CASE(2) GPODE_CASE(3) GPODE_CASE(4) GPODE_CASE(5) GPODE_CASE(6) GPODE_CASE(7) GPODE_CASE(8)
+#undef GPODE_CASE
+    }
+    return -1;
+}
+
+extern "C" int gpode_dopri5_fwd_sets(const float* packed, int D, int M, int S, int n_sets, int64_t set_rows,
+                                     const float* x0, const double* t, int Tg, double rtol, double atol, float* xs,
+                                     float* work, int32_t* stats_out, void* stream) {
+    if (int rc = check(packed, D, M, S, set_rows, Tg)) return rc;
+    GPODE_CHECK_ARG(n_sets >= 1 && n_sets <= 65535, "n_sets=%d outside 1..65535", n_sets);
+    GPODE_CHECK_ARG(rtol > 0 && atol > 0, "rtol/atol must be positive");
+    if (set_rows == 0) return 0;
+    GPODE_CHECK_ARG(x0 && t && xs && work && stats_out, "NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (D) {
+#define GPODE_CASE(D_) \
+    case D_:           \
+        return gpode_dopri5_sets_d##D_(packed, M, S, n_sets, set_rows, x0, t, Tg, rtol, atol, xs, work, stats_out, st);
         GPODE_CASE(1) GPODE_CASE(2) GPODE_CASE(3) GPODE_CASE(4) GPODE_CASE(5) GPODE_CASE(6) GPODE_CASE(7) GPODE_CASE(8)
 #undef GPODE_CASE
     }

@@ -18,3 +18,9 @@ int GPODE_CAT(gpode_dopri5_bwd_d, GPODE_D)(const float* packed, int M, int S, co
                                            float* vrows, float* acc, cudaStream_t st) {
     return launch_dopri5_bwd<GPODE_D>(packed, M, S, t, Tg, B, gxs, ckpt, cap, n_acc, gx0, vrows, acc, st);
 }
+
+int GPODE_CAT(gpode_dopri5_sets_d, GPODE_D)(const float* packed, int M, int S, int n_sets, int64_t set_rows,
+                                            const float* x0, const double* t, int Tg, double rtol, double atol,
+                                            float* xs, float* work, int32_t* stats, cudaStream_t st) {
+    return launch_dopri5_sets<GPODE_D>(packed, M, S, n_sets, set_rows, x0, t, Tg, rtol, atol, xs, work, stats, st);
+}

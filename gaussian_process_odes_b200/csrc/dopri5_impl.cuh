@@ -17,6 +17,7 @@ namespace cg = cooperative_groups;
 namespace {
 
 constexpr int kDpThreads = 128;
+constexpr int kDpSetThreads = 256;  // sets mode: one CTA per parameter set, up to 8 warps = 8 rows in flight
 
 // Dormand-Prince / Shampine tableau (float32 copies, like torchdiffeq's tableau cast to the state dtype)
 __device__ __constant__ float kBeta[6][6] = {
@@ -48,7 +49,10 @@ struct Dopri5Args {
     float* xs;        // [Tg,B,D]
     float* work;      // y | f | y1 | f1 | ymid  (5 x [B,D])
     double* red;      // 4 accumulators (3 rotating for the error norm + 1 spare), zeroed by the host
-    int32_t* stats;   // nfe, accepted, rejected, status
+    int32_t* stats;   // nfe, accepted, rejected, status  (sets mode: 4 per set)
+    // sets mode (batched Monte-Carlo prediction): CTA q integrates rows [q set_rows, (q+1) set_rows) with the packed
+    // block at packed + q set_stride and ITS OWN controller (error norm over the set's rows, as if called per set)
+    int64_t set_rows, set_stride;
     int max_attempts;
     // optional checkpoints of the ACCEPTED steps for the discrete adjoint (all NULL when not training)
     float* ck_y;      // [cap][B][D]    state at the start of accepted step n
@@ -98,33 +102,56 @@ __device__ __forceinline__ void vf_signed(const float* sp, int M, int S, float s
     }
 }
 
-template <int D, bool kWarp>
-__global__ void __launch_bounds__(kDpThreads) dopri5_kernel(const Dopri5Args a) {
+template <int D, bool kWarp, bool kSets = false>
+__global__ void __launch_bounds__(kSets ? kDpSetThreads : kDpThreads) dopri5_kernel(const Dopri5Args a) {
+    static_assert(!kSets || kWarp, "sets mode is warp-per-row");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ double sred[kDpThreads / 32];
+    __shared__ double sred[kDpSetThreads / 32];
+    __shared__ double sset[4];
     cg::grid_group grid = cg::this_grid();
-    const float* sp = stage_params(smem_raw, a.packed, a.total);
+    const float* sp = stage_params(smem_raw, a.packed + (kSets ? blockIdx.x * a.set_stride : 0), a.total);
     const int M = a.M, S = a.S;
     const int64_t B = a.B, plane = B * D;
     // gtid / gstride index ROWS: threads in the row-per-thread mode, warps in the warp-per-row mode (where every lane
     // of a warp carries the same row and only lane 0 stores and contributes to the error norm)
-    const int64_t gtid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / (kWarp ? 32 : 1);
-    const int64_t gstride = ((int64_t)gridDim.x * blockDim.x) / (kWarp ? 32 : 1);
+    const int64_t gtid = kSets ? (threadIdx.x >> 5)
+                               : ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / (kWarp ? 32 : 1);
+    const int64_t gstride = kSets ? (blockDim.x >> 5) : ((int64_t)gridDim.x * blockDim.x) / (kWarp ? 32 : 1);
+    const int64_t row_begin = kSets ? blockIdx.x * a.set_rows : 0;
+    const int64_t row_end = kSets ? row_begin + a.set_rows : B;
+    int32_t* const stats = a.stats + (kSets ? 4 * blockIdx.x : 0);
     const bool writer = !kWarp || (threadIdx.x & 31) == 0;
+    // the only cross-thread quantities: three sums of squares. Grid mode: float64 atomics + grid barrier; sets mode:
+    // the CTA is the whole "batch", so shared memory + __syncthreads.
+    auto publish = [&](double v, int slot) {
+        const double b = block_sum_to(v, sred);
+        if (threadIdx.x == 0) {
+            if constexpr (kSets) sset[slot] = b;
+            else atomicAdd(a.red + slot, b);
+        }
+    };
+    auto barrier = [&]() {
+        if constexpr (kSets) __syncthreads();
+        else grid.sync();
+    };
+    auto total_of = [&](int slot) -> double {
+        if constexpr (kSets) return sset[slot];
+        else return a.red[slot];
+    };
     float* Y = a.work;
     float* F = a.work + plane;
     float* Y1 = a.work + 2 * plane;
     float* F1 = a.work + 3 * plane;
     float* YM = a.work + 4 * plane;
     const float rtol = (float)a.rtol, atol = (float)a.atol;
-    const double n_elem = (double)B * (double)D;
+    const double n_elem = (double)(row_end - row_begin) * (double)D;
     // a decreasing grid is integrated as -f over -t, exactly what torchdiffeq's odeint does
     const double dir = (a.Tg > 1 && a.t[a.Tg - 1] < a.t[0]) ? -1.0 : 1.0;
     const float fsign = (float)dir;
 
     // ---- y = x0, f0 = f(t0, y0); d0, d1 of _select_initial_step ----
     double s0 = 0.0, s1 = 0.0;
-    for (int64_t row = gtid; row < B; row += gstride) {
+    for (int64_t row = row_begin + gtid; row < row_end; row += gstride) {
         float y[1][D], f[1][D];
         ldrow<D>(y, a.x0, row);
         vf_signed<D, kWarp>(sp, M, S, fsign, y, f);
@@ -142,19 +169,13 @@ __global__ void __launch_bounds__(kDpThreads) dopri5_kernel(const Dopri5Args a) 
         }
     }
     if (!writer) s0 = s1 = 0.0;  // warp-per-row mode: a row counts once
-    {
-        const double b0 = block_sum_to(s0, sred);
-        const double b1 = block_sum_to(s1, sred);
-        if (threadIdx.x == 0) {
-            atomicAdd(a.red + 0, b0);
-            atomicAdd(a.red + 1, b1);
-        }
-    }
-    grid.sync();
-    const float d0 = (float)sqrt(a.red[0] / n_elem), d1 = (float)sqrt(a.red[1] / n_elem);
+    publish(s0, 0);
+    publish(s1, 1);
+    barrier();
+    const float d0 = (float)sqrt(total_of(0) / n_elem), d1 = (float)sqrt(total_of(1) / n_elem);
     float h0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6f : 0.01f * d0 / d1;
     double s2 = 0.0;
-    for (int64_t row = gtid; row < B; row += gstride) {
+    for (int64_t row = row_begin + gtid; row < row_end; row += gstride) {
         float y[1][D], f[1][D], y1[1][D], f1[1][D];
         ldrow<D>(y, Y, row);
         ldrow<D>(f, F, row);
@@ -169,22 +190,21 @@ __global__ void __launch_bounds__(kDpThreads) dopri5_kernel(const Dopri5Args a) 
         }
     }
     if (!writer) s2 = 0.0;
-    {
-        const double b2 = block_sum_to(s2, sred);
-        if (threadIdx.x == 0) atomicAdd(a.red + 2, b2);
-    }
-    grid.sync();
+    publish(s2, 2);
+    barrier();
     double dt;
     {
-        const float d2 = (float)sqrt(a.red[2] / n_elem) / h0;
+        const float d2 = (float)sqrt(total_of(2) / n_elem) / h0;
         float h1;
         if (d1 <= 1e-15f && d2 <= 1e-15f) h1 = fmaxf(1e-6f, h0 * 1e-3f);
         else h1 = powf(0.01f / fmaxf(d1, d2), 1.0f / 5.0f);
         dt = (double)fminf(100.f * h0, h1);
     }
-    grid.sync();  // everyone has read red[0..2] before they are recycled as the rotating error accumulators
-    if (gtid == 0) a.red[0] = a.red[1] = a.red[2] = 0.0;
-    grid.sync();
+    barrier();  // everyone has read the three sums before their slots are recycled as the rotating error accumulators
+    if constexpr (!kSets) {
+        if (gtid == 0) a.red[0] = a.red[1] = a.red[2] = 0.0;
+    }
+    barrier();
 
     // ---- main loop: controller state replicated in every thread ----
     double t0 = dir * a.t[0], t1 = dir * a.t[0];
@@ -205,7 +225,7 @@ __global__ void __launch_bounds__(kDpThreads) dopri5_kernel(const Dopri5Args a) 
         }
         const float dts = (float)dt;
         double se = 0.0;
-        for (int64_t row = gtid; row < B; row += gstride) {
+        for (int64_t row = row_begin + gtid; row < row_end; row += gstride) {
             float y[1][D], k[7][1][D], yi[1][D];
             ldrow<D>(y, Y, row);
             ldrow<D>(k[0], F, row);
@@ -246,13 +266,12 @@ __global__ void __launch_bounds__(kDpThreads) dopri5_kernel(const Dopri5Args a) 
             }
         }
         if (!writer) se = 0.0;
-        {
-            const double be = block_sum_to(se, sred);
-            if (threadIdx.x == 0) atomicAdd(a.red + (attempt % 3), be);
+        publish(se, attempt % 3);
+        barrier();
+        const float ratio = (float)sqrt(total_of(attempt % 3) / n_elem);
+        if constexpr (!kSets) {
+            if (gtid == 0) a.red[(attempt + 2) % 3] = 0.0;
         }
-        grid.sync();
-        const float ratio = (float)sqrt(a.red[attempt % 3] / n_elem);
-        if (gtid == 0) a.red[(attempt + 2) % 3] = 0.0;
         const bool accept = ratio <= 1.0f;
         nfe += 6;
         if (accept) {
@@ -260,7 +279,7 @@ __global__ void __launch_bounds__(kDpThreads) dopri5_kernel(const Dopri5Args a) 
             // outputs that fall inside (t1, t1n]
             int jend = jout;
             while (jend < a.Tg && !(dir * a.t[jend] > t1n)) ++jend;
-            for (int64_t row = gtid; row < B; row += gstride) {
+            for (int64_t row = row_begin + gtid; row < row_end; row += gstride) {
                 float y[1][D], f[1][D], y1[1][D], f1[1][D], ym[1][D];
                 ldrow<D>(y1, Y1, row);
                 ldrow<D>(f1, F1, row);
@@ -322,10 +341,10 @@ __global__ void __launch_bounds__(kDpThreads) dopri5_kernel(const Dopri5Args a) 
     (void)t0;
     if (gtid == 0) {
         if (a.out_step != nullptr) a.out_step[0] = -1;
-        a.stats[0] = nfe;
-        a.stats[1] = n_acc;
-        a.stats[2] = n_rej;
-        a.stats[3] = status;
+        stats[0] = nfe;
+        stats[1] = n_acc;
+        stats[2] = n_rej;
+        stats[3] = status;
     }
 }
 
@@ -363,6 +382,8 @@ int launch_dopri5(const float* packed, int M, int S, const float* x0, const doub
     a.work = work;
     a.red = reinterpret_cast<double*>(work + 5 * plane + ((5 * plane) & 1));
     a.stats = stats;
+    a.set_rows = 0;
+    a.set_stride = 0;
     a.max_attempts = 1 << 20;
     a.ck_y = a.ck_k = a.ck_dt = a.out_x = nullptr;
     a.out_step = nullptr;
@@ -381,6 +402,33 @@ int launch_dopri5(const float* packed, int M, int S, const float* x0, const doub
     return 0;
 }
 
+// Batched Monte-Carlo prediction (no checkpoints): one CTA per parameter set, plain launch (no grid barrier needed).
+template <int D>
+int launch_dopri5_sets(const float* packed, int M, int S, int n_sets, int64_t set_rows, const float* x0,
+                       const double* t, int Tg, double rtol, double atol, float* xs, float* work, int32_t* stats,
+                       cudaStream_t st) {
+    const GpodeLayout L = gpode_layout(D, M, S);
+    const size_t smem = 16 + (size_t)L.total * 4;
+    GPODE_CUDA(cudaFuncSetAttribute(dopri5_kernel<D, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    Dopri5Args a;
+    a.packed = packed; a.M = M; a.S = S; a.total = L.total; a.x0 = x0; a.t = t; a.Tg = Tg;
+    a.B = set_rows * n_sets;
+    a.rtol = rtol; a.atol = atol; a.xs = xs;
+    a.work = work;
+    a.red = nullptr;
+    a.stats = stats;
+    a.set_rows = set_rows;
+    a.set_stride = L.total_all;
+    a.max_attempts = 1 << 20;
+    a.ck_y = a.ck_k = a.ck_dt = a.out_x = nullptr;
+    a.out_step = nullptr;
+    a.cap = 0;
+    int warps = (int)(set_rows < kDpSetThreads / 32 ? set_rows : kDpSetThreads / 32);
+    if (warps < 1) warps = 1;
+    dopri5_kernel<D, true, true><<<n_sets, warps * 32, smem, st>>>(a);
+    GPODE_LAUNCH_CHECK();
+    return 0;
+}
 
 // ------------------------------------------------------------------------------------------------------------------
 // Discrete adjoint of the accepted steps (step sizes are constants, exactly as torchdiffeq computes them under

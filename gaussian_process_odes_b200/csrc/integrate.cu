@@ -10,7 +10,9 @@
     int gpode_rk4_bwd_d##D_(const float*, int, int, const float*, int, int64_t, const float*, const float*,         \
                             const float*, float*, float*, float*, float*, cudaStream_t);                            \
     int gpode_vf_bwd_d##D_(const float*, int, int, const float*, const float*, const float*, float*, int64_t,       \
-                           float*, cudaStream_t);
+                           float*, cudaStream_t);                                                                   \
+    int gpode_fwd_sets_d##D_(const float*, int, int, int, int64_t, const float*, const float*, int, float*,         \
+                             cudaStream_t);
 GPODE_FOR_EACH_D(GPODE_DECL)
 #undef GPODE_DECL
 
@@ -59,6 +61,38 @@ extern "C" int gpode_rk4_fwd(const float* packed, int D, int M, int S, const flo
 #define CALL(D_) gpode_rk4_fwd_d##D_(packed, M, S, x0, t, Tg, B, xs, kstages, (cudaStream_t)stream)
     GPODE_SWITCH_D(D, CALL)
 #undef CALL
+}
+
+static int fwd_sets_dispatch(const float* packed, int D, int M, int S, int n_sets, int64_t set_rows, const float* x0,
+                             const float* t, int Tg, float* out, cudaStream_t st) {
+#define CALL(D_) gpode_fwd_sets_d##D_(packed, M, S, n_sets, set_rows, x0, t, Tg, out, st)
+    GPODE_SWITCH_D(D, CALL)
+#undef CALL
+}
+
+static int check_sets(int n_sets, int64_t set_rows) {
+    GPODE_CHECK_ARG(n_sets >= 1 && n_sets <= 65535, "n_sets=%d outside 1..65535", n_sets);
+    GPODE_CHECK_ARG(set_rows >= 0, "negative rows per set %lld", (long long)set_rows);
+    return 0;
+}
+
+extern "C" int gpode_vf_fwd_sets(const float* packed, int D, int M, int S, int n_sets, int64_t set_rows,
+                                 const float* x, float* f, void* stream) {
+    if (int rc = check_common(packed, D, M, S, set_rows)) return rc;
+    if (int rc = check_sets(n_sets, set_rows)) return rc;
+    if (set_rows == 0) return 0;
+    GPODE_CHECK_ARG(x && f, "x / f is NULL");
+    return fwd_sets_dispatch(packed, D, M, S, n_sets, set_rows, x, nullptr, 0, f, (cudaStream_t)stream);
+}
+
+extern "C" int gpode_rk4_fwd_sets(const float* packed, int D, int M, int S, int n_sets, int64_t set_rows,
+                                  const float* x0, const float* t, int Tg, float* xs, void* stream) {
+    if (int rc = check_common(packed, D, M, S, set_rows)) return rc;
+    if (int rc = check_sets(n_sets, set_rows)) return rc;
+    GPODE_CHECK_ARG(Tg >= 1, "time grid needs at least one point, got %d", Tg);
+    if (set_rows == 0) return 0;
+    GPODE_CHECK_ARG(x0 && t && xs, "x0 / t / xs is NULL");
+    return fwd_sets_dispatch(packed, D, M, S, n_sets, set_rows, x0, t, Tg, xs, (cudaStream_t)stream);
 }
 
 static int rk4_bwd_dispatch(const float* packed, int D, int M, int S, const float* t, int Tg, int64_t B,

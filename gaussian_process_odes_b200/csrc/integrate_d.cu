@@ -26,3 +26,7 @@ int GPODE_CAT(gpode_vf_bwd_d, GPODE_D)(const float* packed, int M, int S, const 
                                        const float* gf, float* gx, int64_t B, float* acc, cudaStream_t st) {
     return launch_vf_bwd<GPODE_D>(packed, M, S, x, f, gf, gx, B, acc, st);
 }
+int GPODE_CAT(gpode_fwd_sets_d, GPODE_D)(const float* packed, int M, int S, int n_sets, int64_t set_rows,
+                                         const float* x0, const float* t, int Tg, float* out, cudaStream_t st) {
+    return launch_fwd_sets<GPODE_D>(packed, M, S, n_sets, set_rows, x0, t, Tg, out, st);
+}

@@ -341,6 +341,43 @@ vf_fwd_warp_kernel(const float* __restrict__ packed, const int M, const int S, c
     }
 }
 
+// one trajectory, one warp: the whole fixed grid
+template <int D>
+__device__ __forceinline__ void rk4_row_warp(const float* sp, const int M, const int S, const float* __restrict__ x0,
+                                             const float* __restrict__ ts, const int Tg, const int64_t row,
+                                             const int64_t B, float* __restrict__ xs, float* __restrict__ kst,
+                                             const int lane) {
+    const int64_t plane = B * D;
+    float y[1][D];
+    load_rows<D, 1>(y, x0, row, B, 0);
+    if (lane == 0) store_rows<D, 1>(y, xs, row, B, 0);
+    for (int i = 0; i + 1 < Tg; ++i) {
+        const float dt = __fsub_rn(__ldg(ts + i + 1), __ldg(ts + i));
+        float k1[1][D], k2[1][D], k3[1][D], k4[1][D], ys[1][D];
+        vf_eval_warp<D>(sp, M, S, y, k1, lane);
+        stage2<D, 1>(ys, y, k1, dt);
+        vf_eval_warp<D>(sp, M, S, ys, k2, lane);
+        stage3<D, 1>(ys, y, k1, k2, dt);
+        vf_eval_warp<D>(sp, M, S, ys, k3, lane);
+        stage4<D, 1>(ys, y, k1, k2, k3, dt);
+        vf_eval_warp<D>(sp, M, S, ys, k4, lane);
+        if (kst != nullptr && lane == 0) {
+            float* kb = kst + (int64_t)i * 4 * plane;
+            store_rows<D, 1>(k1, kb, row, B, 0);
+            store_rows<D, 1>(k2, kb + plane, row, B, 0);
+            store_rows<D, 1>(k3, kb + 2 * plane, row, B, 0);
+            store_rows<D, 1>(k4, kb + 3 * plane, row, B, 0);
+        }
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            const float sum = __fadd_rn(__fadd_rn(k1[0][j], __fmul_rn(3.0f, __fadd_rn(k2[0][j], k3[0][j]))),
+                                        k4[0][j]);
+            y[0][j] = __fadd_rn(y[0][j], __fmul_rn(__fmul_rn(sum, dt), 0.125f));
+        }
+        if (lane == 0) store_rows<D, 1>(y, xs + (int64_t)(i + 1) * plane, row, B, 0);
+    }
+}
+
 template <int D>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 rk4_fwd_warp_kernel(const float* __restrict__ packed, const int M, const int S, const int total,
@@ -349,38 +386,44 @@ rk4_fwd_warp_kernel(const float* __restrict__ packed, const int M, const int S, 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const float* sp = stage_params(smem_raw, packed, total);
     const int lane = threadIdx.x & 31;
-    const int64_t plane = B * D;
     for (int64_t row = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); row < B;
-         row += (int64_t)gridDim.x * kWarpsPerCta) {
-        float y[1][D];
-        load_rows<D, 1>(y, x0, row, B, 0);
-        if (lane == 0) store_rows<D, 1>(y, xs, row, B, 0);
-        for (int i = 0; i + 1 < Tg; ++i) {
-            const float dt = __fsub_rn(__ldg(ts + i + 1), __ldg(ts + i));
-            float k1[1][D], k2[1][D], k3[1][D], k4[1][D], ys[1][D];
-            vf_eval_warp<D>(sp, M, S, y, k1, lane);
-            stage2<D, 1>(ys, y, k1, dt);
-            vf_eval_warp<D>(sp, M, S, ys, k2, lane);
-            stage3<D, 1>(ys, y, k1, k2, dt);
-            vf_eval_warp<D>(sp, M, S, ys, k3, lane);
-            stage4<D, 1>(ys, y, k1, k2, k3, dt);
-            vf_eval_warp<D>(sp, M, S, ys, k4, lane);
-            if (kst != nullptr && lane == 0) {
-                float* kb = kst + (int64_t)i * 4 * plane;
-                store_rows<D, 1>(k1, kb, row, B, 0);
-                store_rows<D, 1>(k2, kb + plane, row, B, 0);
-                store_rows<D, 1>(k3, kb + 2 * plane, row, B, 0);
-                store_rows<D, 1>(k4, kb + 3 * plane, row, B, 0);
-            }
-#pragma unroll
-            for (int j = 0; j < D; ++j) {
-                const float sum = __fadd_rn(__fadd_rn(k1[0][j], __fmul_rn(3.0f, __fadd_rn(k2[0][j], k3[0][j]))),
-                                            k4[0][j]);
-                y[0][j] = __fadd_rn(y[0][j], __fmul_rn(__fmul_rn(sum, dt), 0.125f));
-            }
-            if (lane == 0) store_rows<D, 1>(y, xs + (int64_t)(i + 1) * plane, row, B, 0);
-        }
+         row += (int64_t)gridDim.x * kWarpsPerCta)
+        rk4_row_warp<D>(sp, M, S, x0, ts, Tg, row, B, xs, kst, lane);
+}
+
+// ---- batched Monte-Carlo prediction: blockIdx.y = parameter set; set q owns rows [q set_rows, (q+1) set_rows) and the
+// packed block at packed + q set_stride (SURVEY.md 8b item 1 "n_sets", 8f item 3) ------------------------------------
+template <int D>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+vf_fwd_sets_kernel(const float* __restrict__ packed, const int M, const int S, const int total,
+                   const int64_t set_stride, const int64_t set_rows, const float* __restrict__ x,
+                   float* __restrict__ f) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const float* sp = stage_params(smem_raw, packed + blockIdx.y * set_stride, total);
+    const int lane = threadIdx.x & 31;
+    const int64_t B = set_rows * gridDim.y;
+    for (int64_t r = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); r < set_rows;
+         r += (int64_t)gridDim.x * kWarpsPerCta) {
+        const int64_t row = blockIdx.y * set_rows + r;
+        float xr[1][D], fr[1][D];
+        load_rows<D, 1>(xr, x, row, B, 0);
+        vf_eval_warp<D>(sp, M, S, xr, fr, lane);
+        if (lane == 0) store_rows<D, 1>(fr, f, row, B, 0);
     }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+rk4_fwd_sets_kernel(const float* __restrict__ packed, const int M, const int S, const int total,
+                    const int64_t set_stride, const int64_t set_rows, const float* __restrict__ x0,
+                    const float* __restrict__ ts, const int Tg, float* __restrict__ xs) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const float* sp = stage_params(smem_raw, packed + blockIdx.y * set_stride, total);
+    const int lane = threadIdx.x & 31;
+    const int64_t B = set_rows * gridDim.y;
+    for (int64_t r = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); r < set_rows;
+         r += (int64_t)gridDim.x * kWarpsPerCta)
+        rk4_row_warp<D>(sp, M, S, x0, ts, Tg, blockIdx.y * set_rows + r, B, xs, nullptr, lane);
 }
 
 template <int D>
@@ -665,6 +708,31 @@ int launch_rk4_fwd(const float* packed, int M, int S, const float* x0, const flo
     } else {
         if (int rc = shape_for(rk4_fwd_kernel<D, 1>, 1, B, smem, &ls)) return rc;
         rk4_fwd_kernel<D, 1><<<ls.grid, ls.threads, ls.smem, st>>>(packed, M, S, L.total, x0, t, Tg, B, xs, kst);
+    }
+    GPODE_LAUNCH_CHECK();
+    return 0;
+}
+
+// sets: grid = (CTAs per set, n_sets); a CTA never mixes rows of two sets
+template <int D>
+int launch_fwd_sets(const float* packed, int M, int S, int n_sets, int64_t set_rows, const float* x0, const float* t,
+                    int Tg, float* out, cudaStream_t st) {
+    const GpodeLayout L = gpode_layout(D, M, S);
+    const size_t smem = 16 + (size_t)L.total * 4;
+    const int threads = kWarpsPerCta * 32;
+    const int64_t per_set = (set_rows + kWarpsPerCta - 1) / kWarpsPerCta;
+    // enough CTAs per set to spread over the machine, never more than its rows need
+    int64_t want = ((int64_t)num_sms() * 4 + n_sets - 1) / n_sets;
+    if (want > per_set) want = per_set;
+    if (want < 1) want = 1;
+    const dim3 grid((unsigned)want, (unsigned)n_sets);
+    if (t == nullptr) {
+        GPODE_CUDA(cudaFuncSetAttribute(vf_fwd_sets_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        vf_fwd_sets_kernel<D><<<grid, threads, smem, st>>>(packed, M, S, L.total, L.total_all, set_rows, x0, out);
+    } else {
+        GPODE_CUDA(cudaFuncSetAttribute(rk4_fwd_sets_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rk4_fwd_sets_kernel<D><<<grid, threads, smem, st>>>(packed, M, S, L.total, L.total_all, set_rows, x0, t, Tg,
+                                                            out);
     }
     GPODE_LAUNCH_CHECK();
     return 0;

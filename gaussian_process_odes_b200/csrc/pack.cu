@@ -23,10 +23,20 @@ namespace {
 
 // One thread per packed record. Source layouts are the reference's cache tensors (src/core/dsvgp.py:100-103,122):
 // omega (j,s,k), phase (s,k), w (s,k), Z (m,j), nu (k,m), ell (k,j), var (k).
+// blockIdx.y = parameter set (batched Monte-Carlo prediction): omega / phase / w / nu carry a leading set dimension,
+// Z / ell / var are shared; the packed blocks follow each other at stride L.total_all.
 __global__ void pack_kernel(const GpodeLayout L, const float* __restrict__ omega, const float* __restrict__ phase,
                             const float* __restrict__ w, const float* __restrict__ Z, const float* __restrict__ nu,
                             const float* __restrict__ ell, const float* __restrict__ var, float* __restrict__ out) {
     const int D = L.D, M = L.M, S = L.S, S2 = L.S2;
+    {
+        const size_t set = blockIdx.y;
+        omega += set * D * S * D;
+        phase += set * S * D;
+        w += set * S * D;
+        if (nu) nu += set * D * M;
+        out += set * L.total_all;
+    }
     const int n_rff = D * S2, n_kern = M, n_il = D, n_mma = D * L.S8 * 32;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rff + n_kern + n_il + n_mma;
          i += gridDim.x * blockDim.x) {
@@ -86,15 +96,24 @@ __global__ void pack_kernel(const GpodeLayout L, const float* __restrict__ omega
 
 }  // namespace
 
-extern "C" int gpode_pack_cache(const gpode_cache_t* c, float* packed, void* stream) {
+static int pack_sets(const gpode_cache_t* c, int n_sets, float* packed, void* stream) {
     GPODE_CHECK_ARG(c != nullptr && packed != nullptr, "cache / packed is NULL");
+    GPODE_CHECK_ARG(n_sets >= 1 && n_sets <= 65535, "n_sets=%d outside 1..65535", n_sets);
     GPODE_CHECK_ARG(c->D >= 1 && c->D <= GPODE_MAX_D, "state dimension D=%d outside 1..%d", c->D, GPODE_MAX_D);
     GPODE_CHECK_ARG(c->M >= 1 && c->S >= 1, "M=%d and S=%d must be positive", c->M, c->S);
     GPODE_CHECK_ARG(c->omega && c->phase && c->w && c->Z && c->ell && c->var, "cache tensor is NULL");
     const GpodeLayout L = gpode_layout(c->D, c->M, c->S);
     const int n = c->D * L.S2 + c->M + c->D + c->D * L.S8 * 32;
-    pack_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(L, c->omega, c->phase, c->w, c->Z, c->nu, c->ell,
-                                                                   c->var, packed);
+    pack_kernel<<<dim3((n + 127) / 128, n_sets), 128, 0, (cudaStream_t)stream>>>(L, c->omega, c->phase, c->w, c->Z,
+                                                                                 c->nu, c->ell, c->var, packed);
     GPODE_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int gpode_pack_cache(const gpode_cache_t* c, float* packed, void* stream) {
+    return pack_sets(c, 1, packed, stream);
+}
+
+extern "C" int gpode_pack_cache_sets(const gpode_cache_t* c, int n_sets, float* packed, void* stream) {
+    return pack_sets(c, n_sets, packed, stream);
 }

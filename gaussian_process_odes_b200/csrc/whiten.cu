@@ -135,6 +135,42 @@ __global__ void whiten_fwd_kernel(const gpode_cache_t c, const float* __restrict
     for (int m = threadIdx.x; m < M; m += blockDim.x) nu_out[k * M + m] = (float)wv[m];
 }
 
+// Batched Monte-Carlo prediction: n_sets function draws share Z and the hyper-parameters, hence ONE factor L per
+// output dimension; a set only differs in p = rff_forward(Z) and u. One CTA per (output dim, set) reloads the float64
+// factor from L2 and does the two triangular solves: nu = L^-T (u - L^-1 p).
+template <typename Real>
+__global__ void whiten_solve_sets_kernel(gpode_cache_t c, const float* __restrict__ u,
+                                         const double* __restrict__ L_in, float* __restrict__ nu_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int k = blockIdx.x, M = c.M, D = c.D, S = c.S, ld = ld_for(M);
+    {
+        const size_t set = blockIdx.y;
+        c.omega += set * D * S * D;
+        c.phase += set * S * D;
+        c.w += set * S * D;
+        u += set * M * D;
+        nu_out += set * D * M;
+    }
+    Real* L = reinterpret_cast<Real*>(smem_raw);
+    double* pvec = reinterpret_cast<double*>(L + (size_t)M * ld + ((M * ld) & 1));
+    Real* sv = reinterpret_cast<Real*>(pvec + M);
+    for (int i = threadIdx.x; i < M * M; i += blockDim.x) {
+        const int m = i / M, n = i - m * M;
+        L[m * ld + n] = (Real)L_in[(size_t)k * M * M + i];
+    }
+    rff_at_Z(c, k, pvec);
+    __syncthreads();
+    for (int m = threadIdx.x; m < M; m += blockDim.x) sv[m] = (Real)pvec[m];
+    __syncthreads();
+    trsv_lower<Real>(L, M, ld, sv);
+    __syncthreads();
+    for (int m = threadIdx.x; m < M; m += blockDim.x) sv[m] = (Real)u[m * D + k] - sv[m];
+    __syncthreads();
+    trsv_lower_t<Real>(L, M, ld, sv);
+    __syncthreads();
+    for (int m = threadIdx.x; m < M; m += blockDim.x) nu_out[k * M + m] = (float)sv[m];
+}
+
 template <typename Real>
 __global__ void whiten_bwd_kernel(const gpode_cache_t c, const float* __restrict__ u, const double* __restrict__ L_in,
                                   const double* __restrict__ sp_in, const float* __restrict__ gnu,
@@ -324,6 +360,11 @@ size_t fwd_smem(int M) {
     return sizeof(Real) * ((size_t)(M + 1) * ld + 2) + sizeof(double) * M + sizeof(Real) * M + 16;
 }
 template <typename Real>
+size_t solve_smem(int M) {
+    const int ld = (M & 1) ? M : M + 1;
+    return sizeof(Real) * ((size_t)M * ld + 2) + sizeof(double) * M + sizeof(Real) * M + 16;
+}
+template <typename Real>
 size_t bwd_smem(int M, int D) {
     const int ld = (M & 1) ? M : M + 1;
     return sizeof(Real) * (2 * (size_t)M * ld + 4 * M + 2) + sizeof(double) * (D + 2) + 16;
@@ -355,6 +396,26 @@ extern "C" int gpode_whiten_fwd(const gpode_cache_t* c, const float* u, float ji
         const size_t smem = fwd_smem<float>(c->M);
         GPODE_CUDA(cudaFuncSetAttribute(whiten_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         whiten_fwd_kernel<float><<<c->D, threads, smem, (cudaStream_t)stream>>>(*c, u, jitter, nu_out, L_f64, s_f64);
+    }
+    GPODE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gpode_whiten_fwd_sets(const gpode_cache_t* c, const float* u, float jitter, int n_sets, float* nu_out,
+                                     double* L_f64, double* s_f64, void* stream) {
+    GPODE_CHECK_ARG(n_sets >= 1 && n_sets <= 65535, "n_sets=%d outside 1..65535", n_sets);
+    // factor once (set 0 rides along), then the per-set solves
+    if (int rc = gpode_whiten_fwd(c, u, jitter, nu_out, L_f64, s_f64, stream)) return rc;
+    if (n_sets == 1) return 0;
+    const int threads = c->M >= 64 ? 256 : 128;
+    if (c->M <= GPODE_MAX_M_F64) {
+        const size_t smem = solve_smem<double>(c->M);
+        GPODE_CUDA(cudaFuncSetAttribute(whiten_solve_sets_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        whiten_solve_sets_kernel<double><<<dim3(c->D, n_sets), threads, smem, (cudaStream_t)stream>>>(*c, u, L_f64, nu_out);
+    } else {
+        const size_t smem = solve_smem<float>(c->M);
+        GPODE_CUDA(cudaFuncSetAttribute(whiten_solve_sets_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        whiten_solve_sets_kernel<float><<<dim3(c->D, n_sets), threads, smem, (cudaStream_t)stream>>>(*c, u, L_f64, nu_out);
     }
     GPODE_LAUNCH_CHECK();
     return 0;

@@ -44,6 +44,13 @@ class BaseSequenceModel(nn.Module):
     def forward(self, x0, ts):
         return self.build_flow(x0, ts)
 
+    def forward_sets(self, x0, ts, rng="numpy"):
+        """``x0 (n,N,D)`` -> ``(n,N,T,D)``: ``forward`` for n independent GP draws in one launch (prediction only)."""
+        if self.ts_dense_scale < 2:
+            raise ValueError("ts_dense_scale must be >= 2")
+        dense = compute_ts_dense(ts, self.ts_dense_scale)
+        return self.flow.forward_sets(x0, dense, rng=rng)[:, :, ::self.ts_dense_scale - 1, :]
+
 
 class UniformSequenceModel(BaseSequenceModel):
     """Observations on a uniform time grid: every segment spans ``ts[:2]`` (reference ``models.py:88-146``)."""

@@ -437,3 +437,97 @@ def whiten(Z, ell, var, u, omega, phase, w, jitter=1e-5):
 
 def whitened_kl(Um, Us_sqrt_packed):
     return _WhitenedKL.apply(Um, Us_sqrt_packed)
+
+
+# ---- batched Monte-Carlo prediction: n_sets function draws per launch (forward only) ------------------------------
+def _sets_common(Z, ell, var, omega, phase, w):
+    Zc, ec, vc = f32(Z, "Z"), f32(ell, "ell"), f32(var, "var")
+    oc, wc = f32(omega, "omega"), f32(w, "w")
+    M, D = Zc.shape
+    if oc.ndim != 4 or wc.ndim != 3:
+        raise _lib.GpodeError("sets tensors need a leading n_sets axis: omega (n,D,S,D), w (n,S,D); got %s, %s"
+                              % (tuple(oc.shape), tuple(wc.shape)))
+    n, S = wc.shape[0], wc.shape[1]
+    if D > MAX_D_REGISTER:
+        raise _lib.GpodeError("batched prediction needs D <= %d, got %d" % (MAX_D_REGISTER, D))
+    pc_ = f32(phase, "phase").reshape(n, S, D)
+    if tuple(oc.shape) != (n, D, S, D) or tuple(wc.shape) != (n, S, D) or tuple(ec.shape) != (D, D):
+        raise _lib.GpodeError("inconsistent sets shapes: omega %s w %s ell %s" % (
+            tuple(oc.shape), tuple(wc.shape), tuple(ec.shape)))
+    return Zc, ec, vc, oc, pc_, wc, n, D, M, S
+
+
+def whiten_sets(Z, ell, var, u, omega, phase, w, jitter=1e-5):
+    """``u (n,M,D)`` and per-draw ``omega (n,D,S,D)``, ``phase (n,S,D)``, ``w (n,S,D)`` -> ``nu (n,D,M)``. One Kzz
+    factorisation for all draws (``gpode_whiten_fwd_sets``). No gradient."""
+    Zc, ec, vc, oc, pc_, wc, n, D, M, S = _sets_common(Z, ell, var, omega, phase, w)
+    uc = f32(u, "u")
+    if tuple(uc.shape) != (n, M, D):
+        raise _lib.GpodeError("u must be (%d,%d,%d), got %s" % (n, M, D, tuple(uc.shape)))
+    st = _cache_struct(D, M, S, oc, pc_, wc, Zc, None, ec, vc)
+    nu = torch.empty(n, D, M, dtype=torch.float32, device=Zc.device)
+    L = torch.empty(D, M, M, dtype=torch.float64, device=Zc.device)
+    sp = torch.empty(D, 2, M, dtype=torch.float64, device=Zc.device)
+    _lib.call("gpode_whiten_fwd_sets", ctypes.byref(st), ptr(uc), float(jitter), n, ptr(nu), ptr(L), ptr(sp),
+              stream_ptr())
+    return nu
+
+
+class PackedCacheSets:
+    """``n`` sampled GP functions sharing Z and the hyper-parameters, packed back to back (``gpode_pack_cache_sets``)."""
+
+    def __init__(self, Z, ell, var, nu, omega, phase, w):
+        lib = _lib.load()
+        self.keep = _sets_common(Z, ell, var, omega, phase, w)
+        Zc, ec, vc, oc, pc_, wc, self.n, self.D, self.M, self.S = self.keep
+        nc = f32(nu, "nu").reshape(self.n, self.D, self.M)
+        self.keep = self.keep + (nc,)
+        st = _cache_struct(self.D, self.M, self.S, oc, pc_, wc, Zc, nc, ec, vc)
+        stride = lib.gpode_packed_floats(self.D, self.M, self.S)
+        self.packed = torch.empty(self.n * stride, dtype=torch.float32, device=Zc.device)
+        _lib.call("gpode_pack_cache_sets", ctypes.byref(st), self.n, ptr(self.packed), stream_ptr())
+
+
+def _rows_of_sets(x, pcs, name):
+    xc = f32(x, name)
+    if xc.ndim != 3 or xc.shape[0] != pcs.n or xc.shape[2] != pcs.D:
+        raise _lib.GpodeError("%s must be (%d,N,%d), got %s" % (name, pcs.n, pcs.D, tuple(xc.shape)))
+    return xc, xc.shape[1]
+
+
+def vector_field_sets(x, Z, ell, var, nu, omega, phase, w):
+    """``x (n,N,D)`` -> ``f (n,N,D)``: draw q's vector field at its own N points, all draws in one launch."""
+    if torch.is_grad_enabled() and any(a.requires_grad for a in (x, Z, ell, var, nu)):
+        raise _lib.GpodeError("the batched (sets) path is forward only: call it under torch.no_grad()")
+    pcs = PackedCacheSets(Z, ell, var, nu, omega, phase, w)
+    xc, N = _rows_of_sets(x, pcs, "x")
+    f = torch.empty_like(xc)
+    _lib.call("gpode_vf_fwd_sets", ptr(pcs.packed), pcs.D, pcs.M, pcs.S, pcs.n, N, ptr(xc), ptr(f), stream_ptr())
+    return f
+
+
+def integrate_sets(x0, t, Z, ell, var, nu, omega, phase, w, method="dopri5", rtol=1e-6, atol=1e-6):
+    """``x0 (n,N,D)``, shared grid ``t (Tg,)`` -> ``(xs (n,N,Tg,D), stats)``: draw q integrates its own N trajectories
+    with its own function, exactly as n separate ``odeint`` calls would (dopri5: one controller per draw), in ONE
+    launch. ``stats``: device int32 ``(n,4)`` [nfe, accepted, rejected, status] for dopri5, ``None`` for rk4."""
+    if torch.is_grad_enabled() and any(a.requires_grad for a in (x0, Z, ell, var, nu)):
+        raise _lib.GpodeError("the batched (sets) path is forward only: call it under torch.no_grad()")
+    lib = _lib.load()
+    pcs = PackedCacheSets(Z, ell, var, nu, omega, phase, w)
+    xc, N = _rows_of_sets(x0, pcs, "x0")
+    Tg = t.shape[0]
+    xs = torch.empty(Tg, pcs.n * N, pcs.D, dtype=torch.float32, device=xc.device)
+    stats = None
+    if method == "rk4":
+        tc = f32(t.to(device=xc.device, dtype=torch.float32), "t")
+        _lib.call("gpode_rk4_fwd_sets", ptr(pcs.packed), pcs.D, pcs.M, pcs.S, pcs.n, N, ptr(xc), ptr(tc), Tg, ptr(xs),
+                  stream_ptr())
+    elif method == "dopri5":
+        t64 = t.detach().to(device=xc.device, dtype=torch.float64).contiguous()
+        work = torch.empty(lib.gpode_dopri5_work_floats(pcs.D, pcs.n * N), dtype=torch.float32, device=xc.device)
+        stats = torch.zeros(pcs.n, 4, dtype=torch.int32, device=xc.device)
+        _lib.call("gpode_dopri5_fwd_sets", ptr(pcs.packed), pcs.D, pcs.M, pcs.S, pcs.n, N, ptr(xc), ptr(t64), Tg,
+                  float(rtol), float(atol), ptr(xs), ptr(work), ptr(stats), stream_ptr())
+    else:
+        raise _lib.GpodeError("integrate_sets: method %r has no fused CUDA integrator (rk4, dopri5)" % (method,))
+    return xs.view(Tg, pcs.n, N, pcs.D).permute(1, 2, 0, 3), stats

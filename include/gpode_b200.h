@@ -144,6 +144,29 @@ int gpode_vf_fwd_large(const gpode_cache_t* cache, const float* x, float* f, int
 int gpode_rk4_fwd_large(const gpode_cache_t* cache, const float* x0, const float* t, int Tg, int64_t B, float* xs,
                         void* stream);
 
+/* ---- Batched Monte-Carlo prediction: n_sets function draws in one launch (SURVEY.md section 8b item 1 "n_sets",
+ * 8f item 3). Replaces the Python loop of compute_predictions / compute_test_predictions
+ * (src/gpode/model_builder.py:60-96, src/gpode_shooting/mocap_model_builder.py:85-119), which rebuilds the cache
+ * and integrates once per sample. A "sets" cache carries a leading n_sets dimension on the per-draw tensors
+ * (omega [n,D,S,D], phase [n,S,D], w [n,S,D], nu [n,D,M]); Z, ell, var are shared. Set q owns rows
+ * [q set_rows, (q+1) set_rows) of x / x0 / xs ([n_sets*set_rows, D] resp. [Tg, n_sets*set_rows, D]) and the packed
+ * block at packed + q * gpode_packed_floats(D,M,S). Forward only (prediction runs under no_grad). */
+int gpode_pack_cache_sets(const gpode_cache_t* cache_sets, int n_sets, float* packed, void* stream);
+/* u [n_sets,M,D] -> nu_out [n_sets,D,M]: Kzz is factorised ONCE (it does not depend on the draw), then one CTA per
+ * (output dim, set) does the two triangular solves. L_f64 [D,M,M], s_f64 [D,2,M]: float64 scratch. */
+int gpode_whiten_fwd_sets(const gpode_cache_t* cache_sets_without_nu, const float* u, float jitter, int n_sets,
+                          float* nu_out, double* L_f64, double* s_f64, void* stream);
+int gpode_vf_fwd_sets(const float* packed, int D, int M, int S, int n_sets, int64_t set_rows, const float* x,
+                      float* f, void* stream);
+int gpode_rk4_fwd_sets(const float* packed, int D, int M, int S, int n_sets, int64_t set_rows, const float* x0,
+                       const float* t, int Tg, float* xs, void* stream);
+/* dopri5 with one controller PER SET (error norm over that set's rows: exactly the reference loop, which calls
+ * odeint once per sample): one CTA per set, no grid barrier. work: gpode_dopri5_work_floats(D, n_sets*set_rows);
+ * stats_out: 4 int32 per set. */
+int gpode_dopri5_fwd_sets(const float* packed, int D, int M, int S, int n_sets, int64_t set_rows, const float* x0,
+                          const double* t, int Tg, double rtol, double atol, float* xs, float* work,
+                          int32_t* stats_out, void* stream);
+
 /* ---- ELBO side terms either side of the integrator -------------------------------
  * Full-rank Gaussian state posteriors N(mean_r, L_r L_r^T + jitter I), r < R, L_r given as the PACKED lower triangle
  * (the optvar of transforms.LowerTriangular / StackedLowerTriangular, src/misc/transforms.py:70-76,105-112).

@@ -127,15 +127,32 @@ def run_prediction(n_samples=64):
     p, ys, ts, draws, _ = O.make_problem(seed=121, **c)
     model = build_product_model("gpode", p, ys, c["S"], "dopri5", ts_dense_scale=2)
     tsd = ts.cuda()
-    builders.compute_predictions(model, tsd, eval_sample_size=4)
+    builders.compute_predictions(model, tsd, eval_sample_size=4, batched=False)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    out = builders.compute_predictions(model, tsd, eval_sample_size=n_samples)
+    out = builders.compute_predictions(model, tsd, eval_sample_size=n_samples, batched=False)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     res = dict(prediction=True, config="vdp_gpode_notebook", solver="dopri5", samples=n_samples,
                it_per_s=n_samples / dt, ms_per_sample=dt / n_samples * 1e3, out_shape=list(out.shape),
                reference_it_per_s=3.54)
+    # all draws in one whitening + pack + integrator launch (n_sets path)
+    for rng in ("numpy", "device"):
+        for ns in (128, 1024):
+            builders.compute_predictions(model, tsd, eval_sample_size=ns, rng=rng)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(5):
+                outb = builders.compute_predictions(model, tsd, eval_sample_size=ns, rng=rng)
+            torch.cuda.synchronize()
+            dtb = (time.perf_counter() - t0) / 5
+            res["batched_%s_%d_it_per_s" % (rng, ns)] = ns / dtb
+            res["batched_%s_%d_ms_total" % (rng, ns)] = dtb * 1e3
+    res["batched_out_shape"] = list(outb.shape)
+    from gaussian_process_odes_b200 import _lib
+    _lib.profile_start()
+    builders.compute_predictions(model, tsd, eval_sample_size=128, rng="device")
+    res["batched_128_kernels_ms"] = {k: round(v[1], 4) for k, v in _lib.profile_stop().items()}
     try:
         from gaussian_process_odes_b200 import graphs
         gp = graphs.GraphedPrediction(model, tsd)
