@@ -106,3 +106,33 @@ def sharded_shooting_loss(model, ys_local, ts, num_samples, n_global, world):
     ll, cons, ent, k0 = model.build_lowerbound_terms(ys_local, ts, num_samples=num_samples)
     kl = model.build_inducing_kl()
     return combine_shard_terms(ll, cons, ent, k0, kl, ys_local.shape[0], n_global, world)
+
+
+# ---- prediction: the Monte-Carlo draws are independent caches -> shard the draws -------------
+def gather_draws(local, n_total):
+    """All-gather per-rank blocks of draws ``(n_local, ...)`` (block sizes from ``shard_range``) into the full
+    ``(n_total, ...)`` tensor, in rank order, on every rank."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return local
+    world = dist.get_world_size()
+    sizes = [shard_range(n_total, r, world) for r in range(world)]
+    biggest = max(hi - lo for lo, hi in sizes)
+    pad = torch.zeros((biggest,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad)
+    return torch.cat([parts[r][:hi - lo] for r, (lo, hi) in enumerate(sizes)], 0)
+
+
+def sharded_predictions(model, ts, eval_sample_size, predict_fn=None, **kwargs):
+    """``compute_predictions`` with the draws split across ranks: rank r computes draws ``shard_range(S, r, world)``
+    through the batched n_sets path and every rank receives all ``(S,N,T,D)`` trajectories. Seed numpy / torch
+    differently per rank (``seed_ranks`` keeps numpy identical on purpose -- for prediction offset it by the rank),
+    otherwise every rank would integrate the same functions."""
+    from . import builders
+    rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    lo, hi = shard_range(eval_sample_size, rank, world)
+    fn = builders.compute_predictions if predict_fn is None else predict_fn
+    local = fn(model, ts, eval_sample_size=hi - lo, **kwargs)
+    return gather_draws(local, eval_sample_size)

@@ -86,3 +86,33 @@ def test_sharded_elbo_and_gradient_allreduce(tmp_path):
     err = float((got["state_mean_grad"] - pp["state_mean"].grad[lo:hi]).abs().max()
                 / pp["state_mean"].grad.abs().max())
     assert err <= 1e-9
+
+
+def _pred_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port), CUDA_VISIBLE_DEVICES="")
+    from gaussian_process_odes_b200 import distributed
+    torch.set_num_threads(1)
+    r, w, _ = distributed.init_from_env(backend="gloo")
+    S, N, T, D = 7, 2, 5, 3  # 7 draws over 2 ranks: blocks of 4 and 3
+
+    def fake_predict(model, ts, eval_sample_size):  # stands in for the CUDA n_sets path: draw q -> constant q
+        lo, _ = distributed.shard_range(S, r, w)
+        ids = torch.arange(lo, lo + eval_sample_size, dtype=torch.float32)
+        return ids.view(-1, 1, 1, 1).expand(eval_sample_size, N, T, D).contiguous()
+
+    full = distributed.sharded_predictions(None, None, S, predict_fn=fake_predict)
+    if r == 1:
+        torch.save(full, out)
+    torch.distributed.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_sharded_predictions_gathers_draws_in_rank_order(tmp_path):
+    out = str(tmp_path / "rank1.pt")
+    port = 29950 + os.getpid() % 40
+    mp.spawn(_pred_worker, args=(2, port, out), nprocs=2, join=True)
+    full = torch.load(out)
+    assert full.shape == (7, 2, 5, 3)
+    assert torch.equal(full[:, 0, 0, 0], torch.arange(7, dtype=torch.float32))
