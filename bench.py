@@ -93,6 +93,17 @@ class ClockSampler:
         self.index, self.proc, self.lines = index, None, []
 
     def start(self):
+        # NVML polled from a thread every ~5 ms (the timed region is a fraction of a second); nvidia-smi as fallback
+        self.samples, self.halt, self.nv = [], threading.Event(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = (pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nv = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
@@ -102,11 +113,36 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv, h = self.nv
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons",
+                              getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons", None))
+        while not self.halt.is_set():
+            try:
+                mask = int(get_reasons(h)) if get_reasons else 0
+                self.samples.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)),
+                                     float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)),
+                                     nv.nvmlDeviceGetPowerUsage(h) / 1000.0,
+                                     [n for n, b in bits.items() if mask & b]))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nv is not None:
+            self.halt.set()
+            self.thread.join(timeout=1)
+            sm = [x[0] for x in self.samples]
+            reasons = sorted({r for x in self.samples for r in x[3]})
+            return dict(sm_mhz=float(np.median(sm)) if sm else None,
+                        sm_max_mhz=max(x[1] for x in self.samples) if sm else None,
+                        power_w_max=max(x[2] for x in self.samples) if sm else None, samples=len(sm),
+                        source="nvml", reasons=reasons)
         if self.proc is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
         self.proc.terminate()

@@ -59,8 +59,15 @@ struct GpodeLayout {
     // tensor-core (mma.sync m16n8k8 tf32) operand blocks, appended after `total`, one record per (output k, tile of
     // 8 features):  mma  : 80 floats = 64 theta-B fragment (lane-major b0,b1) | 16 (phase, phase', a, a') per quad lane
     //               mmag : 64 floats = G-B fragment (lane-major b0,b1), used by the adjoint only
-    int S8, off_mma, off_mmag, total_all;
+    int S8, off_mma, off_mmag;
+    // tcgen05 (UMMA) operand block, one record of GPODE_UMMA_REC(SU) floats per output k:
+    //   B_hi [SU x 8] | B_lo [SU x 8] | a [SU]   (SU = S rounded up to 32)   -- B = (Omega_k | phase | 0)^T, features x padded input dims, in
+    //   the canonical K-major no-swizzle shared-memory layout of the MMA (8-feature x 16-byte core matrices: feature s,
+    //   slot q at float (s/8) 64 + (q/4) 32 + (s%8) 4 + q%4), pre-split into tf32 hi / lo parts; slot D carries the
+    //   phase (the state tile carries a constant 1 there), so theta leaves the tensor core complete. D <= 7 only.
+    int SU, off_umma, total_all;
 };
+#define GPODE_UMMA_REC(SU) (17 * (SU))
 #define GPODE_MMA_REC 80
 #define GPODE_MMAG_REC 64
 
@@ -81,7 +88,9 @@ __host__ __device__ inline GpodeLayout gpode_layout(int D, int M, int S) {
     L.S8 = (S + 7) / 8;
     L.off_mma = L.total;
     L.off_mmag = L.off_mma + D * L.S8 * GPODE_MMA_REC;
-    L.total_all = L.off_mmag + D * L.S8 * GPODE_MMAG_REC;
+    L.SU = (S + 31) & ~31;  // features padded to whole 32-column TMEM loads (zero weight)
+    L.off_umma = L.off_mmag + D * L.S8 * GPODE_MMAG_REC;
+    L.total_all = L.off_umma + (D <= 7 ? D * GPODE_UMMA_REC(L.SU) : 0);
     return L;
 }
 

@@ -38,7 +38,8 @@ __global__ void pack_kernel(const GpodeLayout L, const float* __restrict__ omega
         out += set * L.total_all;
     }
     const int n_rff = D * S2, n_kern = M, n_il = D, n_mma = D * L.S8 * 32;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rff + n_kern + n_il + n_mma;
+    const int n_umma = D <= 7 ? D * L.SU : 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rff + n_kern + n_il + n_mma + n_umma;
          i += gridDim.x * blockDim.x) {
         if (i < n_rff) {
             const int k = i / S2, s2 = i - k * S2;
@@ -64,6 +65,23 @@ __global__ void pack_kernel(const GpodeLayout L, const float* __restrict__ omega
             float* o = out + L.off_il + (size_t)j * L.WP;
             for (int k = 0; k < L.WP; ++k)
                 o[k] = k < D ? -GPODE_HALF_LOG2E / (ell[k * D + j] * ell[k * D + j]) : 0.f;
+        } else if (i >= n_rff + n_kern + n_il + n_mma) {
+            // tcgen05 operand rows: one feature s of output k (see GpodeLayout)
+            const int q = i - n_rff - n_kern - n_il - n_mma;
+            const int k = q / L.SU, sidx = q - k * L.SU;
+            float* rec = out + L.off_umma + (size_t)k * GPODE_UMMA_REC(L.SU);
+            float* bh = rec + (sidx >> 3) * 64 + (sidx & 7) * 4;
+            float* bl = bh + 8 * L.SU;
+            const bool ok = sidx < S;
+            for (int slot = 0; slot < 8; ++slot) {
+                float v = 0.f;
+                if (ok && slot < D) v = omega[((size_t)slot * S + sidx) * D + k];
+                else if (ok && slot == D) v = phase[sidx * D + k];
+                const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+                bh[(slot >> 2) * 32 + (slot & 3)] = hi;
+                bl[(slot >> 2) * 32 + (slot & 3)] = v - hi;
+            }
+            rec[16 * L.SU + sidx] = ok ? w[sidx * D + k] * sqrtf(var[k] / (float)S) : 0.f;
         } else {
             // tensor-core operand fragments of one (k, feature tile) for one lane (g = lane / 4, t = lane % 4)
             const int q = i - n_rff - n_kern - n_il;
@@ -103,7 +121,7 @@ static int pack_sets(const gpode_cache_t* c, int n_sets, float* packed, void* st
     GPODE_CHECK_ARG(c->M >= 1 && c->S >= 1, "M=%d and S=%d must be positive", c->M, c->S);
     GPODE_CHECK_ARG(c->omega && c->phase && c->w && c->Z && c->ell && c->var, "cache tensor is NULL");
     const GpodeLayout L = gpode_layout(c->D, c->M, c->S);
-    const int n = c->D * L.S2 + c->M + c->D + c->D * L.S8 * 32;
+    const int n = c->D * L.S2 + c->M + c->D + c->D * L.S8 * 32 + (c->D <= 7 ? c->D * L.SU : 0);
     pack_kernel<<<dim3((n + 127) / 128, n_sets), 128, 0, (cudaStream_t)stream>>>(L, c->omega, c->phase, c->w, c->Z,
                                                                                  c->nu, c->ell, c->var, packed);
     GPODE_LAUNCH_CHECK();

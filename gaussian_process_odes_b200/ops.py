@@ -531,3 +531,15 @@ def integrate_sets(x0, t, Z, ell, var, nu, omega, phase, w, method="dopri5", rto
     else:
         raise _lib.GpodeError("integrate_sets: method %r has no fused CUDA integrator (rk4, dopri5)" % (method,))
     return xs.view(Tg, pcs.n, N, pcs.D).permute(1, 2, 0, 3), stats
+
+
+def vector_field_umma(x, Z, ell, var, nu, omega, phase, w):
+    """EXPERIMENTAL, forward only, 2 <= D <= 7: ``vector_field`` with the Fourier-feature projection on the tcgen05
+    tensor cores (``gpode_vf_fwd_umma``: 3xTF32 in TMEM accumulators)."""
+    pc = PackedCache(Z, ell, var, nu, omega, phase, w)
+    xc = f32(x, "x")
+    if xc.ndim != 2 or xc.shape[1] != pc.D:
+        raise _lib.GpodeError("x must be (B,%d), got %s" % (pc.D, tuple(xc.shape)))
+    f = torch.empty_like(xc)
+    _lib.call("gpode_vf_fwd_umma", ptr(pc.packed), pc.D, pc.M, pc.S, ptr(xc), ptr(f), xc.shape[0], stream_ptr())
+    return f

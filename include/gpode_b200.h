@@ -194,6 +194,10 @@ int gpode_loglik_sum(const float* pred, const float* ys, const float* W, const f
 int gpode_constraint_sum(const float* ss, const float* pred, const float* scale, int64_t SN, int T, int D, int laplace,
                          double* sum_out, float* grad_ss, float* grad_pred, void* stream);
 
+/* EXPERIMENTAL (2 <= D <= 7): gpode_vf_fwd with the Fourier-feature projection on the 5th-generation tensor cores
+ * (tcgen05.mma kind::tf32, 3xTF32 error compensation, accumulators in TMEM); same arguments and results. */
+int gpode_vf_fwd_umma(const float* packed, int D, int M, int S, const float* x, float* f, int64_t B, void* stream);
+
 /* Measurement utility (no reference counterpart): sustained FP32 FMA throughput of the current device in TFLOP/s
  * (best of 5 launches of a register-only FMA loop; synchronises the stream). scratch: >= 1 float (device). */
 int gpode_probe_fp32_fma(double* tflops_out_host, double* ms_out_host, float* scratch, void* stream);
