@@ -177,6 +177,27 @@ def test_large_state_dimension_forward(D, M, S, B):
         ops.vector_field(xg, *args)
 
 
+@pytest.mark.parametrize("D,M,S,B", [(16, 100, 256, 300), (33, 20, 64, 40)])
+def test_large_state_dimension_dopri5(D, M, S, B):
+    """8 < D <= 64: the adaptive solver (host-driven controller around the tiled kernel) against the restated dopri5."""
+    from gaussian_process_odes_b200 import ops
+    gp32, c32, gp64, c64, x = _setup(D, M, S, B, seed=D, nu_scale=0.1)
+    args = _cuda_args(gp32, c32)
+    ts = torch.tensor([0.0, 0.05, 0.32], dtype=torch.float32)
+    with torch.no_grad():
+        xs, stats = ops.dopri5_integrate(x.cuda(), ts.cuda(), *args)
+        back, _ = ops.dopri5_integrate(xs[-1].contiguous(), torch.flip(ts, [0]).cuda(), *args)
+    st = {}
+    ref32 = O.odeint(lambda t, y: O.vf_forward(y, gp32['Z'], gp32['ell'], gp32['var'], c32), x, ts, method='dopri5',
+                     rtol=1e-6, atol=1e-6, stats=st)
+    nfe, acc, rej, status = [int(v) for v in stats.cpu()]
+    assert status == 0 and nfe == 2 + 6 * (acc + rej)
+    assert abs(acc - st['accepted']) <= 1 and abs(rej - st['rejected']) <= 1
+    assert torch.equal(xs[0].cpu(), x)
+    assert relerr(xs.cpu(), ref32) <= TOL_TRAJ
+    assert relerr(back[-1].cpu(), x) <= TOL_TRAJ  # decreasing grid: integrate back to the start
+
+
 def test_rk4_decreasing_grid():
     """odeint accepts a decreasing grid (used by initialize_latents_with_data, model_initialization.py:70-73)."""
     from gaussian_process_odes_b200 import ops
