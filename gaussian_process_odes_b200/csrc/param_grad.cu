@@ -27,7 +27,7 @@ param_grad_kernel(const float* __restrict__ packed, const int M, const int S, co
     constexpr int RP = VfShape<D>::RP, KS = VfShape<D>::KS, WP = VfShape<D>::WP;
     constexpr int DP = (D + 3) & ~3;
     constexpr int RW = 2 * DP;  // floats per staged row: y padded to DP, cotangent padded to DP
-    __shared__ __align__(16) float srow[kPgTile * RW];
+    __shared__ __align__(16) float srow[2][kPgTile * RW];  // double buffer: tile t+1 lands while tile t is consumed
 
     const float* __restrict__ kern = packed + D * ((((S + 1) >> 1) + 31) & ~31) * RP;
     const float* __restrict__ wnp = kern + M * KS;  // -w, [j][WP] with outputs k along the row
@@ -65,21 +65,49 @@ param_grad_kernel(const float* __restrict__ packed, const int M, const int S, co
 
     const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta;
     const int64_t r_end = r_begin + rows_per_cta < VR ? r_begin + rows_per_cta : VR;
-    for (int64_t base = r_begin; base < r_end; base += kPgTile) {
-        const int n = (int)((r_end - base) < kPgTile ? (r_end - base) : kPgTile);
-        __syncthreads();
-        for (int i = threadIdx.x; i < n * D; i += blockDim.x) {
-            const int r = i / D, j = i - r * D;
-            srow[r * RW + j] = __ldg(ys + base * D + i);
-            srow[r * RW + DP + j] = __ldg(kbs + base * D + i);
+    // each thread moves up to kPre (y, cotangent) element pairs of a tile: global -> registers (in flight during the
+    // compute of the previous tile) -> shared memory; one barrier per tile
+    constexpr int kPre = (kPgTile * D + 127) / 128;  // the CTA has at least 128 threads
+    float py[kPre], pk[kPre];
+    auto fetch = [&](const int64_t base, const int n) {
+#pragma unroll
+        for (int q = 0; q < kPre; ++q) {
+            const int i = threadIdx.x + q * blockDim.x;
+            const bool ok = i < n * D;
+            py[q] = ok ? __ldg(ys + base * D + i) : 0.f;
+            pk[q] = ok ? __ldg(kbs + base * D + i) : 0.f;
         }
-        __syncthreads();
+    };
+    auto stash = [&](float* __restrict__ dst, const int n) {
+#pragma unroll
+        for (int q = 0; q < kPre; ++q) {
+            const int i = threadIdx.x + q * blockDim.x;
+            if (i < n * D) {
+                const int r = i / D, j = i - r * D;
+                dst[r * RW + j] = py[q];
+                dst[r * RW + DP + j] = pk[q];
+            }
+        }
+    };
+    auto tile_rows = [&](const int64_t base) { return (int)((r_end - base) < kPgTile ? (r_end - base) : kPgTile); };
+    int buf = 0;
+    if (r_begin < r_end) {
+        fetch(r_begin, tile_rows(r_begin));
+        stash(srow[0], tile_rows(r_begin));
+    }
+    __syncthreads();
+    for (int64_t base = r_begin; base < r_end; base += kPgTile, buf ^= 1) {
+        const int n = tile_rows(base);
+        const int64_t next = base + kPgTile;
+        const int n_next = next < r_end ? tile_rows(next) : 0;
+        if (n_next) fetch(next, n_next);
+        const float* __restrict__ cur = srow[buf];
         if (active) {
 #pragma unroll 2
             for (int r = group; r < n; r += G) {
                 float y[DP], kb[DP];
-                lds_vec<DP>(y, srow + r * RW);
-                lds_vec<DP>(kb, srow + r * RW + DP);
+                lds_vec<DP>(y, cur + r * RW);
+                lds_vec<DP>(kb, cur + r * RW + DP);
                 float d[D], dd[D];
 #pragma unroll
                 for (int j = 0; j < D; ++j) {
@@ -101,6 +129,8 @@ param_grad_kernel(const float* __restrict__ packed, const int M, const int S, co
                 }
             }
         }
+        if (n_next) stash(srow[buf ^ 1], n_next);  // the other buffer's readers finished before the previous barrier
+        __syncthreads();
     }
     if (active) {
         const GpodeAcc a = gpode_acc_layout(D, M);
