@@ -53,6 +53,8 @@ SIGNATURES = {
     "gpode_dopri5_ckpt_floats": (_L, [_I, _L, _I, _I]),
     "gpode_dopri5_fwd": (_I, [_P, _I, _I, _I, _P, _P, _I, _L, _D, _D, _P, _P, _P, _P, _I, _P]),
     "gpode_dopri5_bwd": (_I, [_P, _I, _I, _I, _P, _I, _L, _P, _P, _I, _I, _P, _P, _P, _P]),
+    "gpode_dopri5_bwd_dev": (_I, [_P, _I, _I, _I, _P, _I, _L, _P, _P, _I, _P, _P, _P, _P, _P]),
+    "gpode_param_grad_dev": (_I, [_P, _I, _I, _I, _P, _P, _L, _P, _L, _P, _P]),
     "gpode_vf_fwd_umma": (_I, [_P, _I, _I, _I, _P, _P, _L, _P]),
     "gpode_pack_cache_sets": (_I, [_CP, _I, _P, _P]),
     "gpode_whiten_fwd_sets": (_I, [_CP, _P, _F, _I, _P, _P, _P, _P]),
@@ -123,7 +125,9 @@ KERNELS_PER_CALL = {"gpode_pack_cache": 1, "gpode_vf_fwd": 1, "gpode_vf_bwd": 1,
                     "gpode_rk4_bwd": 1, "gpode_param_grad": 1, "gpode_grads_finalize": 1, "gpode_whiten_fwd": 1, "gpode_whiten_bwd": 1,
                     "gpode_kl_fwd": 1, "gpode_kl_bwd": 1, "gpode_dopri5_fwd": 1, "gpode_dopri5_bwd": 1, "gpode_state_fwd": 1, "gpode_state_bwd": 1,
                     "gpode_loglik_sum": 1, "gpode_constraint_sum": 1, "gpode_vf_fwd_large": 1, "gpode_rk4_fwd_large": 1,
-                    "gpode_vf_fwd_umma": 1, "gpode_pack_cache_sets": 1, "gpode_whiten_fwd_sets": 2, "gpode_vf_fwd_sets": 1,
+                    "gpode_dopri5_bwd_dev": (_I, [_P, _I, _I, _I, _P, _I, _L, _P, _P, _I, _P, _P, _P, _P, _P]),
+    "gpode_param_grad_dev": (_I, [_P, _I, _I, _I, _P, _P, _L, _P, _L, _P, _P]),
+    "gpode_dopri5_bwd_dev": 1, "gpode_param_grad_dev": 1, "gpode_vf_fwd_umma": 1, "gpode_pack_cache_sets": 1, "gpode_whiten_fwd_sets": 2, "gpode_vf_fwd_sets": 1,
                     "gpode_rk4_fwd_sets": 1, "gpode_dopri5_fwd_sets": 1}
 LAUNCH_COUNT = {}
 _PROFILE = None  # None, or {name: [(start_event, end_event), ...]}

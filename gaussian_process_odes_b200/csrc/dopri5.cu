@@ -5,7 +5,7 @@
     int gpode_dopri5_fwd_d##D_(const float*, int, int, const float*, const double*, int, int64_t, double, double, \
                                float*, float*, int32_t*, float*, int, cudaStream_t);                              \
     int gpode_dopri5_bwd_d##D_(const float*, int, int, const double*, int, int64_t, const float*, const float*,   \
-                               int, int, float*, float*, float*, cudaStream_t);                                   \
+                               int, int, const int32_t*, float*, float*, float*, cudaStream_t);                   \
     int gpode_dopri5_sets_d##D_(const float*, int, int, int, int64_t, const float*, const double*, int, double,   \
                                 double, float*, float*, int32_t*, cudaStream_t);
 GPODE_DECL(1) GPODE_DECL(2) GPODE_DECL(3) GPODE_DECL(4) GPODE_DECL(5) GPODE_DECL(6) GPODE_DECL(7) GPODE_DECL(8)
@@ -60,7 +60,8 @@ extern "C" int gpode_dopri5_bwd(const float* packed, int D, int M, int S, const 
     switch (D) {
 #define GPODE_CASE(D_) \
     case D_:           \
-        return gpode_dopri5_bwd_d##D_(packed, M, S, t, Tg, B, grad_xs, ckpt, cap, n_accepted, grad_x0, vrows, acc, st);
+        return gpode_dopri5_bwd_d##D_(packed, M, S, t, Tg, B, grad_xs, ckpt, cap, n_accepted, nullptr, grad_x0, vrows, \
+                                      acc, st);
         GPODE_CASE(1) GPODE_CASE(2) GPODE_CASE(3) GPODE_CASE(4) GPODE_CASE(5) GPODE_CASE(6) GPODE_CASE(7) GPODE_CASE(8)
 #undef GPODE_CASE
     }
@@ -80,6 +81,24 @@ extern "C" int gpode_dopri5_fwd_sets(const float* packed, int D, int M, int S, i
 #define GPODE_CASE(D_) \
     case D_:           \
         return gpode_dopri5_sets_d##D_(packed, M, S, n_sets, set_rows, x0, t, Tg, rtol, atol, xs, work, stats_out, st);
+        GPODE_CASE(1) GPODE_CASE(2) GPODE_CASE(3) GPODE_CASE(4) GPODE_CASE(5) GPODE_CASE(6) GPODE_CASE(7) GPODE_CASE(8)
+#undef GPODE_CASE
+    }
+    return -1;
+}
+
+extern "C" int gpode_dopri5_bwd_dev(const float* packed, int D, int M, int S, const double* t, int Tg, int64_t B,
+                                    const float* grad_xs, const float* ckpt, int cap, const int32_t* stats_dev,
+                                    float* grad_x0, float* vrows, float* acc, void* stream) {
+    if (int rc = check(packed, D, M, S, B, Tg)) return rc;
+    if (B == 0) return 0;
+    GPODE_CHECK_ARG(t && grad_xs && ckpt && stats_dev && grad_x0 && vrows && acc, "NULL argument");
+    GPODE_CHECK_ARG(cap > 0, "cap=%d must be positive", cap);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (D) {
+#define GPODE_CASE(D_) \
+    case D_:           \
+        return gpode_dopri5_bwd_d##D_(packed, M, S, t, Tg, B, grad_xs, ckpt, cap, 0, stats_dev, grad_x0, vrows, acc, st);
         GPODE_CASE(1) GPODE_CASE(2) GPODE_CASE(3) GPODE_CASE(4) GPODE_CASE(5) GPODE_CASE(6) GPODE_CASE(7) GPODE_CASE(8)
 #undef GPODE_CASE
     }

@@ -14,9 +14,10 @@ int GPODE_CAT(gpode_dopri5_fwd_d, GPODE_D)(const float* packed, int M, int S, co
 }
 
 int GPODE_CAT(gpode_dopri5_bwd_d, GPODE_D)(const float* packed, int M, int S, const double* t, int Tg, int64_t B,
-                                           const float* gxs, const float* ckpt, int cap, int n_acc, float* gx0,
-                                           float* vrows, float* acc, cudaStream_t st) {
-    return launch_dopri5_bwd<GPODE_D>(packed, M, S, t, Tg, B, gxs, ckpt, cap, n_acc, gx0, vrows, acc, st);
+                                           const float* gxs, const float* ckpt, int cap, int n_acc,
+                                           const int32_t* stats_dev, float* gx0, float* vrows, float* acc,
+                                           cudaStream_t st) {
+    return launch_dopri5_bwd<GPODE_D>(packed, M, S, t, Tg, B, gxs, ckpt, cap, n_acc, stats_dev, gx0, vrows, acc, st);
 }
 
 int GPODE_CAT(gpode_dopri5_sets_d, GPODE_D)(const float* packed, int M, int S, int n_sets, int64_t set_rows,

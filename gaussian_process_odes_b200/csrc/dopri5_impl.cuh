@@ -350,9 +350,35 @@ __global__ void __launch_bounds__(kSets ? kDpSetThreads : kDpThreads) dopri5_ker
 
 }  // namespace
 
+// checkpoint block layout documented at gpode_dopri5_ckpt_floats
+inline void dopri5_set_ckpt(Dopri5Args& a, float* ckpt, int cap, int64_t plane, int Tg) {
+    a.ck_y = a.ck_k = a.ck_dt = a.out_x = nullptr;
+    a.out_step = nullptr;
+    a.cap = 0;
+    if (ckpt != nullptr && cap > 0) {
+        a.cap = cap;
+        a.ck_y = ckpt;
+        a.ck_k = a.ck_y + (int64_t)cap * plane;
+        a.ck_dt = a.ck_k + (int64_t)cap * 7 * plane;
+        a.out_x = a.ck_dt + cap;
+        a.out_step = reinterpret_cast<int32_t*>(a.out_x + Tg);
+    }
+}
+
+template <int D>
+int launch_dopri5_sets(const float* packed, int M, int S, int n_sets, int64_t set_rows, const float* x0,
+                       const double* t, int Tg, double rtol, double atol, float* xs, float* work, int32_t* stats,
+                       cudaStream_t st, float* ckpt = nullptr, int cap = 0);
+
+// a batch this small is one "set": a single CTA (one warp per row, __syncthreads instead of the grid barrier) runs the
+// whole solve -- the reference's own plain-GPODE shapes (N = 1 / 6 trajectories)
+constexpr int64_t kDpOneCtaRows = 16;
+
 template <int D>
 int launch_dopri5(const float* packed, int M, int S, const float* x0, const double* t, int Tg, int64_t B, double rtol,
                   double atol, float* xs, float* work, int32_t* stats, float* ckpt, int cap, cudaStream_t st) {
+    if (B <= kDpOneCtaRows)
+        return launch_dopri5_sets<D>(packed, M, S, 1, B, x0, t, Tg, rtol, atol, xs, work, stats, st, ckpt, cap);
     const GpodeLayout L = gpode_layout(D, M, S);
     const size_t smem = 16 + (size_t)L.total * 4;
     // small batches: one warp per row (the reference's N = 1 / 6 trajectories, a few thousand shooting segments)
@@ -385,17 +411,7 @@ int launch_dopri5(const float* packed, int M, int S, const float* x0, const doub
     a.set_rows = 0;
     a.set_stride = 0;
     a.max_attempts = 1 << 20;
-    a.ck_y = a.ck_k = a.ck_dt = a.out_x = nullptr;
-    a.out_step = nullptr;
-    a.cap = 0;
-    if (ckpt != nullptr && cap > 0) {  // layout documented at gpode_dopri5_ckpt_floats
-        a.cap = cap;
-        a.ck_y = ckpt;
-        a.ck_k = a.ck_y + (int64_t)cap * plane;
-        a.ck_dt = a.ck_k + (int64_t)cap * 7 * plane;
-        a.out_x = a.ck_dt + cap;
-        a.out_step = reinterpret_cast<int32_t*>(a.out_x + Tg);
-    }
+    dopri5_set_ckpt(a, ckpt, cap, plane, Tg);
     GPODE_CUDA(cudaMemsetAsync(a.red, 0, 4 * sizeof(double), st));
     void* params[] = {(void*)&a};
     GPODE_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kDpThreads), params, smem, st));
@@ -406,7 +422,7 @@ int launch_dopri5(const float* packed, int M, int S, const float* x0, const doub
 template <int D>
 int launch_dopri5_sets(const float* packed, int M, int S, int n_sets, int64_t set_rows, const float* x0,
                        const double* t, int Tg, double rtol, double atol, float* xs, float* work, int32_t* stats,
-                       cudaStream_t st) {
+                       cudaStream_t st, float* ckpt, int cap) {
     const GpodeLayout L = gpode_layout(D, M, S);
     const size_t smem = 16 + (size_t)L.total * 4;
     GPODE_CUDA(cudaFuncSetAttribute(dopri5_kernel<D, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -420,9 +436,7 @@ int launch_dopri5_sets(const float* packed, int M, int S, int n_sets, int64_t se
     a.set_rows = set_rows;
     a.set_stride = L.total_all;
     a.max_attempts = 1 << 20;
-    a.ck_y = a.ck_k = a.ck_dt = a.out_x = nullptr;
-    a.out_step = nullptr;
-    a.cap = 0;
+    dopri5_set_ckpt(a, n_sets == 1 ? ckpt : nullptr, cap, a.B * D, Tg);  // checkpoints: single-set (training) use only
     int warps = (int)(set_rows < kDpSetThreads / 32 ? set_rows : kDpSetThreads / 32);
     if (warps < 1) warps = 1;
     dopri5_kernel<D, true, true><<<n_sets, warps * 32, smem, st>>>(a);
@@ -446,6 +460,8 @@ struct Dopri5BwdArgs {
     const float* gxs;     // [Tg,B,D]
     const float* ckpt;    // forward checkpoints
     int cap, n_acc;
+    const int32_t* stats_dev;  // optional: the forward's stats block; n_acc is then read on the device (stats[1]) so
+                               // that no host round trip sits between forward and backward (CUDA-graph capture)
     float* gx0;           // [B,D]
     float* vy;            // virtual rows: stage inputs  [(6 n_acc + 1)][B][D]
     float* vk;            //               cotangents
@@ -465,7 +481,8 @@ __global__ void __launch_bounds__(kDpThreads) dopri5_bwd_kernel(const Dopri5BwdA
 #pragma unroll
         for (int j = 0; j < D; ++j) A[k][j] = 0.f;
     }
-    const int M = a.M, S = a.S, Tg = a.Tg, cap = a.cap, n_acc = a.n_acc;
+    const int M = a.M, S = a.S, Tg = a.Tg, cap = a.cap;
+    const int n_acc = a.stats_dev != nullptr ? min(a.stats_dev[1], cap) : a.n_acc;
     const int64_t B = a.B, plane = B * D;
     const float* ck_y = a.ckpt;
     const float* ck_k = ck_y + (int64_t)cap * plane;
@@ -588,7 +605,8 @@ __global__ void __launch_bounds__(kDpThreads) dopri5_bwd_kernel(const Dopri5BwdA
 
 template <int D>
 int launch_dopri5_bwd(const float* packed, int M, int S, const double* t, int Tg, int64_t B, const float* gxs,
-                      const float* ckpt, int cap, int n_acc, float* gx0, float* vrows, float* acc, cudaStream_t st) {
+                      const float* ckpt, int cap, int n_acc, const int32_t* stats_dev, float* gx0, float* vrows,
+                      float* acc, cudaStream_t st) {
     const GpodeLayout L = gpode_layout(D, M, S);
     const size_t smem = 16 + (size_t)(L.total + D * D + D) * 4;
     GPODE_CUDA(cudaFuncSetAttribute(dopri5_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -605,8 +623,9 @@ int launch_dopri5_bwd(const float* packed, int M, int S, const double* t, int Tg
     const int64_t cap_grid = (int64_t)sms * occ;
     Dopri5BwdArgs a;
     a.packed = packed; a.M = M; a.S = S; a.total = L.total; a.t = t; a.Tg = Tg; a.B = B; a.gxs = gxs; a.ckpt = ckpt;
-    a.cap = cap; a.n_acc = n_acc; a.gx0 = gx0;
-    const int64_t VR = ((int64_t)6 * n_acc + 1) * B;
+    a.cap = cap; a.n_acc = n_acc; a.stats_dev = stats_dev; a.gx0 = gx0;
+    // cotangent rows start after the stage-input rows: exact count, or the capacity when the count lives on the device
+    const int64_t VR = ((int64_t)6 * (stats_dev != nullptr ? cap : n_acc) + 1) * B;
     a.vy = vrows;
     a.vk = vrows + VR * D;
     a.acc = acc;

@@ -17,7 +17,8 @@ GPODE_FOR_EACH_D(GPODE_DECL)
 #undef GPODE_DECL
 
 int gpode_param_grad_launch(const float* packed, int D, int M, int S, const float* ys, const float* kbs, int64_t VR,
-                            float* acc, cudaStream_t stream);  // param_grad.cu
+                            float* acc, cudaStream_t stream, const int32_t* stats_dev = nullptr,
+                            int64_t rows_per_step = 0);  // param_grad.cu
 
 static int check_common(const float* packed, int D, int M, int S, int64_t B) {
     GPODE_CHECK_ARG(packed != nullptr, "packed parameter block is NULL");
@@ -144,6 +145,16 @@ extern "C" int gpode_param_grad(const float* packed, int D, int M, int S, const 
     if (n_rows == 0) return 0;
     GPODE_CHECK_ARG(ys && kbs && acc, "NULL argument");
     return gpode_param_grad_launch(packed, D, M, S, ys, kbs, n_rows, acc, (cudaStream_t)stream);
+}
+
+extern "C" int gpode_param_grad_dev(const float* packed, int D, int M, int S, const float* ys, const float* kbs,
+                                    int64_t n_rows_max, const int32_t* stats_dev, int64_t rows_per_step, float* acc,
+                                    void* stream) {
+    if (int rc = check_common(packed, D, M, S, n_rows_max)) return rc;
+    if (n_rows_max == 0) return 0;
+    GPODE_CHECK_ARG(ys && kbs && acc && stats_dev, "NULL argument");
+    return gpode_param_grad_launch(packed, D, M, S, ys, kbs, n_rows_max, acc, (cudaStream_t)stream, stats_dev,
+                                   rows_per_step);
 }
 
 extern "C" int64_t gpode_vrow_floats(int D, int64_t n_virtual_rows) { return 2 * n_virtual_rows * (int64_t)D; }

@@ -22,8 +22,14 @@ constexpr int kPgTile = 128;  // virtual rows staged per pass
 template <int D>
 __global__ void __launch_bounds__(kPgThreads)
 param_grad_kernel(const float* __restrict__ packed, const int M, const int S, const float* __restrict__ ys,
-                  const float* __restrict__ kbs, const int64_t VR, const int64_t rows_per_cta,
-                  float* __restrict__ acc) {
+                  const float* __restrict__ kbs, const int64_t VR_host, const int64_t rows_per_cta,
+                  float* __restrict__ acc, const int32_t* __restrict__ stats_dev, const int64_t rows_per_step) {
+    // row count: the host's, or (6 accepted_steps + 1) rows_per_step read from the dopri5 stats block on the device
+    int64_t VR = VR_host;
+    if (stats_dev != nullptr) {
+        const int64_t live = ((int64_t)6 * stats_dev[1] + 1) * rows_per_step;
+        VR = live < VR_host ? live : VR_host;
+    }
     constexpr int RP = VfShape<D>::RP, KS = VfShape<D>::KS, WP = VfShape<D>::WP;
     constexpr int DP = (D + 3) & ~3;
     constexpr int RW = 2 * DP;  // floats per staged row: y padded to DP, cotangent padded to DP
@@ -168,7 +174,7 @@ __global__ void grads_finalize_kernel(const int D, const int M, const float* __r
 }  // namespace
 
 int gpode_param_grad_launch(const float* packed, int D, int M, int S, const float* ys, const float* kbs, int64_t VR,
-                            float* acc, cudaStream_t stream) {
+                            float* acc, cudaStream_t stream, const int32_t* stats_dev, int64_t rows_per_step) {
     if (VR == 0) return 0;
     int sms = 148, dev = 0;
     cudaGetDevice(&dev);
@@ -185,7 +191,8 @@ int gpode_param_grad_launch(const float* packed, int D, int M, int S, const floa
     switch (D) {
 #define GPODE_PG_CASE(D_)                                                                                        \
     case D_:                                                                                                     \
-        param_grad_kernel<D_><<<grid, threads, 0, stream>>>(packed, M, S, ys, kbs, VR, rows_per_cta, acc);    \
+        param_grad_kernel<D_><<<grid, threads, 0, stream>>>(packed, M, S, ys, kbs, VR, rows_per_cta, acc,     \
+                                                            stats_dev, rows_per_step);                        \
         break;
         GPODE_PG_CASE(1) GPODE_PG_CASE(2) GPODE_PG_CASE(3) GPODE_PG_CASE(4)
         GPODE_PG_CASE(5) GPODE_PG_CASE(6) GPODE_PG_CASE(7) GPODE_PG_CASE(8)

@@ -10,8 +10,10 @@ work is drawing the GP cache's random numbers with numpy (same generator, same o
     for it in range(n):
         loss = step()          # parameters' .grad hold the new gradients; call optimizer.step() yourself
 
-Only solver='rk4' (and dopri5 under no_grad) can be captured: the adaptive solver's training path reads its step
-count on the host.
+Both solvers can be captured. For dopri5 the number of accepted steps stays on the device (the adjoint and the
+gradient contraction read it there, ``gpode_dopri5_bwd_dev`` / ``gpode_param_grad_dev``) and the checkpoint capacity is
+fixed at capture time (8 x grid length, at least 64 steps); ``GraphedStep.check()`` reads the solver status back and
+raises if an integration ran out of capacity or failed.
 """
 import numpy as np
 import torch
@@ -100,11 +102,25 @@ class GraphedStep:
                 p.grad = None
             self.graph = torch.cuda.CUDAGraph()
             self.draws.cursor = 0
+            from . import ops as _ops
+            n_before = len(_ops.DEVICE_COUNT_STATS)
             with torch.cuda.graph(self.graph):
                 self.loss = loss_fn()
                 self.loss.backward()
+            self.dopri5_stats = _ops.DEVICE_COUNT_STATS[n_before:]   # static tensors of the captured integrations
+            del _ops.DEVICE_COUNT_STATS[n_before:]
         finally:
             self.draws.uninstall()
+
+    def check(self):
+        """Synchronises and raises if a captured dopri5 integration of the LAST replay failed (status 1 attempt limit,
+        2 step-size underflow, 3 checkpoint capacity exceeded). Returns the list of [nfe, accepted, rejected, status]."""
+        out = [[int(v) for v in s.cpu()] for s in self.dopri5_stats]
+        for st in out:
+            if st[3] != 0:
+                from ._lib import GpodeError
+                raise GpodeError("captured dopri5 integration failed: status %d (accepted %d steps)" % (st[3], st[1]))
+        return out
 
     def __call__(self):
         """New GP draw (host numpy -> static buffers), replay fwd+bwd; returns the static loss tensor."""

@@ -363,6 +363,17 @@ def rk4_integrate(x0, t, Z, ell, var, nu, omega, phase, w):
     return _RK4.apply(x0, t, Z, ell, var, nu, omega, phase, w, torch.is_grad_enabled())
 
 
+# dopri5 training without a host round trip (CUDA-graph capture): fixed checkpoint capacity, accepted-step count read on
+# the device by the backward kernels. The stats blocks of such integrations are collected here so that a caller
+# (graphs.GraphedStep.check) can verify status == 0 after the fact.
+DEVICE_COUNT_MODE = False          # force the device-count path outside capture (tests)
+DEVICE_COUNT_STATS = []
+
+
+def _device_count_mode():
+    return DEVICE_COUNT_MODE or torch.cuda.is_current_stream_capturing()
+
+
 class _Dopri5(torch.autograd.Function):
     """xs = odeint(f, x0, t, method='dopri5') (torchdiffeq 0.2.0 controller) via gpode_dopri5_fwd / gpode_dopri5_bwd."""
 
@@ -381,6 +392,17 @@ class _Dopri5(torch.autograd.Function):
         stats = torch.zeros(4, dtype=torch.int32, device=xc.device)
         cap = max(32, 4 * Tg) if need_grad else 0
         ckpt, n_acc = None, 0
+        ctx.on_device = need_grad and _device_count_mode()
+        if ctx.on_device:
+            cap = max(64, 8 * Tg)  # no retry possible without the host: generous capacity, status 3 if exceeded
+            ckpt = torch.empty(lib.gpode_dopri5_ckpt_floats(pc.D, B, Tg, cap), dtype=torch.float32, device=xc.device)
+            _lib.call("gpode_dopri5_fwd", ptr(pc.packed), pc.D, pc.M, pc.S, ptr(xc), ptr(t64), Tg, B, float(rtol),
+                      float(atol), ptr(xs), ptr(work), ptr(stats), ptr(ckpt), cap, stream_ptr())
+            DEVICE_COUNT_STATS.append(stats)
+            ctx.pc, ctx.nu_shape, ctx.cap, ctx.n_acc = pc, nu.shape, cap, -1
+            ctx.save_for_backward(t64, ckpt, stats)
+            ctx.mark_non_differentiable(stats)
+            return xs, stats
         while True:
             if need_grad:
                 ckpt = torch.empty(lib.gpode_dopri5_ckpt_floats(pc.D, B, Tg, cap), dtype=torch.float32,
@@ -407,11 +429,21 @@ class _Dopri5(torch.autograd.Function):
     def backward(ctx, gxs, _gstats):
         lib = _lib.load()
         pc = ctx.pc
-        t64, ckpt = ctx.saved_tensors
         gxs = f32(gxs, "grad_xs")
         Tg, B, D = gxs.shape
         gx0 = torch.empty(B, D, dtype=torch.float32, device=gxs.device)
         acc = pc.new_acc()
+        if ctx.on_device:
+            t64, ckpt, stats = ctx.saved_tensors
+            n_max = (6 * ctx.cap + 1) * B
+            vrows = torch.empty(lib.gpode_vrow_floats(D, n_max), dtype=torch.float32, device=gxs.device)
+            _lib.call("gpode_dopri5_bwd_dev", ptr(pc.packed), pc.D, pc.M, pc.S, ptr(t64), Tg, B, ptr(gxs), ptr(ckpt),
+                      ctx.cap, ptr(stats), ptr(gx0), ptr(vrows), ptr(acc), stream_ptr())
+            _lib.call("gpode_param_grad_dev", ptr(pc.packed), pc.D, pc.M, pc.S, ptr(vrows), ptr(vrows[n_max * D:]),
+                      n_max, ptr(stats), B, ptr(acc), stream_ptr())
+            g_Z, g_ell, g_var, g_nu = pc.finalize(acc)
+            return gx0, None, g_Z, g_ell, g_var, g_nu.reshape(ctx.nu_shape), None, None, None, None, None, None
+        t64, ckpt = ctx.saved_tensors
         n_vr = (6 * ctx.n_acc + 1) * B
         vrows = torch.empty(lib.gpode_vrow_floats(D, n_vr), dtype=torch.float32, device=gxs.device)
         _lib.call("gpode_dopri5_bwd", ptr(pc.packed), pc.D, pc.M, pc.S, ptr(t64), Tg, B, ptr(gxs), ptr(ckpt), ctx.cap,

@@ -138,6 +138,17 @@ int gpode_dopri5_bwd(const float* packed, int D, int M, int S, const double* t, 
                      const float* grad_xs, const float* ckpt, int cap, int n_accepted, float* grad_x0, float* vrows,
                      float* acc, void* stream);
 
+/* The same two steps with the accepted-step count left ON THE DEVICE (stats_dev = the forward's stats_out), so that
+ * nothing between forward and backward needs the host and the whole dopri5 training step can be captured in a CUDA
+ * graph. vrows must hold the capacity, gpode_vrow_floats(D, (6 cap + 1) B) floats; the cotangent rows start at row
+ * (6 cap + 1) B. gpode_param_grad_dev contracts the first (6 stats_dev[1] + 1) * rows_per_step of n_rows_max rows. */
+int gpode_dopri5_bwd_dev(const float* packed, int D, int M, int S, const double* t, int Tg, int64_t B,
+                         const float* grad_xs, const float* ckpt, int cap, const int32_t* stats_dev, float* grad_x0,
+                         float* vrows, float* acc, void* stream);
+int gpode_param_grad_dev(const float* packed, int D, int M, int S, const float* ys, const float* kbs,
+                         int64_t n_rows_max, const int32_t* stats_dev, int64_t rows_per_step, float* acc,
+                         void* stream);
+
 /* Forward-only paths for 8 < D <= GPODE_MAX_D_LARGE (the upper half of the scaling sweep): same arithmetic as
  * gpode_vf_fwd / gpode_rk4_fwd, state tiles in shared memory, Omega streamed from L2; they take the RAW cache. */
 int gpode_vf_fwd_large(const gpode_cache_t* cache, const float* x, float* f, int64_t B, void* stream);

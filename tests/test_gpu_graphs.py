@@ -113,3 +113,66 @@ def test_graphed_prediction_matches_eager(solver):
     many = pred.sample_many(5)
     assert many.shape == (5, 1, 25, 2) and torch.isfinite(many).all()
     assert relerr(many[0], many[1]) > 1e-3  # different function draws
+
+
+@pytest.mark.parametrize("name,kind", [("vdp_gpode_rk4", "gpode"), ("vdp_shooting_rk4", "shooting")])
+def test_dopri5_device_count_path_equals_host_count_path(name, kind):
+    """dopri5 training with the accepted-step count left on the device (what CUDA-graph capture uses) gives the
+    gradients of the default path, which reads the count on the host."""
+    from gaussian_process_odes_b200 import builders, ops
+    from gaussian_process_odes_b200.core import states
+    g = load_golden(name)
+    ys, ts = g['ys'].cuda(), g['ts'].cuda()
+    fixed = {}
+
+    def fixed_noise(shape, dtype, device):
+        key = tuple(shape)
+        if key not in fixed:
+            fixed[key] = torch.randn(shape, dtype=dtype, device=device)
+        return fixed[key]
+
+    def run(device_count):
+        m = build_product_model(kind, g['p'], g['ys'], 256, "dopri5", ts_dense_scale=4)
+        np.random.seed(4)
+        ops.DEVICE_COUNT_MODE = device_count
+        try:
+            if kind == "gpode":
+                loss = builders.compute_loss_gpode(m, ys, ts)[0]
+            else:
+                loss = builders.compute_loss_shooting(m, ys, ts, num_samples=3)[0]
+            loss.backward()
+        finally:
+            ops.DEVICE_COUNT_MODE = False
+        return loss.detach(), {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}
+
+    saved = states._standard_normal
+    states._standard_normal = fixed_noise
+    try:
+        l_host, g_host = run(False)
+        l_dev, g_dev = run(True)
+    finally:
+        states._standard_normal = saved
+        del ops.DEVICE_COUNT_STATS[:]
+    assert relerr(l_dev, l_host) <= 1e-6
+    assert set(g_host) == set(g_dev)
+    for n in g_host:
+        assert relerr(g_dev[n], g_host[n]) <= 1e-4, n
+
+
+def test_graphed_step_with_dopri5_trains_and_reports_status():
+    """The reference's DEFAULT solver inside a captured training step (plain GPODE on VDP data)."""
+    from gaussian_process_odes_b200 import builders, graphs
+    g = load_golden("vdp_gpode_rk4")
+    ys, ts = g['ys'].cuda(), g['ts'].cuda()
+    m = build_product_model("gpode", g['p'], g['ys'], 256, "dopri5", ts_dense_scale=4)
+    step = graphs.GraphedStep(m, lambda: builders.compute_loss_gpode(m, ys, ts)[0])
+    assert len(step.dopri5_stats) == 1
+    opt = torch.optim.Adam(m.parameters(), lr=5e-3)
+    losses = []
+    for _ in range(15):
+        loss = step()
+        opt.step()
+        losses.append(float(loss))
+    stats = step.check()
+    assert stats[0][3] == 0 and stats[0][0] == 2 + 6 * (stats[0][1] + stats[0][2]) and stats[0][1] > 5
+    assert all(np.isfinite(losses)) and min(losses[-3:]) < losses[0]

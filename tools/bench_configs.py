@@ -93,7 +93,7 @@ def run_config(name, c, solver, do_cpu):
                 builders.compute_loss_shooting(model, ysd, tsd, num_samples=c["S_mc"])
 
     out = dict(config=name, solver=solver, rows=(c["S_mc"] * c["N"] * c["T"] if c["kind"] == "shooting" else c["N"]))
-    if solver == "rk4":
+    if True:  # both solvers: dopri5 training is captured with the accepted-step count left on the device
         out["gpu_fwd_bwd_ms"] = gpu_time(step)
         out["gpu_fwd_bwd_wall_ms"] = wall_time(step)
         from gaussian_process_odes_b200 import graphs
@@ -104,6 +104,8 @@ def run_config(name, c, solver, do_cpu):
                                                                                     num_samples=c["S_mc"])[0])
         out["gpu_fwd_bwd_graphed_ms"] = gpu_time(gstep)
         out["gpu_fwd_bwd_graphed_wall_ms"] = wall_time(gstep)
+        if solver == "dopri5":
+            out["graphed_dopri5_stats"] = gstep.check()
     out["gpu_fwd_ms"] = gpu_time(fwd)
     out["nfe"] = model.flow.num_evals()
     if do_cpu:
