@@ -1,9 +1,11 @@
 """Variational posteriors of the initial state q(x0) and of the shooting states q(s_1..T) (mirror of reference
 ``src/core/states.py``; same class names, parameter names and shapes).
 
-These are ELBO side terms that stay PyTorch, written as batched tensor algebra:
-N(m, L L^T + 1e-5 I) is sampled through one batched Cholesky (what ``MultivariateNormal`` does internally, without
-its host-synchronising argument validation), the entropy is the closed form 0.5 D (1 + log 2 pi) + sum log diag."""
+ELBO side terms either side of the integrator: on a CUDA device
+N(m, L L^T + 1e-5 I) is sampled and its entropy taken by the fused ``gpode_state_fwd/_bwd`` kernels straight from the
+packed lower-triangular parameters (one thread per D x D matrix); the spelled-out tensor algebra below -- one batched
+Cholesky, what ``MultivariateNormal`` does internally without its host-synchronising argument validation, and the
+closed-form entropy 0.5 D (1 + log 2 pi) + sum log diag -- serves host-side checks and D > 8."""
 import math
 
 import numpy as np
