@@ -55,6 +55,11 @@ SIGNATURES = {
     "gpode_dopri5_bwd": (_I, [_P, _I, _I, _I, _P, _I, _L, _P, _P, _I, _I, _P, _P, _P, _P]),
     "gpode_dopri5_bwd_dev": (_I, [_P, _I, _I, _I, _P, _I, _L, _P, _P, _I, _P, _P, _P, _P, _P]),
     "gpode_param_grad_dev": (_I, [_P, _I, _I, _I, _P, _P, _L, _P, _L, _P, _P]),
+    "gpode_packed_large_floats": (_L, [_I, _I, _I]),
+    "gpode_rbf_fwd_large": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _L, _P]),
+    "gpode_pack_cache_large": (_I, [_CP, _P, _P]),
+    "gpode_rff_fwd_large": (_I, [_P, _I, _I, _P, _P, _L, _P]),
+    "gpode_vf_fwd_large_add_rbf": (_I, [_CP, _P, _P, _P, _L, _P]),
     "gpode_vf_fwd_umma": (_I, [_P, _I, _I, _I, _P, _P, _L, _P]),
     "gpode_pack_cache_sets": (_I, [_CP, _I, _P, _P]),
     "gpode_whiten_fwd_sets": (_I, [_CP, _P, _F, _I, _P, _P, _P, _P]),
@@ -127,7 +132,7 @@ KERNELS_PER_CALL = {"gpode_pack_cache": 1, "gpode_vf_fwd": 1, "gpode_vf_bwd": 1,
                     "gpode_loglik_sum": 1, "gpode_constraint_sum": 1, "gpode_vf_fwd_large": 1, "gpode_rk4_fwd_large": 1,
                     "gpode_dopri5_bwd_dev": (_I, [_P, _I, _I, _I, _P, _I, _L, _P, _P, _I, _P, _P, _P, _P, _P]),
     "gpode_param_grad_dev": (_I, [_P, _I, _I, _I, _P, _P, _L, _P, _L, _P, _P]),
-    "gpode_dopri5_bwd_dev": 1, "gpode_param_grad_dev": 1, "gpode_vf_fwd_umma": 1, "gpode_pack_cache_sets": 1, "gpode_whiten_fwd_sets": 2, "gpode_vf_fwd_sets": 1,
+    "gpode_pack_cache_large": 1, "gpode_rbf_fwd_large": 1, "gpode_rff_fwd_large": 1, "gpode_vf_fwd_large_add_rbf": 1, "gpode_dopri5_bwd_dev": 1, "gpode_param_grad_dev": 1, "gpode_vf_fwd_umma": 1, "gpode_pack_cache_sets": 1, "gpode_whiten_fwd_sets": 2, "gpode_vf_fwd_sets": 1,
                     "gpode_rk4_fwd_sets": 1, "gpode_dopri5_fwd_sets": 1}
 LAUNCH_COUNT = {}
 _PROFILE = None  # None, or {name: [(start_event, end_event), ...]}

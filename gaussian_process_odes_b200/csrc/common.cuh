@@ -159,6 +159,17 @@ __device__ __forceinline__ void gpode_split_tf32(float v, uint32_t& hi, uint32_t
     hi = __float_as_uint(v) & 0xffffe000u;
     lo = __float_as_uint(v - __uint_as_float(hi));
 }
+// 3xTF32 split for the tcgen05 path, round-to-nearest: hi = tf32(v), lo = tf32(v - hi). Both parts have their 13 low
+// mantissa bits clear, so the tensor core (which truncates) sees them exactly; the residual v - hi - lo is <= 2^-24 |v|
+// and unbiased (a truncating split leaves a one-sided 2^-22 |v|, visible at D = 64 where 65 products add up).
+__device__ __forceinline__ float gpode_round_tf32(float v) {
+    return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+}
+__device__ __forceinline__ void gpode_split_tf32_rn(float v, float& hi, float& lo) {
+    hi = gpode_round_tf32(v);
+    lo = gpode_round_tf32(v - hi);
+}
+
 __device__ __forceinline__ void gpode_mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t b0,
                                                const uint32_t b1) {
     asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"

@@ -31,15 +31,21 @@ struct LdArgs {
 
 // f[r][k] for the tile; xs, fs: shared, TRANSPOSED [D][kTR] (a thread's 8 rows are two LDS.128);
 // thread (k = tid % D, g = tid / D) handles rows g*8 .. g*8+7
+// frff != nullptr: the Fourier-feature term was computed by the tensor-core kernel (large_umma.cu) and is read from
+// global memory [B,D]; only the RBF term is evaluated here.
 __device__ void eval_tile(const LdArgs& a, const float* __restrict__ xs, float* __restrict__ fs, const float* wl,
-                          const int k, const int g, const bool active) {
+                          const int k, const int g, const bool active, const float* __restrict__ frff = nullptr,
+                          const int64_t row0 = 0, const int64_t B = 0) {
     const int D = a.D, S = a.S, M = a.M;
     if (active) {
         float acc[kRG];
 #pragma unroll
-        for (int r = 0; r < kRG; ++r) acc[r] = 0.f;
+        for (int r = 0; r < kRG; ++r) {
+            const int64_t row = row0 + g * kRG + r;
+            acc[r] = (frff != nullptr && row < B) ? __ldg(frff + row * D + k) : 0.f;
+        }
         const float ak = sqrtf(__ldg(a.var + k) / (float)S);
-        for (int s = 0; s < S; ++s) {
+        for (int s = 0; frff == nullptr && s < S; ++s) {
             float th[kRG];
             const float ph = __ldg(a.phase + s * D + k);
 #pragma unroll
@@ -89,7 +95,8 @@ __device__ void eval_tile(const LdArgs& a, const float* __restrict__ xs, float* 
 
 // smem: wl[D*D] | y[kTR*D] | ys | k1 | k2 | k3 | k4
 __global__ void large_d_kernel(const LdArgs a, const float* __restrict__ x0, const float* __restrict__ ts,
-                               const int Tg, const int64_t B, float* __restrict__ xs_out, const int vf_only) {
+                               const int Tg, const int64_t B, float* __restrict__ xs_out, const int vf_only,
+                               const float* __restrict__ frff) {
     extern __shared__ __align__(16) float sm[];
     const int D = a.D;
     float* wl = sm;
@@ -116,7 +123,7 @@ __global__ void large_d_kernel(const LdArgs a, const float* __restrict__ x0, con
         }
         __syncthreads();
         if (vf_only) {
-            eval_tile(a, y, k1, wl, k, g, active);
+            eval_tile(a, y, k1, wl, k, g, active, frff, row0, B);
             for (int i = threadIdx.x; i < kTR * D; i += blockDim.x) {
                 const int r = i / D, j = i - r * D;
                 if (row0 + r < B) xs_out[row0 * D + i] = k1[j * kTR + r];
@@ -156,12 +163,13 @@ __global__ void large_d_kernel(const LdArgs a, const float* __restrict__ x0, con
 }
 
 int launch_large(const gpode_cache_t* c, const float* x0, const float* ts, int Tg, int64_t B, float* out, int vf_only,
-                 cudaStream_t st) {
+                 cudaStream_t st, const float* frff = nullptr) {
     GPODE_CHECK_ARG(c != nullptr, "cache is NULL");
     GPODE_CHECK_ARG(c->D > GPODE_MAX_D && c->D <= GPODE_MAX_D_LARGE, "large-D path needs %d < D <= %d, got %d",
                     GPODE_MAX_D, GPODE_MAX_D_LARGE, c->D);
     GPODE_CHECK_ARG(c->M >= 1 && c->S >= 1 && B >= 0, "bad sizes");
-    GPODE_CHECK_ARG(c->omega && c->phase && c->w && c->Z && c->nu && c->ell && c->var, "cache tensor is NULL");
+    GPODE_CHECK_ARG(c->Z && c->nu && c->ell && c->var, "cache tensor is NULL");
+    GPODE_CHECK_ARG(frff != nullptr || (c->omega && c->phase && c->w), "cache tensor is NULL");
     if (B == 0) return 0;
     GPODE_CHECK_ARG(x0 && out, "NULL argument");
     LdArgs a{c->D, c->M, c->S, c->omega, c->phase, c->w, c->Z, c->nu, c->ell, c->var};
@@ -179,7 +187,8 @@ int launch_large(const gpode_cache_t* c, const float* x0, const float* ts, int T
     }
     const int64_t ntiles = (B + kTR - 1) / kTR;
     const int64_t cap = (int64_t)sms * occ;
-    large_d_kernel<<<(unsigned)(ntiles < cap ? ntiles : cap), threads, smem, st>>>(a, x0, ts, Tg, B, out, vf_only);
+    large_d_kernel<<<(unsigned)(ntiles < cap ? ntiles : cap), threads, smem, st>>>(a, x0, ts, Tg, B, out, vf_only,
+                                                                                            frff);
     GPODE_LAUNCH_CHECK();
     return 0;
 }
@@ -188,6 +197,12 @@ int launch_large(const gpode_cache_t* c, const float* x0, const float* ts, int T
 
 extern "C" int gpode_vf_fwd_large(const gpode_cache_t* cache, const float* x, float* f, int64_t B, void* stream) {
     return launch_large(cache, x, nullptr, 1, B, f, 1, (cudaStream_t)stream);
+}
+
+extern "C" int gpode_vf_fwd_large_add_rbf(const gpode_cache_t* cache, const float* x, const float* f_rff, float* f,
+                                          int64_t B, void* stream) {
+    GPODE_CHECK_ARG(f_rff != nullptr, "f_rff is NULL");
+    return launch_large(cache, x, nullptr, 1, B, f, 1, (cudaStream_t)stream, f_rff);
 }
 
 extern "C" int gpode_rk4_fwd_large(const gpode_cache_t* cache, const float* x0, const float* t, int Tg, int64_t B,

@@ -77,9 +77,10 @@ __global__ void pack_kernel(const GpodeLayout L, const float* __restrict__ omega
                 float v = 0.f;
                 if (ok && slot < D) v = omega[((size_t)slot * S + sidx) * D + k];
                 else if (ok && slot == D) v = phase[sidx * D + k];
-                const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+                float hi, lo;
+                gpode_split_tf32_rn(v, hi, lo);
                 bh[(slot >> 2) * 32 + (slot & 3)] = hi;
-                bl[(slot >> 2) * 32 + (slot & 3)] = v - hi;
+                bl[(slot >> 2) * 32 + (slot & 3)] = lo;
             }
             rec[16 * L.SU + sidx] = ok ? w[sidx * D + k] * sqrtf(var[k] / (float)S) : 0.f;
         } else {

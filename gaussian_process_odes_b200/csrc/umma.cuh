@@ -2,8 +2,8 @@
 // shared-memory matrix descriptors, the instruction descriptor of kind::tf32, TMEM allocation, MMA issue / commit,
 // TMEM -> register loads and bounded mbarrier waits. sm_100a only.
 //
-// Numerics: error-compensated 3xTF32 (hi = v & 0xffffe000, lo = v - hi; D = A_hi B_hi + A_lo B_hi + A_hi B_lo, fp32
-// accumulation in TMEM) keeps theta to ~2^-21 relative, the level the FFMA2 kernels deliver.
+// Numerics: error-compensated 3xTF32 (hi = tf32(v), lo = tf32(v - hi), round to nearest -- gpode_split_tf32_rn;
+// D = A_hi B_hi + A_lo B_hi + A_hi B_lo, fp32 accumulation in TMEM) keeps theta to ~2^-23 relative per product.
 #pragma once
 #include "common.cuh"
 

@@ -95,8 +95,7 @@ vf_fwd_umma_kernel(const float* __restrict__ packed, const int M, const int S, c
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const float v = q < D ? xr[0][q < D ? q : 0] : (q == D ? 1.f : 0.f);
-                    hi[q] = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-                    lo[q] = v - hi[q];
+                    gpode_split_tf32_rn(v, hi[q], lo[q]);
                 }
                 const int o = (tid >> 3) * 64 + (tid & 7) * 4;  // core matrix of the row's group, then its 16-byte line
                 *reinterpret_cast<float4*>(a_hi + o) = make_float4(hi[0], hi[1], hi[2], hi[3]);

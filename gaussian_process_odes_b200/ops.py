@@ -349,17 +349,82 @@ def _large_d_call(name, x, t, Z, ell, var, nu, omega, phase, w):
     return out
 
 
+LARGE_RBF_TENSOR_CORES = True   # False: RBF term in the FP32 tiled kernel (gpode_vf_fwd_large_add_rbf)
+
+
+class LargeField:
+    """One sampled GP function for 8 < D <= 64, forward only: the Fourier-feature term runs on the tcgen05 tensor cores
+    (``gpode_rff_fwd_large`` over the pre-tiled 3xTF32 operand chunks of ``gpode_pack_cache_large``), the RBF term in the
+    tiled FP32 kernel (``gpode_vf_fwd_large_add_rbf``). Pack once, evaluate many times (the host-driven integrators)."""
+
+    def __init__(self, Z, ell, var, nu, omega, phase, w):
+        if torch.is_grad_enabled() and any(a.requires_grad for a in (Z, ell, var, nu)):
+            raise _lib.GpodeError("state dimension %d > %d: only the forward (no_grad) path exists for large D"
+                                  % (Z.shape[1], MAX_D_REGISTER))
+        lib = _lib.load()
+        Zc, ec, vc, oc, wc = f32(Z, "Z"), f32(ell, "ell"), f32(var, "var"), f32(omega, "omega"), f32(w, "w")
+        self.M, self.D = Zc.shape
+        self.S = wc.shape[0]
+        pc_, nc = f32(phase, "phase").reshape(self.S, self.D), f32(nu, "nu").reshape(self.D, self.M)
+        self.keep = (Zc, ec, vc, oc, wc, pc_, nc)
+        self.struct = _cache_struct(self.D, self.M, self.S, oc, pc_, wc, Zc, nc, ec, vc)
+        n = lib.gpode_packed_large_floats(self.D, self.M, self.S)
+        if n < 0:
+            raise _lib.GpodeError("large-D path needs %d < D <= %d, got %d" % (MAX_D_REGISTER, MAX_D_LARGE, self.D))
+        self.packed = torch.empty(n, dtype=torch.float32, device=Zc.device)
+        _lib.call("gpode_pack_cache_large", ctypes.byref(self.struct), ptr(self.packed), stream_ptr())
+
+    def __call__(self, x):
+        if torch.is_grad_enabled() and x.requires_grad:
+            raise _lib.GpodeError("state dimension %d > %d: only the forward (no_grad) path exists for large D"
+                                  % (self.D, MAX_D_REGISTER))
+        xc = f32(x, "x")
+        if xc.ndim != 2 or xc.shape[1] != self.D:
+            raise _lib.GpodeError("x must be (B,%d), got %s" % (self.D, tuple(xc.shape)))
+        B = xc.shape[0]
+        f_rff = torch.empty_like(xc)
+        _lib.call("gpode_rff_fwd_large", ptr(self.packed), self.D, self.S, ptr(xc), ptr(f_rff), B, stream_ptr())
+        f = torch.empty_like(xc)
+        if LARGE_RBF_TENSOR_CORES:
+            _lib.call("gpode_rbf_fwd_large", ptr(self.packed), self.D, self.M, self.S, ptr(self.keep[0]), ptr(xc),
+                      ptr(f_rff), ptr(f), B, stream_ptr())
+        else:
+            _lib.call("gpode_vf_fwd_large_add_rbf", ctypes.byref(self.struct), ptr(xc), ptr(f_rff), ptr(f), B,
+                      stream_ptr())
+        return f
+
+
+def _rk4_large_d(x0, t, field):
+    """torchdiffeq's fixed-grid rk4 (3/8 rule, same operation order) around the large-D vector field, forward only."""
+    y = f32(x0, "x0")
+    tc = t.detach().to(device=y.device, dtype=torch.float32)
+    dts = (tc[1:] - tc[:-1]).tolist()
+    third = 1.0 / 3.0
+    out = [y]
+    for dt in dts:
+        k1 = field(y)
+        k2 = field(y + dt * k1 * third)
+        k3 = field(y + dt * (k2 - k1 * third))
+        k4 = field(y + dt * (k1 - k2 + k3))
+        y = y + (k1 + 3 * (k2 + k3) + k4) * dt * 0.125
+        out.append(y)
+    return torch.stack(out, 0)
+
+
 def vector_field(x, Z, ell, var, nu, omega, phase, w):
     """f(x) of one sampled GP function; differentiable in x, Z, ell, var, nu (forward only for D > 8)."""
     if Z.shape[1] > MAX_D_REGISTER:
-        return _large_d_call("gpode_vf_fwd_large", x, None, Z, ell, var, nu, omega, phase, w)
+        return LargeField(Z, ell, var, nu, omega, phase, w)(x)
     return _VectorField.apply(x, Z, ell, var, nu, omega, phase, w)
 
 
 def rk4_integrate(x0, t, Z, ell, var, nu, omega, phase, w):
     """Fixed-grid RK4 (3/8 rule) over the float32 grid ``t``; returns ``(len(t), B, D)`` like torchdiffeq."""
     if Z.shape[1] > MAX_D_REGISTER:
-        return _large_d_call("gpode_rk4_fwd_large", x0, t, Z, ell, var, nu, omega, phase, w)
+        if torch.is_grad_enabled() and x0.requires_grad:
+            raise _lib.GpodeError("state dimension %d > %d: only the forward (no_grad) path exists for large D"
+                                  % (Z.shape[1], MAX_D_REGISTER))
+        return _rk4_large_d(x0, t, LargeField(Z, ell, var, nu, omega, phase, w))
     return _RK4.apply(x0, t, Z, ell, var, nu, omega, phase, w, torch.is_grad_enabled())
 
 
@@ -480,8 +545,10 @@ def _dopri5_large_d(x0, t, Z, ell, var, nu, omega, phase, w, rtol, atol, max_att
     sign = -1.0 if (t64.numel() > 1 and t64[-1] < t64[0]) else 1.0
     tt = (t64 * sign).tolist()
 
+    field = LargeField(Z, ell, var, nu, omega, phase, w)
+
     def f(y):
-        out = _large_d_call("gpode_vf_fwd_large", y.contiguous(), None, Z, ell, var, nu, omega, phase, w)
+        out = field(y.contiguous())
         return out if sign > 0 else -out
 
     rms = lambda v: float(v.pow(2).mean().sqrt())

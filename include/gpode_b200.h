@@ -155,6 +155,19 @@ int gpode_vf_fwd_large(const gpode_cache_t* cache, const float* x, float* f, int
 int gpode_rk4_fwd_large(const gpode_cache_t* cache, const float* x0, const float* t, int Tg, int64_t B, float* xs,
                         void* stream);
 
+/* Tensor-core route for the same sizes: the Fourier-feature term as tcgen05 kind::tf32 GEMMs (3xTF32, TMEM
+ * accumulators) over operand chunks pre-tiled by gpode_pack_cache_large (gpode_packed_large_floats(D,M,S) floats) and
+ * streamed from L2 through a shared-memory ring; gpode_vf_fwd_large_add_rbf adds the RBF term: f = f_rff + K(x,Z) nu. */
+int64_t gpode_packed_large_floats(int D, int M, int S);
+int gpode_pack_cache_large(const gpode_cache_t* cache, float* packed_large, void* stream);
+int gpode_rff_fwd_large(const float* packed_large, int D, int S, const float* x, float* f_rff, int64_t B, void* stream);
+int gpode_vf_fwd_large_add_rbf(const gpode_cache_t* cache, const float* x, const float* f_rff, float* f, int64_t B,
+                               void* stream);
+/* ... and the RBF term on the tensor cores as well: per inducing point one [128 rows x D] x [D x D] GEMM of the
+ * squared differences (built on the fly) against -W^T; f = f_rff + sum_m c_km 2^(...). Z: the raw [M,D] tensor. */
+int gpode_rbf_fwd_large(const float* packed_large, int D, int M, int S, const float* Z, const float* x,
+                        const float* f_rff, float* f, int64_t B, void* stream);
+
 /* ---- Batched Monte-Carlo prediction: n_sets function draws in one launch (SURVEY.md section 8b item 1 "n_sets",
  * 8f item 3). Replaces the Python loop of compute_predictions / compute_test_predictions
  * (src/gpode/model_builder.py:60-96, src/gpode_shooting/mocap_model_builder.py:85-119), which rebuilds the cache

@@ -166,10 +166,15 @@ def test_large_state_dimension_forward(D, M, S, B):
         f = ops.vector_field(x.cuda(), *args).cpu()
         ts = _grid(4, 0.02, 2)
         xs = ops.rk4_integrate(x.cuda(), ts.cuda(), *args).cpu()
+        # the all-FP32 tiled kernels (the tensor-core route's predecessor, still exported)
+        f_fma = ops._large_d_call("gpode_vf_fwd_large", x.cuda(), None, *args).cpu()
+        xs_fma = ops._large_d_call("gpode_rk4_fwd_large", x.cuda(), ts.cuda(), *args).cpu()
     f32 = O.vf_forward(x, gp32['Z'], gp32['ell'], gp32['var'], c32)
     c64n = dict(c64, nu=c32['nu'].double())
     f64 = O.vf_forward(x.double(), gp64['Z'], gp64['ell'], gp64['var'], c64n)
     assert_parity("large-D vf", f, f32, f64, TOL_VF)
+    assert_parity("large-D vf (fp32 tiles)", f_fma, f32, f64, TOL_VF)
+    assert relerr(xs_fma, xs) <= TOL_TRAJ
     ref32 = O.odeint(lambda t, y: O.vf_forward(y, gp32['Z'], gp32['ell'], gp32['var'], c32), x, ts, method='rk4')
     assert relerr(xs, ref32) <= TOL_TRAJ
     xg = x.cuda().requires_grad_(True)

@@ -181,12 +181,21 @@ def run_sweep(D, M, S, B, K, do_cpu):
     args = [a.cuda().contiguous() for a in (gp['Z'], gp['ell'], gp['var'], nu, omega, d['phase_u'] * 2 * np.pi, d['w'])]
     x = torch.randn(B, D, device="cuda")
     tg = (torch.arange(K + 1, dtype=torch.float32) * 0.01).cuda()
+    reps = 10 if D <= 8 else 3
     with torch.no_grad():
-        ms = gpu_time(lambda: ops.rk4_integrate(x, tg, *args), warm=3, reps=10)
+        ms = gpu_time(lambda: ops.rk4_integrate(x, tg, *args), warm=2, reps=reps)
     fv = D * (S * (2 * D + 4) + M * (3 * D + 4))
     evals = B * 4 * K
     out = dict(sweep=True, D=D, M=M, S=S, B=B, rk4_steps=K, ms=ms, evals_per_s=evals / (ms * 1e-3),
                algorithmic_tflops=evals * fv / (ms * 1e-3) / 1e12)
+    if K == 32:  # batch-norm dopri5 over [0, 0.32], rtol = atol = 1e-6
+        td = torch.tensor([0.0, 0.32], device="cuda")
+        with torch.no_grad():
+            _, st = ops.dopri5_integrate(x, td, *args)
+            ms5 = gpu_time(lambda: ops.dopri5_integrate(x, td, *args), warm=1, reps=max(reps // 2, 2))
+        nfe = int(st[0])
+        out.update(dopri5_ms=ms5, dopri5_nfe=nfe, dopri5_evals_per_s=B * nfe / (ms5 * 1e-3),
+                   dopri5_algorithmic_tflops=B * nfe * fv / (ms5 * 1e-3) / 1e12)
     if do_cpu and B <= 100000:
         c = dict(rff_omega=omega, rff_phase=d['phase_u'] * 2 * np.pi, rff_weights=d['w'], nu=nu.unsqueeze(2))
         xc = x.cpu()
@@ -216,8 +225,13 @@ def main():
         print(json.dumps(r), flush=True)
         res.append(r)
     if not args.only or args.only == "sweep":
-        for D, M in ((2, 16), (4, 100), (5, 100), (8, 100)):
-            for B, K in ((10000, 32), (100000, 32), (1000000, 1), (1000000, 32)):
+        only_d = [int(v) for v in os.environ.get("SWEEP_D", "").split(",") if v]
+        for D, M in ((2, 16), (4, 100), (5, 100), (8, 100), (16, 100), (32, 100), (64, 100)):
+            if only_d and D not in only_d:
+                continue
+            shapes = ((10000, 32), (100000, 32), (1000000, 1), (1000000, 32)) if D <= 8 else \
+                     ((10000, 32), (100000, 1), (100000, 32))
+            for B, K in shapes:
                 r = run_sweep(D, M, 256, B, K, not args.no_cpu)
                 print(json.dumps(r), flush=True)
                 res.append(r)
