@@ -20,12 +20,15 @@ namespace {
 
 constexpr int kLuThreads = 160;
 constexpr int kLuRows = 128;
-constexpr int kLuNC = 64;        // features per chunk = TMEM columns per accumulator buffer
-constexpr int kLuTmemCols = 128;
+constexpr int kRbTmemCols = 128;  // RBF kernel: two buffers of up to 64 exponent columns
+constexpr int kLuRing = 2;       // operand ring slots (4 was measured: no gain at D = 64, lower occupancy at D = 32)
 
 __host__ __device__ inline int lu_kp(int D) { return (D + 1 + 7) & ~7; }          // padded K (input dims + phase slot)
-__host__ __device__ inline int lu_su(int S) { return (S + kLuNC - 1) / kLuNC * kLuNC; }
-__host__ __device__ inline int64_t lu_rec(int D) { return 2 * (int64_t)lu_kp(D) * kLuNC; }  // floats per chunk record
+// chunk width: every MMA re-reads the 128 x 8 state slice from shared memory whatever its N, so wide chunks pay once
+// D is large (measured at D = 64: 2.67 -> 1.65 ms); at smaller D the smaller ring keeps more CTAs per SM
+__host__ __device__ inline int lu_nc(int D) { return D > 40 ? 128 : 64; }
+__host__ __device__ inline int lu_su(int D, int S) { return (S + lu_nc(D) - 1) / lu_nc(D) * lu_nc(D); }
+__host__ __device__ inline int64_t lu_rec(int D) { return 2 * (int64_t)lu_kp(D) * lu_nc(D); }  // floats per chunk record
 
 // canonical K-major no-swizzle tile of `rows` rows: [K/4 chunks][rows/8 groups][8 rows][4 floats]
 __host__ __device__ inline int lu_off(int rows, int r, int q) {
@@ -41,7 +44,8 @@ __global__ void pack_large_kernel(const int D, const int S, const int M, const f
                                   const float* __restrict__ phase, const float* __restrict__ w,
                                   const float* __restrict__ var, const float* __restrict__ ell,
                                   const float* __restrict__ nu, float* __restrict__ out) {
-    const int KP = lu_kp(D), SU = lu_su(S), NCH = SU / kLuNC;
+    const int NC = lu_nc(D);
+    const int KP = lu_kp(D), SU = lu_su(D, S), NCH = SU / NC;
     const int64_t rec = lu_rec(D);
     const int64_t n_elem = (int64_t)D * SU * KP;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_elem; i += (int64_t)gridDim.x * blockDim.x) {
@@ -55,10 +59,10 @@ __global__ void pack_large_kernel(const int D, const int S, const int M, const f
         }
         float hi, lo;
         gpode_split_tf32_rn(v, hi, lo);
-        float* r = out + ((int64_t)k * NCH + s / kLuNC) * rec;
-        const int o = lu_off(kLuNC, s % kLuNC, q);
+        float* r = out + ((int64_t)k * NCH + s / NC) * rec;
+        const int o = lu_off(NC, s % NC, q);
         r[o] = hi;
-        r[(int64_t)KP * kLuNC + o] = lo;
+        r[(int64_t)KP * NC + o] = lo;
     }
     float* aw = out + (int64_t)D * NCH * rec;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)D * SU;
@@ -90,7 +94,7 @@ __global__ void pack_large_kernel(const int D, const int S, const int M, const f
 }
 
 struct LuSmem {  // byte offsets
-    static constexpr int bar_afull = 0, bar_full = 8, bar_empty = 24, bar_bfull = 40, bar_bfree = 56, tmem_ptr = 72;
+    static constexpr int bar_afull = 0, bar_full = 8, bar_empty = 24, bar_bfull = 40, bar_bfree = 72, tmem_ptr = 104;
     static constexpr int tiles = 128;
 };
 
@@ -104,13 +108,14 @@ rff_large_umma_kernel(const float* __restrict__ packed, const int D, const int S
     uint64_t* bar_bfull = reinterpret_cast<uint64_t*>(smem + LuSmem::bar_bfull);
     uint64_t* bar_bfree = reinterpret_cast<uint64_t*>(smem + LuSmem::bar_bfree);
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + LuSmem::tmem_ptr);
-    const int KP = lu_kp(D), SU = lu_su(S), NCH = SU / kLuNC;
+    const int NC = lu_nc(D);
+    const int KP = lu_kp(D), SU = lu_su(D, S), NCH = SU / NC;
     const int64_t rec = lu_rec(D);
     const int a_floats = KP * kLuRows;          // one of A_hi / A_lo
     const int b_floats = (int)rec;              // one ring slot: B_hi | B_lo
     float* a_hi = reinterpret_cast<float*>(smem + LuSmem::tiles);
     float* a_lo = a_hi + a_floats;
-    float* ring = a_lo + a_floats;              // [2][b_floats]
+    float* ring = a_lo + a_floats;              // [kLuRing][b_floats]
     const float* __restrict__ aw = packed + (int64_t)D * NCH * rec;
     const int tid = threadIdx.x, warp = tid >> 5;
 
@@ -119,13 +124,15 @@ rff_large_umma_kernel(const float* __restrict__ packed, const int D, const int S
         for (int i = 0; i < 2; ++i) {
             gpode_mbar_init(bar_full + i, 1);
             gpode_mbar_init(bar_empty + i, kLuRows);
+        }
+        for (int i = 0; i < kLuRing; ++i) {
             gpode_mbar_init(bar_bfull + i, 1);
             gpode_mbar_init(bar_bfree + i, 1);
         }
     }
     if (warp == 4) {
         __syncwarp();
-        tmem_alloc(tmem_ptr, kLuTmemCols);
+        tmem_alloc(tmem_ptr, 2u * (uint32_t)NC);
     }
     tc_fence_before_sync();
     __syncthreads();
@@ -137,6 +144,9 @@ rff_large_umma_kernel(const float* __restrict__ packed, const int D, const int S
     int64_t my_tiles = 0;
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) ++my_tiles;
     const int64_t total_chunks = my_tiles * chunks_per_tile;
+    // every CTA walks the output dimensions in its own rotation, so that the SMs do not all pull the same operand
+    // chunk from the same L2 lines at the same moment
+    const int k_rot = (int)(blockIdx.x % (unsigned)D);
 
     if (warp < 4) {
         uint32_t g = 0;
@@ -160,36 +170,40 @@ rff_large_umma_kernel(const float* __restrict__ packed, const int D, const int S
             fence_proxy_async_smem();
             mbar_arrive(bar_afull);
             const int64_t row = row0 + tid;
-            for (int k = 0; k < D; ++k) {
+            for (int kk = 0; kk < D; ++kk) {
+                const int k = kk + k_rot < D ? kk + k_rot : kk + k_rot - D;
                 float acc0 = 0.f, acc1 = 0.f;
                 for (int c = 0; c < NCH; ++c, ++g) {
                     const int buf = g & 1;
                     mbar_wait_bounded(bar_full + buf, (g >> 1) & 1);
                     tc_fence_after_sync();
-                    const uint32_t t0 = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * kLuNC);
-                    const float* __restrict__ wg = aw + (int64_t)k * SU + c * kLuNC;
+                    const uint32_t t0 = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * NC);
+                    const float* __restrict__ wg = aw + (int64_t)k * SU + c * NC;
                     uint32_t ra[32], rb[32];
+                    auto consume = [&](const uint32_t (&r)[32], const float* __restrict__ wgt) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            const float4 w4 = __ldg(reinterpret_cast<const float4*>(wgt + i));
+                            acc0 = fmaf(w4.x, __cosf(__uint_as_float(r[i])), acc0);
+                            acc1 = fmaf(w4.y, __cosf(__uint_as_float(r[i + 1])), acc1);
+                            acc0 = fmaf(w4.z, __cosf(__uint_as_float(r[i + 2])), acc0);
+                            acc1 = fmaf(w4.w, __cosf(__uint_as_float(r[i + 3])), acc1);
+                        }
+                    };
+                    // 32-column blocks, the next block's TMEM load in flight while the current one is on the MUFU
                     tmem_ld32_issue(t0, ra);
-                    tmem_ld_wait(ra);
-                    tmem_ld32_issue(t0 + 32, rb);
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        const float4 w4 = __ldg(reinterpret_cast<const float4*>(wg + i));
-                        acc0 = fmaf(w4.x, __cosf(__uint_as_float(ra[i])), acc0);
-                        acc1 = fmaf(w4.y, __cosf(__uint_as_float(ra[i + 1])), acc1);
-                        acc0 = fmaf(w4.z, __cosf(__uint_as_float(ra[i + 2])), acc0);
-                        acc1 = fmaf(w4.w, __cosf(__uint_as_float(ra[i + 3])), acc1);
-                    }
-                    tmem_ld_wait(rb);
-                    tc_fence_before_sync();
-                    mbar_arrive(bar_empty + buf);  // both halves are in registers: the buffer may be overwritten
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        const float4 w4 = __ldg(reinterpret_cast<const float4*>(wg + 32 + i));
-                        acc0 = fmaf(w4.x, __cosf(__uint_as_float(rb[i])), acc0);
-                        acc1 = fmaf(w4.y, __cosf(__uint_as_float(rb[i + 1])), acc1);
-                        acc0 = fmaf(w4.z, __cosf(__uint_as_float(rb[i + 2])), acc0);
-                        acc1 = fmaf(w4.w, __cosf(__uint_as_float(rb[i + 3])), acc1);
+                    for (int cc = 0; cc < NC; cc += 64) {
+                        tmem_ld_wait(ra);
+                        tmem_ld32_issue(t0 + cc + 32, rb);
+                        consume(ra, wg + cc);
+                        tmem_ld_wait(rb);
+                        if (cc + 64 < NC) {
+                            tmem_ld32_issue(t0 + cc + 64, ra);
+                        } else {
+                            tc_fence_before_sync();
+                            mbar_arrive(bar_empty + buf);  // everything is in registers: the buffer may be overwritten
+                        }
+                        consume(rb, wg + cc + 32);
                     }
                 }
                 if (row < B) f_rff[row * D + k] = acc0 + acc1;
@@ -198,10 +212,13 @@ rff_large_umma_kernel(const float* __restrict__ packed, const int D, const int S
     } else if (tid == 128) {
         // ---- producer: operand copies one chunk ahead, then the MMAs of the current chunk ----
         const uint32_t copy_bytes = (uint32_t)b_floats * 4u;
-        auto load = [&](const int64_t gq) {  // chunk gq of this CTA's sequence -> ring slot gq & 1
-            const int slot = (int)(gq & 1);
-            if (gq >= 2) mbar_wait_bounded(bar_bfree + slot, (uint32_t)(((gq >> 1) - 1) & 1));
-            const float* src = packed + (gq % chunks_per_tile) * rec;
+        auto load = [&](const int64_t gq) {  // chunk gq of this CTA's sequence -> ring slot gq % kLuRing
+            const int slot = (int)(gq % kLuRing);
+            if (gq >= kLuRing) mbar_wait_bounded(bar_bfree + slot, (uint32_t)((gq / kLuRing - 1) & 1));
+            const int64_t local = gq % chunks_per_tile;              // (kk, c) of the tile, kk rotated like the rows do
+            const int kk = (int)(local / NCH), c = (int)(local - (int64_t)kk * NCH);
+            const int k = kk + k_rot < D ? kk + k_rot : kk + k_rot - D;
+            const float* src = packed + ((int64_t)k * NCH + c) * rec;
             float* dst = ring + (size_t)slot * b_floats;
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gpode_smem_u32(bar_bfull + slot)),
                          "r"(copy_bytes)
@@ -215,41 +232,48 @@ rff_large_umma_kernel(const float* __restrict__ packed, const int D, const int S
                     : "memory");
             }
         };
-        const uint32_t idesc = umma_idesc_tf32(kLuRows, kLuNC);
-        const uint32_t lbo_a = kLuRows * 16, lbo_b = kLuNC * 16;  // bytes between consecutive 16-byte K chunks
+        const uint32_t idesc = umma_idesc_tf32(kLuRows, NC);
+        const uint32_t lbo_a = kLuRows * 16, lbo_b = (uint32_t)NC * 16;  // bytes between consecutive 16-byte K chunks
+        const uint64_t desc_a_hi = umma_smem_desc(gpode_smem_u32(a_hi), lbo_a, 128);
+        const uint64_t desc_a_lo = umma_smem_desc(gpode_smem_u32(a_lo), lbo_a, 128);
+        const uint64_t step_a = (2u * lbo_a) >> 4, step_b = (2u * lbo_b) >> 4;  // one K-step = two K chunks
         int64_t gq = 0;
         uint32_t tile_it = 0;
-        if (total_chunks > 0) load(0);
+        for (int64_t q = 0; q < kLuRing - 1 && q < total_chunks; ++q) load(q);
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
             mbar_wait_bounded(bar_afull, tile_it & 1);
             tc_fence_after_sync();
             for (int ci = 0; ci < chunks_per_tile; ++ci, ++gq) {
-                const int slot = (int)(gq & 1);
-                if (gq + 1 < total_chunks) load(gq + 1);
-                mbar_wait_bounded(bar_bfull + slot, (uint32_t)((gq >> 1) & 1));
-                if (gq >= 2) mbar_wait_bounded(bar_empty + slot, (uint32_t)(((gq >> 1) - 1) & 1));
+                const int slot = (int)(gq % kLuRing), tb = (int)(gq & 1);
+                if (gq + kLuRing - 1 < total_chunks) load(gq + kLuRing - 1);
+                mbar_wait_bounded(bar_bfull + slot, (uint32_t)((gq / kLuRing) & 1));
+                if (gq >= 2) mbar_wait_bounded(bar_empty + tb, (uint32_t)(((gq >> 1) - 1) & 1));
                 tc_fence_after_sync();
-                const uint32_t d = tmem_base + (uint32_t)(slot * kLuNC);
+                const uint32_t d = tmem_base + (uint32_t)(tb * NC);
                 const float* bh = ring + (size_t)slot * b_floats;
-                const float* bl = bh + KP * kLuNC;
-                for (int ks = 0; ks < KP / 8; ++ks) {
-                    const uint32_t ao = (uint32_t)ks * 2u * lbo_a, bo = (uint32_t)ks * 2u * lbo_b;
-                    const uint64_t ah = umma_smem_desc(gpode_smem_u32(a_hi) + ao, lbo_a, 128);
-                    const uint64_t al = umma_smem_desc(gpode_smem_u32(a_lo) + ao, lbo_a, 128);
-                    const uint64_t bhd = umma_smem_desc(gpode_smem_u32(bh) + bo, lbo_b, 128);
-                    const uint64_t bld = umma_smem_desc(gpode_smem_u32(bl) + bo, lbo_b, 128);
-                    umma_tf32_ss(d, ah, bhd, idesc, ks > 0 ? 1u : 0u);
+                const float* bl = bh + KP * NC;
+                // descriptors are built once per chunk; a K-step only advances the 16-byte-granular start address
+                // (the issuing thread's own instruction latency is what paces back-to-back MMAs)
+                uint64_t ah = desc_a_hi, al = desc_a_lo;
+                uint64_t bhd = umma_smem_desc(gpode_smem_u32(bh), lbo_b, 128);
+                uint64_t bld = umma_smem_desc(gpode_smem_u32(bl), lbo_b, 128);
+                umma_tf32_ss(d, ah, bhd, idesc, 0u);
+                umma_tf32_ss(d, al, bhd, idesc, 1u);
+                umma_tf32_ss(d, ah, bld, idesc, 1u);
+                for (int ks = 1; ks < KP / 8; ++ks) {
+                    ah += step_a; al += step_a; bhd += step_b; bld += step_b;
+                    umma_tf32_ss(d, ah, bhd, idesc, 1u);
                     umma_tf32_ss(d, al, bhd, idesc, 1u);
                     umma_tf32_ss(d, ah, bld, idesc, 1u);
                 }
-                umma_commit(bar_full + slot);   // theta of this chunk is complete -> rows
-                umma_commit(bar_bfree + slot);  // ... and the ring slot has been read -> next copy
+                umma_commit(bar_full + tb);     // theta of this chunk is complete -> rows
+                umma_commit(bar_bfree + slot);  // ... and the ring slot has been read -> a later copy
             }
         }
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem_base, kLuTmemCols);
+    if (warp == 4) tmem_dealloc(tmem_base, 2u * (uint32_t)NC);
 }
 
 
@@ -280,7 +304,7 @@ rbf_large_umma_kernel(const float* __restrict__ packed, const int D, const int S
     uint64_t* bar_empty = reinterpret_cast<uint64_t*>(smem + RbSmem::bar_empty);  // [2] 128 consumer arrivals
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + RbSmem::tmem_ptr);
     const int KD = lu_kd(D), ND = lu_nd(D), K4 = KD / 4;
-    const int SU = lu_su(S), NCH = SU / kLuNC;
+    const int SU = lu_su(D, S), NCH = SU / lu_nc(D);
     const float* __restrict__ wt_g = packed + (int64_t)D * NCH * lu_rec(D) + (int64_t)D * SU;
     const float* __restrict__ cp_g = wt_g + 2 * ND * KD;
     float* wt = reinterpret_cast<float*>(smem + RbSmem::data);   // [-W^T hi | lo], 2 ND KD floats
@@ -305,7 +329,7 @@ rbf_large_umma_kernel(const float* __restrict__ packed, const int D, const int S
     }
     if (warp == 8) {
         __syncwarp();
-        tmem_alloc(tmem_ptr, kLuTmemCols);
+        tmem_alloc(tmem_ptr, kRbTmemCols);
     }
     fence_proxy_async_smem();  // -W^T was written with ordinary stores and is read by the tensor core
     tc_fence_before_sync();
@@ -325,7 +349,7 @@ rbf_large_umma_kernel(const float* __restrict__ packed, const int D, const int S
                 const int buf = g & 1;
                 mbar_wait_bounded(bar_full + buf, (g >> 1) & 1);
                 tc_fence_after_sync();
-                const uint32_t t0 = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * kLuNC);
+                const uint32_t t0 = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * 64);
                 const float* __restrict__ cm = cp_g + (int64_t)m * ND;
                 uint32_t ra[32], rb[32];
                 tmem_ld32_issue(t0, ra);
@@ -408,6 +432,13 @@ rbf_large_umma_kernel(const float* __restrict__ packed, const int D, const int S
         // ---- MMA issue ----
         const uint32_t idesc = umma_idesc_tf32(kLuRows, ND);
         const uint32_t lbo_a = kLuRows * 16, lbo_b = (uint32_t)ND * 16;
+        // all descriptors up front; a K-step advances the 16-byte-granular start address by two K chunks
+        const uint64_t desc_a[2] = {umma_smem_desc(gpode_smem_u32(at), lbo_a, 128),
+                                    umma_smem_desc(gpode_smem_u32(at + 2 * a_floats), lbo_a, 128)};
+        const uint64_t lo_a = ((uint32_t)a_floats * 4u) >> 4;
+        const uint64_t desc_b_hi = umma_smem_desc(gpode_smem_u32(wt), lbo_b, 128);
+        const uint64_t desc_b_lo = umma_smem_desc(gpode_smem_u32(wt + ND * KD), lbo_b, 128);
+        const uint64_t step_a = (2u * lbo_a) >> 4, step_b = (2u * lbo_b) >> 4;
         uint32_t g = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             for (int m = 0; m < M; ++m, ++g) {
@@ -415,16 +446,15 @@ rbf_large_umma_kernel(const float* __restrict__ packed, const int D, const int S
                 mbar_wait_bounded(bar_afull + slot, (g >> 1) & 1);
                 if (g >= 2) mbar_wait_bounded(bar_empty + slot, ((g >> 1) - 1) & 1);
                 tc_fence_after_sync();
-                const uint32_t d = tmem_base + (uint32_t)(slot * kLuNC);
-                const float* ah = at + (size_t)slot * 2 * a_floats;
-                const float* al = ah + a_floats;
-                for (int ks = 0; ks < KD / 8; ++ks) {
-                    const uint32_t ao = (uint32_t)ks * 2u * lbo_a, bo = (uint32_t)ks * 2u * lbo_b;
-                    const uint64_t ahd = umma_smem_desc(gpode_smem_u32(ah) + ao, lbo_a, 128);
-                    const uint64_t ald = umma_smem_desc(gpode_smem_u32(al) + ao, lbo_a, 128);
-                    const uint64_t bhd = umma_smem_desc(gpode_smem_u32(wt) + bo, lbo_b, 128);
-                    const uint64_t bld = umma_smem_desc(gpode_smem_u32(wt + ND * KD) + bo, lbo_b, 128);
-                    umma_tf32_ss(d, ahd, bhd, idesc, ks > 0 ? 1u : 0u);
+                const uint32_t d = tmem_base + (uint32_t)(slot * 64);
+                uint64_t ahd = desc_a[slot], ald = desc_a[slot] + lo_a;
+                uint64_t bhd = desc_b_hi, bld = desc_b_lo;
+                umma_tf32_ss(d, ahd, bhd, idesc, 0u);
+                umma_tf32_ss(d, ald, bhd, idesc, 1u);
+                umma_tf32_ss(d, ahd, bld, idesc, 1u);
+                for (int ks = 1; ks < KD / 8; ++ks) {
+                    ahd += step_a; ald += step_a; bhd += step_b; bld += step_b;
+                    umma_tf32_ss(d, ahd, bhd, idesc, 1u);
                     umma_tf32_ss(d, ald, bhd, idesc, 1u);
                     umma_tf32_ss(d, ahd, bld, idesc, 1u);
                 }
@@ -435,15 +465,15 @@ rbf_large_umma_kernel(const float* __restrict__ packed, const int D, const int S
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem_base, kLuTmemCols);
+    if (warp == 8) tmem_dealloc(tmem_base, kRbTmemCols);
 }
 
 }  // namespace
 
 extern "C" int64_t gpode_packed_large_floats(int D, int M, int S) {
     if (D <= GPODE_MAX_D || D > GPODE_MAX_D_LARGE || S < 1 || M < 1) return -1;
-    const int SU = lu_su(S);
-    return (int64_t)D * (SU / kLuNC) * lu_rec(D) + (int64_t)D * SU + 2 * (int64_t)lu_nd(D) * lu_kd(D) +
+    const int SU = lu_su(D, S);
+    return (int64_t)D * (SU / lu_nc(D)) * lu_rec(D) + (int64_t)D * SU + 2 * (int64_t)lu_nd(D) * lu_kd(D) +
            (int64_t)M * lu_nd(D);
 }
 
@@ -465,13 +495,13 @@ extern "C" int gpode_rff_fwd_large(const float* packed_large, int D, int S, cons
     GPODE_CHECK_ARG(D > GPODE_MAX_D && D <= GPODE_MAX_D_LARGE && S >= 1 && B >= 0, "bad sizes D=%d S=%d", D, S);
     if (B == 0) return 0;
     const int KP = lu_kp(D);
-    const size_t smem = LuSmem::tiles + (size_t)(2 * KP * kLuRows + 2 * lu_rec(D)) * 4;
+    const size_t smem = LuSmem::tiles + (size_t)(2 * KP * kLuRows + kLuRing * lu_rec(D)) * 4;
     GPODE_CUDA(cudaFuncSetAttribute(rff_large_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int sms = 148, dev = 0;
     GPODE_CUDA(cudaGetDevice(&dev));
     GPODE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     int occ = (int)((227u * 1024u) / (smem + 1024u));   // shared memory and TMEM (512 columns) bound the residency
-    if (occ > 512 / kLuTmemCols) occ = 512 / kLuTmemCols;
+    if (occ > 512 / (2 * lu_nc(D))) occ = 512 / (2 * lu_nc(D));
     if (occ < 1) {
         gpode_set_error("large-D tensor-core kernel does not fit on an SM (smem %zu bytes)", smem);
         return -2;
@@ -496,7 +526,7 @@ extern "C" int gpode_rbf_fwd_large(const float* packed_large, int D, int M, int 
     GPODE_CUDA(cudaGetDevice(&dev));
     GPODE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     int occ = (int)((227u * 1024u) / (smem + 1024u));
-    if (occ > 512 / kLuTmemCols) occ = 512 / kLuTmemCols;
+    if (occ > 512 / kRbTmemCols) occ = 512 / kRbTmemCols;
     if (occ * kRbThreads > 2048) occ = 2048 / kRbThreads;
     if (occ < 1) occ = 1;
     const int64_t tiles = (B + kLuRows - 1) / kLuRows, cap = (int64_t)sms * occ;
