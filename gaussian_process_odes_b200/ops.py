@@ -372,6 +372,7 @@ class LargeField:
         if n < 0:
             raise _lib.GpodeError("large-D path needs %d < D <= %d, got %d" % (MAX_D_REGISTER, MAX_D_LARGE, self.D))
         self.packed = torch.empty(n, dtype=torch.float32, device=Zc.device)
+        self.rbf_on_tensor_cores = True
         _lib.call("gpode_pack_cache_large", ctypes.byref(self.struct), ptr(self.packed), stream_ptr())
 
     def __call__(self, x):
@@ -385,10 +386,16 @@ class LargeField:
         f_rff = torch.empty_like(xc)
         _lib.call("gpode_rff_fwd_large", ptr(self.packed), self.D, self.S, ptr(xc), ptr(f_rff), B, stream_ptr())
         f = torch.empty_like(xc)
-        if LARGE_RBF_TENSOR_CORES:
-            _lib.call("gpode_rbf_fwd_large", ptr(self.packed), self.D, self.M, self.S, ptr(self.keep[0]), ptr(xc),
-                      ptr(f_rff), ptr(f), B, stream_ptr())
-        else:
+        if LARGE_RBF_TENSOR_CORES and self.rbf_on_tensor_cores:
+            try:
+                _lib.call("gpode_rbf_fwd_large", ptr(self.packed), self.D, self.M, self.S, ptr(self.keep[0]), ptr(xc),
+                          ptr(f_rff), ptr(f), B, stream_ptr())
+                return f
+            except _lib.GpodeError as e:
+                if "too large for the shared-memory copy of Z" not in str(e):
+                    raise
+                self.rbf_on_tensor_cores = False  # many inducing points at large D: the FP32 tiled CUDA kernel instead
+        if True:
             _lib.call("gpode_vf_fwd_large_add_rbf", ctypes.byref(self.struct), ptr(xc), ptr(f_rff), ptr(f), B,
                       stream_ptr())
         return f

@@ -156,7 +156,7 @@ def test_rk4_forward(D, M, S, B, Tg, h):
 
 
 @pytest.mark.parametrize("D,M,S,B", [(16, 100, 256, 1000), (32, 40, 64, 77), (64, 100, 256, 300), (9, 10, 17, 5),
-                                      (24, 7, 33, 64)])
+                                      (24, 7, 33, 64), (64, 150, 64, 130), (41, 30, 200, 257)])
 def test_large_state_dimension_forward(D, M, S, B):
     """8 < D <= 64 (upper half of the scaling sweep): forward-only tiled kernels, same parity bars."""
     from gaussian_process_odes_b200 import ops, _lib
