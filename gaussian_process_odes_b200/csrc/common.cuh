@@ -58,8 +58,15 @@ struct GpodeLayout {
     int off_rff, off_kern, off_il, total;  // in floats; every offset and `total` is a multiple of 4 (16 bytes)
     // tensor-core (mma.sync m16n8k8 tf32) operand blocks, appended after `total`, one record per (output k, tile of
     // 8 features):  mma  : 80 floats = 64 theta-B fragment (lane-major b0,b1) | 16 (phase, phase', a, a') per quad lane
-    //               mmag : 64 floats = G-B fragment (lane-major b0,b1), used by the adjoint only
-    int S8, off_mma, off_mmag;
+    //               mmah : the adjoint's operands for mma.sync m16n8k16 f16 (vjp_mma.cuh), 144 words per (output k,
+    //                      tile of 8 features; tiles padded to an even count S8P with zero records):
+    //                        [0,64)    theta-B, lane-major (b0,b1) half2 pairs: contraction slots 0..D-1 = Omega_hi,
+    //                                  D..2D-1 = Omega_lo, 2D..3D-1 = Omega_hi (the state tile carries x_hi, x_hi, x_lo)
+    //                        [64,80)   per quad lane t: phase(2t), phase(2t+1), phase(2t), phase(2t+1)  (fp32, the MMA's C)
+    //                        [80,112)  G-B hi, one half2 per lane: (Bp_hi[2t][g], Bp_hi[2t+1][g]),
+    //                                  Bp[s][j] = GPODE_MMAH_SCALE a_s Omega_{j,s,k}
+    //                        [112,144) G-B lo, same arrangement
+    int S8, off_mma, off_mmag, S8P;
     // tcgen05 (UMMA) operand block, one record of GPODE_UMMA_REC(SU) floats per output k:
     //   B_hi [SU x 8] | B_lo [SU x 8] | a [SU]   (SU = S rounded up to 32)   -- B = (Omega_k | phase | 0)^T, features x padded input dims, in
     //   the canonical K-major no-swizzle shared-memory layout of the MMA (8-feature x 16-byte core matrices: feature s,
@@ -69,7 +76,9 @@ struct GpodeLayout {
 };
 #define GPODE_UMMA_REC(SU) (17 * (SU))
 #define GPODE_MMA_REC 80
-#define GPODE_MMAG_REC 64
+#define GPODE_MMAH_REC 144
+#define GPODE_MMAH_MAX_D 5  // 3 D contraction slots (x_hi, x_hi, x_lo) must fit the 16 of one m16n8k16
+#define GPODE_MMAH_SCALE 256.f  // keeps the fp16 low parts of a Omega out of the subnormal range
 
 __host__ __device__ inline int gpode_round_up4(int x) { return (x + 3) & ~3; }
 
@@ -89,7 +98,8 @@ __host__ __device__ inline GpodeLayout gpode_layout(int D, int M, int S) {
     L.off_mma = L.total;
     L.off_mmag = L.off_mma + D * L.S8 * GPODE_MMA_REC;
     L.SU = (S + 31) & ~31;  // features padded to whole 32-column TMEM loads (zero weight)
-    L.off_umma = L.off_mmag + D * L.S8 * GPODE_MMAG_REC;
+    L.S8P = (L.S8 + 1) & ~1;
+    L.off_umma = L.off_mmag + (D <= GPODE_MMAH_MAX_D ? D * L.S8P * GPODE_MMAH_REC : 0);
     L.total_all = L.off_umma + (D <= 7 ? D * GPODE_UMMA_REC(L.SU) : 0);
     return L;
 }

@@ -11,6 +11,7 @@
 #pragma once
 #include <stdlib.h>
 #include "vf_mma.cuh"
+#include "vjp_mma.cuh"
 
 namespace {
 
@@ -589,6 +590,162 @@ vf_fwd_mma_kernel(const float* __restrict__ packed, const int M, const int S, co
     }
 }
 
+// ---- tensor-core adjoint kernels (vjp_mma.cuh) -------------------------------------------------------------------
+// One CTA of kHWarps warps per SM (the f16 operand records take ~92 KB at D = 5, S = 256, so they are staged once per
+// SM); a warp owns 32 rows, lane = row.
+// dynamic shared memory: [0,16) mbarrier | [kern | il] | mmah records | (D*D + D) block-reduction floats | per-warp stage
+constexpr int kHWarps = 12;
+constexpr int kHThreads = kHWarps * 32;
+
+struct HParams {
+    int M, S8P, off_kern, n_small, off_mmah, n_mmah;
+    int parts;  // tuning: bit 0 = RFF part, bit 1 = RBF part (3 = the real thing)
+};
+
+template <int D>
+struct HSmem {
+    const float* small;
+    const uint32_t* mmah;
+    float* red;
+    float* stage;
+    __device__ __forceinline__ HSmem(unsigned char* smem_raw, const HParams& p) {
+        float* sp = reinterpret_cast<float*>(smem_raw + 16);
+        small = sp;
+        mmah = reinterpret_cast<const uint32_t*>(sp + p.n_small);
+        red = sp + p.n_small + p.n_mmah;
+        stage = red + ((D * D + D + 3) & ~3) + (threadIdx.x >> 5) * HShape<D>::kStageFloats;
+    }
+};
+
+template <int D>
+__device__ __forceinline__ void hacc_reduce(const HAcc<D>& qa, const float* __restrict__ small, const int M,
+                                            float* __restrict__ acc, float* red) {
+    float A[D][D], V[D];
+    qa.expand(small + M * VfShape<D>::KS, threadIdx.x & 3, A, V);
+    __syncthreads();
+    reduce_AV<D>(A, V, acc, red);
+}
+
+template <int D>
+__global__ void __launch_bounds__(kHThreads, 1)
+vf_bwd_mma_kernel(const float* __restrict__ packed, const HParams p, const float* __restrict__ x,
+                  const float* __restrict__ f, const float* __restrict__ gf, float* __restrict__ gx, const int64_t B,
+                  float* __restrict__ acc) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    stage_params_h(smem_raw, packed, p.off_kern, p.n_small, p.off_mmah, p.n_mmah);
+    const HSmem<D> sm(smem_raw, p);
+    for (int i = threadIdx.x; i < D * D + D; i += blockDim.x) sm.red[i] = 0.f;
+    HAcc<D> qa;
+    qa.clear();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t nblocks = (B + 31) / 32;
+    for (int64_t blk = (int64_t)blockIdx.x * kHWarps + warp; blk < nblocks; blk += (int64_t)gridDim.x * kHWarps) {
+        const int64_t row = blk * 32 + lane;
+        float xr[1][D], fr[1][D], kb[1][D], xb[1][D];
+        load_rows<D, 1>(xr, x, row, B, 0);
+        load_rows<D, 1>(fr, f, row, B, 0);
+        load_rows<D, 1>(kb, gf, row, B, 0);
+        vf_vjp_h<D>(sm.small, sm.mmah, sm.stage, p.M, p.S8P, xr, kb, fr, xb, qa, lane, p.parts);
+        store_rows<D, 1>(xb, gx, row, B, 0);
+    }
+    hacc_reduce<D>(qa, sm.small, p.M, acc, sm.red);
+}
+
+// Discrete adjoint of the 3/8-rule RK4 grid: the recursion, checkpoint reads and virtual-row outputs of
+// rk4_bwd_kernel<D, 1>, with the four VJPs of a step on the tensor cores.
+template <int D>
+__global__ void __launch_bounds__(kHThreads, 1)
+rk4_bwd_mma_kernel(const float* __restrict__ packed, const HParams p, const float* __restrict__ ts, const int Tg,
+                   const int64_t B, const float* __restrict__ xs, const float* __restrict__ kst,
+                   const float* __restrict__ gxs, float* __restrict__ gx0, float* __restrict__ vy,
+                   float* __restrict__ vk, float* __restrict__ acc) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    stage_params_h(smem_raw, packed, p.off_kern, p.n_small, p.off_mmah, p.n_mmah);
+    const HSmem<D> sm(smem_raw, p);
+    for (int i = threadIdx.x; i < D * D + D; i += blockDim.x) sm.red[i] = 0.f;
+    HAcc<D> qa;
+    qa.clear();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int R = 1;
+
+    const int64_t nblocks = (B + 31) / 32;
+    const int64_t plane = B * D;
+    for (int64_t blk = (int64_t)blockIdx.x * kHWarps + warp; blk < nblocks; blk += (int64_t)gridDim.x * kHWarps) {
+        const int64_t row0 = blk * 32 + lane;
+        float lam[R][D];
+        load_rows<D, R>(lam, gxs + (int64_t)(Tg - 1) * plane, row0, B, 0);
+        for (int i = Tg - 2; i >= 0; --i) {
+            const float h = __fsub_rn(__ldg(ts + i + 1), __ldg(ts + i));
+            const float* kb = kst + (int64_t)i * 4 * plane;
+            float* vyi = vy + (int64_t)i * 4 * plane;
+            float* vki = vk + (int64_t)i * 4 * plane;
+            float y[R][D], k1[R][D], k2[R][D], ks[R][D], ys[R][D], kbar[R][D], yb[R][D];
+            float sumyb[R][D], yb4[R][D], yb23[R][D];
+            load_rows<D, R>(y, xs + (int64_t)i * plane, row0, B, 0);
+            load_rows<D, R>(k1, kb, row0, B, 0);
+            load_rows<D, R>(k2, kb + plane, row0, B, 0);
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                kbar[0][j] = 0.125f * h * lam[0][j];
+                sumyb[0][j] = yb4[0][j] = yb23[0][j] = 0.f;
+            }
+            // the four stages share ONE inlined VJP (code size): stage input, forward value and the cotangent
+            // bookkeeping are selected by uniform branches around it
+#pragma unroll 1
+            for (int st = 4; st >= 1; --st) {
+                if (st == 4) {
+                    load_rows<D, R>(ks, kb + 2 * plane, row0, B, 0);  // k3
+                    stage4<D, R>(ys, y, k1, k2, ks, h);
+                    load_rows<D, R>(ks, kb + 3 * plane, row0, B, 0);  // k4 = f(y4)
+                } else if (st == 3) {
+                    stage3<D, R>(ys, y, k1, k2, h);
+                    load_rows<D, R>(ks, kb + 2 * plane, row0, B, 0);  // k3 = f(y3)
+                } else if (st == 2) {
+                    stage2<D, R>(ys, y, k1, h);
+#pragma unroll
+                    for (int j = 0; j < D; ++j) ks[0][j] = k2[0][j];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < D; ++j) {
+                        ys[0][j] = y[0][j];
+                        ks[0][j] = k1[0][j];
+                    }
+                }
+                store_rows<D, R>(ys, vyi + (int64_t)(st - 1) * plane, row0, B, 0);
+                store_rows<D, R>(kbar, vki + (int64_t)(st - 1) * plane, row0, B, 0);
+                vf_vjp_h<D>(sm.small, sm.mmah, sm.stage, p.M, p.S8P, ys, kbar, ks, yb, qa, lane, p.parts);
+                if (st == 4) {
+#pragma unroll
+                    for (int j = 0; j < D; ++j) {
+                        yb4[0][j] = yb[0][j];
+                        kbar[0][j] = fmaf(0.375f * h, lam[0][j], h * yb4[0][j]);
+                    }
+                } else if (st == 3) {
+#pragma unroll
+                    for (int j = 0; j < D; ++j) {
+                        sumyb[0][j] = yb4[0][j] + yb[0][j];
+                        kbar[0][j] = fmaf(0.375f * h, lam[0][j], h * (yb[0][j] - yb4[0][j]));  // kb2
+                        yb23[0][j] = -yb[0][j];
+                    }
+                } else if (st == 2) {
+#pragma unroll
+                    for (int j = 0; j < D; ++j) {
+                        sumyb[0][j] += yb[0][j];
+                        yb23[0][j] += yb[0][j];  // yb2 - yb3
+                        kbar[0][j] = fmaf(0.125f * h, lam[0][j], fmaf(h * GPODE_THIRD, yb23[0][j], h * yb4[0][j]));
+                    }
+                }
+            }
+            float gi[R][D];
+            load_rows<D, R>(gi, gxs + (int64_t)i * plane, row0, B, 0);
+#pragma unroll
+            for (int j = 0; j < D; ++j) lam[0][j] = gi[0][j] + lam[0][j] + (sumyb[0][j] + yb[0][j]);
+        }
+        store_rows<D, R>(lam, gx0, row0, B, 0);
+    }
+    hacc_reduce<D>(qa, sm.small, p.M, acc, sm.red);
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // host-side launch helpers
 // ------------------------------------------------------------------------------------------------------------------
@@ -657,6 +814,42 @@ template <int D, int R>
 inline bool use_wide(int64_t B) {
     static const bool force_narrow = getenv("GPODE_FORCE_NARROW") != nullptr;  // tuning knob: one row per thread
     return !force_narrow && R > 1 && B >= (int64_t)num_sms() * 2 * kThreads * R;
+}
+
+
+// Tensor-core adjoint (vjp_mma.cuh): state dimensions whose three split parts fit one k = 16 contraction, batches that
+// fill the machine. GPODE_BWD_MMA=0 keeps the FFMA2 adjoint.
+template <int D>
+constexpr bool kMmaBwd = (D >= 4 && D <= GPODE_MMAH_MAX_D);  // D = 3: measured slower than FFMA2 (1.77 vs 1.56 ms)
+inline bool use_mma_bwd(int64_t B) {
+    const char* e = getenv("GPODE_BWD_MMA");  // read per call: the parity tests run both adjoints in one process
+    if (e != nullptr && e[0] == '0') return false;
+    return B >= (int64_t)num_sms() * kHThreads;
+}
+template <int D>
+inline HParams h_params(const GpodeLayout& L) {
+    HParams p;
+    p.M = L.M; p.S8P = L.S8P;
+    p.off_kern = L.off_kern; p.n_small = L.total - L.off_kern;
+    p.off_mmah = L.off_mmag; p.n_mmah = D * L.S8P * GPODE_MMAH_REC;
+    const char* e = getenv("GPODE_MMA_PARTS");
+    p.parts = e ? atoi(e) : 3;
+    return p;
+}
+template <int D>
+inline size_t h_smem(const HParams& p) {
+    return 16 + ((size_t)p.n_small + p.n_mmah + ((D * D + D + 3) & ~3) + (size_t)kHWarps * HShape<D>::kStageFloats) * 4;
+}
+template <typename K>
+inline int h_grid(K kernel, int64_t B, size_t smem, int* grid) {
+    if (smem > 227 * 1024) {
+        gpode_set_error("tensor-core adjoint needs %zu bytes of shared memory", smem);
+        return -2;
+    }
+    GPODE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t want = (B + kHThreads - 1) / kHThreads, cap = num_sms();
+    *grid = (int)(want < cap ? want : cap);
+    return 0;
 }
 
 template <int D>
@@ -746,6 +939,17 @@ int launch_rk4_bwd(const float* packed, int M, int S, const float* t, int Tg, in
     const size_t smem = 16 + (size_t)(L.total + D * D + D) * 4;
     LaunchShape ls;
     constexpr int RW = RowsBwd<D>::value;
+    if constexpr (kMmaBwd<D>) {
+        const HParams hp = h_params<D>(L);
+        if (use_mma_bwd(B) && h_smem<D>(hp) <= 227 * 1024) {
+            int grid = 0;
+            if (int rc = h_grid(rk4_bwd_mma_kernel<D>, B, h_smem<D>(hp), &grid)) return rc;
+            rk4_bwd_mma_kernel<D><<<grid, kHThreads, h_smem<D>(hp), st>>>(packed, hp, t, Tg, B, xs, kst, gxs, gx0, vy,
+                                                                          vk, acc);
+            GPODE_LAUNCH_CHECK();
+            return 0;
+        }
+    }
     if (B <= kWarpPathMaxRows) {
         if (int rc = warp_shape_for(rk4_bwd_warp_kernel<D>, B, smem, &ls)) return rc;
         rk4_bwd_warp_kernel<D><<<ls.grid, ls.threads, ls.smem, st>>>(packed, M, S, L.total, t, Tg, B, xs, kst, gxs,
@@ -770,6 +974,16 @@ int launch_vf_bwd(const float* packed, int M, int S, const float* x, const float
     const size_t smem = 16 + (size_t)(L.total + D * D + D) * 4;
     LaunchShape ls;
     constexpr int RW = RowsBwd<D>::value;
+    if constexpr (kMmaBwd<D>) {
+        const HParams hp = h_params<D>(L);
+        if (use_mma_bwd(B) && h_smem<D>(hp) <= 227 * 1024) {
+            int grid = 0;
+            if (int rc = h_grid(vf_bwd_mma_kernel<D>, B, h_smem<D>(hp), &grid)) return rc;
+            vf_bwd_mma_kernel<D><<<grid, kHThreads, h_smem<D>(hp), st>>>(packed, hp, x, f, gf, gx, B, acc);
+            GPODE_LAUNCH_CHECK();
+            return 0;
+        }
+    }
     if (B <= kWarpPathMaxRows) {
         if (int rc = warp_shape_for(vf_bwd_warp_kernel<D>, B, smem, &ls)) return rc;
         vf_bwd_warp_kernel<D><<<ls.grid, ls.threads, ls.smem, st>>>(packed, M, S, L.total, x, f, gf, gx, B, acc);

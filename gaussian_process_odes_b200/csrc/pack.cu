@@ -1,6 +1,7 @@
 // Error plumbing, ABI version, and the cache repacking kernel.
 #include "common.cuh"
 #include <string.h>
+#include <cuda_fp16.h>
 
 static thread_local char g_err[512] = "";
 
@@ -39,9 +40,49 @@ __global__ void pack_kernel(const GpodeLayout L, const float* __restrict__ omega
     }
     const int n_rff = D * S2, n_kern = M, n_il = D, n_mma = D * L.S8 * 32;
     const int n_umma = D <= 7 ? D * L.SU : 0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rff + n_kern + n_il + n_mma + n_umma;
+    const int n_mmah = D <= GPODE_MMAH_MAX_D ? D * L.S8P * 32 : 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rff + n_kern + n_il + n_mma + n_umma + n_mmah;
          i += gridDim.x * blockDim.x) {
-        if (i < n_rff) {
+        if (i >= n_rff + n_kern + n_il + n_mma + n_umma) {
+            // f16 tensor-core operands of the adjoint (see GpodeLayout::mmah) for one lane of one (k, feature tile)
+            const int q = i - (n_rff + n_kern + n_il + n_mma + n_umma);
+            const int lane = q & 31, rec = q >> 5;          // rec = k * S8P + ft
+            const int k = rec / L.S8P, ft = rec - k * L.S8P;
+            const int g = lane >> 2, t = lane & 3;
+            uint32_t* o = reinterpret_cast<uint32_t*>(out + L.off_mmag + (size_t)rec * GPODE_MMAH_REC);
+            auto om = [&](int j, int sidx) -> float {
+                return (j < D && sidx < S) ? omega[((size_t)j * S + sidx) * D + k] : 0.f;
+            };
+            auto split = [](float v, __half& hi, __half& lo) {
+                hi = __float2half_rn(v);
+                lo = __float2half_rn(v - __half2float(hi));
+            };
+            auto pack2 = [](__half a, __half b) -> uint32_t {
+                return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+            };
+            auto slotB = [&](int slot, int sidx) -> __half {  // theta-B[slot][feature]
+                __half hi = __float2half_rn(0.f), lo = hi;
+                if (slot < 3 * D) split(om(slot % D, sidx), hi, lo);
+                return (slot >= D && slot < 2 * D) ? lo : hi;
+            };
+            const int sg = 8 * ft + g;
+            o[lane * 2 + 0] = pack2(slotB(2 * t, sg), slotB(2 * t + 1, sg));
+            o[lane * 2 + 1] = pack2(slotB(2 * t + 8, sg), slotB(2 * t + 9, sg));
+            const float ak = sqrtf(var[k] / (float)S) * GPODE_MMAH_SCALE;
+            __half bh[2], bl[2];
+            for (int h = 0; h < 2; ++h) {
+                const int sidx = 8 * ft + 2 * t + h;
+                const float a = sidx < S ? w[sidx * D + k] * ak : 0.f;
+                split(a * om(g, sidx), bh[h], bl[h]);
+                if (g == 0) {
+                    const float ph = sidx < S ? phase[sidx * D + k] : 0.f;
+                    reinterpret_cast<float*>(o)[64 + t * 4 + h] = ph;
+                    reinterpret_cast<float*>(o)[64 + t * 4 + 2 + h] = ph;
+                }
+            }
+            o[80 + lane] = pack2(bh[0], bh[1]);
+            o[112 + lane] = pack2(bl[0], bl[1]);
+        } else if (i < n_rff) {
             const int k = i / S2, s2 = i - k * S2;
             // element e of the record lives at chunk e/4, slot e%4 of the chunk-major group layout
             float* base = out + L.off_rff + ((size_t)k * L.S2P + (s2 & ~31)) * L.RP + (s2 & 31) * 4;
@@ -90,17 +131,12 @@ __global__ void pack_kernel(const GpodeLayout L, const float* __restrict__ omega
             const int k = rec / L.S8, ft = rec - k * L.S8;
             const int g = lane >> 2, t = lane & 3;
             float* o = out + L.off_mma + (size_t)rec * GPODE_MMA_REC;
-            float* og = out + L.off_mmag + (size_t)rec * GPODE_MMAG_REC;
             auto om = [&](int j, int sidx) -> float {
                 return (j < D && sidx < S) ? omega[((size_t)j * S + sidx) * D + k] : 0.f;
             };
             // theta = x Omega: B is (j x feature), b0 = B[t][g], b1 = B[t+4][g]
             o[lane * 2 + 0] = om(t, 8 * ft + g);
             o[lane * 2 + 1] = om(t + 4, 8 * ft + g);
-            // G = g Omega^T: B is (feature x j) with the feature order of the theta accumulator fragment
-            // (A columns t, t+4 hold features 2t, 2t+1): b0 = Omega[j=g][2t], b1 = Omega[j=g][2t+1]
-            og[lane * 2 + 0] = om(g, 8 * ft + 2 * t);
-            og[lane * 2 + 1] = om(g, 8 * ft + 2 * t + 1);
             if (g == 0) {
                 const float ak = sqrtf(var[k] / (float)S);
                 for (int h = 0; h < 2; ++h) {
@@ -122,7 +158,8 @@ static int pack_sets(const gpode_cache_t* c, int n_sets, float* packed, void* st
     GPODE_CHECK_ARG(c->M >= 1 && c->S >= 1, "M=%d and S=%d must be positive", c->M, c->S);
     GPODE_CHECK_ARG(c->omega && c->phase && c->w && c->Z && c->ell && c->var, "cache tensor is NULL");
     const GpodeLayout L = gpode_layout(c->D, c->M, c->S);
-    const int n = c->D * L.S2 + c->M + c->D + c->D * L.S8 * 32 + (c->D <= 7 ? c->D * L.SU : 0);
+    const int n = c->D * L.S2 + c->M + c->D + c->D * L.S8 * 32 + (c->D <= 7 ? c->D * L.SU : 0) +
+                  (c->D <= GPODE_MMAH_MAX_D ? c->D * L.S8P * 32 : 0);
     pack_kernel<<<dim3((n + 127) / 128, n_sets), 128, 0, (cudaStream_t)stream>>>(L, c->omega, c->phase, c->w, c->Z,
                                                                                  c->nu, c->ell, c->var, packed);
     GPODE_LAUNCH_CHECK();

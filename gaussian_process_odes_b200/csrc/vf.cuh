@@ -44,7 +44,7 @@ template <int D, int R, bool kWarp = false>
 __device__ __forceinline__ void vf_eval(const float* __restrict__ sp, const int M, const int S,
                                         const float (&x)[R][D], float (&f)[R][D], const int i0 = 0,
                                         const int istep = 1) {
-    constexpr int RP = VfShape<D>::RP, KS = VfShape<D>::KS, WP = VfShape<D>::WP, KP = VfShape<D>::KP;
+    constexpr int RP = VfShape<D>::RP, KS = VfShape<D>::KS, WP = VfShape<D>::WP;
     const int S2 = (S + 1) >> 1, S2P = (S2 + 31) & ~31;
     const float* __restrict__ rff = sp;
     const float* __restrict__ kern = sp + D * S2P * RP;
@@ -83,19 +83,28 @@ __device__ __forceinline__ void vf_eval(const float* __restrict__ sp, const int 
         }
     }
 
-    float2 wn[D][KP];  // -w, output pairs
+    // Full output pairs ride in FFMA2; the odd last output (D = 1, 3, 5, 7) takes scalar FMAs instead of a half-empty
+    // pair, which would cost the FMA pipe as much as a full one (the pipe bounds this part: ncu math_pipe_throttle).
+    constexpr int KF = D / 2;
+    constexpr bool kOdd = (D & 1) != 0;
+    float2 wn[D][KF > 0 ? KF : 1];  // -w, output pairs
+    float wl[D];                    // -w of the last output
 #pragma unroll
     for (int j = 0; j < D; ++j) {
         float t[WP];
         lds_vec<WP>(t, wnp + j * WP);
 #pragma unroll
-        for (int kp = 0; kp < KP; ++kp) wn[j][kp] = make_float2(t[2 * kp], t[2 * kp + 1]);
+        for (int kp = 0; kp < KF; ++kp) wn[j][kp] = make_float2(t[2 * kp], t[2 * kp + 1]);
+        wl[j] = t[D - 1];
     }
-    float2 fk[R][KP];
+    float2 fk[R][KF > 0 ? KF : 1];
+    float fl[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r)
+    for (int r = 0; r < R; ++r) {
+        fl[r] = 0.f;
 #pragma unroll
-        for (int kp = 0; kp < KP; ++kp) fk[r][kp] = make_float2(0.f, 0.f);
+        for (int kp = 0; kp < KF; ++kp) fk[r][kp] = make_float2(0.f, 0.f);
+    }
 
 #pragma unroll 2
     for (int m = i0; m < M; m += istep) {
@@ -110,22 +119,29 @@ __device__ __forceinline__ void vf_eval(const float* __restrict__ sp, const int 
                 dd[j] = d * d;
             }
 #pragma unroll
-            for (int kp = 0; kp < KP; ++kp) {
+            for (int kp = 0; kp < KF; ++kp) {
                 float2 e = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int j = 0; j < D; ++j) e = ffma2(dd[j], wn[j][kp], e);
-                float2 K;
-                K.x = gpode_ex2(e.x);
-                K.y = (2 * kp + 1 < D) ? gpode_ex2(e.y) : 0.f;
+                const float2 K = make_float2(gpode_ex2(e.x), gpode_ex2(e.y));
                 fk[r][kp] = ffma2(make_float2(kp_[D + 2 * kp], kp_[D + 2 * kp + 1]), K, fk[r][kp]);
+            }
+            if constexpr (kOdd) {
+                float e = 0.f;
+#pragma unroll
+                for (int j = 0; j < D; ++j) e = fmaf(dd[j], wl[j], e);
+                fl[r] = fmaf(kp_[2 * D - 1], gpode_ex2(e), fl[r]);
             }
         }
     }
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
-        for (int k = 0; k < D; ++k)
-            f[r][k] = (fr[r][k].x + fr[r][k].y) + ((k & 1) ? fk[r][k >> 1].y : fk[r][k >> 1].x);
+        for (int k = 0; k < D; ++k) {
+            const float u = (kOdd && k == D - 1) ? fl[r] : ((k & 1) ? fk[r][(k >> 1) < KF ? (k >> 1) : 0].y
+                                                                   : fk[r][(k >> 1) < KF ? (k >> 1) : 0].x);
+            f[r][k] = (fr[r][k].x + fr[r][k].y) + u;
+        }
 }
 
 // VJP at x with cotangent kb: xb = J(x)^T kb, and the per-thread partial sums of the shared-parameter gradients that
@@ -138,7 +154,7 @@ __device__ __forceinline__ void vf_vjp(const float* __restrict__ sp, const int M
                                        const float (&x)[R][D], const float (&kb)[R][D], const float (&fst)[R][D],
                                        float (&xb)[R][D], float (&A)[D][D], float (&V)[D], const int i0 = 0,
                                        const int istep = 1) {
-    constexpr int RP = VfShape<D>::RP, KS = VfShape<D>::KS, WP = VfShape<D>::WP, KP = VfShape<D>::KP;
+    constexpr int RP = VfShape<D>::RP, KS = VfShape<D>::KS, WP = VfShape<D>::WP;
     const int S2 = (S + 1) >> 1, S2P = (S2 + 31) & ~31;
     const float* __restrict__ rff = sp;
     const float* __restrict__ kern = sp + D * S2P * RP;
@@ -194,30 +210,42 @@ __device__ __forceinline__ void vf_vjp(const float* __restrict__ sp, const int M
             }
     }
 
-    // ---- RBF part: inducing point m outer, output pairs inner ----
-    float2 wn[D][KP];
+    // ---- RBF part: inducing point m outer, output pairs inner (odd last output: scalar FMAs, see vf_eval) ----
+    constexpr int KF = D / 2;
+    constexpr bool kOdd = (D & 1) != 0;
+    float2 wn[D][KF > 0 ? KF : 1];
+    float wl[D];
 #pragma unroll
     for (int j = 0; j < D; ++j) {
         float t[WP];
         lds_vec<WP>(t, wnp + j * WP);
 #pragma unroll
-        for (int kp = 0; kp < KP; ++kp) wn[j][kp] = make_float2(t[2 * kp], t[2 * kp + 1]);
+        for (int kp = 0; kp < KF; ++kp) wn[j][kp] = make_float2(t[2 * kp], t[2 * kp + 1]);
+        wl[j] = t[D - 1];
     }
-    float2 fu[R][KP], A2[KP][D];
+    float2 fu[R][KF > 0 ? KF : 1], A2[KF > 0 ? KF : 1][D];
+    float ful[R], A2l[D];
 #pragma unroll
-    for (int kp = 0; kp < KP; ++kp) {
+    for (int j = 0; j < D; ++j) A2l[j] = 0.f;
+#pragma unroll
+    for (int r = 0; r < R; ++r) ful[r] = 0.f;
+#pragma unroll
+    for (int kp = 0; kp < KF; ++kp) {
 #pragma unroll
         for (int r = 0; r < R; ++r) fu[r][kp] = make_float2(0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < D; ++j) A2[kp][j] = make_float2(0.f, 0.f);
     }
-    float2 kbn[R][KP];  // 2 ln2 * kb, output pairs  (q' = -2 ln2 kb c K and u = q' w = (2 ln2 kb c K)(-w))
+    // 2 ln2 * kb  (q' = -2 ln2 kb c K and u = q' w = (2 ln2 kb c K)(-w))
+    float2 kbn[R][KF > 0 ? KF : 1];
+    float kbl[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r)
+    for (int r = 0; r < R; ++r) {
 #pragma unroll
-        for (int kp = 0; kp < KP; ++kp)
-            kbn[r][kp] = make_float2(-GPODE_NEG_2LN2 * kb[r][2 * kp],
-                                     (2 * kp + 1 < D) ? -GPODE_NEG_2LN2 * kb[r][(2 * kp + 1 < D) ? 2 * kp + 1 : 0] : 0.f);
+        for (int kp = 0; kp < KF; ++kp)
+            kbn[r][kp] = make_float2(-GPODE_NEG_2LN2 * kb[r][2 * kp], -GPODE_NEG_2LN2 * kb[r][2 * kp + 1]);
+        kbl[r] = -GPODE_NEG_2LN2 * kb[r][D - 1];
+    }
 
 #pragma unroll 2
     for (int m = i0; m < M; m += istep) {
@@ -232,16 +260,18 @@ __device__ __forceinline__ void vf_vjp(const float* __restrict__ sp, const int M
                 dd[j] = d[j] * d[j];
             }
             float2 tq[D];  // t_j = sum_k q'_k (-w_kj), one partial per output of the pair
+            float tl[D];
 #pragma unroll
-            for (int j = 0; j < D; ++j) tq[j] = make_float2(0.f, 0.f);
+            for (int j = 0; j < D; ++j) {
+                tq[j] = make_float2(0.f, 0.f);
+                tl[j] = 0.f;
+            }
 #pragma unroll
-            for (int kp = 0; kp < KP; ++kp) {
+            for (int kp = 0; kp < KF; ++kp) {
                 float2 e = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int j = 0; j < D; ++j) e = ffma2(dd[j], wn[j][kp], e);
-                float2 K;
-                K.x = gpode_ex2(e.x);
-                K.y = (2 * kp + 1 < D) ? gpode_ex2(e.y) : 0.f;
+                const float2 K = make_float2(gpode_ex2(e.x), gpode_ex2(e.y));
                 const float2 cK = fmul2(make_float2(kp_[D + 2 * kp], kp_[D + 2 * kp + 1]), K);
                 fu[r][kp] = fadd2(fu[r][kp], cK);
                 const float2 q = fmul2(kbn[r][kp], cK);
@@ -251,8 +281,21 @@ __device__ __forceinline__ void vf_vjp(const float* __restrict__ sp, const int M
                     A2[kp][j] = ffma2(dd[j], q, A2[kp][j]);   // the factor -w_kj is applied once, at the very end
                 }
             }
+            if constexpr (kOdd) {
+                float e = 0.f;
 #pragma unroll
-            for (int j = 0; j < D; ++j) xb2[r][j].x = fmaf(d[j], tq[j].x + tq[j].y, xb2[r][j].x);
+                for (int j = 0; j < D; ++j) e = fmaf(dd[j], wl[j], e);
+                const float cK = kp_[2 * D - 1] * gpode_ex2(e);
+                ful[r] += cK;
+                const float q = kbl[r] * cK;
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    tl[j] = q * wl[j];
+                    A2l[j] = fmaf(dd[j], q, A2l[j]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < D; ++j) xb2[r][j].x = fmaf(d[j], (tq[j].x + tq[j].y) + tl[j], xb2[r][j].x);
         }
     }
 #pragma unroll
@@ -261,15 +304,20 @@ __device__ __forceinline__ void vf_vjp(const float* __restrict__ sp, const int M
         for (int j = 0; j < D; ++j) xb[r][j] = xb2[r][j].x + xb2[r][j].y;
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-            const float fuk = (k & 1) ? fu[r][k >> 1].y : fu[r][k >> 1].x;
+            const int kp = (k >> 1) < KF ? (k >> 1) : 0;
+            const float fuk = (kOdd && k == D - 1) ? ful[r] : ((k & 1) ? fu[r][kp].y : fu[r][kp].x);
             V[k] = fmaf(kb[r][k], fst[r][k] + fuk, V[k]);
         }
     }
 #pragma unroll
     for (int k = 0; k < D; ++k)
 #pragma unroll
-        for (int j = 0; j < D; ++j)
-            A[k][j] = fmaf((k & 1) ? wn[j][k >> 1].y : wn[j][k >> 1].x, (k & 1) ? A2[k >> 1][j].y : A2[k >> 1][j].x, A[k][j]);
+        for (int j = 0; j < D; ++j) {
+            const int kp = (k >> 1) < KF ? (k >> 1) : 0;
+            const float w = (kOdd && k == D - 1) ? wl[j] : ((k & 1) ? wn[j][kp].y : wn[j][kp].x);
+            const float a = (kOdd && k == D - 1) ? A2l[j] : ((k & 1) ? A2[kp][j].y : A2[kp][j].x);
+            A[k][j] = fmaf(w, a, A[k][j]);
+        }
 }
 
 // ---- staging of the packed block into shared memory (bulk async copy + mbarrier) -------------------------------

@@ -314,3 +314,54 @@ def test_errors_are_loud():
         ops.vector_field(torch.zeros(4, 3, device="cuda"), *args)
     # empty batch is legal
     assert ops.vector_field(torch.zeros(0, 2, device="cuda"), *args).shape == (0, 2)
+
+
+@pytest.mark.parametrize("D,M,S,B", [(5, 100, 256, 40000), (3, 24, 64, 38000), (4, 33, 100, 40001), (6, 20, 48, 39000),
+                                     (7, 17, 43, 40000)])
+def test_rk4_backward_tensor_core_adjoint(D, M, S, B, monkeypatch):
+    """3 <= D <= 7 and a batch that fills the machine: the adjoint's two Fourier projections run as 3xTF32 mma.sync
+    (csrc/vjp_mma.cuh). Checked against the oracle's autograd and against the FFMA2 adjoint (GPODE_BWD_MMA=0)."""
+    from gaussian_process_odes_b200 import ops
+    gp32, c32, gp64, c64, x = _setup(D, M, S, B, seed=D + B, nu_scale=0.3)
+    Tg = 3
+    ts = _grid(Tg, 0.1, Tg)
+    cot = torch.tensor(np.random.default_rng(9).normal(size=(Tg, B, D)), dtype=torch.float32)
+
+    def run(mode):
+        monkeypatch.setenv("GPODE_BWD_MMA", mode)
+        args = [a.detach().clone().requires_grad_(i < 4) for i, a in enumerate(_cuda_args(gp32, c32))]
+        xc = x.cuda().requires_grad_(True)
+        xs = ops.rk4_integrate(xc, ts.cuda(), *args)
+        xs.backward(cot.cuda())
+        return dict(x=xc.grad, Z=args[0].grad, ell=args[1].grad, var=args[2].grad, nu=args[3].grad)
+
+    got, base = run("1"), run("0")
+    out, leaves = _grads_oracle(
+        lambda l, cc: O.odeint(lambda t, y: O.vf_forward(y, l['Z'], l['ell'], l['var'], cc), l['x'],
+                               ts.to(l['x'].dtype), method='rk4'), gp32, c32, x, torch.float32)
+    out.backward(cot)
+    for k in got:
+        assert relerr(got[k], base[k]) <= TOL_GRAD, k
+        assert relerr(got[k].cpu().reshape(leaves[k].grad.shape), leaves[k].grad) <= 3 * TOL_GRAD, k
+
+
+@pytest.mark.parametrize("D,M,S,B", [(5, 100, 256, 50000), (3, 16, 40, 38011)])
+def test_vf_backward_tensor_core_adjoint(D, M, S, B, monkeypatch):
+    from gaussian_process_odes_b200 import ops
+    gp32, c32, gp64, c64, x = _setup(D, M, S, B, seed=D * 7 + B, nu_scale=0.3)
+    cot = torch.tensor(np.random.default_rng(5).normal(size=(B, D)), dtype=torch.float32)
+
+    def run(mode):
+        monkeypatch.setenv("GPODE_BWD_MMA", mode)
+        args = [a.detach().clone().requires_grad_(i < 4) for i, a in enumerate(_cuda_args(gp32, c32))]
+        xc = x.cuda().requires_grad_(True)
+        ops.vector_field(xc, *args).backward(cot.cuda())
+        return dict(x=xc.grad, Z=args[0].grad, ell=args[1].grad, var=args[2].grad, nu=args[3].grad)
+
+    got, base = run("1"), run("0")
+    out, leaves = _grads_oracle(lambda l, cc: O.vf_forward(l['x'], l['Z'], l['ell'], l['var'], cc), gp32, c32, x,
+                                torch.float32)
+    out.backward(cot)
+    for k in got:
+        assert relerr(got[k], base[k]) <= TOL_GRAD, k
+        assert relerr(got[k].cpu().reshape(leaves[k].grad.shape), leaves[k].grad) <= 3 * TOL_GRAD, k
