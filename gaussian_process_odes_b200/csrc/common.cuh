@@ -63,9 +63,9 @@ struct GpodeLayout {
     //                        [0,64)    theta-B, lane-major (b0,b1) half2 pairs: contraction slots 0..D-1 = Omega_hi,
     //                                  D..2D-1 = Omega_lo, 2D..3D-1 = Omega_hi (the state tile carries x_hi, x_hi, x_lo)
     //                        [64,80)   per quad lane t: phase(2t), phase(2t+1), phase(2t), phase(2t+1)  (fp32, the MMA's C)
-    //                        [80,112)  G-B hi, one half2 per lane: (Bp_hi[2t][g], Bp_hi[2t+1][g]),
-    //                                  Bp[s][j] = GPODE_MMAH_SCALE a_s Omega_{j,s,k}
-    //                        [112,144) G-B lo, same arrangement
+    //                        [80,144)  G-B of the tile PAIR (2i, 2i+1), lane-major (b0,b1): the even record holds the hi
+    //                                  parts (tile 2i, tile 2i+1), the odd record the lo parts; one half2 =
+    //                                  (Bp[2t][g], Bp[2t+1][g]), Bp[s][j] = GPODE_MMAH_SCALE a_s Omega_{j,s,k}
     int S8, off_mma, off_mmag, S8P;
     // tcgen05 (UMMA) operand block, one record of GPODE_UMMA_REC(SU) floats per output k:
     //   B_hi [SU x 8] | B_lo [SU x 8] | a [SU]   (SU = S rounded up to 32)   -- B = (Omega_k | phase | 0)^T, features x padded input dims, in

@@ -80,8 +80,12 @@ __global__ void pack_kernel(const GpodeLayout L, const float* __restrict__ omega
                     reinterpret_cast<float*>(o)[64 + t * 4 + 2 + h] = ph;
                 }
             }
-            o[80 + lane] = pack2(bh[0], bh[1]);
-            o[112 + lane] = pack2(bl[0], bl[1]);
+            // G-B operands of a tile PAIR (2i, 2i+1) sit together so that each MMA's (b0, b1) comes out of one LDS.64:
+            // even record [80,144): lane-major (hi of tile 2i, hi of tile 2i+1); odd record [80,144): (lo, lo)
+            uint32_t* even = (ft & 1) ? o - GPODE_MMAH_REC : o;
+            uint32_t* odd = even + GPODE_MMAH_REC;
+            even[80 + lane * 2 + (ft & 1)] = pack2(bh[0], bh[1]);
+            odd[80 + lane * 2 + (ft & 1)] = pack2(bl[0], bl[1]);
         } else if (i < n_rff) {
             const int k = i / S2, s2 = i - k * S2;
             // element e of the record lives at chunk e/4, slot e%4 of the chunk-major group layout

@@ -18,9 +18,10 @@
 // replication). For the tensor-core phase the warp re-reads its rows from a shared-memory stage in the MMA fragment
 // layout, lane = (g = lane / 4, t = lane % 4), two 16-row tiles:
 //   theta tile  C[16 x 8 features] = A[16 x 16 slots] B[16 x 8] + phase; lane (g,t) gets features 2t, 2t+1 of rows g, g+8.
-//   G tile      C'[16 x 8 dims] += A'[16 x (8 hi | 8 lo features)] B'[(Bp_hi ; Bp_hi)], Bp = a Omega^T (pre-scaled, see
-//               GPODE_MMAH_SCALE): the fp32 accumulator pairs of theta ARE the half2 A' fragment after sin and split,
-//               no shuffle; the third term g_hi Bp_lo of two consecutive feature tiles shares one more MMA.
+//   G tile      C'[16 x 8 dims] += A'[16 x 16 features of a tile pair] B'[16 x 8], Bp = a Omega^T (pre-scaled, see
+//               GPODE_MMAH_SCALE), once per split term (g_hi Bp_hi, g_lo Bp_hi, g_hi Bp_lo; three independent
+//               accumulators): the fp32 accumulator pairs of theta ARE the half2 A' fragment after sin and split --
+//               no shuffle, no register copy.
 //               Lane (g,t) gets G for input dimensions 2t, 2t+1 of rows g, g+8 and hands the row cotangent back
 //               through the stage.
 #pragma once
@@ -160,54 +161,52 @@ __device__ __forceinline__ void vf_vjp_h(const float* __restrict__ small, const 
 
 #pragma unroll 1   // one copy of the feature loop: the instruction cache is the scarce resource with 12 warps per SM
             for (int k = 0; k < D; ++k) {
-                // three independent accumulation chains per row tile: hi/lo terms of the even and of the odd feature tile,
-                // and the shared g_hi Bp_lo term
-                float Ga[2][4], Gb[2][4], Gl[2][4];
+                // three independent accumulation chains per row tile, one per split term: g_hi Bp_hi, g_lo Bp_hi, g_hi Bp_lo
+            float Ga[2][4], Gb[2][4], Gl[2][4];
 #pragma unroll
-                for (int mt = 0; mt < 2; ++mt)
+            for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) Ga[mt][i] = Gb[mt][i] = Gl[mt][i] = 0.f;
+                for (int i = 0; i < 4; ++i) Ga[mt][i] = Gb[mt][i] = Gl[mt][i] = 0.f;
 
-                const uint32_t* __restrict__ rec = mmah + (size_t)k * S8P * GPODE_MMAH_REC;
+            const uint32_t* __restrict__ rec = mmah + (size_t)k * S8P * GPODE_MMAH_REC;
 #pragma unroll 1
-                for (int ft = 0; ft < S8P; ft += 2, rec += 2 * GPODE_MMAH_REC) {
-                    uint32_t hq[2][2][2];  // [feature tile][row tile][row g | row g+8]: g_hi pairs, reused by the lo term
-                    uint32_t bl[2];
+            for (int ft = 0; ft < S8P; ft += 2, rec += 2 * GPODE_MMAH_REC) {
+                // The G MMAs contract over the 16 features of a tile PAIR (slots 0..7 = even tile, 8..15 = odd tile),
+                // so every A fragment is written in place by the conversions and every B pair is one LDS.64.
+                uint32_t ah[2][4], al[2][4];  // [row tile][row g: even tile | row g+8: even | row g: odd | row g+8: odd]
+                const uint2 bh = *reinterpret_cast<const uint2*>(rec + 80 + lane * 2);
+                const uint2 bl = *reinterpret_cast<const uint2*>(rec + GPODE_MMAH_REC + 80 + lane * 2);
 #pragma unroll
-                    for (int tl = 0; tl < 2; ++tl) {
-                        const uint32_t* __restrict__ rc = rec + tl * GPODE_MMAH_REC;
-                        const uint2 b = *reinterpret_cast<const uint2*>(rc + lane * 2);
-                        const float4 ph = *reinterpret_cast<const float4*>(rc + 64 + t * 4);
-                        const uint32_t bh = rc[80 + lane];
-                        bl[tl] = rc[112 + lane];
-                        float c[2][4];
-                        gpode_mma_f16(c[0], ax[0], b.x, b.y, ph);
-                        gpode_mma_f16(c[1], ax[1], b.x, b.y, ph);
-#pragma unroll
-                        for (int mt = 0; mt < 2; ++mt) {
-                            float h[4], l[4];
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const float v = __sinf(c[mt][i]);
-                                h[i] = gpode_trunc11(v);
-                                l[i] = v - h[i];
-                            }
-                            uint32_t a[4];
-                            a[0] = hq[tl][mt][0] = gpode_pack_h2(h[0], h[1]);
-                            a[1] = hq[tl][mt][1] = gpode_pack_h2(h[2], h[3]);
-                            a[2] = gpode_pack_h2(l[0], l[1]);
-                            a[3] = gpode_pack_h2(l[2], l[3]);
-                            if (tl == 0) gpode_mma_f16_acc(Ga[mt], a, bh, bh);
-                            else gpode_mma_f16_acc(Gb[mt], a, bh, bh);
-                        }
-                    }
+                for (int tl = 0; tl < 2; ++tl) {
+                    const uint32_t* __restrict__ rc = rec + tl * GPODE_MMAH_REC;
+                    const uint2 b = *reinterpret_cast<const uint2*>(rc + lane * 2);
+                    const float4 ph = *reinterpret_cast<const float4*>(rc + 64 + t * 4);
+                    float c[2][4];
+                    gpode_mma_f16(c[0], ax[0], b.x, b.y, ph);
+                    gpode_mma_f16(c[1], ax[1], b.x, b.y, ph);
 #pragma unroll
                     for (int mt = 0; mt < 2; ++mt) {
-                        const uint32_t a[4] = {hq[0][mt][0], hq[0][mt][1], hq[1][mt][0], hq[1][mt][1]};
-                        gpode_mma_f16_acc(Gl[mt], a, bl[0], bl[1]);
+                        float h[4], l[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float v = __sinf(c[mt][i]);
+                            h[i] = gpode_trunc11(v);
+                            l[i] = v - h[i];
+                        }
+                        ah[mt][2 * tl + 0] = gpode_pack_h2(h[0], h[1]);
+                        ah[mt][2 * tl + 1] = gpode_pack_h2(h[2], h[3]);
+                        al[mt][2 * tl + 0] = gpode_pack_h2(l[0], l[1]);
+                        al[mt][2 * tl + 1] = gpode_pack_h2(l[2], l[3]);
                     }
                 }
-                // the row's factor (2 ln2 kb_k; sign and scale are folded into cG) once per output, after the feature loop
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    gpode_mma_f16_acc(Ga[mt], ah[mt], bh.x, bh.y);
+                    gpode_mma_f16_acc(Gb[mt], al[mt], bh.x, bh.y);
+                    gpode_mma_f16_acc(Gl[mt], ah[mt], bl.x, bl.y);
+                }
+            }
+            // the row's factor (2 ln2 kb_k; sign and scale are folded into cG) once per output, after the feature loop
                 float aq[2] = {0.f, 0.f};
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt)
