@@ -51,19 +51,26 @@ param_grad_kernel(const float* __restrict__ packed, const int M, const int S, co
     const bool active = m < M;
     const int mm = active ? m : 0;
 
-    constexpr int KP = VfShape<D>::KP;
-    float z[D];
-    float2 wn[D][KP];  // -w, output pairs (same packing as the integrator kernels)
+    // full output pairs ride in FFMA2, the odd last output in scalar FMAs (a half-empty pair costs the FMA pipe,
+    // which bounds this kernel, as much as a full one)
+    constexpr int KF = D / 2, KFA = KF > 0 ? KF : 1;
+    constexpr bool kOdd = (D & 1) != 0;
+    float z[D], wl[D];
+    float2 wn[D][KFA];  // -w, output pairs (same packing as the integrator kernels)
 #pragma unroll
     for (int j = 0; j < D; ++j) {
         z[j] = __ldg(kern + mm * KS + j);
 #pragma unroll
-        for (int kp = 0; kp < KP; ++kp)
+        for (int kp = 0; kp < KF; ++kp)
             wn[j][kp] = make_float2(__ldg(wnp + j * WP + 2 * kp), __ldg(wnp + j * WP + 2 * kp + 1));
+        wl[j] = __ldg(wnp + j * WP + D - 1);
     }
-    float2 T2[KP], W2[KP][D];
+    float2 T2[KFA], W2[KFA][D];
+    float Tl = 0.f, Wl[D];
 #pragma unroll
-    for (int kp = 0; kp < KP; ++kp) {
+    for (int j = 0; j < D; ++j) Wl[j] = 0.f;
+#pragma unroll
+    for (int kp = 0; kp < KF; ++kp) {
         T2[kp] = make_float2(0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < D; ++j) W2[kp][j] = make_float2(0.f, 0.f);
@@ -121,17 +128,24 @@ param_grad_kernel(const float* __restrict__ packed, const int M, const int S, co
                     dd[j] = d[j] * d[j];
                 }
 #pragma unroll
-                for (int kp = 0; kp < KP; ++kp) {
+                for (int kp = 0; kp < KF; ++kp) {
                     float2 e = make_float2(0.f, 0.f);
 #pragma unroll
                     for (int j = 0; j < D; ++j) e = ffma2(dd[j], wn[j][kp], e);
-                    float2 K;
-                    K.x = gpode_ex2(e.x);
-                    K.y = (2 * kp + 1 < D) ? gpode_ex2(e.y) : 0.f;
-                    const float2 p = fmul2(make_float2(kb[2 * kp], (2 * kp + 1 < D) ? kb[(2 * kp + 1 < DP) ? 2 * kp + 1 : 0] : 0.f), K);
+                    const float2 K = make_float2(gpode_ex2(e.x), gpode_ex2(e.y));
+                    const float2 p = fmul2(make_float2(kb[2 * kp], kb[2 * kp + 1]), K);
                     T2[kp] = fadd2(T2[kp], p);
 #pragma unroll
                     for (int j = 0; j < D; ++j) W2[kp][j] = ffma2(d[j], p, W2[kp][j]);
+                }
+                if constexpr (kOdd) {
+                    float e = 0.f;
+#pragma unroll
+                    for (int j = 0; j < D; ++j) e = fmaf(dd[j], wl[j], e);
+                    const float p = kb[D - 1] * gpode_ex2(e);
+                    Tl += p;
+#pragma unroll
+                    for (int j = 0; j < D; ++j) Wl[j] = fmaf(d[j], p, Wl[j]);
                 }
             }
         }
@@ -142,10 +156,12 @@ param_grad_kernel(const float* __restrict__ packed, const int M, const int S, co
         const GpodeAcc a = gpode_acc_layout(D, M);
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-            atomicAdd(acc + a.off_T + k * M + m, (k & 1) ? T2[k >> 1].y : T2[k >> 1].x);
+            const bool last = kOdd && k == D - 1;
+            const int kp = (k >> 1) < KF ? (k >> 1) : 0;
+            atomicAdd(acc + a.off_T + k * M + m, last ? Tl : ((k & 1) ? T2[kp].y : T2[kp].x));
 #pragma unroll
             for (int j = 0; j < D; ++j)
-                atomicAdd(acc + a.off_W + (k * M + m) * D + j, (k & 1) ? W2[k >> 1][j].y : W2[k >> 1][j].x);
+                atomicAdd(acc + a.off_W + (k * M + m) * D + j, last ? Wl[j] : ((k & 1) ? W2[kp][j].y : W2[kp][j].x));
         }
     }
 }
