@@ -14,6 +14,7 @@ import torch
 from .. import ops
 from ..misc import transforms
 from ..misc.param import Param
+from ..misc.torch_utils import host_to_device
 from .kernels import RBF
 
 jitter = 1e-5
@@ -59,7 +60,7 @@ class DSVGP_Layer(torch.nn.Module):
 
     def sample_inducing(self):
         """u ~ q(u) = N(Um, Us Us^T) in whitened coordinates, ``(M, D_out)`` (reference ``dsvgp.py:78-90``)."""
-        epsilon = sample_normal(shape=(self.M, self.D_out), seed=None).to(self._device)
+        epsilon = host_to_device(sample_normal(shape=(self.M, self.D_out), seed=None), self._device)
         if self.q_diag:
             ZS = self.Us_sqrt() * epsilon
         else:
@@ -78,10 +79,10 @@ class DSVGP_Layer(torch.nn.Module):
         form (reference ``dsvgp.py:92-122``). Draw order on the host RNG is the reference's: weights, omega, phase,
         epsilon."""
         dev = self._device
-        self.rff_weights = sample_normal((self.S, self.D_out)).to(dev)
+        self.rff_weights = host_to_device(sample_normal((self.S, self.D_out)), dev)
         self.rff_omega = self.kern.sample_freq(self.S)
         phase_shape = (1, self.S, self.D_out) if self.dimwise else (1, self.S)
-        self.rff_phase = sample_uniform(phase_shape).to(dev) * 2 * np.pi
+        self.rff_phase = host_to_device(sample_uniform(phase_shape), dev) * 2 * np.pi
         inducing_val = self.sample_inducing()
         nu = ops.whiten(self.inducing_loc(), self.kern.lengthscales_dimwise(), self.kern.variance_dimwise(),
                         inducing_val, self._omega_dimwise(), self._phase_dimwise(), self.rff_weights, jitter)

@@ -11,6 +11,7 @@ from torch.nn import init
 
 from ..misc.constraint_utils import invsoftplus, softplus
 from ..misc.settings import settings
+from ..misc.torch_utils import host_to_device
 
 
 def sample_normal(shape, seed=None):
@@ -73,6 +74,6 @@ class RBF(nn.Module):
     def sample_freq(self, S, seed=None):
         """omega = eps / lengthscale, ``(D_in, S, D_out)`` if dimwise else ``(D_in, S)`` (``kernels.py:101-112``)."""
         shape = (self.D_in, S, self.D_out) if self.dimwise else (self.D_in, S)
-        eps = sample_normal(shape, seed).to(self.unconstrained_lengthscales.device)
+        eps = host_to_device(sample_normal(shape, seed), self.unconstrained_lengthscales.device)
         ls = self.lengthscales.T.unsqueeze(1) if self.dimwise else self.lengthscales.unsqueeze(1)
         return eps / ls

@@ -15,6 +15,7 @@ from torch import nn
 from .. import ops
 from ..misc import transforms
 from ..misc.param import Param
+from ..misc.torch_utils import host_to_device
 
 initial_state_scale = 1e-1
 jitter = 1e-5
@@ -119,7 +120,8 @@ class StateInitialVariationalGaussian(StateInitialDistribution):
         return _FullRankGaussian(self.mean(), self.lchol, self.param_lchol.optvar)
 
     def sample_numpy(self, num_samples=1, seed=None):
-        eps = sample_normal(shape=(num_samples, self.dim_n, self.dim_d), seed=seed).to(self.param_mean.optvar.device)
+        eps = host_to_device(sample_normal(shape=(num_samples, self.dim_n, self.dim_d), seed=seed),
+                             self.param_mean.optvar.device)
         return torch.einsum('nij, snj -> sni', self.lchol(), eps) + self.mean().unsqueeze(0)
 
     def sample(self, num_samples=1, seed=None):
@@ -187,7 +189,7 @@ class StateSequenceVariationalFactorizedGaussian(StateSequenceVariationalDistrib
 
     def sample_numpy(self, num_samples=1, seed=None):
         dev = self.param_mean.optvar.device
-        eps = sample_normal(shape=(num_samples, self.dim_n, self.dim_t, self.dim_d), seed=seed).to(dev)
+        eps = host_to_device(sample_normal(shape=(num_samples, self.dim_n, self.dim_t, self.dim_d), seed=seed), dev)
         zs = torch.einsum('ntij, sntj->snti', self.lchol(), eps)
         return torch.cat([self.x0.sample(num_samples, seed).unsqueeze(2), zs + self.mean().unsqueeze(0)], 2)
 

@@ -77,3 +77,15 @@ def seed_everything(seed):
     torch.manual_seed(seed)
     if torch.cuda.is_available():
         torch.cuda.manual_seed(seed)
+
+
+def host_to_device(t, device):
+    """Move a small host-side random draw to ``device`` WITHOUT synchronising the host with the stream: a pageable
+    ``tensor.to('cuda')`` blocks the caller until every kernel already queued has drained (once per draw, i.e. four
+    times per ``build_cache``), which leaves the GPU idle while the next step's launches are being issued. The draw is
+    staged in pinned memory (PyTorch's caching host allocator keeps the block alive until the copy has run) and
+    copied asynchronously. Tensors already on ``device`` (CUDA-graph static buffers) pass through."""
+    device = torch.device(device)
+    if t.device.type != 'cpu' or device.type != 'cuda' or os.environ.get('GPODE_SYNC_DRAWS'):
+        return t.to(device)
+    return t.pin_memory().to(device, non_blocking=True)

@@ -155,8 +155,13 @@ def test_dopri5_device_count_path_equals_host_count_path(name, kind):
         del ops.DEVICE_COUNT_STATS[:]
     assert relerr(l_dev, l_host) <= 1e-6
     assert set(g_host) == set(g_dev)
+    # The two paths run the same kernels; what differs is the order of the float32 atomic partial sums (grid shapes
+    # follow the row capacity). With the 1e-3 shooting-constraint scale the cotangents are ~1e6 and the lengthscale
+    # gradient is a heavily cancelling sum: measured run-to-run spread of ONE path against itself is up to 2.5e-4
+    # (loss bit-identical), so 1e-4 here failed about one run in four. 1e-3 still catches a wrong step count or a
+    # stale checkpoint, which show up at the 1e-1 level.
     for n in g_host:
-        assert relerr(g_dev[n], g_host[n]) <= 1e-4, n
+        assert relerr(g_dev[n], g_host[n]) <= 1e-3, n
 
 
 def test_graphed_step_with_dopri5_trains_and_reports_status():
