@@ -280,6 +280,8 @@ def run_ours(args):
     y_bufs = [torch.empty_like(ys_dev) for _ in range(2)]
     t_bufs = [torch.empty(ts_host.shape, dtype=ts_host.dtype, device=dev) for _ in range(2)]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
+    loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
     state = {"i": 0, "left": 0}
 
     def prefetch(i):
@@ -302,7 +304,17 @@ def run_ours(args):
             prefetch(i + 1)  # next step's inputs: in flight during this step's backward
         loss.backward()
         distributed.allreduce_shared_grads(model)
-        e2e_body.last = float(loss.detach().item())
+        # device -> host read of every step's loss: copied to pinned host memory on the compute stream right after the
+        # step, consumed one step later (so the host keeps issuing the next step instead of idling the GPU behind a
+        # blocking .item()); the last step's value is awaited inside the timed region
+        loss_host[i % 2].copy_(loss.detach(), non_blocking=True)
+        loss_ready[i % 2].record()
+        if state["left"] < state["total"] - 1:
+            loss_ready[(i - 1) % 2].synchronize()
+            e2e_body.last = float(loss_host[(i - 1) % 2])
+        if state["left"] == 0:
+            loss_ready[i % 2].synchronize()
+            e2e_body.last = float(loss_host[i % 2])
         state["i"] = i + 1
 
     def e2e_run(n):
@@ -313,7 +325,9 @@ def run_ours(args):
     ms_e2e = e2e_run(args.steps) / args.steps
     e2e = {"value": evals_per_step / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
            "h2d_bytes_per_step": int((ys_pinned.numel() + ts_host.numel()) * 4 * world), "d2h_bytes_per_step": 4 * world,
-           "h2d": "pinned host -> device every step, double-buffered on a copy stream (step i+1's copy overlaps step i)"}
+           "h2d": "pinned host -> device every step, double-buffered on a copy stream (step i+1's copy overlaps step i)",
+           "d2h": "every step's loss -> pinned host (async copy after the step), read by the host one step later; the "
+                  "last one is awaited inside the timed region"}
 
     # ---- per-kernel breakdown (separate pass, CUDA events around every C-ABI call) and the roofline ----
     _lib.profile_start()
