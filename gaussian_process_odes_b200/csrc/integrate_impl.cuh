@@ -652,7 +652,11 @@ vf_bwd_mma_kernel(const float* __restrict__ packed, const HParams p, const float
 }
 
 // Discrete adjoint of the 3/8-rule RK4 grid: the recursion, checkpoint reads and virtual-row outputs of
-// rk4_bwd_kernel<D, 1>, with the four VJPs of a step on the tensor cores.
+// rk4_bwd_kernel<D, 1>, with the four VJPs of a step on the tensor cores. The adjoint state that merely waits while a
+// VJP runs (lambda, y, k1, k2 and the three running cotangent sums: 7 D floats per row) rests in shared memory
+// ([field][component][lane], conflict-free), so the VJP has the 168 registers of a 12-warp CTA to itself -- with that
+// state in registers ptxas spilled inside the VJP loops (3.82 ms; 8 warps at 239 registers: 3.69 ms).
+constexpr int kHRowFields = 7;
 template <int D>
 __global__ void __launch_bounds__(kHThreads, 1)
 rk4_bwd_mma_kernel(const float* __restrict__ packed, const HParams p, const float* __restrict__ ts, const int Tg,
@@ -667,80 +671,117 @@ rk4_bwd_mma_kernel(const float* __restrict__ packed, const HParams p, const floa
     qa.clear();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int R = 1;
+    enum { F_LAM = 0, F_Y = 1, F_K1 = 2, F_K2 = 3, F_SUM = 4, F_YB4 = 5, F_Y23 = 6 };
+    float* __restrict__ rs = sm.red + ((D * D + D + 3) & ~3) + kHWarps * HShape<D>::kStageFloats +
+                             warp * (kHRowFields * D * 32) + lane;
+    auto put = [&](const int f, const float (&v)[R][D]) {
+#pragma unroll
+        for (int j = 0; j < D; ++j) rs[(f * D + j) * 32] = v[0][j];
+    };
+    auto get = [&](const int f, float (&v)[R][D]) {
+#pragma unroll
+        for (int j = 0; j < D; ++j) v[0][j] = rs[(f * D + j) * 32];
+    };
 
     const int64_t nblocks = (B + 31) / 32;
     const int64_t plane = B * D;
     for (int64_t blk = (int64_t)blockIdx.x * kHWarps + warp; blk < nblocks; blk += (int64_t)gridDim.x * kHWarps) {
         const int64_t row0 = blk * 32 + lane;
-        float lam[R][D];
-        load_rows<D, R>(lam, gxs + (int64_t)(Tg - 1) * plane, row0, B, 0);
+        {
+            float lam[R][D];
+            load_rows<D, R>(lam, gxs + (int64_t)(Tg - 1) * plane, row0, B, 0);
+            put(F_LAM, lam);
+        }
         for (int i = Tg - 2; i >= 0; --i) {
             const float h = __fsub_rn(__ldg(ts + i + 1), __ldg(ts + i));
             const float* kb = kst + (int64_t)i * 4 * plane;
             float* vyi = vy + (int64_t)i * 4 * plane;
             float* vki = vk + (int64_t)i * 4 * plane;
-            float y[R][D], k1[R][D], k2[R][D], ks[R][D], ys[R][D], kbar[R][D], yb[R][D];
-            float sumyb[R][D], yb4[R][D], yb23[R][D];
-            load_rows<D, R>(y, xs + (int64_t)i * plane, row0, B, 0);
-            load_rows<D, R>(k1, kb, row0, B, 0);
-            load_rows<D, R>(k2, kb + plane, row0, B, 0);
+            float ks[R][D], ys[R][D], kbar[R][D], yb[R][D];
+            {
+                float t[R][D];
+                load_rows<D, R>(t, xs + (int64_t)i * plane, row0, B, 0);
+                put(F_Y, t);
+                load_rows<D, R>(t, kb, row0, B, 0);
+                put(F_K1, t);
+                load_rows<D, R>(t, kb + plane, row0, B, 0);
+                put(F_K2, t);
+                get(F_LAM, t);
 #pragma unroll
-            for (int j = 0; j < D; ++j) {
-                kbar[0][j] = 0.125f * h * lam[0][j];
-                sumyb[0][j] = yb4[0][j] = yb23[0][j] = 0.f;
+                for (int j = 0; j < D; ++j) kbar[0][j] = 0.125f * h * t[0][j];
             }
             // the four stages share ONE inlined VJP (code size): stage input, forward value and the cotangent
             // bookkeeping are selected by uniform branches around it
 #pragma unroll 1
             for (int st = 4; st >= 1; --st) {
-                if (st == 4) {
-                    load_rows<D, R>(ks, kb + 2 * plane, row0, B, 0);  // k3
-                    stage4<D, R>(ys, y, k1, k2, ks, h);
-                    load_rows<D, R>(ks, kb + 3 * plane, row0, B, 0);  // k4 = f(y4)
-                } else if (st == 3) {
-                    stage3<D, R>(ys, y, k1, k2, h);
-                    load_rows<D, R>(ks, kb + 2 * plane, row0, B, 0);  // k3 = f(y3)
-                } else if (st == 2) {
-                    stage2<D, R>(ys, y, k1, h);
+                {
+                    float y[R][D], k1[R][D], k2[R][D];
+                    get(F_Y, y);
+                    get(F_K1, k1);
+                    get(F_K2, k2);
+                    if (st == 4) {
+                        load_rows<D, R>(ks, kb + 2 * plane, row0, B, 0);  // k3
+                        stage4<D, R>(ys, y, k1, k2, ks, h);
+                        load_rows<D, R>(ks, kb + 3 * plane, row0, B, 0);  // k4 = f(y4)
+                    } else if (st == 3) {
+                        stage3<D, R>(ys, y, k1, k2, h);
+                        load_rows<D, R>(ks, kb + 2 * plane, row0, B, 0);  // k3 = f(y3)
+                    } else if (st == 2) {
+                        stage2<D, R>(ys, y, k1, h);
 #pragma unroll
-                    for (int j = 0; j < D; ++j) ks[0][j] = k2[0][j];
-                } else {
+                        for (int j = 0; j < D; ++j) ks[0][j] = k2[0][j];
+                    } else {
 #pragma unroll
-                    for (int j = 0; j < D; ++j) {
-                        ys[0][j] = y[0][j];
-                        ks[0][j] = k1[0][j];
+                        for (int j = 0; j < D; ++j) {
+                            ys[0][j] = y[0][j];
+                            ks[0][j] = k1[0][j];
+                        }
                     }
                 }
                 store_rows<D, R>(ys, vyi + (int64_t)(st - 1) * plane, row0, B, 0);
                 store_rows<D, R>(kbar, vki + (int64_t)(st - 1) * plane, row0, B, 0);
                 vf_vjp_h<D>(sm.small, sm.mmah, sm.stage, p.M, p.S8P, ys, kbar, ks, yb, qa, lane, p.parts);
+                float lam[R][D];
+                get(F_LAM, lam);
                 if (st == 4) {
+                    put(F_YB4, yb);
 #pragma unroll
-                    for (int j = 0; j < D; ++j) {
-                        yb4[0][j] = yb[0][j];
-                        kbar[0][j] = fmaf(0.375f * h, lam[0][j], h * yb4[0][j]);
-                    }
+                    for (int j = 0; j < D; ++j) kbar[0][j] = fmaf(0.375f * h, lam[0][j], h * yb[0][j]);
                 } else if (st == 3) {
+                    float yb4[R][D], sum[R][D], y23[R][D];
+                    get(F_YB4, yb4);
 #pragma unroll
                     for (int j = 0; j < D; ++j) {
-                        sumyb[0][j] = yb4[0][j] + yb[0][j];
+                        sum[0][j] = yb4[0][j] + yb[0][j];
                         kbar[0][j] = fmaf(0.375f * h, lam[0][j], h * (yb[0][j] - yb4[0][j]));  // kb2
-                        yb23[0][j] = -yb[0][j];
+                        y23[0][j] = -yb[0][j];
                     }
+                    put(F_SUM, sum);
+                    put(F_Y23, y23);
                 } else if (st == 2) {
+                    float yb4[R][D], sum[R][D], y23[R][D];
+                    get(F_YB4, yb4);
+                    get(F_SUM, sum);
+                    get(F_Y23, y23);
 #pragma unroll
                     for (int j = 0; j < D; ++j) {
-                        sumyb[0][j] += yb[0][j];
-                        yb23[0][j] += yb[0][j];  // yb2 - yb3
-                        kbar[0][j] = fmaf(0.125f * h, lam[0][j], fmaf(h * GPODE_THIRD, yb23[0][j], h * yb4[0][j]));
+                        sum[0][j] += yb[0][j];
+                        y23[0][j] += yb[0][j];  // yb2 - yb3
+                        kbar[0][j] = fmaf(0.125f * h, lam[0][j], fmaf(h * GPODE_THIRD, y23[0][j], h * yb4[0][j]));
                     }
+                    put(F_SUM, sum);
+                } else {
+                    float sum[R][D], gi[R][D];
+                    get(F_SUM, sum);
+                    load_rows<D, R>(gi, gxs + (int64_t)i * plane, row0, B, 0);
+#pragma unroll
+                    for (int j = 0; j < D; ++j) lam[0][j] = gi[0][j] + lam[0][j] + (sum[0][j] + yb[0][j]);
+                    put(F_LAM, lam);
                 }
             }
-            float gi[R][D];
-            load_rows<D, R>(gi, gxs + (int64_t)i * plane, row0, B, 0);
-#pragma unroll
-            for (int j = 0; j < D; ++j) lam[0][j] = gi[0][j] + lam[0][j] + (sumyb[0][j] + yb[0][j]);
         }
+        float lam[R][D];
+        get(F_LAM, lam);
         store_rows<D, R>(lam, gx0, row0, B, 0);
     }
     hacc_reduce<D>(qa, sm.small, p.M, acc, sm.red);
@@ -837,8 +878,9 @@ inline HParams h_params(const GpodeLayout& L) {
     return p;
 }
 template <int D>
-inline size_t h_smem(const HParams& p) {
-    return 16 + ((size_t)p.n_small + p.n_mmah + ((D * D + D + 3) & ~3) + (size_t)kHWarps * HShape<D>::kStageFloats) * 4;
+inline size_t h_smem(const HParams& p, bool rk4 = true) {
+    return 16 + ((size_t)p.n_small + p.n_mmah + ((D * D + D + 3) & ~3) + (size_t)kHWarps * HShape<D>::kStageFloats +
+                 (rk4 ? (size_t)kHWarps * kHRowFields * D * 32 : 0)) * 4;
 }
 template <typename K>
 inline int h_grid(K kernel, int64_t B, size_t smem, int* grid) {
@@ -978,8 +1020,8 @@ int launch_vf_bwd(const float* packed, int M, int S, const float* x, const float
         const HParams hp = h_params<D>(L);
         if (use_mma_bwd(B) && h_smem<D>(hp) <= 227 * 1024) {
             int grid = 0;
-            if (int rc = h_grid(vf_bwd_mma_kernel<D>, B, h_smem<D>(hp), &grid)) return rc;
-            vf_bwd_mma_kernel<D><<<grid, kHThreads, h_smem<D>(hp), st>>>(packed, hp, x, f, gf, gx, B, acc);
+            if (int rc = h_grid(vf_bwd_mma_kernel<D>, B, h_smem<D>(hp, false), &grid)) return rc;
+            vf_bwd_mma_kernel<D><<<grid, kHThreads, h_smem<D>(hp, false), st>>>(packed, hp, x, f, gf, gx, B, acc);
             GPODE_LAUNCH_CHECK();
             return 0;
         }
