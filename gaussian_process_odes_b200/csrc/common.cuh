@@ -58,7 +58,7 @@ struct GpodeLayout {
     int off_rff, off_kern, off_il, total;  // in floats; every offset and `total` is a multiple of 4 (16 bytes)
     // tensor-core (mma.sync m16n8k8 tf32) operand blocks, appended after `total`, one record per (output k, tile of
     // 8 features):  mma  : 80 floats = 64 theta-B fragment (lane-major b0,b1) | 16 (phase, phase', a, a') per quad lane
-    //               mmah : the adjoint's operands for mma.sync m16n8k16 f16 (vjp_mma.cuh), 144 words per (output k,
+    //               mmah : operands for mma.sync m16n8k16 f16 (vjp_mma.cuh: adjoint and forward), 152 words per (output k,
     //                      tile of 8 features; tiles padded to an even count S8P with zero records):
     //                        [0,64)    theta-B, lane-major (b0,b1) half2 pairs: contraction slots 0..D-1 = Omega_hi,
     //                                  D..2D-1 = Omega_lo, 2D..3D-1 = Omega_hi (the state tile carries x_hi, x_hi, x_lo)
@@ -66,6 +66,7 @@ struct GpodeLayout {
     //                        [80,144)  G-B of the tile PAIR (2i, 2i+1), lane-major (b0,b1): the even record holds the hi
     //                                  parts (tile 2i, tile 2i+1), the odd record the lo parts; one half2 =
     //                                  (Bp[2t][g], Bp[2t+1][g]), Bp[s][j] = GPODE_MMAH_SCALE a_s Omega_{j,s,k}
+    //                        [144,152) a_s of the tile's 8 features (fp32; the forward's cosine weights)
     int S8, off_mma, off_mmag, S8P;
     // tcgen05 (UMMA) operand block, one record of GPODE_UMMA_REC(SU) floats per output k:
     //   B_hi [SU x 8] | B_lo [SU x 8] | a [SU]   (SU = S rounded up to 32)   -- B = (Omega_k | phase | 0)^T, features x padded input dims, in
@@ -76,7 +77,7 @@ struct GpodeLayout {
 };
 #define GPODE_UMMA_REC(SU) (17 * (SU))
 #define GPODE_MMA_REC 80
-#define GPODE_MMAH_REC 144
+#define GPODE_MMAH_REC 152
 #define GPODE_MMAH_MAX_D 5  // 3 D contraction slots (x_hi, x_hi, x_lo) must fit the 16 of one m16n8k16
 #define GPODE_MMAH_SCALE 256.f  // keeps the fp16 low parts of a Omega out of the subnormal range
 

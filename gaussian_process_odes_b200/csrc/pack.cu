@@ -78,6 +78,7 @@ __global__ void pack_kernel(const GpodeLayout L, const float* __restrict__ omega
                     const float ph = sidx < S ? phase[sidx * D + k] : 0.f;
                     reinterpret_cast<float*>(o)[64 + t * 4 + h] = ph;
                     reinterpret_cast<float*>(o)[64 + t * 4 + 2 + h] = ph;
+                    reinterpret_cast<float*>(o)[144 + t * 2 + h] = a / GPODE_MMAH_SCALE;
                 }
             }
             // G-B operands of a tile PAIR (2i, 2i+1) sit together so that each MMA's (b0, b1) comes out of one LDS.64:

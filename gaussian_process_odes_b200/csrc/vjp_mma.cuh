@@ -306,6 +306,130 @@ __device__ __forceinline__ void vf_vjp_h(const float* __restrict__ small, const 
     for (int j = 0; j < D; ++j) xb[0][j] = fmaf(cG, sxb[lane * 8 + j], xbp[j]);
 }
 
+// f = vf(x) for the lane's row with the Fourier projection on the tensor cores: theta as in vf_vjp_h (one split-fp16
+// MMA per 16 rows x 8 features), then per feature-output FMUL.RZ + MUFU.COS + one FMA on the weights a_s. The FFMA2
+// forward spends D packed FMAs per feature pair on theta and is dispatch-bound next to the MUFU pipe (ncu: FMA pipe
+// 64 %, XU 70 %); here theta costs the CUDA cores nothing. The RBF term is the FFMA2 one (lane = row).
+template <int D>
+__device__ __forceinline__ void vf_eval_h(const float* __restrict__ small, const uint32_t* __restrict__ mmah,
+                                          float* __restrict__ stage, const int M, const int S8P, const float (&x)[1][D],
+                                          float (&f)[1][D], const int lane, const bool stagger = true) {
+    static_assert(D <= GPODE_MMAH_MAX_D, "x_hi | x_hi | x_lo must fit the 16 contraction slots");
+    constexpr int KS = VfShape<D>::KS, WP = VfShape<D>::WP, SXS = HShape<D>::SXS;
+    const float* __restrict__ kern = small;
+    const float* __restrict__ wnp = kern + M * KS;
+    float* __restrict__ sx = stage;
+    float* __restrict__ sxb = stage + 2 * 32 * SXS;
+    const int g = lane >> 2, t = lane & 3;
+    __syncwarp();  // the previous call's readers are done with the stage
+#pragma unroll
+    for (int j = 0; j < D; ++j) sx[lane * SXS + j] = x[0][j];
+    __syncwarp();
+    constexpr int KF = D / 2;
+    constexpr bool kOdd = (D & 1) != 0;
+    float2 wn[D][KF > 0 ? KF : 1];
+    float wl[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        float w[WP];
+        lds_vec<WP>(w, wnp + j * WP);
+#pragma unroll
+        for (int kp = 0; kp < KF; ++kp) wn[j][kp] = make_float2(w[2 * kp], w[2 * kp + 1]);
+        wl[j] = w[D - 1];
+    }
+    float2 fu[KF > 0 ? KF : 1];
+    float fl = 0.f;
+#pragma unroll
+    for (int kp = 0; kp < KF; ++kp) fu[kp] = make_float2(0.f, 0.f);
+    // The RFF part is bound by the MUFU pipe (cos), the RBF part by FMA dispatch: half of the warps of every scheduler
+    // take them in the opposite order so that the two kinds of work meet on the SM at the same time.
+    const int warp_id = threadIdx.x >> 5;
+    const bool rbf_first = stagger && ((warp_id ^ (warp_id >> 2)) & 1) != 0;
+#pragma unroll 1
+    for (int part = 0; part < 2; ++part) {
+        if ((part == 0) != rbf_first) {
+        {
+            uint32_t ax[2][4];
+            auto slotA = [&](const int row, const int s) -> float {  // x_hi | x_hi | x_lo | 0
+                const int kind = s / D, j = s - kind * D;
+                const float v = kind < 3 ? sx[row * SXS + j] : 0.f;
+                const float hi = gpode_trunc11(v);
+                return kind == 2 ? v - hi : hi;
+            };
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                const int r0 = 16 * mt + g, r1 = r0 + 8;
+                ax[mt][0] = gpode_pack_h2(slotA(r0, 2 * t), slotA(r0, 2 * t + 1));
+                ax[mt][1] = gpode_pack_h2(slotA(r1, 2 * t), slotA(r1, 2 * t + 1));
+                ax[mt][2] = gpode_pack_h2(slotA(r0, 2 * t + 8), slotA(r0, 2 * t + 9));
+                ax[mt][3] = gpode_pack_h2(slotA(r1, 2 * t + 8), slotA(r1, 2 * t + 9));
+            }
+#pragma unroll 1
+            for (int k = 0; k < D; ++k) {
+                float fk[4] = {0.f, 0.f, 0.f, 0.f};  // rows g, g+8, g+16, g+24; this lane's features 2t, 2t+1 of every tile
+                const uint32_t* __restrict__ rc = mmah + (size_t)k * S8P * GPODE_MMAH_REC;
+#pragma unroll 2
+                for (int ft = 0; ft < S8P; ++ft, rc += GPODE_MMAH_REC) {
+                    const uint2 b = *reinterpret_cast<const uint2*>(rc + lane * 2);
+                    const float4 ph = *reinterpret_cast<const float4*>(rc + 64 + t * 4);
+                    const float2 a2 = *reinterpret_cast<const float2*>(rc + 144 + t * 2);
+                    float c[2][4];
+                    gpode_mma_f16(c[0], ax[0], b.x, b.y, ph);
+                    gpode_mma_f16(c[1], ax[1], b.x, b.y, ph);
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        fk[2 * mt] = fmaf(a2.x, __cosf(c[mt][0]), fk[2 * mt]);
+                        fk[2 * mt] = fmaf(a2.y, __cosf(c[mt][1]), fk[2 * mt]);
+                        fk[2 * mt + 1] = fmaf(a2.x, __cosf(c[mt][2]), fk[2 * mt + 1]);
+                        fk[2 * mt + 1] = fmaf(a2.y, __cosf(c[mt][3]), fk[2 * mt + 1]);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    float v = fk[r];
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    if (r == t) sxb[(g + 8 * r) * 8 + k] = v;
+                }
+            }
+        }
+        } else {
+#pragma unroll 2
+        for (int m = 0; m < M; ++m) {
+            float kp_[KS];
+            lds_vec<KS>(kp_, kern + m * KS);
+            float dd[D];
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                const float d = x[0][j] - kp_[j];
+                dd[j] = d * d;
+            }
+#pragma unroll
+            for (int kp = 0; kp < KF; ++kp) {
+                float2 e = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < D; ++j) e = ffma2(dd[j], wn[j][kp], e);
+                const float2 K = make_float2(gpode_ex2(e.x), gpode_ex2(e.y));
+                fu[kp] = ffma2(make_float2(kp_[D + 2 * kp], kp_[D + 2 * kp + 1]), K, fu[kp]);
+            }
+            if constexpr (kOdd) {
+                float e = 0.f;
+#pragma unroll
+                for (int j = 0; j < D; ++j) e = fmaf(dd[j], wl[j], e);
+                fl = fmaf(kp_[2 * D - 1], gpode_ex2(e), fl);
+            }
+        }
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        const int kp = (k >> 1) < KF ? (k >> 1) : 0;
+        const float u = (kOdd && k == D - 1) ? fl : ((k & 1) ? fu[kp].y : fu[kp].x);
+        f[0][k] = sxb[lane * 8 + k] + u;
+    }
+}
+
 // stage [kern | il] and the f16 operand records into shared memory (two bulk async copies, one mbarrier);
 // dynamic shared memory layout: [0,16) mbarrier | small | mmah | ...
 __device__ __forceinline__ void stage_params_h(unsigned char* smem_raw, const float* __restrict__ packed,

@@ -30,11 +30,11 @@ def test_pure_host_entry_points():
     from gaussian_process_odes_b200 import _lib
     lib = _lib.load()
     # layout arithmetic only: rff D*roundup32(S/2)*roundup4(2D+4) + kern M*roundup4(D+2*ceil(D/2)) + w D*roundup4(2*ceil(D/2))
-    # + mma.sync tf32 operand blocks D*ceil(S/8)*80 + f16 adjoint operand blocks D*roundup2(ceil(S/8))*144 (D <= 5)
+    # + mma.sync tf32 operand blocks D*ceil(S/8)*80 + f16 adjoint operand blocks D*roundup2(ceil(S/8))*152 (D <= 5)
     # + tcgen05 operand blocks D*17*roundup32(S) (D <= 7)
-    assert lib.gpode_packed_floats(2, 16, 256) == 2 * 128 * 8 + 16 * 4 + 2 * 4 + 2 * 32 * (80 + 144) + 2 * 17 * 256
-    assert lib.gpode_packed_floats(5, 100, 256) == 5 * 128 * 16 + 100 * 12 + 5 * 8 + 5 * 32 * (80 + 144) + 5 * 17 * 256
-    assert lib.gpode_packed_floats(3, 24, 64) == 3 * 32 * 12 + 24 * 8 + 3 * 4 + 3 * 8 * (80 + 144) + 3 * 17 * 64
+    assert lib.gpode_packed_floats(2, 16, 256) == 2 * 128 * 8 + 16 * 4 + 2 * 4 + 2 * 32 * (80 + 152) + 2 * 17 * 256
+    assert lib.gpode_packed_floats(5, 100, 256) == 5 * 128 * 16 + 100 * 12 + 5 * 8 + 5 * 32 * (80 + 152) + 5 * 17 * 256
+    assert lib.gpode_packed_floats(3, 24, 64) == 3 * 32 * 12 + 24 * 8 + 3 * 4 + 3 * 8 * (80 + 152) + 3 * 17 * 64
     assert lib.gpode_packed_floats(8, 10, 40) == 8 * 32 * 20 + 10 * 16 + 8 * 8 + 8 * 5 * 80
     assert lib.gpode_packed_floats(0, 1, 1) == -1
     assert lib.gpode_acc_floats(5, 100) == 25 + 5 + 500 + 2500

@@ -365,3 +365,26 @@ def test_vf_backward_tensor_core_adjoint(D, M, S, B, monkeypatch):
     for k in got:
         assert relerr(got[k], base[k]) <= TOL_GRAD, k
         assert relerr(got[k].cpu().reshape(leaves[k].grad.shape), leaves[k].grad) <= 3 * TOL_GRAD, k
+
+
+@pytest.mark.parametrize("D,M,S,B", [(5, 100, 256, 50000), (4, 33, 100, 38017), (5, 17, 43, 40000)])
+def test_forward_tensor_core_path(D, M, S, B, monkeypatch):
+    """D = 4, 5 and a batch that fills the machine: theta = x Omega of the forward pass as split-fp16 mma.sync
+    (vf_eval_h). Vector field and a 3-step RK4 trajectory against the oracle and against the FFMA2 kernels
+    (GPODE_FWD_MMA=0)."""
+    from gaussian_process_odes_b200 import ops
+    gp32, c32, gp64, c64, x = _setup(D, M, S, B, seed=D + B, nu_scale=0.3)
+    ts = _grid(4, 0.1, 4)
+
+    def run(mode):
+        monkeypatch.setenv("GPODE_FWD_MMA", mode)
+        with torch.no_grad():
+            args = _cuda_args(gp32, c32)
+            return ops.vector_field(x.cuda(), *args).cpu(), ops.rk4_integrate(x.cuda(), ts.cuda(), *args).cpu()
+
+    (f1, xs1), (f0, xs0) = run("1"), run("0")
+    f32 = O.vf_forward(x, gp32['Z'], gp32['ell'], gp32['var'], c32)
+    out = O.odeint(lambda t, y: O.vf_forward(y, gp32['Z'], gp32['ell'], gp32['var'], c32), x, ts, method='rk4')
+    assert relerr(f1, f0) <= TOL_VF and relerr(f1, f32) <= TOL_VF
+    assert relerr(xs1, xs0) <= TOL_TRAJ and relerr(xs1, out) <= TOL_TRAJ
+    assert torch.equal(xs1[0], x)

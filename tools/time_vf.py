@@ -24,16 +24,24 @@ for D, M in shapes:
                                             draws["w"])]
     B = 1000000
     x = torch.randn(B, D, device="cuda")
-    with torch.no_grad():
-        for _ in range(3):
-            ops.vector_field(x, *args)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(5):
-            ops.vector_field(x, *args)
-        e1.record()
-        torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 5
-    fv = D * (S * (2 * D + 4) + M * (3 * D + 4))
-    print(json.dumps(dict(mma=os.environ.get("GPODE_USE_MMA"), D=D, ms=round(ms, 4), tflops=round(B * fv / (ms * 1e-3) / 1e12, 2))))
+    for fmode in ("0", "1"):
+        os.environ["GPODE_FWD_MMA"] = fmode
+        tg = torch.tensor([0.0, 0.01], device="cuda")
+        with torch.no_grad():
+            for _ in range(3):
+                ops.vector_field(x, *args)
+                ops.rk4_integrate(x, tg, *args)
+            torch.cuda.synchronize()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
+            for _ in range(5):
+                ops.vector_field(x, *args)
+            ev[1].record()
+            for _ in range(5):
+                ops.rk4_integrate(x, tg, *args)
+            ev[2].record()
+            torch.cuda.synchronize()
+        ms = ev[0].elapsed_time(ev[1]) / 5
+        fv = D * (S * (2 * D + 4) + M * (3 * D + 4))
+        print(json.dumps(dict(fwd_mma=fmode, D=D, ms=round(ms, 4), tflops=round(B * fv / (ms * 1e-3) / 1e12, 2),
+                              rk4_step_ms=round(ev[1].elapsed_time(ev[2]) / 5, 4))), flush=True)
