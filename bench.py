@@ -364,10 +364,11 @@ def run_ours(args):
                 "peak_source": "measured here: gpode_probe_fp32_fma (register-only FMA loop, best of 5); "
                                "MEASURED_PEAKS.json has no FP32 entry",
                 "algorithmic_flops_per_launch": flops[dom], "kernel_ms": ms_dom,
-                "pipes": "gpode_rk4_bwd at 4 <= D <= 5 runs the two Fourier projections of every VJP (theta = x Omega, "
-                         "G = g Omega^T: 10 of the 14 algorithmic FMAs per feature-output) as split-fp16 mma.sync on the "
-                         "tensor cores (csrc/vjp_mma.cuh); the flop count stays the algorithmic FP32 one and the peak "
-                         "stays the FP32 FMA peak, so frac measures the whole kernel against the CUDA-core roofline",
+                "pipes": "at 4 <= D <= 5 gpode_rk4_bwd runs the two Fourier projections of every VJP (theta = x Omega, "
+                         "G = g Omega^T: 10 of the 14 algorithmic FMAs per feature-output) and gpode_rk4_fwd the projection "
+                         "theta as split-fp16 mma.sync on the tensor cores (csrc/vjp_mma.cuh); the flop count stays the "
+                         "algorithmic FP32 one and the peak stays the FP32 FMA peak, so frac measures the whole kernel "
+                         "against the CUDA-core roofline",
                 "also": {other: {"achieved": flops[other] / (kern[other]["ms_per_step"] * 1e-3) / 1e12,
                                  "frac": flops[other] / (kern[other]["ms_per_step"] * 1e-3) / 1e12 / tf.value,
                                  "kernel_ms": kern[other]["ms_per_step"]}},
