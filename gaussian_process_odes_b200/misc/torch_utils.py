@@ -79,13 +79,52 @@ def seed_everything(seed):
         torch.cuda.manual_seed(seed)
 
 
+class _PinnedRing:
+    """Pinned staging buffers for ``host_to_device``: per (device, shape, dtype) a small ring of page-locked tensors,
+    each with the CUDA event of its last copy. Re-using a slot waits for that event (normally long complete: a slot
+    comes round again ``depth`` draws of the same shape later), so the host can run at most ``depth`` steps ahead of
+    the stream. Costs a host memcpy, one async copy and one event record per draw -- ``Tensor.pin_memory()`` per draw
+    was measured at ~0.1 ms each on the launch-bound training shapes."""
+
+    depth = 4
+
+    def __init__(self):
+        self.slots = {}
+
+    def stage(self, t, device):
+        key = (device, tuple(t.shape), t.dtype)
+        ring = self.slots.get(key)
+        if ring is None:
+            ring = self.slots[key] = {"i": 0, "buf": [torch.empty(t.shape, dtype=t.dtype).pin_memory()
+                                                      for _ in range(self.depth)],
+                                      "ev": [None] * self.depth}
+        i = ring["i"]
+        ring["i"] = (i + 1) % self.depth
+        if ring["ev"][i] is not None:
+            ring["ev"][i].synchronize()
+        buf = ring["buf"][i]
+        buf.copy_(t)
+        with torch.cuda.device(device):
+            out = torch.empty(t.shape, dtype=t.dtype, device=device)
+            out.copy_(buf, non_blocking=True)
+            ev = ring["ev"][i] or torch.cuda.Event()
+            ev.record()
+            ring["ev"][i] = ev
+        return out
+
+
+_pinned_ring = _PinnedRing()
+
+
 def host_to_device(t, device):
     """Move a small host-side random draw to ``device`` WITHOUT synchronising the host with the stream: a pageable
     ``tensor.to('cuda')`` blocks the caller until every kernel already queued has drained (once per draw, i.e. four
     times per ``build_cache``), which leaves the GPU idle while the next step's launches are being issued. The draw is
-    staged in pinned memory (PyTorch's caching host allocator keeps the block alive until the copy has run) and
-    copied asynchronously. Tensors already on ``device`` (CUDA-graph static buffers) pass through."""
+    staged in a pinned ring buffer and copied asynchronously. Tensors already on ``device`` (CUDA-graph static
+    buffers) pass through; ``GPODE_SYNC_DRAWS=1`` restores the blocking copy."""
     device = torch.device(device)
     if t.device.type != 'cpu' or device.type != 'cuda' or os.environ.get('GPODE_SYNC_DRAWS'):
         return t.to(device)
-    return t.pin_memory().to(device, non_blocking=True)
+    if torch.cuda.is_current_stream_capturing():
+        return t.to(device)  # never reached by GraphedStep (its samplers return device buffers); fail loudly if it is
+    return _pinned_ring.stage(t, device)
