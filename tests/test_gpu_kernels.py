@@ -316,10 +316,10 @@ def test_errors_are_loud():
     assert ops.vector_field(torch.zeros(0, 2, device="cuda"), *args).shape == (0, 2)
 
 
-@pytest.mark.parametrize("D,M,S,B", [(5, 100, 256, 40000), (3, 24, 64, 38000), (4, 33, 100, 40001), (6, 20, 48, 39000),
-                                     (7, 17, 43, 40000)])
+# the tensor-core kernels take over at B >= SMs * 384 rows (56 832 on a B200)
+@pytest.mark.parametrize("D,M,S,B", [(5, 100, 256, 60000), (4, 33, 100, 57001), (5, 17, 43, 58000)])
 def test_rk4_backward_tensor_core_adjoint(D, M, S, B, monkeypatch):
-    """3 <= D <= 7 and a batch that fills the machine: the adjoint's two Fourier projections run as 3xTF32 mma.sync
+    """D = 4, 5 and a batch that fills the machine: the adjoint's two Fourier projections run as split-fp16 mma.sync
     (csrc/vjp_mma.cuh). Checked against the oracle's autograd and against the FFMA2 adjoint (GPODE_BWD_MMA=0)."""
     from gaussian_process_odes_b200 import ops
     gp32, c32, gp64, c64, x = _setup(D, M, S, B, seed=D + B, nu_scale=0.3)
@@ -329,6 +329,7 @@ def test_rk4_backward_tensor_core_adjoint(D, M, S, B, monkeypatch):
 
     def run(mode):
         monkeypatch.setenv("GPODE_BWD_MMA", mode)
+        monkeypatch.setenv("GPODE_FWD_MMA", mode)
         args = [a.detach().clone().requires_grad_(i < 4) for i, a in enumerate(_cuda_args(gp32, c32))]
         xc = x.cuda().requires_grad_(True)
         xs = ops.rk4_integrate(xc, ts.cuda(), *args)
@@ -345,7 +346,7 @@ def test_rk4_backward_tensor_core_adjoint(D, M, S, B, monkeypatch):
         assert relerr(got[k].cpu().reshape(leaves[k].grad.shape), leaves[k].grad) <= 3 * TOL_GRAD, k
 
 
-@pytest.mark.parametrize("D,M,S,B", [(5, 100, 256, 50000), (3, 16, 40, 38011)])
+@pytest.mark.parametrize("D,M,S,B", [(5, 100, 256, 58000), (4, 16, 40, 57011)])
 def test_vf_backward_tensor_core_adjoint(D, M, S, B, monkeypatch):
     from gaussian_process_odes_b200 import ops
     gp32, c32, gp64, c64, x = _setup(D, M, S, B, seed=D * 7 + B, nu_scale=0.3)
@@ -367,7 +368,7 @@ def test_vf_backward_tensor_core_adjoint(D, M, S, B, monkeypatch):
         assert relerr(got[k].cpu().reshape(leaves[k].grad.shape), leaves[k].grad) <= 3 * TOL_GRAD, k
 
 
-@pytest.mark.parametrize("D,M,S,B", [(5, 100, 256, 50000), (4, 33, 100, 38017), (5, 17, 43, 40000)])
+@pytest.mark.parametrize("D,M,S,B", [(5, 100, 256, 60000), (4, 33, 100, 57017), (5, 17, 43, 58000)])
 def test_forward_tensor_core_path(D, M, S, B, monkeypatch):
     """D = 4, 5 and a batch that fills the machine: theta = x Omega of the forward pass as split-fp16 mma.sync
     (vf_eval_h). Vector field and a 3-step RK4 trajectory against the oracle and against the FFMA2 kernels

@@ -118,3 +118,20 @@ def test_training_step_decreases_loss():
         losses.append(float(loss.detach()))
     assert all(l == l for l in losses)
     assert min(losses[-3:]) < losses[0]
+
+
+def test_host_draws_reach_the_device_intact_through_the_pinned_ring():
+    """misc.torch_utils.host_to_device: async copies through a 4-slot pinned ring; slots are re-used only after their
+    copy's event, so 20 back-to-back draws of one shape (5 rounds of the ring) must all arrive unchanged."""
+    import numpy as np
+    from gaussian_process_odes_b200.misc.torch_utils import host_to_device
+    rng = np.random.default_rng(0)
+    host = [torch.tensor(rng.normal(size=(256, 5)).astype(np.float32)) for _ in range(20)]
+    big = torch.randn(4096, 4096, device="cuda")
+    for _ in range(3):
+        big = big @ big.t() * 1e-4  # keep the stream busy while the draws are enqueued
+    dev = [host_to_device(h, "cuda") for h in host]
+    torch.cuda.synchronize()
+    for h, d in zip(host, dev):
+        assert d.device.type == "cuda" and torch.equal(d.cpu(), h)
+    assert host_to_device(dev[0], "cuda") is dev[0] or torch.equal(host_to_device(dev[0], "cuda"), dev[0])
