@@ -47,8 +47,10 @@ SIGNATURES = {
     "gpode_rk4_fwd_large": (_I, [_CP, _P, _P, _I, _L, _P, _P]),
     "gpode_state_fwd": (_I, [_P, _P, _P, _I, _L, _I, _F, _P, _P, _P]),
     "gpode_state_bwd": (_I, [_P, _P, _I, _L, _I, _F, _P, _P, _P, _P, _P]),
-    "gpode_loglik_sum": (_I, [_P, _P, _P, _P, _P, _I, _L, _I, _I, _P, _P, _P, _P]),
-    "gpode_constraint_sum": (_I, [_P, _P, _P, _L, _I, _I, _I, _P, _P, _P, _P]),
+    "gpode_loglik_sum": (_I, [_P, _P, _P, _P, _P, _I, _L, _I, _I, _P, _P, _P, _P, _P]),
+    "gpode_constraint_sum": (_I, [_P, _P, _P, _L, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "gpode_side_work_doubles": (_L, []),
+    "gpode_acc_header_floats": (_L, []),
     "gpode_probe_fp32_fma": (_I, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), _P, _P]),
     "gpode_dopri5_ckpt_floats": (_L, [_I, _L, _I, _I]),
     "gpode_dopri5_fwd": (_I, [_P, _I, _I, _I, _P, _P, _I, _L, _D, _D, _P, _P, _P, _P, _I, _P]),
@@ -126,14 +128,18 @@ def f32(t, name="tensor"):
 
 # ---- launch accounting and optional per-call CUDA-event timing (used by bench.py) --------------------------------
 # kernels enqueued by one C-ABI call (memsets / memcpys not counted)
-KERNELS_PER_CALL = {"gpode_pack_cache": 1, "gpode_vf_fwd": 1, "gpode_vf_bwd": 1, "gpode_rk4_fwd": 1,
-                    "gpode_rk4_bwd": 1, "gpode_param_grad": 1, "gpode_grads_finalize": 1, "gpode_whiten_fwd": 1, "gpode_whiten_bwd": 1,
-                    "gpode_kl_fwd": 1, "gpode_kl_bwd": 1, "gpode_dopri5_fwd": 1, "gpode_dopri5_bwd": 1, "gpode_state_fwd": 1, "gpode_state_bwd": 1,
-                    "gpode_loglik_sum": 1, "gpode_constraint_sum": 1, "gpode_vf_fwd_large": 1, "gpode_rk4_fwd_large": 1,
-                    "gpode_dopri5_bwd_dev": (_I, [_P, _I, _I, _I, _P, _I, _L, _P, _P, _I, _P, _P, _P, _P, _P]),
-    "gpode_param_grad_dev": (_I, [_P, _I, _I, _I, _P, _P, _L, _P, _L, _P, _P]),
-    "gpode_pack_cache_large": 1, "gpode_rbf_fwd_large": 1, "gpode_rff_fwd_large": 1, "gpode_vf_fwd_large_add_rbf": 1, "gpode_dopri5_bwd_dev": 1, "gpode_param_grad_dev": 1, "gpode_vf_fwd_umma": 1, "gpode_pack_cache_sets": 1, "gpode_whiten_fwd_sets": 2, "gpode_vf_fwd_sets": 1,
-                    "gpode_rk4_fwd_sets": 1, "gpode_dopri5_fwd_sets": 1}
+KERNELS_PER_CALL = {
+    "gpode_pack_cache": 1, "gpode_vf_fwd": 1, "gpode_vf_bwd": 1, "gpode_rk4_fwd": 1, "gpode_rk4_bwd": 1,
+    "gpode_param_grad": 1, "gpode_grads_finalize": 1, "gpode_whiten_fwd": 1, "gpode_whiten_bwd": 1,
+    "gpode_kl_fwd": 1, "gpode_kl_bwd": 1, "gpode_dopri5_fwd": 1, "gpode_dopri5_bwd": 1, "gpode_state_fwd": 1,
+    "gpode_state_bwd": 1, "gpode_loglik_sum": 2, "gpode_constraint_sum": 2, "gpode_vf_fwd_large": 1,
+    "gpode_rk4_fwd_large": 1, "gpode_pack_cache_large": 1, "gpode_rbf_fwd_large": 1, "gpode_rff_fwd_large": 1,
+    "gpode_vf_fwd_large_add_rbf": 1, "gpode_dopri5_bwd_dev": 1, "gpode_param_grad_dev": 1, "gpode_vf_fwd_umma": 1,
+    "gpode_pack_cache_sets": 1, "gpode_whiten_fwd_sets": 2, "gpode_vf_fwd_sets": 1, "gpode_rk4_fwd_sets": 1,
+    "gpode_dopri5_fwd_sets": 1,
+}
+assert all(isinstance(v, int) for v in KERNELS_PER_CALL.values()), "KERNELS_PER_CALL holds launch counts"
+assert set(KERNELS_PER_CALL) <= set(SIGNATURES), sorted(set(KERNELS_PER_CALL) - set(SIGNATURES))
 LAUNCH_COUNT = {}
 _PROFILE = None  # None, or {name: [(start_event, end_event), ...]}
 

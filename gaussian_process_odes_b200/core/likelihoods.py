@@ -47,7 +47,10 @@ class Gaussian(nn.Module):
             if Y.shape[-1] == W.shape[1] and W.shape[0] <= 8 and W.shape[1] <= 128 and (
                     ylead == lead or (len(ylead) == len(lead) and ylead[0] == 1 and ylead[1:] == lead[1:])):
                 from .. import ops
-                return ops.loglik_mean(F, Y, W, b, self.variance)
+                var = self.variance
+                if var.numel() != W.shape[1]:  # e.g. the class default Gaussian(ndim=1): broadcast like log_prob does
+                    var = var.expand(W.shape[1])
+                return ops.loglik_mean(F, Y, W, b, var)
         return self.log_prob(F, Y).mean()
 
 

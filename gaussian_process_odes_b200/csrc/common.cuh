@@ -105,17 +105,27 @@ __host__ __device__ inline GpodeLayout gpode_layout(int D, int M, int S) {
     return L;
 }
 
-// accumulator block of the backward kernels: A[D,D] | V[D] | T[D,M] | W[D,M,D]
+// Accumulator block of the backward kernels. Shared-parameter gradients contract over every row of the batch; to keep
+// them BITWISE REPRODUCIBLE (no floating-point atomics anywhere) each CTA writes its partial sums to a row of its own
+// and gpode_grads_finalize adds the rows up in row order, in float64:
+//   [0, 4)            header (int32): hdr[0] = AV rows written, hdr[1] = TW rows written (zeroed by the caller)
+//   av rows           cap_av x (D*D + D):   A[k][j] | V[k]            one row per CTA of the adjoint / VJP kernel
+//   tw rows           cap_tw x M*(D + D*D): per inducing point m:  T[k] (k < D) | W[j][k] (j, k < D)
+//                                           one row per CTA (blockIdx.x) of param_grad_kernel
+#define GPODE_ACC_HDR 4
+#define GPODE_ACC_CAP_AV 4096
+#define GPODE_ACC_CAP_TW 1024
 struct GpodeAcc {
-    int off_A, off_V, off_T, off_W, total;
+    int n_av, n_tw_m;  // floats per AV row; floats per inducing point of a TW row
+    int64_t off_av, off_tw, total;
 };
 __host__ __device__ inline GpodeAcc gpode_acc_layout(int D, int M) {
     GpodeAcc a;
-    a.off_A = 0;
-    a.off_V = D * D;
-    a.off_T = a.off_V + D;
-    a.off_W = a.off_T + D * M;
-    a.total = a.off_W + D * M * D;
+    a.n_av = D * D + D;
+    a.n_tw_m = D + D * D;
+    a.off_av = GPODE_ACC_HDR;
+    a.off_tw = a.off_av + (int64_t)GPODE_ACC_CAP_AV * a.n_av;
+    a.total = a.off_tw + (int64_t)GPODE_ACC_CAP_TW * M * a.n_tw_m;
     return a;
 }
 
@@ -130,6 +140,42 @@ __device__ __forceinline__ float gpode_ex2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+
+// ---- accurate sine / cosine for the latency-bound (warp-per-row) kernels ------------------------------------------
+// Cody-Waite reduction by pi/2 in three float32 pieces (each product exact inside the FMA) + the Cephes minimax
+// polynomials on [-pi/4, pi/4]: |error| <= 9.3e-8 for |x| <= 3e4 (checked against float64 over 1e7 points), no local
+// memory (libm's cosf/sinf carry a Payne-Hanek slow path with a stack array). MUFU.COS / MUFU.SIN, which the wide
+// kernels use, are ~1e-6 absolute at the |theta| ~ 10..30 rad this model produces.
+__device__ __forceinline__ void gpode_trig_reduce(const float x, float& r, int& n) {
+    const float q = rintf(x * 0.63661977236758138f);
+    r = fmaf(q, -1.5707963705062866f, x);
+    r = fmaf(q, 4.371138828673793e-08f, r);
+    r = fmaf(q, 1.7151245100058819e-15f, r);
+    n = (int)q;
+}
+__device__ __forceinline__ float gpode_sin_poly(const float r, const float z) {
+    return fmaf(fmaf(fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f), z, -1.6666654611e-1f), z * r, r);
+}
+__device__ __forceinline__ float gpode_cos_poly(const float z) {
+    return fmaf(fmaf(fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f), z, 4.166664568298827e-2f), z * z,
+                fmaf(-0.5f, z, 1.0f));
+}
+__device__ __forceinline__ float gpode_cos_cw(const float x) {
+    float r;
+    int n;
+    gpode_trig_reduce(x, r, n);
+    const float z = r * r;
+    const float v = (n & 1) ? gpode_sin_poly(r, z) : gpode_cos_poly(z);
+    return ((n + 1) & 2) ? -v : v;   // quadrants 0..3: cos, -sin, -cos, sin
+}
+__device__ __forceinline__ float gpode_sin_cw(const float x) {
+    float r;
+    int n;
+    gpode_trig_reduce(x, r, n);
+    const float z = r * r;
+    const float v = (n & 1) ? gpode_cos_poly(z) : gpode_sin_poly(r, z);
+    return (n & 2) ? -v : v;         // quadrants 0..3: sin, cos, -sin, -cos
 }
 
 // ---- packed dual-FP32 arithmetic (sm_100: one issue slot, two FMAs) ---------------------------------------------
@@ -231,5 +277,39 @@ __device__ __forceinline__ float gpode_warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+// Deterministic second stage of every cross-CTA sum in this library: `n_rows` rows of `chunk` contiguous values (one
+// row per producer CTA, `stride` values apart) are added up in float64 with a FIXED assignment -- warp w takes rows
+// w, w + nwarps, ... in order, lanes take the columns, the warps' partial sums are then added in warp order -- so the
+// result does not depend on how the producer CTAs were scheduled. tot[i], i < chunk, is valid after the call for the
+// whole CTA. part: [nwarps][chunk_cap] float64 scratch in shared memory.
+template <int PER_LANE, typename T>
+__device__ __forceinline__ void gpode_sum_rows_ordered(const T* __restrict__ base, const size_t stride, const int n_rows,
+                                                       const int chunk, const int chunk_cap, double* part, double* tot) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    double s[PER_LANE];
+#pragma unroll
+    for (int q = 0; q < PER_LANE; ++q) s[q] = 0.0;
+    for (int r = warp; r < n_rows; r += nwarps) {
+        const T* __restrict__ rowp = base + (size_t)r * stride;
+#pragma unroll
+        for (int q = 0; q < PER_LANE; ++q) {
+            const int i = lane + 32 * q;
+            if (i < chunk) s[q] += (double)__ldcg(rowp + i);  // written by other CTAs / an earlier kernel: bypass L1
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < PER_LANE; ++q) {
+        const int i = lane + 32 * q;
+        if (i < chunk) part[warp * chunk_cap + i] = s[q];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < chunk; i += blockDim.x) {
+        double t = 0.0;
+        for (int w = 0; w < nwarps; ++w) t += part[w * chunk_cap + i];
+        tot[i] = t;
+    }
+    __syncthreads();
 }
 #endif  // __CUDACC__

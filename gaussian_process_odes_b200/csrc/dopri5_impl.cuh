@@ -473,7 +473,6 @@ __global__ void __launch_bounds__(kDpThreads) dopri5_bwd_kernel(const Dopri5BwdA
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const float* sp = stage_params(smem_raw, a.packed, a.total);
     float* red = reinterpret_cast<float*>(smem_raw + 16) + a.total;
-    for (int i = threadIdx.x; i < D * D + D; i += blockDim.x) red[i] = 0.f;
     float A[D][D], V[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) {
@@ -608,7 +607,7 @@ int launch_dopri5_bwd(const float* packed, int M, int S, const double* t, int Tg
                       const float* ckpt, int cap, int n_acc, const int32_t* stats_dev, float* gx0, float* vrows,
                       float* acc, cudaStream_t st) {
     const GpodeLayout L = gpode_layout(D, M, S);
-    const size_t smem = 16 + (size_t)(L.total + D * D + D) * 4;
+    const size_t smem = 16 + (size_t)(L.total + kRedFloats<D>) * 4;
     GPODE_CUDA(cudaFuncSetAttribute(dopri5_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0, sms = 148, dev = 0;
     GPODE_CUDA(cudaGetDevice(&dev));
@@ -620,7 +619,8 @@ int launch_dopri5_bwd(const float* packed, int M, int S, const double* t, int Tg
     }
     const int wpc = kDpThreads / 32;
     const int64_t want = (B + wpc - 1) / wpc;
-    const int64_t cap_grid = (int64_t)sms * occ;
+    int64_t cap_grid = (int64_t)sms * occ;
+    if (cap_grid > GPODE_ACC_CAP_AV) cap_grid = GPODE_ACC_CAP_AV;  // one accumulator row per CTA
     Dopri5BwdArgs a;
     a.packed = packed; a.M = M; a.S = S; a.total = L.total; a.t = t; a.Tg = Tg; a.B = B; a.gxs = gxs; a.ckpt = ckpt;
     a.cap = cap; a.n_acc = n_acc; a.stats_dev = stats_dev; a.gx0 = gx0;

@@ -170,7 +170,6 @@ rk4_bwd_kernel(const float* __restrict__ packed, const int M, const int S, const
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const float* sp = stage_params(smem_raw, packed, total);
     float* red = reinterpret_cast<float*>(smem_raw + 16) + total;
-    for (int i = threadIdx.x; i < D * D + D; i += blockDim.x) red[i] = 0.f;
 
     float A[D][D], V[D];
 #pragma unroll
@@ -270,7 +269,6 @@ vf_bwd_kernel(const float* __restrict__ packed, const int M, const int S, const 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const float* sp = stage_params(smem_raw, packed, total);
     float* red = reinterpret_cast<float*>(smem_raw + 16) + total;
-    for (int i = threadIdx.x; i < D * D + D; i += blockDim.x) red[i] = 0.f;
     float A[D][D], V[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) {
@@ -436,7 +434,6 @@ rk4_bwd_warp_kernel(const float* __restrict__ packed, const int M, const int S, 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const float* sp = stage_params(smem_raw, packed, total);
     float* red = reinterpret_cast<float*>(smem_raw + 16) + total;
-    for (int i = threadIdx.x; i < D * D + D; i += blockDim.x) red[i] = 0.f;
     float A[D][D], V[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) {
@@ -524,7 +521,6 @@ vf_bwd_warp_kernel(const float* __restrict__ packed, const int M, const int S, c
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const float* sp = stage_params(smem_raw, packed, total);
     float* red = reinterpret_cast<float*>(smem_raw + 16) + total;
-    for (int i = threadIdx.x; i < D * D + D; i += blockDim.x) red[i] = 0.f;
     float A[D][D], V[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) {
@@ -614,7 +610,7 @@ struct HSmem {
         small = sp;
         mmah = reinterpret_cast<const uint32_t*>(sp + p.n_small);
         red = sp + p.n_small + p.n_mmah;
-        stage = red + ((D * D + D + 3) & ~3) + (threadIdx.x >> 5) * HShape<D>::kStageFloats;
+        stage = red + kRedFloats<D> + (threadIdx.x >> 5) * HShape<D>::kStageFloats;
     }
 };
 
@@ -635,7 +631,6 @@ vf_bwd_mma_kernel(const float* __restrict__ packed, const HParams p, const float
     extern __shared__ __align__(16) unsigned char smem_raw[];
     stage_params_h(smem_raw, packed, p.off_kern, p.n_small, p.off_mmah, p.n_mmah);
     const HSmem<D> sm(smem_raw, p);
-    for (int i = threadIdx.x; i < D * D + D; i += blockDim.x) sm.red[i] = 0.f;
     HAcc<D> qa;
     qa.clear();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -745,13 +740,12 @@ rk4_bwd_mma_kernel(const float* __restrict__ packed, const HParams p, const floa
     extern __shared__ __align__(16) unsigned char smem_raw[];
     stage_params_h(smem_raw, packed, p.off_kern, p.n_small, p.off_mmah, p.n_mmah);
     const HSmem<D> sm(smem_raw, p);
-    for (int i = threadIdx.x; i < D * D + D; i += blockDim.x) sm.red[i] = 0.f;
     HAcc<D> qa;
     qa.clear();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int R = 1;
     enum { F_LAM = 0, F_Y = 1, F_K1 = 2, F_K2 = 3, F_SUM = 4, F_YB4 = 5, F_Y23 = 6 };
-    float* __restrict__ rs = sm.red + ((D * D + D + 3) & ~3) + kHWarps * HShape<D>::kStageFloats +
+    float* __restrict__ rs = sm.red + kRedFloats<D> + kHWarps * HShape<D>::kStageFloats +
                              warp * (kHRowFields * D * 32) + lane;
     auto put = [&](const int f, const float (&v)[R][D]) {
 #pragma unroll
@@ -898,7 +892,8 @@ inline int shape_for(K kernel, int R, int64_t B, size_t smem, LaunchShape* out) 
     }
     const int64_t tile_rows = (int64_t)threads * R;
     const int64_t ntiles = (B + tile_rows - 1) / tile_rows;
-    const int64_t cap = (int64_t)num_sms() * occ;
+    int64_t cap = (int64_t)num_sms() * occ;
+    if (cap > GPODE_ACC_CAP_AV) cap = GPODE_ACC_CAP_AV;  // one accumulator row per CTA (common.cuh, GpodeAcc)
     out->threads = threads;
     out->grid = (int)(ntiles < cap ? ntiles : cap);
     out->smem = smem;
@@ -923,7 +918,8 @@ inline int warp_shape_for(K kernel, int64_t B, size_t smem, LaunchShape* out) {
         return -2;
     }
     const int64_t want = (B + kWarpsPerCta - 1) / kWarpsPerCta;
-    const int64_t cap = (int64_t)num_sms() * occ;
+    int64_t cap = (int64_t)num_sms() * occ;
+    if (cap > GPODE_ACC_CAP_AV) cap = GPODE_ACC_CAP_AV;  // one accumulator row per CTA (common.cuh, GpodeAcc)
     out->threads = kWarpsPerCta * 32;
     out->grid = (int)(want < cap ? want : cap);
     out->smem = smem;
@@ -963,7 +959,7 @@ inline HParams h_params(const GpodeLayout& L) {
 }
 template <int D>
 inline size_t h_smem(const HParams& p, bool rk4 = true, int warps = kHWarps) {
-    return 16 + ((size_t)p.n_small + p.n_mmah + ((D * D + D + 3) & ~3) + (size_t)warps * HShape<D>::kStageFloats +
+    return 16 + ((size_t)p.n_small + p.n_mmah + kRedFloats<D> + (size_t)warps * HShape<D>::kStageFloats +
                  (rk4 ? (size_t)warps * kHRowFields * D * 32 : 0)) * 4;
 }
 template <typename K>
@@ -1084,7 +1080,7 @@ int launch_rk4_bwd(const float* packed, int M, int S, const float* t, int Tg, in
                    const float* kst, const float* gxs, float* gx0, float* vy, float* vk, float* acc,
                    cudaStream_t st) {
     const GpodeLayout L = gpode_layout(D, M, S);
-    const size_t smem = 16 + (size_t)(L.total + D * D + D) * 4;
+    const size_t smem = 16 + (size_t)(L.total + kRedFloats<D>) * 4;
     LaunchShape ls;
     constexpr int RW = RowsBwd<D>::value;
     if constexpr (kMmaBwd<D>) {
@@ -1119,7 +1115,7 @@ template <int D>
 int launch_vf_bwd(const float* packed, int M, int S, const float* x, const float* f, const float* gf, float* gx,
                   int64_t B, float* acc, cudaStream_t st) {
     const GpodeLayout L = gpode_layout(D, M, S);
-    const size_t smem = 16 + (size_t)(L.total + D * D + D) * 4;
+    const size_t smem = 16 + (size_t)(L.total + kRedFloats<D>) * 4;
     LaunchShape ls;
     constexpr int RW = RowsBwd<D>::value;
     if constexpr (kMmaBwd<D>) {

@@ -33,7 +33,8 @@ param_grad_kernel(const float* __restrict__ packed, const int M, const int S, co
     constexpr int RP = VfShape<D>::RP, KS = VfShape<D>::KS, WP = VfShape<D>::WP;
     constexpr int DP = (D + 3) & ~3;
     constexpr int RW = 2 * DP;  // floats per staged row: y padded to DP, cotangent padded to DP
-    __shared__ __align__(16) float srow[2][kPgTile * RW];  // double buffer: tile t+1 lands while tile t is consumed
+    extern __shared__ __align__(16) float pg_smem[];  // [2][kPgTile * RW] double buffer: tile t+1 lands while tile t is
+    float* const srow[2] = {pg_smem, pg_smem + kPgTile * RW};  // consumed; re-used for the group reduction at the end
 
     const float* __restrict__ kern = packed + D * ((((S + 1) >> 1) + 31) & ~31) * RP;
     const float* __restrict__ wnp = kern + M * KS;  // -w, [j][WP] with outputs k along the row
@@ -152,42 +153,92 @@ param_grad_kernel(const float* __restrict__ packed, const int M, const int S, co
         if (n_next) stash(srow[buf ^ 1], n_next);  // the other buffer's readers finished before the previous barrier
         __syncthreads();
     }
-    if (active) {
-        const GpodeAcc a = gpode_acc_layout(D, M);
+    // ---- this CTA's partial sums -> its own row of the accumulator block (no atomics: the result must not depend on
+    // scheduling). The G row-groups of the CTA are added in group order through shared memory.
+    const GpodeAcc a = gpode_acc_layout(D, M);
+    constexpr int NE = D + D * D;  // per inducing point: T[k] | W[j][k]
+    float val[NE];
 #pragma unroll
-        for (int k = 0; k < D; ++k) {
-            const bool last = kOdd && k == D - 1;
-            const int kp = (k >> 1) < KF ? (k >> 1) : 0;
-            atomicAdd(acc + a.off_T + k * M + m, last ? Tl : ((k & 1) ? T2[kp].y : T2[kp].x));
+    for (int k = 0; k < D; ++k) {
+        const bool last = kOdd && k == D - 1;
+        const int kp = (k >> 1) < KF ? (k >> 1) : 0;
+        val[k] = last ? Tl : ((k & 1) ? T2[kp].y : T2[kp].x);
 #pragma unroll
-            for (int j = 0; j < D; ++j)
-                atomicAdd(acc + a.off_W + (k * M + m) * D + j, last ? Wl[j] : ((k & 1) ? W2[kp][j].y : W2[kp][j].x));
-        }
+        for (int j = 0; j < D; ++j) val[D + j * D + k] = last ? Wl[j] : ((k & 1) ? W2[kp][j].y : W2[kp][j].x);
     }
+    float* __restrict__ row = acc + a.off_tw + (size_t)blockIdx.x * M * NE;
+    if (G == 1) {
+        if (active) {
+#pragma unroll
+            for (int e = 0; e < NE; ++e) row[(size_t)m * NE + e] = val[e];
+        }
+    } else {
+        float* __restrict__ red = pg_smem;  // [M][NE]; the staged tiles are dead (barrier at the end of the loop)
+        for (int g = 0; g < G; ++g) {
+            if (active && group == g) {
+#pragma unroll
+                for (int e = 0; e < NE; ++e) red[m * NE + e] = (g == 0 ? 0.f : red[m * NE + e]) + val[e];
+            }
+            __syncthreads();
+        }
+        for (int i = threadIdx.x; i < M * NE; i += blockDim.x) row[i] = red[i];
+    }
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) reinterpret_cast<int*>(acc)[1] = (int)gridDim.x;
 }
 
-// acc -> parameter gradients (tiny; one CTA)
-__global__ void grads_finalize_kernel(const int D, const int M, const float* __restrict__ Z,
-                                      const float* __restrict__ nu, const float* __restrict__ ell,
-                                      const float* __restrict__ var, const float* __restrict__ acc,
-                                      float* __restrict__ g_ell, float* __restrict__ g_var, float* __restrict__ g_Z,
-                                      float* __restrict__ g_nu) {
+// Accumulator rows -> parameter gradients. Rows are added in row order in float64 (fixed assignment of rows to warps,
+// warps added in warp order), the contractions with nu / var / ell are done in float64 as well, and every output is
+// rounded to float32 once. CTA b < ceil(M / kFinM) owns kFinM inducing points (grad_nu, grad_Z), the last CTA the
+// lengthscale / variance sums (grad_ell, grad_var).
+constexpr int kFinM = 4, kFinThreads = 256, kFinWarps = kFinThreads / 32;
+constexpr int kFinMaxChunk = kFinM * (GPODE_MAX_D + GPODE_MAX_D * GPODE_MAX_D);  // 288
+constexpr int kFinPerLane = (kFinMaxChunk + 31) / 32;                             // 9
+
+__global__ void __launch_bounds__(kFinThreads)
+grads_finalize_kernel(const int D, const int M, const float* __restrict__ nu, const float* __restrict__ ell,
+                      const float* __restrict__ var, const float* __restrict__ acc, float* __restrict__ g_ell,
+                      float* __restrict__ g_var, float* __restrict__ g_Z, float* __restrict__ g_nu) {
+    __shared__ double part[kFinWarps][kFinMaxChunk];
+    __shared__ double tot[kFinMaxChunk];
     const GpodeAcc a = gpode_acc_layout(D, M);
-    for (int i = threadIdx.x; i < D * D; i += blockDim.x) g_ell[i] = -acc[a.off_A + i] / ell[i];
-    for (int k = threadIdx.x; k < D; k += blockDim.x) g_var[k] = 0.5f * acc[a.off_V + k] / var[k];
-    for (int i = threadIdx.x; i < D * M; i += blockDim.x) g_nu[i] = var[i / M] * acc[a.off_T + i];
-    for (int i = threadIdx.x; i < M * D; i += blockDim.x) {
-        const int m = i / D, j = i - m * D;
-        float s = 0.f;
+    const int* hdr = reinterpret_cast<const int*>(acc);
+    const int n_mg = (M + kFinM - 1) / kFinM;
+    const bool av = (int)blockIdx.x == n_mg;
+    const int NE = a.n_tw_m;
+    const int m0 = blockIdx.x * kFinM, cnt = av ? 0 : (M - m0 < kFinM ? M - m0 : kFinM);
+    const int chunk = av ? a.n_av : cnt * NE;                       // contiguous floats of every row this CTA adds up
+    const int n_rows = av ? hdr[0] : hdr[1];
+    const size_t stride = av ? (size_t)a.n_av : (size_t)M * NE;
+    const float* __restrict__ base = acc + (av ? a.off_av : a.off_tw + (size_t)m0 * NE);
+    gpode_sum_rows_ordered<kFinPerLane>(base, stride, n_rows, chunk, kFinMaxChunk, &part[0][0], tot);
+    if (av) {
+        for (int i = threadIdx.x; i < D * D; i += blockDim.x) g_ell[i] = (float)(-tot[i] / (double)ell[i]);
+        for (int k = threadIdx.x; k < D; k += blockDim.x) g_var[k] = (float)(0.5 * tot[D * D + k] / (double)var[k]);
+        return;
+    }
+    for (int i = threadIdx.x; i < cnt * D; i += blockDim.x) {   // grad_nu[k][m] = var_k T[k][m]
+        const int mm = i / D, k = i - mm * D;
+        g_nu[k * M + m0 + mm] = (float)((double)var[k] * tot[mm * NE + k]);
+    }
+    for (int i = threadIdx.x; i < cnt * D; i += blockDim.x) {   // grad_Z[m][j] = sum_k var_k nu_km W[k][m][j] / ell_kj^2
+        const int mm = i / D, j = i - mm * D;
+        double sz = 0.0;
         for (int k = 0; k < D; ++k) {
-            const float l = ell[k * D + j];
-            s += var[k] * nu[k * M + m] * acc[a.off_W + (k * M + m) * D + j] / (l * l);
+            const double l = (double)ell[k * D + j];
+            sz += (double)var[k] * (double)nu[k * M + m0 + mm] * tot[mm * NE + D + j * D + k] / (l * l);
         }
-        g_Z[i] = s;
+        g_Z[(m0 + mm) * D + j] = (float)sz;
     }
 }
 
 }  // namespace
+
+static size_t pg_smem_bytes(int D, int M) {
+    const int DP = (D + 3) & ~3;
+    const size_t tiles = (size_t)2 * kPgTile * 2 * DP * sizeof(float);
+    const size_t red = M < kPgThreads / 2 + 1 ? (size_t)M * (D + D * D) * sizeof(float) : 0;  // only when G >= 2
+    return tiles > red ? tiles : red;
+}
 
 int gpode_param_grad_launch(const float* packed, int D, int M, int S, const float* ys, const float* kbs, int64_t VR,
                             float* acc, cudaStream_t stream, const int32_t* stats_dev, int64_t rows_per_step) {
@@ -199,6 +250,7 @@ int gpode_param_grad_launch(const float* packed, int D, int M, int S, const floa
     // rows per CTA: enough CTAs to fill the machine (~4 per SM across gy), but at least one full tile each
     int64_t want_ctas = (int64_t)sms * 4 / gy;
     if (want_ctas < 1) want_ctas = 1;
+    if (want_ctas > GPODE_ACC_CAP_TW) want_ctas = GPODE_ACC_CAP_TW;  // one accumulator row per blockIdx.x
     int64_t rows_per_cta = (VR + want_ctas - 1) / want_ctas;
     rows_per_cta = ((rows_per_cta + kPgTile - 1) / kPgTile) * kPgTile;
     const int64_t gx = (VR + rows_per_cta - 1) / rows_per_cta;
@@ -207,8 +259,8 @@ int gpode_param_grad_launch(const float* packed, int D, int M, int S, const floa
     switch (D) {
 #define GPODE_PG_CASE(D_)                                                                                        \
     case D_:                                                                                                     \
-        param_grad_kernel<D_><<<grid, threads, 0, stream>>>(packed, M, S, ys, kbs, VR, rows_per_cta, acc,     \
-                                                            stats_dev, rows_per_step);                        \
+        param_grad_kernel<D_><<<grid, threads, pg_smem_bytes(D_, M), stream>>>(                                 \
+            packed, M, S, ys, kbs, VR, rows_per_cta, acc, stats_dev, rows_per_step);                             \
         break;
         GPODE_PG_CASE(1) GPODE_PG_CASE(2) GPODE_PG_CASE(3) GPODE_PG_CASE(4)
         GPODE_PG_CASE(5) GPODE_PG_CASE(6) GPODE_PG_CASE(7) GPODE_PG_CASE(8)
@@ -222,14 +274,17 @@ int gpode_param_grad_launch(const float* packed, int D, int M, int S, const floa
 }
 
 extern "C" int64_t gpode_acc_floats(int D, int M) { return gpode_acc_layout(D, M).total; }
+extern "C" int64_t gpode_acc_header_floats(void) { return GPODE_ACC_HDR; }
 
 extern "C" int gpode_grads_finalize(const gpode_cache_t* c, const float* acc, float* grad_ell, float* grad_var,
                                     float* grad_Z, float* grad_nu, void* stream) {
     GPODE_CHECK_ARG(c != nullptr && acc != nullptr, "cache / acc is NULL");
     GPODE_CHECK_ARG(c->Z && c->nu && c->ell && c->var, "cache needs Z, nu, ell, var");
     GPODE_CHECK_ARG(grad_ell && grad_var && grad_Z && grad_nu, "NULL output");
-    grads_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(c->D, c->M, c->Z, c->nu, c->ell, c->var, acc, grad_ell,
-                                                              grad_var, grad_Z, grad_nu);
+    GPODE_CHECK_ARG(c->D >= 1 && c->D <= GPODE_MAX_D, "state dimension D=%d outside 1..%d", c->D, GPODE_MAX_D);
+    const int n_mg = (c->M + kFinM - 1) / kFinM;
+    grads_finalize_kernel<<<n_mg + 1, kFinThreads, 0, (cudaStream_t)stream>>>(c->D, c->M, c->nu, c->ell, c->var, acc,
+                                                                             grad_ell, grad_var, grad_Z, grad_nu);
     GPODE_LAUNCH_CHECK();
     return 0;
 }

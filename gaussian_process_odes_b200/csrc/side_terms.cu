@@ -203,8 +203,9 @@ constexpr int kLlPasses = 4;  // Dobs <= 128
 __global__ void __launch_bounds__(256)
 loglik_kernel(const float* __restrict__ pred, const float* __restrict__ ys, const float* __restrict__ W,
               const float* __restrict__ bias, const float* __restrict__ var, const int S, const int64_t R, const int D,
-              const int Dobs, double* __restrict__ out, float* __restrict__ g_pred, float* __restrict__ g_var) {
+              const int Dobs, double* __restrict__ work, float* __restrict__ g_pred) {
     __shared__ double s_sum[8];
+    __shared__ float s_gv[8][32 * kLlPasses];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     float w[kLlPasses][kLlMaxD], b[kLlPasses], iv[kLlPasses], lv[kLlPasses], gv[kLlPasses];
 #pragma unroll
@@ -274,21 +275,38 @@ loglik_kernel(const float* __restrict__ pred, const float* __restrict__ ys, cons
         }
         acc += (double)local;
     }
+    // this CTA's partial sums -> row blockIdx.x of `work` ([1 + Dobs] float64: log-density | variance gradients); the
+    // rows are added in row order by side_sum_kernel (no atomics: bitwise reproducible)
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) s_sum[warp] = acc;
+#pragma unroll
+    for (int p = 0; p < kLlPasses; ++p) s_gv[warp][p * 32 + lane] = gv[p];
     __syncthreads();
+    double* __restrict__ row = work + (size_t)blockIdx.x * (1 + Dobs);
     if (threadIdx.x == 0) {
         double t = 0.0;
         for (int i = 0; i < nwarps; ++i) t += s_sum[i];
-        atomicAdd(out, t);
+        row[0] = t;
     }
-    if (g_var != nullptr) {
-#pragma unroll
-        for (int p = 0; p < kLlPasses; ++p) {
-            const int d = p * 32 + lane;
-            if (d < Dobs) atomicAdd(g_var + d, gv[p]);
-        }
+    for (int d = threadIdx.x; d < Dobs; d += blockDim.x) {
+        double t = 0.0;
+        for (int i = 0; i < nwarps; ++i) t += (double)s_gv[i][d];
+        row[1 + d] = t;
     }
+}
+
+// rows of float64 partial sums -> out[0] (float64) and, optionally, g[0..cols-1) (float32); one CTA
+constexpr int kSideCap = 2048;                  // most CTAs (= rows of `work`) any side-term kernel launches
+constexpr int kSideCols = 1 + 32 * kLlPasses;   // widest row
+__global__ void __launch_bounds__(256)
+side_sum_kernel(const double* __restrict__ work, const int n_rows, const int cols, double* __restrict__ out,
+                float* __restrict__ g) {
+    __shared__ double part[8 * kSideCols];
+    __shared__ double tot[kSideCols];
+    gpode_sum_rows_ordered<(kSideCols + 31) / 32>(work, (size_t)cols, n_rows, cols, kSideCols, part, tot);
+    if (threadIdx.x == 0) out[0] = tot[0];
+    if (g != nullptr)
+        for (int i = threadIdx.x; i + 1 < cols; i += blockDim.x) g[i] = (float)tot[1 + i];
 }
 
 // ---- shooting-constraint term: sum over (s, n, t < T-1, d) of log N(ss[s,n,t+1,d] | pred[s,n,t,d], scale) ----------
@@ -296,7 +314,7 @@ loglik_kernel(const float* __restrict__ pred, const float* __restrict__ ys, cons
 // value and both gradients in one pass (the result is a scalar, so backward is a scale).
 __global__ void __launch_bounds__(256)
 constraint_kernel(const float* __restrict__ ss, const float* __restrict__ pred, const float* __restrict__ scale_p,
-                  const int64_t SN, const int T, const int D, const int laplace, double* __restrict__ out,
+                  const int64_t SN, const int T, const int D, const int laplace, double* __restrict__ work,
                   float* __restrict__ g_ss, float* __restrict__ g_pred) {
     __shared__ double s_sum[8];
     const float scale = scale_p[0];
@@ -328,7 +346,7 @@ constraint_kernel(const float* __restrict__ ss, const float* __restrict__ pred, 
     if (threadIdx.x == 0) {
         double t = 0.0;
         for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s_sum[i];
-        atomicAdd(out, t);
+        work[blockIdx.x] = t;  // added in row order by side_sum_kernel
     }
 }
 
@@ -382,29 +400,34 @@ extern "C" int gpode_state_bwd(const float* L_packed, const float* eps, int S, i
 
 extern "C" int gpode_loglik_sum(const float* pred, const float* ys, const float* W, const float* bias,
                                 const float* var, int S, int64_t R, int D, int D_obs, double* sum_out,
-                                float* grad_pred, float* grad_var, void* stream) {
+                                float* grad_pred, float* grad_var, double* work, void* stream) {
     GPODE_CHECK_ARG(D >= 1 && D <= GPODE_MAX_D, "latent dimension D=%d outside 1..%d", D, GPODE_MAX_D);
     GPODE_CHECK_ARG(D_obs >= 1 && D_obs <= 32 * kLlPasses, "observed dimension %d outside 1..%d", D_obs, 32 * kLlPasses);
     GPODE_CHECK_ARG(S >= 1 && R >= 0, "bad sizes S=%d R=%lld", S, (long long)R);
-    GPODE_CHECK_ARG(pred && ys && W && var && sum_out, "NULL argument");
+    GPODE_CHECK_ARG(pred && ys && W && var && sum_out && work, "NULL argument");
     cudaStream_t st = (cudaStream_t)stream;
-    GPODE_CUDA(cudaMemsetAsync(sum_out, 0, sizeof(double), st));
-    if (grad_var) GPODE_CUDA(cudaMemsetAsync(grad_var, 0, sizeof(float) * D_obs, st));
-    if (R == 0) return 0;
+    if (R == 0) {
+        GPODE_CUDA(cudaMemsetAsync(sum_out, 0, sizeof(double), st));
+        if (grad_var) GPODE_CUDA(cudaMemsetAsync(grad_var, 0, sizeof(float) * D_obs, st));
+        return 0;
+    }
     int sms = 148, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int64_t want = (R + 7) / 8;
-    const int64_t cap = (int64_t)sms * 8;
+    int64_t cap = (int64_t)sms * 8;
+    if (cap > kSideCap) cap = kSideCap;
     const unsigned grid = (unsigned)(want < cap ? want : cap);
-    loglik_kernel<<<grid, 256, 0, st>>>(pred, ys, W, bias, var, S, R, D, D_obs, sum_out, grad_pred, grad_var);
+    loglik_kernel<<<grid, 256, 0, st>>>(pred, ys, W, bias, var, S, R, D, D_obs, work, grad_pred);
+    side_sum_kernel<<<1, 256, 0, st>>>(work, (int)grid, 1 + D_obs, sum_out, grad_var);
     GPODE_LAUNCH_CHECK();
     return 0;
 }
 
 extern "C" int gpode_constraint_sum(const float* ss, const float* pred, const float* scale, int64_t SN, int T, int D,
-                                    int laplace, double* sum_out, float* grad_ss, float* grad_pred, void* stream) {
-    GPODE_CHECK_ARG(ss && pred && scale && sum_out, "NULL argument");
+                                    int laplace, double* sum_out, float* grad_ss, float* grad_pred, double* work,
+                                    void* stream) {
+    GPODE_CHECK_ARG(ss && pred && scale && sum_out && work, "NULL argument");
     GPODE_CHECK_ARG(SN >= 0 && T >= 1 && D >= 1, "bad sizes SN=%lld T=%d D=%d", (long long)SN, T, D);
     cudaStream_t st = (cudaStream_t)stream;
     GPODE_CUDA(cudaMemsetAsync(sum_out, 0, sizeof(double), st));
@@ -417,9 +440,13 @@ extern "C" int gpode_constraint_sum(const float* ss, const float* pred, const fl
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int64_t want = (total + 255) / 256;
-    const int64_t cap = (int64_t)sms * 8;
-    constraint_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(ss, pred, scale, SN, T, D, laplace, sum_out,
-                                                                          grad_ss, grad_pred);
+    int64_t cap = (int64_t)sms * 8;
+    if (cap > kSideCap) cap = kSideCap;
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
+    constraint_kernel<<<grid, 256, 0, st>>>(ss, pred, scale, SN, T, D, laplace, work, grad_ss, grad_pred);
+    side_sum_kernel<<<1, 256, 0, st>>>(work, (int)grid, 1, sum_out, nullptr);
     GPODE_LAUNCH_CHECK();
     return 0;
 }
+
+extern "C" int64_t gpode_side_work_doubles(void) { return (int64_t)kSideCap * kSideCols; }

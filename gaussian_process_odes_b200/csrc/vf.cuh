@@ -67,7 +67,9 @@ __device__ __forceinline__ void vf_eval(const float* __restrict__ sp, const int 
                 float2 th = make_float2(prm[2 * D], prm[2 * D + 1]);
 #pragma unroll
                 for (int j = 0; j < D; ++j) th = ffma2(x[r][j], make_float2(prm[2 * j], prm[2 * j + 1]), th);
-                const float2 c = make_float2(__cosf(th.x), __cosf(th.y));
+                // small batches (warp-per-row kernels) are latency-bound: the range-reduced polynomial cosine costs
+                // nothing there and is good to 1e-7 at any |theta|; the wide kernels use MUFU.COS (abs err ~1e-6)
+                const float2 c = kWarp ? make_float2(gpode_cos_cw(th.x), gpode_cos_cw(th.y)) : make_float2(__cosf(th.x), __cosf(th.y));
                 fr[r][k] = ffma2(c, make_float2(prm[2 * D + 2], prm[2 * D + 3]), fr[r][k]);
             }
         }
@@ -183,7 +185,7 @@ __device__ __forceinline__ void vf_vjp(const float* __restrict__ sp, const int M
                 float2 th = make_float2(prm[2 * D], prm[2 * D + 1]);
 #pragma unroll
                 for (int j = 0; j < D; ++j) th = ffma2(x[r][j], make_float2(prm[2 * j], prm[2 * j + 1]), th);
-                const float2 sn = make_float2(__sinf(th.x), __sinf(th.y));
+                const float2 sn = kWarp ? make_float2(gpode_sin_cw(th.x), gpode_sin_cw(th.y)) : make_float2(__sinf(th.x), __sinf(th.y));
                 const float2 g = fmul2(a2, sn);   // the row's factor -kb_k is applied once, after the feature loop
 #pragma unroll
                 for (int j = 0; j < D; ++j) G[r][j] = ffma2(g, make_float2(prm[2 * j], prm[2 * j + 1]), G[r][j]);
@@ -335,21 +337,33 @@ __device__ __forceinline__ const float* stage_params(unsigned char* smem_raw, co
     return sp;
 }
 
-// A[D][D] | V[D] per-thread partials -> block reduction -> one atomicAdd per value per CTA
+// A[D][D] | V[D] per-thread partials -> fixed-order block reduction -> this CTA's row of the accumulator block
+// (common.cuh, GpodeAcc). No atomics: warp shuffles, then one thread per value adds the warps in warp order, so the
+// result does not depend on scheduling; gpode_grads_finalize adds the rows in row order.
+// red_smem: at least kRedWarps * (D*D + D) floats.
+constexpr int kRedWarps = 16;  // widest CTA of any adjoint kernel is 12 warps
+template <int D>
+constexpr int kRedFloats = (kRedWarps * (D * D + D) + 3) & ~3;
 template <int D>
 __device__ __forceinline__ void reduce_AV(float (&A)[D][D], float (&V)[D], float* __restrict__ acc, float* red_smem) {
-    // red_smem: at least (D*D + D) floats, zero-initialised by the caller before the barrier below
-    const int lane = threadIdx.x & 31;
+    constexpr int N = D * D + D;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
 #pragma unroll
     for (int k = 0; k < D; ++k) {
 #pragma unroll
         for (int j = 0; j < D; ++j) {
             const float v = gpode_warp_sum(A[k][j]);
-            if (lane == 0) atomicAdd(&red_smem[k * D + j], v);
+            if (lane == 0) red_smem[warp * N + k * D + j] = v;
         }
         const float v = gpode_warp_sum(V[k]);
-        if (lane == 0) atomicAdd(&red_smem[D * D + k], v);
+        if (lane == 0) red_smem[warp * N + D * D + k] = v;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < D * D + D; i += blockDim.x) atomicAdd(&acc[i], red_smem[i]);
+    float* __restrict__ row = acc + GPODE_ACC_HDR + (size_t)blockIdx.x * N;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        float s = 0.f;
+        for (int w = 0; w < nwarps; ++w) s += red_smem[w * N + i];
+        row[i] = s;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) reinterpret_cast<int*>(acc)[0] = (int)gridDim.x;
 }

@@ -12,7 +12,9 @@
 // has a condition number around 1e5, so float64 accumulation keeps nu at the float64-arbiter level instead of adding
 // this kernel's round-off on top of the reference's (tests/ arbitrate with the float64 oracle).
 #include "common.cuh"
+#include <cooperative_groups.h>
 #include <math.h>
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -184,7 +186,10 @@ __global__ void whiten_bwd_kernel(const gpode_cache_t c, const float* __restrict
     Real* pb = rb + M;              // M
     Real* wv = pb + M;              // M
     Real* sv = wv + M;              // M
-    double* red = reinterpret_cast<double*>(sv + M + ((4 * M + 2 * M * ld) & 1));  // D + 1 doubles (+ scratch)
+    // float64 block-reduction scratch: [16 warps][D + 1] lengthscale / variance partials, then this CTA's share of
+    // grad_Z, gzs[M][D] (read by cluster rank 0 through distributed shared memory)
+    double* red = reinterpret_cast<double*>(sv + M + ((4 * M + 2 * M * ld) & 1));
+    double* gzs = red + 16 * (D + 1);
 
     const float* ellk = c.ell + k * D;
     const double vark = (double)c.var[k];
@@ -200,7 +205,6 @@ __global__ void whiten_bwd_kernel(const gpode_cache_t c, const float* __restrict
         wv[m] = (Real)u[m * D + k] - s;
         rb[m] = (Real)gnu[k * M + m];
     }
-    for (int i = threadIdx.x; i < D + 1; i += blockDim.x) red[i] = 0.0;
     __syncthreads();
     trsv_lower<Real>(L, M, ld, rb);  // rb = L^-1 nub  (= grad wrt u_k)
     __syncthreads();
@@ -244,16 +248,17 @@ __global__ void whiten_bwd_kernel(const gpode_cache_t c, const float* __restrict
         }
         __syncthreads();
     }
+    // No floating-point atomics below: every sum is taken in a fixed order, so repeated calls are bitwise identical.
     // RBF backward with Kb = (X + X^T)/2: thread = (inducing point m, slice of the partner points n)
+    double gvar = 0.0;           // this thread's share of the variance / lengthscale gradients (both parts)
+    double gl[GPODE_MAX_D];
+    for (int j = 0; j < D; ++j) gl[j] = 0.0;
     {
-        double gvar = 0.0;
-        double gl[GPODE_MAX_D];
-        for (int j = 0; j < D; ++j) gl[j] = 0.0;
         const int parts = blockDim.x / M;  // launches use 128 threads for M < 64 and 512 for M <= 160: parts >= 1
         const int m = threadIdx.x % M, part = threadIdx.x / M;
+        double gz[GPODE_MAX_D];
+        for (int j = 0; j < D; ++j) gz[j] = 0.0;
         if (part < parts) {
-            double gz[GPODE_MAX_D];
-            for (int j = 0; j < D; ++j) gz[j] = 0.0;
             for (int n = part; n < M; n += parts) {
                 const double kb = 0.5 * ((double)P[m * ld + n] + (double)P[n * ld + m]);
                 const double E = kb * rbf_entry(c.Z, inv_l, vark, D, m, n);
@@ -264,25 +269,18 @@ __global__ void whiten_bwd_kernel(const gpode_cache_t c, const float* __restrict
                     gl[j] += E * d * d * inv_l[j];
                 }
             }
-            for (int j = 0; j < D; ++j) atomicAdd(g_Z + m * D + j, (float)gz[j]);
         }
-        // warp-reduce first: shared-memory float64 atomics are CAS loops and serialise badly under contention
         gvar /= vark;
-        for (int o = 16; o > 0; o >>= 1) gvar += __shfl_xor_sync(0xffffffffu, gvar, o);
-        for (int j = 0; j < D; ++j)
-            for (int o = 16; o > 0; o >>= 1) gl[j] += __shfl_xor_sync(0xffffffffu, gl[j], o);
-        if ((threadIdx.x & 31) == 0) {
-            atomicAdd(&red[D], gvar);
-            for (int j = 0; j < D; ++j) atomicAdd(&red[j], gl[j]);
+        for (int p = 0; p < parts; ++p) {  // the slices of one inducing point are added in slice order
+            if (part == p)
+                for (int j = 0; j < D; ++j) gzs[m * D + j] = (p == 0 ? 0.0 : gzs[m * D + j]) + gz[j];
+            __syncthreads();
         }
     }
     // RFF VJP at x = Z with cotangent pb (only output dim k): one warp per inducing point, lanes over features
     {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
         const float ak = sqrtf(c.var[k] / (float)S);
-        double gvar = 0.0;
-        double glw[GPODE_MAX_D];
-        for (int j = 0; j < D; ++j) glw[j] = 0.0;
         for (int m = warp; m < M; m += nwarps) {
             double G[GPODE_MAX_D];
             for (int j = 0; j < D; ++j) G[j] = 0.0;
@@ -297,20 +295,40 @@ __global__ void whiten_bwd_kernel(const gpode_cache_t c, const float* __restrict
                 double v = G[j];
                 for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
                 if (lane == 0) {
-                    atomicAdd(g_Z + m * D + j, (float)v);
-                    glw[j] += -v * (double)c.Z[m * D + j] / (double)ellk[j];
+                    gzs[m * D + j] += v;  // inducing point m belongs to this warp alone
+                    gl[j] += -v * (double)c.Z[m * D + j] / (double)ellk[j];
                 }
             }
             if (lane == 0) gvar += pbm * sp_in[((size_t)k * 2 + 1) * M + m] / (2.0 * vark);
         }
+        // block sums of gvar, gl[j]: warp shuffles, then the warps in warp order
+        for (int o = 16; o > 0; o >>= 1) gvar += __shfl_xor_sync(0xffffffffu, gvar, o);
+        for (int j = 0; j < D; ++j)
+            for (int o = 16; o > 0; o >>= 1) gl[j] += __shfl_xor_sync(0xffffffffu, gl[j], o);
         if (lane == 0) {
-            atomicAdd(&red[D], gvar);
-            for (int j = 0; j < D; ++j) atomicAdd(&red[j], glw[j]);
+            red[warp * (D + 1) + D] = gvar;
+            for (int j = 0; j < D; ++j) red[warp * (D + 1) + j] = gl[j];
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < D + 1; j += blockDim.x) {
+            double t = 0.0;
+            for (int w = 0; w < nwarps; ++w) t += red[w * (D + 1) + j];
+            if (j < D) g_ell[k * D + j] = (float)t;
+            else g_var[k] = (float)t;
         }
     }
-    __syncthreads();
-    for (int j = threadIdx.x; j < D; j += blockDim.x) g_ell[k * D + j] = (float)red[j];
-    if (threadIdx.x == 0) g_var[k] = (float)red[D];
+    // grad_Z sums over the output dimensions = over the CTAs of this cluster: rank 0 adds them in rank order, reading
+    // the other CTAs' gzs through distributed shared memory
+    cg::cluster_group cluster = cg::this_cluster();
+    cluster.sync();
+    if (cluster.block_rank() == 0) {
+        for (int i = threadIdx.x; i < M * D; i += blockDim.x) {
+            double t = 0.0;
+            for (int r = 0; r < D; ++r) t += cluster.map_shared_rank(gzs, r)[i];
+            g_Z[i] = (float)t;
+        }
+    }
+    cluster.sync();  // keep every CTA's shared memory alive until rank 0 has read it
 }
 
 // ---- whitened KL (dsvgp.py:199-230): one CTA, float64 accumulation ---------------------------------------------
@@ -367,7 +385,7 @@ size_t solve_smem(int M) {
 template <typename Real>
 size_t bwd_smem(int M, int D) {
     const int ld = (M & 1) ? M : M + 1;
-    return sizeof(Real) * (2 * (size_t)M * ld + 4 * M + 2) + sizeof(double) * (D + 2) + 16;
+    return sizeof(Real) * (2 * (size_t)M * ld + 4 * M + 2) + sizeof(double) * (16 * (D + 1) + (size_t)M * D + 1) + 16;
 }
 
 int check_cache(const gpode_cache_t* c, bool need_nu) {
@@ -426,18 +444,31 @@ extern "C" int gpode_whiten_bwd(const gpode_cache_t* c, const float* u, const do
                                 void* stream) {
     if (int rc = check_cache(c, false)) return rc;
     GPODE_CHECK_ARG(u && L_f64 && s_f64 && grad_nu && grad_u && grad_Z && grad_ell && grad_var, "NULL argument");
-    GPODE_CUDA(cudaMemsetAsync(grad_Z, 0, sizeof(float) * c->M * c->D, (cudaStream_t)stream));
     const int threads = c->M >= 64 ? 512 : 128;
+    // one CTA per output dimension, all D of them in ONE thread-block cluster (D <= 8 = the portable cluster size)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(c->D);
+    cfg.blockDim = dim3(threads);
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = c->D;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     if (c->M <= GPODE_MAX_M_F64) {
-        const size_t smem = bwd_smem<double>(c->M, c->D);
-        GPODE_CUDA(cudaFuncSetAttribute(whiten_bwd_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        whiten_bwd_kernel<double><<<c->D, threads, smem, (cudaStream_t)stream>>>(*c, u, L_f64, s_f64, grad_nu, grad_u,
-                                                                                 grad_Z, grad_ell, grad_var);
+        cfg.dynamicSmemBytes = bwd_smem<double>(c->M, c->D);
+        GPODE_CUDA(cudaFuncSetAttribute(whiten_bwd_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)cfg.dynamicSmemBytes));
+        GPODE_CUDA(cudaLaunchKernelEx(&cfg, whiten_bwd_kernel<double>, *c, u, L_f64, s_f64, grad_nu, grad_u, grad_Z,
+                                      grad_ell, grad_var));
     } else {
-        const size_t smem = bwd_smem<float>(c->M, c->D);
-        GPODE_CUDA(cudaFuncSetAttribute(whiten_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        whiten_bwd_kernel<float><<<c->D, threads, smem, (cudaStream_t)stream>>>(*c, u, L_f64, s_f64, grad_nu, grad_u,
-                                                                                grad_Z, grad_ell, grad_var);
+        cfg.dynamicSmemBytes = bwd_smem<float>(c->M, c->D);
+        GPODE_CUDA(cudaFuncSetAttribute(whiten_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)cfg.dynamicSmemBytes));
+        GPODE_CUDA(cudaLaunchKernelEx(&cfg, whiten_bwd_kernel<float>, *c, u, L_f64, s_f64, grad_nu, grad_u, grad_Z,
+                                      grad_ell, grad_var));
     }
     GPODE_LAUNCH_CHECK();
     return 0;

@@ -25,9 +25,12 @@ from .core import kernels as _kernels
 class _StaticDraws:
     """Replaces the three host samplers by static device buffers that ``refresh()`` refills in call order."""
 
+    RING = 4   # pinned staging buffers per slot: the host may run at most RING refreshes ahead of the stream
+
     def __init__(self, device):
         self.device = device
-        self.slots = []      # (kind, shape, pinned_host, device_buffer)
+        self.slots = []      # (kind, shape, pinned host ring [{"buf", "ev"}], device_buffer)
+        self.turn = []       # next ring entry of every slot
         self.cursor = 0
         self.recording = True
         self._saved = None
@@ -35,9 +38,11 @@ class _StaticDraws:
     def _provide(self, kind, shape):
         shape = tuple(shape)
         if self.recording:
-            host = torch.empty(shape, dtype=torch.float32).pin_memory()
+            host = [{"buf": torch.empty(shape, dtype=torch.float32).pin_memory(), "ev": None}
+                    for _ in range(self.RING)]
             dev = torch.empty(shape, dtype=torch.float32, device=self.device)
             self.slots.append((kind, shape, host, dev))
+            self.turn.append(0)
             self._fill(len(self.slots) - 1)
             return dev
         kind_, shape_, _, dev = self.slots[self.cursor]
@@ -46,13 +51,23 @@ class _StaticDraws:
         return dev
 
     def _fill(self, i):
-        kind, shape, host, dev = self.slots[i]
+        kind, shape, ring, dev = self.slots[i]
         if kind == "uniform":
             arr = np.random.uniform(low=0.0, high=1.0, size=shape)
         else:
             arr = np.random.normal(size=shape)
-        host.copy_(torch.from_numpy(arr.astype(np.float32)))
-        dev.copy_(host, non_blocking=True)
+        # A replay takes milliseconds, a refresh microseconds: the host runs ahead of the stream. A pinned buffer is
+        # therefore re-used only after the event recorded behind ITS last copy (same protocol as
+        # misc.torch_utils._PinnedRing); overwriting it earlier would tear the draw of a step still in flight.
+        ent = ring[self.turn[i]]
+        self.turn[i] = (self.turn[i] + 1) % self.RING
+        if ent["ev"] is not None:
+            ent["ev"].synchronize()
+        ent["buf"].copy_(torch.from_numpy(arr.astype(np.float32)))
+        dev.copy_(ent["buf"], non_blocking=True)
+        if ent["ev"] is None:
+            ent["ev"] = torch.cuda.Event()
+        ent["ev"].record()
 
     def refresh(self):
         for i in range(len(self.slots)):

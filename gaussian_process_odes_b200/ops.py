@@ -46,8 +46,12 @@ class PackedCache:
         _lib.call("gpode_pack_cache", ctypes.byref(self.struct), ptr(self.packed), stream_ptr())
 
     def new_acc(self):
-        n = _lib.load().gpode_acc_floats(self.D, self.M)
-        return torch.zeros(n, dtype=torch.float32, device=self.Z.device)
+        """Accumulator block of ONE backward pass: per-CTA partial-sum rows (added in a fixed order by
+        ``gpode_grads_finalize``: bitwise reproducible); only the 4-word header has to be zero."""
+        lib = _lib.load()
+        acc = torch.empty(lib.gpode_acc_floats(self.D, self.M), dtype=torch.float32, device=self.Z.device)
+        acc[:lib.gpode_acc_header_floats()].zero_()
+        return acc
 
     def finalize(self, acc):
         """acc -> (grad_Z, grad_ell, grad_var, grad_nu)"""
@@ -243,6 +247,11 @@ class _StateEntropy(torch.autograd.Function):
         return gl, None, None
 
 
+def _side_work(device):
+    """float64 scratch of the side-term sums (per-CTA partial rows, summed in a fixed order)."""
+    return torch.empty(_lib.load().gpode_side_work_doubles(), dtype=torch.float64, device=device)
+
+
 class _LoglikMean(torch.autograd.Function):
     """mean over all elements of log N(ys | pred W + b, var), value and gradients in one kernel (gpode_loglik_sum)."""
 
@@ -257,8 +266,11 @@ class _LoglikMean(torch.autograd.Function):
         total = torch.empty((), dtype=torch.float64, device=pc.device)
         gp = torch.empty_like(pc) if need_p else None
         gv = torch.empty_like(vc) if need_v else None
+        if vc.numel() != Dobs or (bc is not None and bc.numel() != Dobs):
+            raise _lib.GpodeError("loglik_mean: var (and bias) must hold one value per observed dimension (%d), got %d"
+                                  % (Dobs, vc.numel()))
         _lib.call("gpode_loglik_sum", ptr(pc), ptr(yc), ptr(wc), ptr(bc), ptr(vc), S, R, D, Dobs, ptr(total), ptr(gp),
-                  ptr(gv), stream_ptr())
+                  ptr(gv), ptr(_side_work(pc.device)), stream_ptr())
         count = float(S * R * Dobs)
         ctx.count = count
         ctx.save_for_backward(*(t for t in (gp, gv) if t is not None))
@@ -290,7 +302,7 @@ class _ConstraintSum(torch.autograd.Function):
         gs = torch.empty_like(sc) if need_s else None
         gp = torch.empty_like(pc) if need_p else None
         _lib.call("gpode_constraint_sum", ptr(sc), ptr(pc), ptr(kc), SN, T, D, int(bool(laplace)), ptr(total), ptr(gs),
-                  ptr(gp), stream_ptr())
+                  ptr(gp), ptr(_side_work(sc.device)), stream_ptr())
         ctx.save_for_backward(*(t for t in (gs, gp) if t is not None))
         ctx.have = (need_s, need_p)
         return total.to(torch.float32)
@@ -395,9 +407,8 @@ class LargeField:
                 if "too large for the shared-memory copy of Z" not in str(e):
                     raise
                 self.rbf_on_tensor_cores = False  # many inducing points at large D: the FP32 tiled CUDA kernel instead
-        if True:
-            _lib.call("gpode_vf_fwd_large_add_rbf", ctypes.byref(self.struct), ptr(xc), ptr(f_rff), ptr(f), B,
-                      stream_ptr())
+        _lib.call("gpode_vf_fwd_large_add_rbf", ctypes.byref(self.struct), ptr(xc), ptr(f_rff), ptr(f), B,
+                  stream_ptr())
         return f
 
 

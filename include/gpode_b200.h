@@ -61,8 +61,8 @@ int gpode_pack_cache(const gpode_cache_t* cache, float* packed, void* stream);
 int gpode_vf_fwd(const float* packed, int D, int M, int S, const float* x, float* f, int64_t B, void* stream);
 
 /* Vector-Jacobian product of the above (what autograd does through dsvgp.py:172-197), row part:
- *   grad_x [B,D]; the lengthscale / variance partial sums ACCUMULATE into `acc` (gpode_acc_floats floats, zero it
- *   first); f [B,D] is the forward output (saved by the caller). Follow with gpode_param_grad(x, grad_f, B) for the
+ *   grad_x [B,D]; every CTA writes its lengthscale / variance partial sums to a row of its own in `acc` (see
+ *   gpode_acc_floats below); f [B,D] is the forward output (saved by the caller). Follow with gpode_param_grad(x, grad_f, B) for the
  *   per-inducing-point part and gpode_grads_finalize. */
 int gpode_vf_bwd(const float* packed, int D, int M, int S, const float* x, const float* f, const float* grad_f,
                  float* grad_x, float* acc, int64_t B, void* stream);
@@ -75,24 +75,30 @@ int gpode_rk4_fwd(const float* packed, int D, int M, int S, const float* x0, con
                   float* xs, float* kstages, void* stream);
 
 /* Discrete adjoint of gpode_rk4_fwd == autograd through the unrolled solver (use_adjoint=False, the reference
- * default, train_vdp_gpode.py:52). grad_xs [Tg,B,D] -> grad_x0 [B,D]; lengthscale / variance partial sums accumulate
- * into `acc`. vrows (gpode_vrow_floats(D, (Tg-1)*4*B) floats) receives, for every step and stage, the stage input
+ * default, train_vdp_gpode.py:52). grad_xs [Tg,B,D] -> grad_x0 [B,D]; lengthscale / variance partial sums go to this
+ * call's rows of `acc`. vrows (gpode_vrow_floats(D, (Tg-1)*4*B) floats) receives, for every step and stage, the stage input
  * and its cotangent: rows [0, n) hold the stage inputs, rows [n, 2n) the cotangents, n = (Tg-1)*4*B. Follow with
  * gpode_param_grad(vrows, vrows + n*D, n) and gpode_grads_finalize. */
 int gpode_rk4_bwd(const float* packed, int D, int M, int S, const float* t, int Tg, int64_t B, const float* xs,
                   const float* kstages, const float* grad_xs, float* grad_x0, float* vrows, float* acc,
                   void* stream);
 
-/* Per-inducing-point gradient contraction over n_rows (point y, cotangent kb) pairs: accumulates
- * T[k,m] += kb_k K_km(y) and W[k,m,j] += kb_k K_km(y) (y_j - Z_mj) into `acc` (autograd through
+/* Per-inducing-point gradient contraction over n_rows (point y, cotangent kb) pairs: partial sums
+ * T[k,m] = sum kb_k K_km(y) and W[k,m,j] = sum kb_k K_km(y) (y_j - Z_mj), one row of `acc` per CTA (autograd through
  * src/core/kernels.py:53-99 and the einsum of src/core/dsvgp.py:192 w.r.t. nu and Z).  ys, kbs: [n_rows,D]. */
 int gpode_param_grad(const float* packed, int D, int M, int S, const float* ys, const float* kbs, int64_t n_rows,
                      float* acc, void* stream);
 
 /* Accumulator block shared by the *_bwd entry points and its conversion to parameter gradients.
- *   acc layout (floats): A[D,D] | V[D] | T[D,M] | W[D,M,D]
+ * Shared-parameter gradients contract over every row of the batch. To make them BITWISE REPRODUCIBLE the library uses
+ * no floating-point atomics: each CTA of a *_bwd / param_grad kernel writes its partial sums to a row of its own
+ * and gpode_grads_finalize adds the rows up in row order in float64 (and contracts with nu / var / ell in float64).
+ *   acc layout (floats): header[gpode_acc_header_floats() = 4: int32 row counts, ZEROED BY THE CALLER before the
+ *   first *_bwd call] | rows of A[D,D] | V[D] (one per adjoint CTA) | rows of {T[k], W[j,k]} per inducing point
+ *   (one per param_grad CTA). One acc block serves ONE backward pass (one *_bwd call + one gpode_param_grad call).
  *   gpode_grads_finalize: grad_ell[D,D], grad_var[D], grad_Z[M,D], grad_nu[D,M] (overwritten). grad_ell already
  *   contains the path through omega = eps/ell (kernels.py:110-112). */
+int64_t gpode_acc_header_floats(void);
 int64_t gpode_acc_floats(int D, int M);
 int64_t gpode_vrow_floats(int D, int64_t n_virtual_rows);
 int gpode_grads_finalize(const gpode_cache_t* cache, const float* acc, float* grad_ell, float* grad_var,
@@ -207,16 +213,20 @@ int gpode_state_bwd(const float* L_packed, const float* eps, int S, int64_t R, i
  * (Gaussian / ProjectedGaussian.log_prob, src/core/likelihoods.py:27-28,38-45, decoder = affine map as in
  * src/misc/mocap_utils.py:24-34): pred [S,R,D], ys [R,D_obs], W [D,D_obs], bias [D_obs] or NULL, var [D_obs].
  * sum_out (device float64) = sum log N(ys | pred W + bias, var); grad_pred [S,R,D] / grad_var [D_obs] (may be NULL)
- * are the derivatives of that SUM. */
+ * are the derivatives of that SUM. work: gpode_side_work_doubles() float64 of scratch (per-CTA partial sums, added in
+ * a fixed order by a second kernel: the result is bitwise reproducible, no atomics). */
 int gpode_loglik_sum(const float* pred, const float* ys, const float* W, const float* bias, const float* var, int S,
-                     int64_t R, int D, int D_obs, double* sum_out, float* grad_pred, float* grad_var, void* stream);
+                     int64_t R, int D, int D_obs, double* sum_out, float* grad_pred, float* grad_var, double* work,
+                     void* stream);
+int64_t gpode_side_work_doubles(void);
 
 /* Shooting-constraint term of UniformSequenceModel (src/gpode_shooting/models.py:134-135,143 with
  * src/core/constraints.py:26-36 Gaussian / :56-66 Laplace): sum over sequences, t < T-1 and dims of
  * log p(ss[.,t+1,.] | loc = pred[.,t,.], scale). ss, pred: [SN,T,D]; scale: 1 float (device). grad_ss / grad_pred
- * ([SN,T,D], may be NULL) receive the derivatives of that SUM (untouched slots are zeroed). */
+ * ([SN,T,D], may be NULL) receive the derivatives of that SUM (untouched slots are zeroed). work: as for
+ * gpode_loglik_sum. */
 int gpode_constraint_sum(const float* ss, const float* pred, const float* scale, int64_t SN, int T, int D, int laplace,
-                         double* sum_out, float* grad_ss, float* grad_pred, void* stream);
+                         double* sum_out, float* grad_ss, float* grad_pred, double* work, void* stream);
 
 /* EXPERIMENTAL (2 <= D <= 7): gpode_vf_fwd with the Fourier-feature projection on the 5th-generation tensor cores
  * (tcgen05.mma kind::tf32, 3xTF32 error compensation, accumulators in TMEM); same arguments and results. */

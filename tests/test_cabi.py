@@ -37,7 +37,10 @@ def test_pure_host_entry_points():
     assert lib.gpode_packed_floats(3, 24, 64) == 3 * 32 * 12 + 24 * 8 + 3 * 4 + 3 * 8 * (80 + 152) + 3 * 17 * 64
     assert lib.gpode_packed_floats(8, 10, 40) == 8 * 32 * 20 + 10 * 16 + 8 * 8 + 8 * 5 * 80
     assert lib.gpode_packed_floats(0, 1, 1) == -1
-    assert lib.gpode_acc_floats(5, 100) == 25 + 5 + 500 + 2500
+    # header | 4096 adjoint-CTA rows of A[D,D] | V[D] | 1024 param-grad-CTA rows of M x {T[k], W[j,k]}
+    assert lib.gpode_acc_header_floats() == 4
+    assert lib.gpode_acc_floats(5, 100) == 4 + 4096 * (25 + 5) + 1024 * 100 * (5 + 25)
+    assert lib.gpode_side_work_doubles() == 2048 * 129
     assert lib.gpode_vrow_floats(5, 1000) == 10000
     assert lib.gpode_dopri5_work_floats(2, 10) >= 5 * 20 + 8
     # argument errors are reported through the return code + gpode_last_error, before any CUDA call

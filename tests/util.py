@@ -157,3 +157,42 @@ def product_grads(model, kind):
         g.update(x0_mean=sd.x0.param_mean.optvar.grad, x0_lchol_packed=sd.x0.param_lchol.optvar.grad,
                  state_mean=sd.param_mean.optvar.grad, state_lchol_packed=sd.param_lchol.optvar.grad)
     return g
+
+
+def elbo_errors(kind, kw, solver, extra, seed):
+    """One ELBO forward+backward of a seeded synthetic problem through the product (CUDA) path and through the oracle
+    port in float32 and float64 (CPU). -> {name: (cuda-vs-fp64, port32-vs-fp64, cuda-vs-port32)} for the loss and every
+    parameter gradient (relative = max-abs error / max-abs value)."""
+    from gaussian_process_odes_b200 import builders
+    p, ys, ts, draws, proj = O.make_problem(seed=seed, **kw)
+    res = {}
+    for dtype in (torch.float32, torch.float64):
+        pp = {k: v.detach().clone().to(dtype).requires_grad_(True) for k, v in p.items()}
+        pj = proj
+        if proj is not None and dtype == torch.float64:
+            comp = proj.components.double()
+            pj = lambda x: torch.einsum('ntl,ld->ntd', x, comp)
+        if kind == "gpode":
+            r = O.elbo_gpode(pp, ys.to(dtype), ts.to(dtype), O.cast(draws, dtype), method=solver, project=pj, **extra)
+        else:
+            r = O.elbo_shooting(pp, ys.to(dtype), ts.to(dtype), O.cast(draws, dtype), method=solver, project=pj)
+        r['loss'].backward()
+        res[dtype] = (r['loss'].detach(), {k: v.grad for k, v in pp.items() if v.grad is not None})
+    model = build_product_model(kind, p, ys, kw['S'], solver, ts_dense_scale=extra.get('ts_dense_scale', 4),
+                                proj=proj.components if proj is not None else None)
+    if kind == "gpode":
+        with injected_draws(draws, mvn_order=("eps_x0",)):
+            loss = builders.compute_loss_gpode(model, ys.cuda(), ts.cuda())[0]
+    else:
+        with injected_draws(draws, mvn_order=("eps_x0", "eps_states")):
+            ll, c, e, k0 = model.build_lowerbound_terms(ys.cuda(), ts.cuda(), num_samples=kw['S_mc'])
+            loss = -(ll + c + e - k0 - model.build_inducing_kl())
+    loss.backward()
+    g = product_grads(model, kind)
+    (l32, g32), (l64, g64) = res[torch.float32], res[torch.float64]
+    rows = {"loss": (relerr(loss.cpu(), l64), relerr(l32, l64), relerr(loss.cpu(), l32))}
+    for k, v in g.items():
+        rows[k] = (relerr(v.cpu(), g64[k]), relerr(g32[k], g64[k]), relerr(v.cpu(), g32[k]))
+    return rows
+
+
