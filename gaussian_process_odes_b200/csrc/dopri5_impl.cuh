@@ -94,7 +94,7 @@ __device__ __forceinline__ void vf_signed(const float* sp, int M, int S, float s
     if constexpr (kWarp) {
         vf_eval<D, 1, true>(sp, M, S, x, f, threadIdx.x & 31, 32);
 #pragma unroll
-        for (int j = 0; j < D; ++j) f[0][j] = gpode_warp_sum(f[0][j]) * sgn;
+        for (int j = 0; j < D; ++j) f[0][j] = (float)gpode_warp_sum_f64((double)f[0][j]) * sgn;
     } else {
         vf_eval<D, 1>(sp, M, S, x, f);
 #pragma unroll
@@ -472,14 +472,9 @@ template <int D>
 __global__ void __launch_bounds__(kDpThreads) dopri5_bwd_kernel(const Dopri5BwdArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const float* sp = stage_params(smem_raw, a.packed, a.total);
-    float* red = reinterpret_cast<float*>(smem_raw + 16) + a.total;
-    float A[D][D], V[D];
-#pragma unroll
-    for (int k = 0; k < D; ++k) {
-        V[k] = 0.f;
-#pragma unroll
-        for (int j = 0; j < D; ++j) A[k][j] = 0.f;
-    }
+    double* slabs = reinterpret_cast<double*>(reinterpret_cast<float*>(smem_raw + 16) + a.total);
+    WarpAcc64<D> wa;
+    wa.init(slabs);
     const int M = a.M, S = a.S, Tg = a.Tg, cap = a.cap;
     const int n_acc = a.stats_dev != nullptr ? min(a.stats_dev[1], cap) : a.n_acc;
     const int64_t B = a.B, plane = B * D;
@@ -549,19 +544,16 @@ __global__ void __launch_bounds__(kDpThreads) dopri5_bwd_kernel(const Dopri5BwdA
                     for (int l = 0; l < i; ++l) s = fmaf(k[l][0][j], __fmul_rn(kBeta[i - 1][l], dt), s);
                     Yi[0][j] = y0[0][j] + s;
                     kbi[0][j] = fsign * kb[i][j];   // cotangent of f(Y_i); the integrated k is fsign * f
-                    fst[0][j] = lane == 0 ? fsign * k[i][0][j] : 0.f;  // f(Y_i) enters the variance sum once per row
+                    fst[0][j] = fsign * k[i][0][j];
                 }
                 const int64_t slot = (int64_t)n * 6 + (i - 1);
                 if (lane == 0) {
                     strow<D>(Yi, a.vy + slot * plane, row);
                     strow<D>(kbi, a.vk + slot * plane, row);
                 }
-                vf_vjp<D, 1, true>(sp, M, S, Yi, kbi, fst, Yb, A, V, lane, 32);
+                vf_vjp_warp<D>(sp, M, S, Yi, kbi, fst, Yb, wa, lane);
 #pragma unroll
-                for (int j = 0; j < D; ++j) {
-                    Yb[0][j] = gpode_warp_sum(Yb[0][j]);
-                    yb0[j] += Yb[0][j];
-                }
+                for (int j = 0; j < D; ++j) yb0[j] += Yb[0][j];
 #pragma unroll
                 for (int l = 0; l < i; ++l)
 #pragma unroll
@@ -575,16 +567,16 @@ __global__ void __launch_bounds__(kDpThreads) dopri5_bwd_kernel(const Dopri5BwdA
 #pragma unroll
                 for (int j = 0; j < D; ++j) {
                     kbi[0][j] = fsign * kb[0][j];
-                    fst[0][j] = lane == 0 ? fsign * k[0][0][j] : 0.f;
+                    fst[0][j] = fsign * k[0][0][j];
                 }
                 const int64_t slot = (int64_t)n_acc * 6;
                 if (lane == 0) {
                     strow<D>(y0, a.vy + slot * plane, row);
                     strow<D>(kbi, a.vk + slot * plane, row);
                 }
-                vf_vjp<D, 1, true>(sp, M, S, y0, kbi, fst, Yb, A, V, lane, 32);
+                vf_vjp_warp<D>(sp, M, S, y0, kbi, fst, Yb, wa, lane);
 #pragma unroll
-                for (int j = 0; j < D; ++j) yb0[j] += gpode_warp_sum(Yb[0][j]);
+                for (int j = 0; j < D; ++j) yb0[j] += Yb[0][j];
             }
 #pragma unroll
             for (int j = 0; j < D; ++j) lam[j] = yb0[j];
@@ -599,7 +591,7 @@ __global__ void __launch_bounds__(kDpThreads) dopri5_bwd_kernel(const Dopri5BwdA
         }
     }
     __syncthreads();
-    reduce_AV<D>(A, V, a.acc, red);
+    reduce_AV64<D>(wa, a.acc, slabs + (kDpThreads / 32) * WarpAcc64<D>::kSlabDoubles);
 }
 
 template <int D>
@@ -607,7 +599,7 @@ int launch_dopri5_bwd(const float* packed, int M, int S, const double* t, int Tg
                       const float* ckpt, int cap, int n_acc, const int32_t* stats_dev, float* gx0, float* vrows,
                       float* acc, cudaStream_t st) {
     const GpodeLayout L = gpode_layout(D, M, S);
-    const size_t smem = 16 + (size_t)(L.total + kRedFloats<D>) * 4;
+    const size_t smem = 16 + (size_t)L.total * 4 + (size_t)kWarpAccDoubles<D>(kDpThreads / 32) * 8;
     GPODE_CUDA(cudaFuncSetAttribute(dopri5_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0, sms = 148, dev = 0;
     GPODE_CUDA(cudaGetDevice(&dev));

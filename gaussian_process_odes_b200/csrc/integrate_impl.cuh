@@ -301,30 +301,6 @@ vf_bwd_kernel(const float* __restrict__ packed, const int M, const int S, const 
 constexpr int kWarpsPerCta = 4;
 
 template <int D>
-__device__ __forceinline__ void warp_allreduce(float (&v)[1][D]) {
-#pragma unroll
-    for (int j = 0; j < D; ++j) v[0][j] = gpode_warp_sum(v[0][j]);
-}
-
-template <int D>
-__device__ __forceinline__ void vf_eval_warp(const float* sp, int M, int S, const float (&x)[1][D], float (&f)[1][D],
-                                             int lane) {
-    vf_eval<D, 1, true>(sp, M, S, x, f, lane, 32);
-    warp_allreduce<D>(f);
-}
-
-template <int D>
-__device__ __forceinline__ void vf_vjp_warp(const float* sp, int M, int S, const float (&x)[1][D],
-                                            const float (&kb)[1][D], const float (&fst)[1][D], float (&xb)[1][D],
-                                            float (&A)[D][D], float (&V)[D], int lane) {
-    float fm[1][D];  // f(x) enters the variance partial sum once per row, not once per lane
-#pragma unroll
-    for (int j = 0; j < D; ++j) fm[0][j] = lane == 0 ? fst[0][j] : 0.f;
-    vf_vjp<D, 1, true>(sp, M, S, x, kb, fm, xb, A, V, lane, 32);
-    warp_allreduce<D>(xb);
-}
-
-template <int D>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 vf_fwd_warp_kernel(const float* __restrict__ packed, const int M, const int S, const int total,
                    const float* __restrict__ x, float* __restrict__ f, const int64_t B) {
@@ -433,14 +409,9 @@ rk4_bwd_warp_kernel(const float* __restrict__ packed, const int M, const int S, 
                     float* __restrict__ vy, float* __restrict__ vk, float* __restrict__ acc) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const float* sp = stage_params(smem_raw, packed, total);
-    float* red = reinterpret_cast<float*>(smem_raw + 16) + total;
-    float A[D][D], V[D];
-#pragma unroll
-    for (int k = 0; k < D; ++k) {
-        V[k] = 0.f;
-#pragma unroll
-        for (int j = 0; j < D; ++j) A[k][j] = 0.f;
-    }
+    double* slabs = reinterpret_cast<double*>(reinterpret_cast<float*>(smem_raw + 16) + total);
+    WarpAcc64<D> wa;
+    wa.init(slabs);
     const int lane = threadIdx.x & 31;
     const int64_t plane = B * D;
     for (int64_t row = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); row < B;
@@ -467,7 +438,7 @@ rk4_bwd_warp_kernel(const float* __restrict__ packed, const int M, const int S, 
                 store_rows<D, 1>(ys, vyi + 3 * plane, row, B, 0);
                 store_rows<D, 1>(kbar, vki + 3 * plane, row, B, 0);
             }
-            vf_vjp_warp<D>(sp, M, S, ys, kbar, k4, yb4, A, V, lane);
+            vf_vjp_warp<D>(sp, M, S, ys, kbar, k4, yb4, wa, lane);
             // stage 3
             stage3<D, 1>(ys, y, k1, k2, h);
 #pragma unroll
@@ -476,7 +447,7 @@ rk4_bwd_warp_kernel(const float* __restrict__ packed, const int M, const int S, 
                 store_rows<D, 1>(ys, vyi + 2 * plane, row, B, 0);
                 store_rows<D, 1>(kbar, vki + 2 * plane, row, B, 0);
             }
-            vf_vjp_warp<D>(sp, M, S, ys, kbar, k3, yb, A, V, lane);
+            vf_vjp_warp<D>(sp, M, S, ys, kbar, k3, yb, wa, lane);
 #pragma unroll
             for (int j = 0; j < D; ++j) {
                 sumyb[0][j] = yb4[0][j] + yb[0][j];
@@ -489,7 +460,7 @@ rk4_bwd_warp_kernel(const float* __restrict__ packed, const int M, const int S, 
                 store_rows<D, 1>(ys, vyi + plane, row, B, 0);
                 store_rows<D, 1>(kbar, vki + plane, row, B, 0);
             }
-            vf_vjp_warp<D>(sp, M, S, ys, kbar, k2, yb, A, V, lane);
+            vf_vjp_warp<D>(sp, M, S, ys, kbar, k2, yb, wa, lane);
 #pragma unroll
             for (int j = 0; j < D; ++j) {
                 sumyb[0][j] += yb[0][j];
@@ -501,7 +472,7 @@ rk4_bwd_warp_kernel(const float* __restrict__ packed, const int M, const int S, 
                 store_rows<D, 1>(y, vyi, row, B, 0);
                 store_rows<D, 1>(kbar, vki, row, B, 0);
             }
-            vf_vjp_warp<D>(sp, M, S, y, kbar, k1, yb, A, V, lane);
+            vf_vjp_warp<D>(sp, M, S, y, kbar, k1, yb, wa, lane);
             float gi[1][D];
             load_rows<D, 1>(gi, gxs + (int64_t)i * plane, row, B, 0);
 #pragma unroll
@@ -510,7 +481,7 @@ rk4_bwd_warp_kernel(const float* __restrict__ packed, const int M, const int S, 
         if (lane == 0) store_rows<D, 1>(lam, gx0, row, B, 0);
     }
     __syncthreads();
-    reduce_AV<D>(A, V, acc, red);
+    reduce_AV64<D>(wa, acc, slabs + kWarpsPerCta * WarpAcc64<D>::kSlabDoubles);
 }
 
 template <int D>
@@ -520,14 +491,9 @@ vf_bwd_warp_kernel(const float* __restrict__ packed, const int M, const int S, c
                    float* __restrict__ gx, const int64_t B, float* __restrict__ acc) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const float* sp = stage_params(smem_raw, packed, total);
-    float* red = reinterpret_cast<float*>(smem_raw + 16) + total;
-    float A[D][D], V[D];
-#pragma unroll
-    for (int k = 0; k < D; ++k) {
-        V[k] = 0.f;
-#pragma unroll
-        for (int j = 0; j < D; ++j) A[k][j] = 0.f;
-    }
+    double* slabs = reinterpret_cast<double*>(reinterpret_cast<float*>(smem_raw + 16) + total);
+    WarpAcc64<D> wa;
+    wa.init(slabs);
     const int lane = threadIdx.x & 31;
     for (int64_t row = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); row < B;
          row += (int64_t)gridDim.x * kWarpsPerCta) {
@@ -535,11 +501,11 @@ vf_bwd_warp_kernel(const float* __restrict__ packed, const int M, const int S, c
         load_rows<D, 1>(xr, x, row, B, 0);
         load_rows<D, 1>(fr, f, row, B, 0);
         load_rows<D, 1>(kb, gf, row, B, 0);
-        vf_vjp_warp<D>(sp, M, S, xr, kb, fr, xb, A, V, lane);
+        vf_vjp_warp<D>(sp, M, S, xr, kb, fr, xb, wa, lane);
         if (lane == 0) store_rows<D, 1>(xb, gx, row, B, 0);
     }
     __syncthreads();
-    reduce_AV<D>(A, V, acc, red);
+    reduce_AV64<D>(wa, acc, slabs + kWarpsPerCta * WarpAcc64<D>::kSlabDoubles);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -1095,7 +1061,8 @@ int launch_rk4_bwd(const float* packed, int M, int S, const float* t, int Tg, in
         }
     }
     if (B <= kWarpPathMaxRows) {
-        if (int rc = warp_shape_for(rk4_bwd_warp_kernel<D>, B, smem, &ls)) return rc;
+        const size_t smem_w = 16 + (size_t)L.total * 4 + (size_t)kWarpAccDoubles<D>(kWarpsPerCta) * 8;
+        if (int rc = warp_shape_for(rk4_bwd_warp_kernel<D>, B, smem_w, &ls)) return rc;
         rk4_bwd_warp_kernel<D><<<ls.grid, ls.threads, ls.smem, st>>>(packed, M, S, L.total, t, Tg, B, xs, kst, gxs,
                                                                      gx0, vy, vk, acc);
     } else if (use_wide<D, RW>(B)) {
@@ -1129,7 +1096,8 @@ int launch_vf_bwd(const float* packed, int M, int S, const float* x, const float
         }
     }
     if (B <= kWarpPathMaxRows) {
-        if (int rc = warp_shape_for(vf_bwd_warp_kernel<D>, B, smem, &ls)) return rc;
+        const size_t smem_w = 16 + (size_t)L.total * 4 + (size_t)kWarpAccDoubles<D>(kWarpsPerCta) * 8;
+        if (int rc = warp_shape_for(vf_bwd_warp_kernel<D>, B, smem_w, &ls)) return rc;
         vf_bwd_warp_kernel<D><<<ls.grid, ls.threads, ls.smem, st>>>(packed, M, S, L.total, x, f, gf, gx, B, acc);
     } else if (use_wide<D, RW>(B)) {
         if (int rc = shape_for(vf_bwd_kernel<D, RW>, RW, B, smem, &ls)) return rc;

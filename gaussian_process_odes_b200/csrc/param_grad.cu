@@ -173,15 +173,16 @@ param_grad_kernel(const float* __restrict__ packed, const int M, const int S, co
             for (int e = 0; e < NE; ++e) row[(size_t)m * NE + e] = val[e];
         }
     } else {
-        float* __restrict__ red = pg_smem;  // [M][NE]; the staged tiles are dead (barrier at the end of the loop)
+        // [M][NE] float64; the staged tiles are dead (barrier at the end of the loop)
+        double* __restrict__ red = reinterpret_cast<double*>(pg_smem);
         for (int g = 0; g < G; ++g) {
             if (active && group == g) {
 #pragma unroll
-                for (int e = 0; e < NE; ++e) red[m * NE + e] = (g == 0 ? 0.f : red[m * NE + e]) + val[e];
+                for (int e = 0; e < NE; ++e) red[m * NE + e] = (g == 0 ? 0.0 : red[m * NE + e]) + (double)val[e];
             }
             __syncthreads();
         }
-        for (int i = threadIdx.x; i < M * NE; i += blockDim.x) row[i] = red[i];
+        for (int i = threadIdx.x; i < M * NE; i += blockDim.x) row[i] = (float)red[i];
     }
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) reinterpret_cast<int*>(acc)[1] = (int)gridDim.x;
 }
@@ -236,7 +237,7 @@ grads_finalize_kernel(const int D, const int M, const float* __restrict__ nu, co
 static size_t pg_smem_bytes(int D, int M) {
     const int DP = (D + 3) & ~3;
     const size_t tiles = (size_t)2 * kPgTile * 2 * DP * sizeof(float);
-    const size_t red = M < kPgThreads / 2 + 1 ? (size_t)M * (D + D * D) * sizeof(float) : 0;  // only when G >= 2
+    const size_t red = M < kPgThreads / 2 + 1 ? (size_t)M * (D + D * D) * sizeof(double) : 0;  // only when G >= 2
     return tiles > red ? tiles : red;
 }
 
@@ -259,6 +260,8 @@ int gpode_param_grad_launch(const float* packed, int D, int M, int S, const floa
     switch (D) {
 #define GPODE_PG_CASE(D_)                                                                                        \
     case D_:                                                                                                     \
+        GPODE_CUDA(cudaFuncSetAttribute(param_grad_kernel<D_>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                        (int)pg_smem_bytes(D_, M)));                                             \
         param_grad_kernel<D_><<<grid, threads, pg_smem_bytes(D_, M), stream>>>(                                 \
             packed, M, S, ys, kbs, VR, rows_per_cta, acc, stats_dev, rows_per_step);                             \
         break;

@@ -367,3 +367,88 @@ __device__ __forceinline__ void reduce_AV(float (&A)[D][D], float (&V)[D], float
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) reinterpret_cast<int*>(acc)[0] = (int)gridDim.x;
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Warp-per-row helpers (small batches: one warp owns one trajectory, its lanes split the Fourier features and the
+// inducing points). The lane partial sums of the pathwise update are individually ~|nu| = 1e2 times larger than their
+// total (they cancel across inducing points), so everything that crosses lanes or accumulates over time is done in
+// FLOAT64 here: the cross-lane sums of f and J^T kb, and the lengthscale / variance partial sums, which live in a
+// shared-memory slab [D*D + D][32 lanes] of doubles per warp for the whole kernel. These kernels are latency-bound;
+// the float64 work is a few percent of an evaluation. (Measured on 20 seeds of the VDP plain-GPODE ELBO: see
+// profiles/r02_seed_table_vdp_gpode_rk4.md.)
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double gpode_warp_sum_f64(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int D>
+__device__ __forceinline__ void vf_eval_warp(const float* sp, int M, int S, const float (&x)[1][D], float (&f)[1][D],
+                                             int lane) {
+    vf_eval<D, 1, true>(sp, M, S, x, f, lane, 32);
+#pragma unroll
+    for (int j = 0; j < D; ++j) f[0][j] = (float)gpode_warp_sum_f64((double)f[0][j]);
+}
+
+template <int D>
+struct WarpAcc64 {
+    static constexpr int N = D * D + D;
+    static constexpr int kSlabDoubles = N * 32;  // per warp
+    double* w;                                    // this lane's column of the warp's slab
+    __device__ __forceinline__ void init(double* slabs) {
+        w = slabs + (size_t)(threadIdx.x >> 5) * kSlabDoubles + (threadIdx.x & 31);
+#pragma unroll
+        for (int i = 0; i < N; ++i) w[i * 32] = 0.0;
+    }
+    __device__ __forceinline__ void add(const float (&A)[D][D], const float (&V)[D]) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+#pragma unroll
+            for (int j = 0; j < D; ++j) w[(k * D + j) * 32] += (double)A[k][j];
+            w[(D * D + k) * 32] += (double)V[k];
+        }
+    }
+};
+// shared-memory doubles a warp-per-row adjoint kernel with `nwarps` warps needs for WarpAcc64 + its block reduction
+template <int D>
+constexpr int kWarpAccDoubles(int nwarps) { return nwarps * (WarpAcc64<D>::kSlabDoubles + WarpAcc64<D>::N); }
+
+// xb = J(x)^T kb for the warp's row (all lanes get the full sum); parameter partial sums -> wa. fst = f(x).
+template <int D>
+__device__ __forceinline__ void vf_vjp_warp(const float* sp, int M, int S, const float (&x)[1][D],
+                                            const float (&kb)[1][D], const float (&fst)[1][D], float (&xb)[1][D],
+                                            WarpAcc64<D>& wa, int lane) {
+    float fm[1][D], A[D][D], V[D];  // f(x) enters the variance partial sum once per row, not once per lane
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        fm[0][k] = lane == 0 ? fst[0][k] : 0.f;
+        V[k] = 0.f;
+#pragma unroll
+        for (int j = 0; j < D; ++j) A[k][j] = 0.f;
+    }
+    vf_vjp<D, 1, true>(sp, M, S, x, kb, fm, xb, A, V, lane, 32);
+    wa.add(A, V);
+#pragma unroll
+    for (int j = 0; j < D; ++j) xb[0][j] = (float)gpode_warp_sum_f64((double)xb[0][j]);
+}
+
+// WarpAcc64 slabs -> this CTA's row of the accumulator block: lanes by shuffle, warps in warp order, all in float64
+template <int D>
+__device__ __forceinline__ void reduce_AV64(const WarpAcc64<D>& wa, float* __restrict__ acc, double* red64) {
+    constexpr int N = D * D + D;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double v = gpode_warp_sum_f64(wa.w[i * 32]);
+        if (lane == 0) red64[warp * N + i] = v;
+    }
+    __syncthreads();
+    float* __restrict__ row = acc + GPODE_ACC_HDR + (size_t)blockIdx.x * N;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        double s = 0.0;
+        for (int w = 0; w < nwarps; ++w) s += red64[w * N + i];
+        row[i] = (float)s;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) reinterpret_cast<int*>(acc)[0] = (int)gridDim.x;
+}
