@@ -22,6 +22,30 @@ import reference_harness as H  # noqa: E402
 GOLDEN = os.path.join(os.path.dirname(HERE), "tests", "golden")
 
 
+def _reference_f64(mods, dimwise, q_diag, D, M, S, N, T, S_mc, state_dict, ys, ts, draws, xp):
+    with H.reference_in_float64():
+        gp = mods['dsvgp'].DSVGP_Layer(D_in=D, D_out=D, M=M, S=S, dimwise=dimwise, q_diag=q_diag)
+        flow = mods['flow'].Flow(diffeq=gp, solver='rk4', use_adjoint=False)
+        lik = mods['likelihoods'].Gaussian(ndim=D)
+        cons = mods['constraints'].Gaussian(d=1, scale=1e-2, requires_grad=False)
+        sd = mods['states'].StateSequenceVariationalFactorizedGaussian(dim_n=N, dim_t=T - 1, dim_d=D)
+        model = mods['shooting_models'].UniformSequenceModel(flow=flow, num_observations=N * T * D,
+                                                             state_distribution=sd, likelihood=lik, constraint=cons)
+        model = model.double()
+        model.load_state_dict({k: v.detach().double() for k, v in state_dict.items()})
+        d64 = {k: v.double() for k, v in draws.items()}
+        with H.injected_draws(mods, d64, mvn_order=("eps_x0", "eps_states")):
+            loss, _ = H.reference_shooting_loss(model, ys.double(), ts.double(), num_samples=S_mc)
+        assert loss.dtype == torch.float64
+        loss.backward()
+        with torch.no_grad():
+            probe = gp(None, xp.double())
+        assert probe.dtype == torch.float64
+        grads = {n: p.grad.detach().numpy() for n, p in model.named_parameters() if p.grad is not None}
+        assert all(g.dtype == np.float64 for g in grads.values())
+        return loss.detach().numpy(), grads, probe.numpy()
+
+
 def run(name, dimwise, q_diag, D=2, M=16, S=64, N=2, T=9, S_mc=3, seed=31):
     mods = H._import_reference()
     rng = np.random.default_rng(seed)
@@ -91,6 +115,15 @@ def run(name, dimwise, q_diag, D=2, M=16, S=64, N=2, T=9, S_mc=3, seed=31):
               float(np.abs(blob["ref_grad_" + pre + "kern.unconstrained_lengthscales"]
                            - blob["f64_grad_" + pre + "kern.unconstrained_lengthscales"]).max()
                     / np.abs(blob["f64_grad_" + pre + "kern.unconstrained_lengthscales"]).max()))
+    # float64 arbiter from the reference itself (every branch, including dimwise=False)
+    l64, g64, p64 = _reference_f64(mods, dimwise, q_diag, D, M, S, N, T, S_mc, model.state_dict(), ys, ts, draws, xp)
+    blob["r64_loss"], blob["r64_probe_f"] = l64, p64
+    blob.update({"r64_grad_" + n: g for n, g in g64.items()})
+    worst = max(float(np.abs(blob["ref_grad_" + n] - g).max() / (np.abs(g).max() + 1e-300)) for n, g in g64.items())
+    print("   reference float64 pass: loss %.10f (float32 %.10f), worst ref32-vs-ref64 gradient error %.2e, probe f %.2e"
+          % (float(l64), float(loss), worst, float(np.abs(probe.numpy() - p64).max() / np.abs(p64).max())))
+    if "f64_loss" in blob:
+        print("   oracle-port float64 vs reference float64: loss %.2e" % abs(float(blob["f64_loss"]) - float(l64)))
     np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **blob)
     print(name, "loss", float(loss), "grads", sorted(k for k in blob if k.startswith("ref_grad_")))
 

@@ -81,6 +81,26 @@ class injected_draws:
         return False
 
 
+class reference_in_float64:
+    """Evaluate the UNMODIFIED reference in float64: its global dtype singleton (src/misc/settings.py:21-27) and
+    torch's default dtype are switched for the duration of the block. Used as the arbiter of the branches the oracle
+    port does not restate (dimwise=False)."""
+
+    def __enter__(self):
+        _import_reference()
+        import src.misc.settings as rs
+        self.cls = type(rs.settings)
+        self.saved = (self.cls.torch_float, self.cls.numpy_float, torch.get_default_dtype())
+        self.cls.torch_float = property(lambda self: torch.float64)
+        self.cls.numpy_float = property(lambda self: np.float64)
+        torch.set_default_dtype(torch.float64)
+
+    def __exit__(self, *exc):
+        self.cls.torch_float, self.cls.numpy_float = self.saved[0], self.saved[1]
+        torch.set_default_dtype(self.saved[2])
+        return False
+
+
 def _set(param, value):
     with torch.no_grad():
         param.copy_(value)

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from util import GOLDEN, assert_parity, injected_draws, relerr
+from util import GOLDEN, TOL_GRAD, TOL_VF, assert_parity, injected_draws
 
 pytestmark = pytest.mark.gpu
 
@@ -29,22 +29,23 @@ def test_non_default_layer_options(name):
     with injected_draws(draws, mvn_order=("eps_x0", "eps_states")):
         loss, nll, state_term, k0, kl = builders.compute_loss_shooting(model, ys.cuda(), ts.cuda(), num_samples=S_mc)
     loss.backward()
-    assert relerr(loss, torch.tensor(z["ref_loss"])) <= 1e-4
+    # Arbiter: the UNMODIFIED reference evaluated in float64 (oracle/reference_harness.py::reference_in_float64).
+    # Its own float32 run is 2e-4 .. 2e-3 away from that on these random-Z problems (|var nu| ~ 1e2), so every check is
+    # "within the north-star tolerance of the float32 reference, or at least as close to float64 as it is (x1.5)".
+    t = lambda k: torch.tensor(z[k])
+    assert_parity(name + " loss", loss.detach().cpu(), t("ref_loss"), t("r64_loss"), TOL_GRAD)
     gp = model.flow.odefunc.diffeq
     # reference attribute shapes of the cache
     assert gp.nu.shape == ((D, M, 1) if dimwise else (M, D))
     assert gp.rff_omega.shape == ((D, S, D) if dimwise else (D, S))
     with torch.no_grad():
-        f = gp(None, torch.tensor(z["probe_x"]).cuda())
-    # whitened nu with random Z: |var nu| ~ 1e2 amplifies float32 round-off on both sides and these branches have no
-    # float64 arbiter, so f(x) is only checked coarsely here; the ELBO value and the gradients below are the real test
-    assert relerr(f, torch.tensor(z["ref_probe_f"])) <= 1e-3
+        f = gp(None, t("probe_x").cuda())
+    assert_parity(name + " probe f", f.cpu(), t("ref_probe_f"), t("r64_probe_f"), TOL_VF)
+    n_checked = 0
     for n, p in model.named_parameters():
         key = "ref_grad_" + n
         if key in z.files:
             assert p.grad is not None, n
-            f64key = "f64_grad_" + n
-            if f64key in z.files:  # dimwise branches: float64 arbiter from the oracle port
-                assert_parity(name + " grad " + n, p.grad.cpu(), torch.tensor(z[key]), torch.tensor(z[f64key]), 1e-4)
-            else:  # dimwise=False has no restatement: plain comparison with the reference's float32 gradients
-                assert relerr(p.grad, torch.tensor(z[key])) <= 5e-4, (n, relerr(p.grad, torch.tensor(z[key])))
+            assert_parity(name + " grad " + n, p.grad.cpu(), t(key), t("r64_grad_" + n), TOL_GRAD)
+            n_checked += 1
+    assert n_checked >= 9
