@@ -21,6 +21,14 @@ class GpodeCache(ctypes.Structure):
                 ("Z", ctypes.c_void_p), ("nu", ctypes.c_void_p), ("ell", ctypes.c_void_p), ("var", ctypes.c_void_p)]
 
 
+class GpodeShoot(ctypes.Structure):
+    """``gpode_shoot_t`` of include/gpode_b200.h."""
+    _fields_ = [("S_mc", ctypes.c_int32), ("N", ctypes.c_int32), ("T", ctypes.c_int32), ("D_obs", ctypes.c_int32),
+                ("laplace", ctypes.c_int32), ("ys", ctypes.c_void_p), ("W", ctypes.c_void_p), ("bias", ctypes.c_void_p),
+                ("lik_var", ctypes.c_void_p), ("cons_scale", ctypes.c_void_p), ("row_lo", ctypes.c_int64),
+                ("row_hi", ctypes.c_int64)]
+
+
 _I, _L, _P, _D, _F = ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_double, ctypes.c_float
 _CP = ctypes.POINTER(GpodeCache)
 
@@ -50,6 +58,9 @@ SIGNATURES = {
     "gpode_loglik_sum": (_I, [_P, _P, _P, _P, _P, _I, _L, _I, _I, _P, _P, _P, _P, _P]),
     "gpode_constraint_sum": (_I, [_P, _P, _P, _L, _I, _I, _I, _P, _P, _P, _P, _P]),
     "gpode_side_work_doubles": (_L, []),
+    "gpode_shoot_work_doubles": (_L, []),
+    "gpode_shoot_fwd": (_I, [_P, _I, _I, _I, ctypes.POINTER(GpodeShoot), _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gpode_shoot_bwd": (_I, [_P, _I, _I, _I, ctypes.POINTER(GpodeShoot), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gpode_acc_header_floats": (_L, []),
     "gpode_probe_fp32_fma": (_I, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), _P, _P]),
     "gpode_dopri5_ckpt_floats": (_L, [_I, _L, _I, _I]),
@@ -136,7 +147,7 @@ KERNELS_PER_CALL = {
     "gpode_rk4_fwd_large": 1, "gpode_pack_cache_large": 1, "gpode_rbf_fwd_large": 1, "gpode_rff_fwd_large": 1,
     "gpode_vf_fwd_large_add_rbf": 1, "gpode_dopri5_bwd_dev": 1, "gpode_param_grad_dev": 1, "gpode_vf_fwd_umma": 1,
     "gpode_pack_cache_sets": 1, "gpode_whiten_fwd_sets": 2, "gpode_vf_fwd_sets": 1, "gpode_rk4_fwd_sets": 1,
-    "gpode_dopri5_fwd_sets": 1,
+    "gpode_dopri5_fwd_sets": 1, "gpode_shoot_fwd": 2, "gpode_shoot_bwd": 1,
 }
 assert all(isinstance(v, int) for v in KERNELS_PER_CALL.values()), "KERNELS_PER_CALL holds launch counts"
 assert set(KERNELS_PER_CALL) <= set(SIGNATURES), sorted(set(KERNELS_PER_CALL) - set(SIGNATURES))

@@ -30,3 +30,15 @@ int GPODE_CAT(gpode_fwd_sets_d, GPODE_D)(const float* packed, int M, int S, int 
                                          const float* x0, const float* t, int Tg, float* out, cudaStream_t st) {
     return launch_fwd_sets<GPODE_D>(packed, M, S, n_sets, set_rows, x0, t, Tg, out, st);
 }
+int GPODE_CAT(gpode_shoot_fwd_d, GPODE_D)(const float* packed, int M, int S, const float* x0, const float* t, int64_t B,
+                                          float* kst, const ShootArgs* sh, int* grid_out, cudaStream_t st) {
+    return launch_rk4_fwd<GPODE_D, true>(packed, M, S, x0, t, 2, B, nullptr, kst, st, *sh, grid_out);
+}
+int GPODE_CAT(gpode_shoot_bwd_d, GPODE_D)(const float* packed, int M, int S, const float* t, int64_t B,
+                                          const float* x0, const float* kst, float* vy, float* vk, float* acc,
+                                          const float* seeds, const float* g_ll, const float* g_cons, float* grad_ss,
+                                          int64_t row_lo, int64_t n_total, cudaStream_t st) {
+    ShootBwd sb;
+    sb.seeds = seeds; sb.g_ll = g_ll; sb.g_cons = g_cons; sb.grad_ss = grad_ss; sb.row_lo = row_lo; sb.n_total = n_total;
+    return launch_rk4_bwd<GPODE_D, true>(packed, M, S, t, 2, B, x0, kst, nullptr, nullptr, vy, vk, acc, st, sb);
+}

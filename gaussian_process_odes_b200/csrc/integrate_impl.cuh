@@ -12,6 +12,7 @@
 #include <stdlib.h>
 #include "vf_mma.cuh"
 #include "vjp_mma.cuh"
+#include "shoot.cuh"
 
 namespace {
 
@@ -47,6 +48,53 @@ __device__ __forceinline__ void store_rows(const float (&v)[R][D], float* __rest
         if (row < B) {
 #pragma unroll
             for (int j = 0; j < D; ++j) base[row * D + j] = v[r][j];
+        }
+    }
+}
+
+// Adjoint side of the fused shooting epilogue (shoot.cuh): the adjoint starts from lambda_T = g_ll seed_ll + g_cons seed_c
+// and the gradient w.r.t. the sampled states also receives the constraint's pull on the NEXT state of the sequence,
+// d cons / d ss[row + 1] = -seed_c[row].
+struct ShootBwd {
+    const float* seeds;   // [2, B, D]: d loglik / d pred | d constraint / d pred
+    const float* g_ll;    // upstream gradient of the log-likelihood SUM (device scalar)
+    const float* g_cons;  // upstream gradient of the constraint SUM (device scalar)
+    float* grad_ss;       // [n_total, D] gradient w.r.t. all sampled states (rows outside this launch pre-zeroed)
+    int64_t row_lo, n_total;
+};
+
+template <int D, int R>
+__device__ __forceinline__ void shoot_lambda(float (&lam)[R][D], const ShootBwd& sb, const int64_t row0, const int64_t B,
+                                             const int stride) {
+    const float a = __ldg(sb.g_ll), b = __ldg(sb.g_cons);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int64_t row = row0 + (int64_t)r * stride;
+#pragma unroll
+        for (int j = 0; j < D; ++j)
+            lam[r][j] = row < B ? a * __ldg(sb.seeds + row * D + j) + b * __ldg(sb.seeds + (B + row) * D + j) : 0.f;
+    }
+}
+
+template <int D, int R>
+__device__ __forceinline__ void shoot_store_grad(const float (&lam)[R][D], const ShootBwd& sb, const int64_t row0,
+                                                 const int64_t B, const int stride) {
+    const float b = __ldg(sb.g_cons);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int64_t row = row0 + (int64_t)r * stride;
+        if (row < B) {
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                // the previous row's constraint pulls on this row's state (its seed is zero at a sequence end)
+                const float pull = row >= 1 ? -b * __ldg(sb.seeds + (B + row - 1) * D + j) : 0.f;
+                sb.grad_ss[(sb.row_lo + row) * D + j] = lam[r][j] + pull;
+            }
+            if (row == B - 1 && sb.row_lo + B < sb.n_total) {  // sharded launch: the state just past our last row
+#pragma unroll
+                for (int j = 0; j < D; ++j)
+                    sb.grad_ss[(sb.row_lo + B) * D + j] = -b * __ldg(sb.seeds + (B + row) * D + j);
+            }
         }
     }
 }
@@ -106,13 +154,16 @@ __device__ __forceinline__ void stage4(float (&o)[R][D], const float (&y)[R][D],
             o[r][j] = __fadd_rn(y[r][j], __fmul_rn(dt, __fadd_rn(__fsub_rn(k1[r][j], k2[r][j]), k3[r][j])));
 }
 
-template <int D, int R>
+template <int D, int R, bool kShoot = false>
 __global__ void __launch_bounds__(kThreads)
 rk4_fwd_kernel(const float* __restrict__ packed, const int M, const int S, const int total,
                const float* __restrict__ x0, const float* __restrict__ ts, const int Tg, const int64_t B,
-               float* __restrict__ xs, float* __restrict__ kst) {
+               float* __restrict__ xs, float* __restrict__ kst, const ShootArgs sh) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const float* sp = stage_params(smem_raw, packed, total);
+    ShootSmem<D> ssm;
+    double sh_ll = 0.0, sh_cs = 0.0;
+    if constexpr (kShoot) ssm.init(smem_raw + 16 + (size_t)total * 4, sh);
     const int64_t tile_rows = (int64_t)blockDim.x * R;
     const int64_t ntiles = (B + tile_rows - 1) / tile_rows;
     const int64_t plane = B * D;
@@ -120,7 +171,7 @@ rk4_fwd_kernel(const float* __restrict__ packed, const int M, const int S, const
         const int64_t row0 = tile * tile_rows + threadIdx.x;
         float y[R][D];
         load_rows<D, R>(y, x0, row0, B, blockDim.x);
-        store_rows<D, R>(y, xs, row0, B, blockDim.x);
+        if constexpr (!kShoot) store_rows<D, R>(y, xs, row0, B, blockDim.x);
         for (int i = 0; i + 1 < Tg; ++i) {
             const float dt = __fsub_rn(__ldg(ts + i + 1), __ldg(ts + i));
             float k1[R][D], k2[R][D], k3[R][D], k4[R][D], ys[R][D];
@@ -146,9 +197,17 @@ rk4_fwd_kernel(const float* __restrict__ packed, const int M, const int S, const
                         __fadd_rn(k1[r][j], __fmul_rn(3.0f, __fadd_rn(k2[r][j], k3[r][j]))), k4[r][j]);
                     y[r][j] = __fadd_rn(y[r][j], __fmul_rn(__fmul_rn(sum, dt), 0.125f));
                 }
-            store_rows<D, R>(y, xs + (int64_t)(i + 1) * plane, row0, B, blockDim.x);
+            if constexpr (!kShoot) store_rows<D, R>(y, xs + (int64_t)(i + 1) * plane, row0, B, blockDim.x);
+        }
+        if constexpr (kShoot) {  // ELBO terms on the end point while it is in registers (shoot.cuh)
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int64_t row = row0 + (int64_t)r * blockDim.x;
+                shoot_epilogue<D, true>(sh, ssm, row < B, row, B, y[r], sh_ll, sh_cs);
+            }
         }
     }
+    if constexpr (kShoot) shoot_finish<D>(sh, ssm, sh_ll, sh_cs);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -161,12 +220,12 @@ rk4_fwd_kernel(const float* __restrict__ packed, const int M, const int S, const
 // Stage inputs are rebuilt bit-exactly from the checkpointed stage derivatives; (stage input, cotangent) pairs are
 // written out as "virtual rows" for the per-inducing-point gradient kernel (param_grad.cu).
 // ------------------------------------------------------------------------------------------------------------------
-template <int D, int R>
+template <int D, int R, bool kShoot = false>
 __global__ void __launch_bounds__(kThreads)
 rk4_bwd_kernel(const float* __restrict__ packed, const int M, const int S, const int total,
                const float* __restrict__ ts, const int Tg, const int64_t B, const float* __restrict__ xs,
                const float* __restrict__ kst, const float* __restrict__ gxs, float* __restrict__ gx0,
-               float* __restrict__ vy, float* __restrict__ vk, float* __restrict__ acc) {
+               float* __restrict__ vy, float* __restrict__ vk, float* __restrict__ acc, const ShootBwd sb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const float* sp = stage_params(smem_raw, packed, total);
     float* red = reinterpret_cast<float*>(smem_raw + 16) + total;
@@ -185,7 +244,8 @@ rk4_bwd_kernel(const float* __restrict__ packed, const int M, const int S, const
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t row0 = tile * tile_rows + threadIdx.x;
         float lam[R][D];
-        load_rows<D, R>(lam, gxs + (int64_t)(Tg - 1) * plane, row0, B, blockDim.x);
+        if constexpr (kShoot) shoot_lambda<D, R>(lam, sb, row0, B, blockDim.x);
+        else load_rows<D, R>(lam, gxs + (int64_t)(Tg - 1) * plane, row0, B, blockDim.x);
         for (int i = Tg - 2; i >= 0; --i) {
             const float h = __fsub_rn(__ldg(ts + i + 1), __ldg(ts + i));
             const float* kb = kst + (int64_t)i * 4 * plane;
@@ -248,13 +308,21 @@ rk4_bwd_kernel(const float* __restrict__ packed, const int M, const int S, const
             vf_vjp<D, R>(sp, M, S, y, kbar, k1, yb, A, V);
 
             float gi[R][D];
-            load_rows<D, R>(gi, gxs + (int64_t)i * plane, row0, B, blockDim.x);
+            if constexpr (kShoot) {
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+#pragma unroll
+                    for (int j = 0; j < D; ++j) gi[r][j] = 0.f;   // the segment start is not an output of the fused op
+            } else {
+                load_rows<D, R>(gi, gxs + (int64_t)i * plane, row0, B, blockDim.x);
+            }
 #pragma unroll
             for (int r = 0; r < R; ++r)
 #pragma unroll
                 for (int j = 0; j < D; ++j) lam[r][j] = gi[r][j] + lam[r][j] + (sumyb[r][j] + yb[r][j]);
         }
-        store_rows<D, R>(lam, gx0, row0, B, blockDim.x);
+        if constexpr (kShoot) shoot_store_grad<D, R>(lam, sb, row0, B, blockDim.x);
+        else store_rows<D, R>(lam, gx0, row0, B, blockDim.x);
     }
     __syncthreads();
     reduce_AV<D>(A, V, acc, red);
@@ -321,11 +389,10 @@ template <int D>
 __device__ __forceinline__ void rk4_row_warp(const float* sp, const int M, const int S, const float* __restrict__ x0,
                                              const float* __restrict__ ts, const int Tg, const int64_t row,
                                              const int64_t B, float* __restrict__ xs, float* __restrict__ kst,
-                                             const int lane) {
+                                             const int lane, float (&y)[1][D]) {
     const int64_t plane = B * D;
-    float y[1][D];
     load_rows<D, 1>(y, x0, row, B, 0);
-    if (lane == 0) store_rows<D, 1>(y, xs, row, B, 0);
+    if (lane == 0 && xs != nullptr) store_rows<D, 1>(y, xs, row, B, 0);
     for (int i = 0; i + 1 < Tg; ++i) {
         const float dt = __fsub_rn(__ldg(ts + i + 1), __ldg(ts + i));
         float k1[1][D], k2[1][D], k3[1][D], k4[1][D], ys[1][D];
@@ -349,21 +416,30 @@ __device__ __forceinline__ void rk4_row_warp(const float* sp, const int M, const
                                         k4[0][j]);
             y[0][j] = __fadd_rn(y[0][j], __fmul_rn(__fmul_rn(sum, dt), 0.125f));
         }
-        if (lane == 0) store_rows<D, 1>(y, xs + (int64_t)(i + 1) * plane, row, B, 0);
+        if (lane == 0 && xs != nullptr) store_rows<D, 1>(y, xs + (int64_t)(i + 1) * plane, row, B, 0);
     }
 }
 
-template <int D>
+template <int D, bool kShoot = false>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 rk4_fwd_warp_kernel(const float* __restrict__ packed, const int M, const int S, const int total,
                     const float* __restrict__ x0, const float* __restrict__ ts, const int Tg, const int64_t B,
-                    float* __restrict__ xs, float* __restrict__ kst) {
+                    float* __restrict__ xs, float* __restrict__ kst, const ShootArgs sh) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const float* sp = stage_params(smem_raw, packed, total);
+    ShootSmem<D> ssm;
+    double sh_ll = 0.0, sh_cs = 0.0;
+    if constexpr (kShoot) ssm.init(smem_raw + 16 + (size_t)total * 4, sh);
     const int lane = threadIdx.x & 31;
     for (int64_t row = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); row < B;
-         row += (int64_t)gridDim.x * kWarpsPerCta)
-        rk4_row_warp<D>(sp, M, S, x0, ts, Tg, row, B, xs, kst, lane);
+         row += (int64_t)gridDim.x * kWarpsPerCta) {
+        float y[1][D];
+        rk4_row_warp<D>(sp, M, S, x0, ts, Tg, row, B, kShoot ? nullptr : xs, kst, lane, y);
+        if constexpr (kShoot) {  // every lane holds the same end point: lane 0 evaluates the ELBO terms of the row
+            if (lane == 0) shoot_epilogue<D, false>(sh, ssm, true, row, B, y[0], sh_ll, sh_cs);
+        }
+    }
+    if constexpr (kShoot) shoot_finish<D>(sh, ssm, sh_ll, sh_cs);
 }
 
 // ---- batched Monte-Carlo prediction: blockIdx.y = parameter set; set q owns rows [q set_rows, (q+1) set_rows) and the
@@ -398,15 +474,18 @@ rk4_fwd_sets_kernel(const float* __restrict__ packed, const int M, const int S, 
     const int64_t B = set_rows * gridDim.y;
     for (int64_t r = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); r < set_rows;
          r += (int64_t)gridDim.x * kWarpsPerCta)
-        rk4_row_warp<D>(sp, M, S, x0, ts, Tg, blockIdx.y * set_rows + r, B, xs, nullptr, lane);
+    {
+        float yend[1][D];
+        rk4_row_warp<D>(sp, M, S, x0, ts, Tg, blockIdx.y * set_rows + r, B, xs, nullptr, lane, yend);
+    }
 }
 
-template <int D>
+template <int D, bool kShoot = false>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 rk4_bwd_warp_kernel(const float* __restrict__ packed, const int M, const int S, const int total,
                     const float* __restrict__ ts, const int Tg, const int64_t B, const float* __restrict__ xs,
                     const float* __restrict__ kst, const float* __restrict__ gxs, float* __restrict__ gx0,
-                    float* __restrict__ vy, float* __restrict__ vk, float* __restrict__ acc) {
+                    float* __restrict__ vy, float* __restrict__ vk, float* __restrict__ acc, const ShootBwd sb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const float* sp = stage_params(smem_raw, packed, total);
     double* slabs = reinterpret_cast<double*>(reinterpret_cast<float*>(smem_raw + 16) + total);
@@ -417,7 +496,8 @@ rk4_bwd_warp_kernel(const float* __restrict__ packed, const int M, const int S, 
     for (int64_t row = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); row < B;
          row += (int64_t)gridDim.x * kWarpsPerCta) {
         float lam[1][D];
-        load_rows<D, 1>(lam, gxs + (int64_t)(Tg - 1) * plane, row, B, 0);
+        if constexpr (kShoot) shoot_lambda<D, 1>(lam, sb, row, B, 0);
+        else load_rows<D, 1>(lam, gxs + (int64_t)(Tg - 1) * plane, row, B, 0);
         for (int i = Tg - 2; i >= 0; --i) {
             const float h = __fsub_rn(__ldg(ts + i + 1), __ldg(ts + i));
             const float* kb = kst + (int64_t)i * 4 * plane;
@@ -474,11 +554,19 @@ rk4_bwd_warp_kernel(const float* __restrict__ packed, const int M, const int S, 
             }
             vf_vjp_warp<D>(sp, M, S, y, kbar, k1, yb, wa, lane);
             float gi[1][D];
-            load_rows<D, 1>(gi, gxs + (int64_t)i * plane, row, B, 0);
+            if constexpr (kShoot) {
+#pragma unroll
+                for (int j = 0; j < D; ++j) gi[0][j] = 0.f;
+            } else {
+                load_rows<D, 1>(gi, gxs + (int64_t)i * plane, row, B, 0);
+            }
 #pragma unroll
             for (int j = 0; j < D; ++j) lam[0][j] = gi[0][j] + lam[0][j] + (sumyb[0][j] + yb[0][j]);
         }
-        if (lane == 0) store_rows<D, 1>(lam, gx0, row, B, 0);
+        if (lane == 0) {
+            if constexpr (kShoot) shoot_store_grad<D, 1>(lam, sb, row, B, 0);
+            else store_rows<D, 1>(lam, gx0, row, B, 0);
+        }
     }
     __syncthreads();
     reduce_AV64<D>(wa, acc, slabs + kWarpsPerCta * WarpAcc64<D>::kSlabDoubles);
@@ -635,14 +723,17 @@ vf_fwd_h_kernel(const float* __restrict__ packed, const HParams p, const float* 
 }
 
 // rk4_fwd_kernel<D, 1> with the evaluations on the tensor cores; the four stages loop around ONE inlined evaluation
-template <int D>
+template <int D, bool kShoot = false>
 __global__ void __launch_bounds__(kHFThreads, 1)
 rk4_fwd_h_kernel(const float* __restrict__ packed, const HParams p, const float* __restrict__ x0,
                  const float* __restrict__ ts, const int Tg, const int64_t B, float* __restrict__ xs,
-                 float* __restrict__ kst) {
+                 float* __restrict__ kst, const ShootArgs sh, const int shoot_off) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     stage_params_h(smem_raw, packed, p.off_kern, p.n_small, p.off_mmah, p.n_mmah);
     const HSmem<D> sm(smem_raw, p);
+    ShootSmem<D> ssm;
+    double sh_ll = 0.0, sh_cs = 0.0;
+    if constexpr (kShoot) ssm.init(smem_raw + shoot_off, sh);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int R = 1;
     const int64_t nblocks = (B + 31) / 32;
@@ -651,7 +742,7 @@ rk4_fwd_h_kernel(const float* __restrict__ packed, const HParams p, const float*
         const int64_t row0 = blk * 32 + lane;
         float y[R][D];
         load_rows<D, R>(y, x0, row0, B, 0);
-        store_rows<D, R>(y, xs, row0, B, 0);
+        if constexpr (!kShoot) store_rows<D, R>(y, xs, row0, B, 0);
         for (int i = 0; i + 1 < Tg; ++i) {
             const float dt = __fsub_rn(__ldg(ts + i + 1), __ldg(ts + i));
             float k1[R][D], k2[R][D], k3[R][D], k4[R][D], ys[R][D], kk[R][D];
@@ -686,9 +777,11 @@ rk4_fwd_h_kernel(const float* __restrict__ packed, const HParams p, const float*
                 const float sum = __fadd_rn(__fadd_rn(k1[0][j], __fmul_rn(3.0f, __fadd_rn(k2[0][j], k3[0][j]))), k4[0][j]);
                 y[0][j] = __fadd_rn(y[0][j], __fmul_rn(__fmul_rn(sum, dt), 0.125f));
             }
-            store_rows<D, R>(y, xs + (int64_t)(i + 1) * plane, row0, B, 0);
+            if constexpr (!kShoot) store_rows<D, R>(y, xs + (int64_t)(i + 1) * plane, row0, B, 0);
         }
+        if constexpr (kShoot) shoot_epilogue<D, true>(sh, ssm, row0 < B, row0, B, y[0], sh_ll, sh_cs);
     }
+    if constexpr (kShoot) shoot_finish<D>(sh, ssm, sh_ll, sh_cs);
 }
 
 // Discrete adjoint of the 3/8-rule RK4 grid: the recursion, checkpoint reads and virtual-row outputs of
@@ -697,12 +790,12 @@ rk4_fwd_h_kernel(const float* __restrict__ packed, const HParams p, const float*
 // ([field][component][lane], conflict-free), so the VJP has the 168 registers of a 12-warp CTA to itself -- with that
 // state in registers ptxas spilled inside the VJP loops (3.82 ms; 8 warps at 239 registers: 3.69 ms).
 constexpr int kHRowFields = 7;
-template <int D>
+template <int D, bool kShoot = false>
 __global__ void __launch_bounds__(kHThreads, 1)
 rk4_bwd_mma_kernel(const float* __restrict__ packed, const HParams p, const float* __restrict__ ts, const int Tg,
                    const int64_t B, const float* __restrict__ xs, const float* __restrict__ kst,
                    const float* __restrict__ gxs, float* __restrict__ gx0, float* __restrict__ vy,
-                   float* __restrict__ vk, float* __restrict__ acc) {
+                   float* __restrict__ vk, float* __restrict__ acc, const ShootBwd sb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     stage_params_h(smem_raw, packed, p.off_kern, p.n_small, p.off_mmah, p.n_mmah);
     const HSmem<D> sm(smem_raw, p);
@@ -728,7 +821,8 @@ rk4_bwd_mma_kernel(const float* __restrict__ packed, const HParams p, const floa
         const int64_t row0 = blk * 32 + lane;
         {
             float lam[R][D];
-            load_rows<D, R>(lam, gxs + (int64_t)(Tg - 1) * plane, row0, B, 0);
+            if constexpr (kShoot) shoot_lambda<D, R>(lam, sb, row0, B, 0);
+            else load_rows<D, R>(lam, gxs + (int64_t)(Tg - 1) * plane, row0, B, 0);
             put(F_LAM, lam);
         }
         for (int i = Tg - 2; i >= 0; --i) {
@@ -812,7 +906,12 @@ rk4_bwd_mma_kernel(const float* __restrict__ packed, const HParams p, const floa
                 } else {
                     float sum[R][D], gi[R][D];
                     get(F_SUM, sum);
-                    load_rows<D, R>(gi, gxs + (int64_t)i * plane, row0, B, 0);
+                    if constexpr (kShoot) {
+#pragma unroll
+                        for (int j = 0; j < D; ++j) gi[0][j] = 0.f;
+                    } else {
+                        load_rows<D, R>(gi, gxs + (int64_t)i * plane, row0, B, 0);
+                    }
 #pragma unroll
                     for (int j = 0; j < D; ++j) lam[0][j] = gi[0][j] + lam[0][j] + (sum[0][j] + yb[0][j]);
                     put(F_LAM, lam);
@@ -821,7 +920,8 @@ rk4_bwd_mma_kernel(const float* __restrict__ packed, const HParams p, const floa
         }
         float lam[R][D];
         get(F_LAM, lam);
-        store_rows<D, R>(lam, gx0, row0, B, 0);
+        if constexpr (kShoot) shoot_store_grad<D, R>(lam, sb, row0, B, 0);
+        else store_rows<D, R>(lam, gx0, row0, B, 0);
     }
     hacc_reduce<D>(qa, sm.small, p.M, acc, sm.red);
 }
@@ -984,35 +1084,43 @@ int launch_vf_fwd(const float* packed, int M, int S, const float* x, float* f, i
     return 0;
 }
 
-template <int D>
+template <int D, bool kShoot = false>
 int launch_rk4_fwd(const float* packed, int M, int S, const float* x0, const float* t, int Tg, int64_t B, float* xs,
-                   float* kst, cudaStream_t st) {
+                   float* kst, cudaStream_t st, const ShootArgs sh = ShootArgs{}, int* grid_out = nullptr) {
     const GpodeLayout L = gpode_layout(D, M, S);
-    const size_t smem = 16 + (size_t)L.total * 4;
+    auto shoot_bytes = [&](int nwarps) { return kShoot ? shoot_smem_bytes(D, sh.Dobs, nwarps) : (size_t)0; };
+    const size_t smem = 16 + (size_t)L.total * 4 + shoot_bytes(kThreads / 32);
     LaunchShape ls;
     constexpr int RW = RowsFwd<D>::value;
     if constexpr (kMmaBwd<D>) {
         const HParams hp = h_params<D>(L);
-        const size_t hs = h_smem<D>(hp, false, kHFWarps);
+        const size_t hs0 = (h_smem<D>(hp, false, kHFWarps) + 7) & ~(size_t)7;
+        const size_t hs = hs0 + shoot_bytes(kHFWarps);
         if (use_mma_fwd(B) && hs <= 227 * 1024) {
             int grid = 0;
-            if (int rc = h_grid(rk4_fwd_h_kernel<D>, B, hs, &grid, kHFThreads)) return rc;
-            rk4_fwd_h_kernel<D><<<grid, kHFThreads, hs, st>>>(packed, hp, x0, t, Tg, B, xs, kst);
+            if (int rc = h_grid(rk4_fwd_h_kernel<D, kShoot>, B, hs, &grid, kHFThreads)) return rc;
+            rk4_fwd_h_kernel<D, kShoot><<<grid, kHFThreads, hs, st>>>(packed, hp, x0, t, Tg, B, xs, kst, sh, (int)hs0);
             GPODE_LAUNCH_CHECK();
+            if (grid_out) *grid_out = grid;
             return 0;
         }
     }
     if (B <= kWarpPathMaxRows) {
-        if (int rc = warp_shape_for(rk4_fwd_warp_kernel<D>, B, smem, &ls)) return rc;
-        rk4_fwd_warp_kernel<D><<<ls.grid, ls.threads, ls.smem, st>>>(packed, M, S, L.total, x0, t, Tg, B, xs, kst);
+        const size_t smem_w = 16 + (size_t)L.total * 4 + shoot_bytes(kWarpsPerCta);
+        if (int rc = warp_shape_for(rk4_fwd_warp_kernel<D, kShoot>, B, smem_w, &ls)) return rc;
+        rk4_fwd_warp_kernel<D, kShoot><<<ls.grid, ls.threads, ls.smem, st>>>(packed, M, S, L.total, x0, t, Tg, B, xs,
+                                                                             kst, sh);
     } else if (use_wide<D, RW>(B)) {
-        if (int rc = shape_for(rk4_fwd_kernel<D, RW>, RW, B, smem, &ls)) return rc;
-        rk4_fwd_kernel<D, RW><<<ls.grid, ls.threads, ls.smem, st>>>(packed, M, S, L.total, x0, t, Tg, B, xs, kst);
+        if (int rc = shape_for(rk4_fwd_kernel<D, RW, kShoot>, RW, B, smem, &ls)) return rc;
+        rk4_fwd_kernel<D, RW, kShoot><<<ls.grid, ls.threads, ls.smem, st>>>(packed, M, S, L.total, x0, t, Tg, B, xs,
+                                                                            kst, sh);
     } else {
-        if (int rc = shape_for(rk4_fwd_kernel<D, 1>, 1, B, smem, &ls)) return rc;
-        rk4_fwd_kernel<D, 1><<<ls.grid, ls.threads, ls.smem, st>>>(packed, M, S, L.total, x0, t, Tg, B, xs, kst);
+        if (int rc = shape_for(rk4_fwd_kernel<D, 1, kShoot>, 1, B, smem, &ls)) return rc;
+        rk4_fwd_kernel<D, 1, kShoot><<<ls.grid, ls.threads, ls.smem, st>>>(packed, M, S, L.total, x0, t, Tg, B, xs, kst,
+                                                                           sh);
     }
     GPODE_LAUNCH_CHECK();
+    if (grid_out) *grid_out = ls.grid;
     return 0;
 }
 
@@ -1041,10 +1149,10 @@ int launch_fwd_sets(const float* packed, int M, int S, int n_sets, int64_t set_r
     return 0;
 }
 
-template <int D>
+template <int D, bool kShoot = false>
 int launch_rk4_bwd(const float* packed, int M, int S, const float* t, int Tg, int64_t B, const float* xs,
                    const float* kst, const float* gxs, float* gx0, float* vy, float* vk, float* acc,
-                   cudaStream_t st) {
+                   cudaStream_t st, const ShootBwd sb = ShootBwd{}) {
     const GpodeLayout L = gpode_layout(D, M, S);
     const size_t smem = 16 + (size_t)(L.total + kRedFloats<D>) * 4;
     LaunchShape ls;
@@ -1053,26 +1161,26 @@ int launch_rk4_bwd(const float* packed, int M, int S, const float* t, int Tg, in
         const HParams hp = h_params<D>(L);
         if (use_mma_bwd(B) && h_smem<D>(hp) <= 227 * 1024) {
             int grid = 0;
-            if (int rc = h_grid(rk4_bwd_mma_kernel<D>, B, h_smem<D>(hp), &grid)) return rc;
-            rk4_bwd_mma_kernel<D><<<grid, kHThreads, h_smem<D>(hp), st>>>(packed, hp, t, Tg, B, xs, kst, gxs, gx0, vy,
-                                                                          vk, acc);
+            if (int rc = h_grid(rk4_bwd_mma_kernel<D, kShoot>, B, h_smem<D>(hp), &grid)) return rc;
+            rk4_bwd_mma_kernel<D, kShoot><<<grid, kHThreads, h_smem<D>(hp), st>>>(packed, hp, t, Tg, B, xs, kst, gxs,
+                                                                                  gx0, vy, vk, acc, sb);
             GPODE_LAUNCH_CHECK();
             return 0;
         }
     }
     if (B <= kWarpPathMaxRows) {
         const size_t smem_w = 16 + (size_t)L.total * 4 + (size_t)kWarpAccDoubles<D>(kWarpsPerCta) * 8;
-        if (int rc = warp_shape_for(rk4_bwd_warp_kernel<D>, B, smem_w, &ls)) return rc;
-        rk4_bwd_warp_kernel<D><<<ls.grid, ls.threads, ls.smem, st>>>(packed, M, S, L.total, t, Tg, B, xs, kst, gxs,
-                                                                     gx0, vy, vk, acc);
+        if (int rc = warp_shape_for(rk4_bwd_warp_kernel<D, kShoot>, B, smem_w, &ls)) return rc;
+        rk4_bwd_warp_kernel<D, kShoot><<<ls.grid, ls.threads, ls.smem, st>>>(packed, M, S, L.total, t, Tg, B, xs, kst,
+                                                                             gxs, gx0, vy, vk, acc, sb);
     } else if (use_wide<D, RW>(B)) {
-        if (int rc = shape_for(rk4_bwd_kernel<D, RW>, RW, B, smem, &ls)) return rc;
-        rk4_bwd_kernel<D, RW><<<ls.grid, ls.threads, ls.smem, st>>>(packed, M, S, L.total, t, Tg, B, xs, kst, gxs, gx0,
-                                                                     vy, vk, acc);
+        if (int rc = shape_for(rk4_bwd_kernel<D, RW, kShoot>, RW, B, smem, &ls)) return rc;
+        rk4_bwd_kernel<D, RW, kShoot><<<ls.grid, ls.threads, ls.smem, st>>>(packed, M, S, L.total, t, Tg, B, xs, kst,
+                                                                            gxs, gx0, vy, vk, acc, sb);
     } else {
-        if (int rc = shape_for(rk4_bwd_kernel<D, 1>, 1, B, smem, &ls)) return rc;
-        rk4_bwd_kernel<D, 1><<<ls.grid, ls.threads, ls.smem, st>>>(packed, M, S, L.total, t, Tg, B, xs, kst, gxs, gx0,
-                                                                    vy, vk, acc);
+        if (int rc = shape_for(rk4_bwd_kernel<D, 1, kShoot>, 1, B, smem, &ls)) return rc;
+        rk4_bwd_kernel<D, 1, kShoot><<<ls.grid, ls.threads, ls.smem, st>>>(packed, M, S, L.total, t, Tg, B, xs, kst,
+                                                                           gxs, gx0, vy, vk, acc, sb);
     }
     GPODE_LAUNCH_CHECK();
     return 0;

@@ -40,12 +40,14 @@ def shard_range(n_total, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def seed_ranks(seed, rank):
-    """numpy (GP function draws: identical on every rank) vs torch (state samples: different per rank)."""
+def seed_ranks(seed, rank, same_states=False):
+    """numpy (GP function draws: identical on every rank) vs torch (state samples: different per rank when the
+    sequences are sharded, identical -- ``same_states=True`` -- when the rows of one replicated batch are sharded)."""
     np.random.seed(seed)
-    torch.manual_seed(seed + 1000003 * (rank + 1))
+    tseed = seed + (0 if same_states else 1000003 * (rank + 1))
+    torch.manual_seed(tseed)
     if torch.cuda.is_available():
-        torch.cuda.manual_seed(seed + 1000003 * (rank + 1))
+        torch.cuda.manual_seed(tseed)
 
 
 def shared_parameters(model):
@@ -106,6 +108,51 @@ def sharded_shooting_loss(model, ys_local, ts, num_samples, n_global, world):
     ll, cons, ent, k0 = model.build_lowerbound_terms(ys_local, ts, num_samples=num_samples)
     kl = model.build_inducing_kl()
     return combine_shard_terms(ll, cons, ent, k0, kl, ys_local.shape[0], n_global, world)
+
+
+# ---- segment-row sharding: fewer sequences than GPUs (VDP: N = 1, MoCap-09: N = 6) -----------------------------------
+# The (S_mc, N, T) segment batch of one ELBO evaluation (reference src/gpode_shooting/models.py:119-125) is cut into
+# contiguous row blocks, one per rank, across Monte-Carlo samples, sequences AND time. Every rank keeps ALL variational
+# parameters and draws the same state samples and the same GP function, so the constraint's neighbour state
+# (models.py:134-135: the state one row past a block's end) is already local -- the halo of a block is one row of the
+# replicated sample tensor, no exchange -- and the only collective is ONE all-reduce(sum) of the flattened gradient of
+# every parameter: a rank's gradient w.r.t. the sampled states is non-zero only on its rows (+ the halo row).
+def enable_row_sharding(model, rank=None, world=None):
+    """Make ``model.build_lowerbound_terms`` integrate only this rank's block of segment rows (fused shooting step)."""
+    if rank is None:
+        rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    model.row_shard = (int(rank), int(world)) if world > 1 else None
+    return model
+
+
+def row_sharded_shooting_loss(model, ys, ts, num_samples, world=None):
+    """Rank-local loss whose SUM over ranks is the global negative ELBO: the observation and constraint terms are this
+    rank's share, the replicated terms (entropy, initial-state KL, inducing KL) are counted ``1/world`` times each."""
+    if world is None:
+        world = model.row_shard[1] if model.row_shard is not None else 1
+    ll, cons, ent, k0 = model.build_lowerbound_terms(ys, ts, num_samples=num_samples)
+    kl = model.build_inducing_kl()
+    return -(ll + cons + (ent - k0 - kl) / float(world))
+
+
+def allreduce_all_grads(model):
+    """ONE all-reduce(sum) over the flattened gradients of EVERY parameter (row sharding: all parameters are replicated)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return 0
+    params = [p for p in model.parameters() if p.requires_grad]
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    off = 0
+    for p in params:
+        n = p.numel()
+        g = flat[off:off + n].view_as(p)
+        if p.grad is None:
+            p.grad = g.clone()
+        else:
+            p.grad.copy_(g)
+        off += n
+    return flat.numel()
 
 
 # ---- prediction: the Monte-Carlo draws are independent caches -> shard the draws (SURVEY.md section 8e) -------------

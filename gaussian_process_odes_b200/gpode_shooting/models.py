@@ -55,11 +55,63 @@ class BaseSequenceModel(nn.Module):
 class UniformSequenceModel(BaseSequenceModel):
     """Observations on a uniform time grid: every segment spans ``ts[:2]`` (reference ``models.py:88-146``)."""
 
+    # rows of the (S,N,T) segment batch this process integrates: None = all, or (rank, world) set by
+    # ``distributed.enable_row_sharding`` (contiguous row blocks; every rank samples the same states)
+    row_shard = None
+    fuse_elbo = True   # False: the unfused path (separate integrator / likelihood / constraint launches)
+
+    def _fused_terms(self, ss_samples, ys, ts):
+        """Observation log-likelihood mean and constraint total through ONE integrator launch with the two terms
+        evaluated on the segment end points inside the kernel (``ops.shooting_step``), or None when the configuration
+        has no fused kernel (solver other than rk4, D > 8, non-affine decoder, trainable constraint scale, CPU)."""
+        from ..core.dsvgp import DSVGP_Layer
+        from ..core.constraints import _ScaleFamily
+        flow, lik, cons = self.flow, self.likelihood, self.constraint
+        layer = flow.odefunc.diffeq
+        S, N, T, D = ss_samples.shape
+        affine = getattr(lik, "_affine", None)
+        if not (self.fuse_elbo and ss_samples.is_cuda and flow.solver == "rk4" and isinstance(layer, DSVGP_Layer)
+                and D <= 8 and affine is not None and isinstance(cons, _ScaleFamily)
+                and not cons.unconstrained_scale.requires_grad and cons.unconstrained_scale.numel() == 1):
+            return None
+        aff = affine(ss_samples)
+        if aff is None:
+            return None
+        W, b = aff
+        Dobs = W.shape[1]
+        if W.shape[0] != D or Dobs > 128 or tuple(ys.shape) != (N, T, Dobs):
+            return None
+        from .. import ops
+        var = lik.variance
+        if var.numel() != Dobs:
+            var = var.expand(Dobs)
+        rows = None
+        if self.row_shard is not None:
+            from ..distributed import shard_range
+            rows = shard_range(S * N * T, *self.row_shard)
+        flow.odefunc.before_odeint(return_divergence=False, rebuild_cache=True)
+        ll_sum, cons_sum, _ = ops.shooting_step(ss_samples, ts[:2], *layer.cache_tensors(), ys, W, b, var,
+                                                cons.scale.detach(), laplace=cons._laplace, rows=rows)
+        flow.odefunc.count_evals(4)
+        return ll_sum / float(S * N * T * Dobs), cons_sum / S
+
     def build_lowerbound_terms(self, ys, ts, num_samples=1, **kwargs):
         """-> (observation log-lik mean, constraint log-lik, state entropy, initial-state KL), the last three scaled
-        by ``1/num_observations`` (reference ``models.py:108-146``)."""
+        by ``1/num_observations`` (reference ``models.py:108-146``). With ``row_shard`` set the first two are this
+        process's share (sums over its rows with the global normalisation): they add up over the ranks."""
         ss_samples = self.state_distribution.sample(num_samples=num_samples)  # (S,N,T,D)
         (S, N, T, D) = ss_samples.shape
+        fused = self._fused_terms(ss_samples, ys, ts)
+        if fused is not None:
+            observation_loglik_mean, constraint_total = fused
+            state_entropy = self.state_distribution.entropy()  # (N,T-1)
+            initial_state_kl = self.state_distribution.x0.kl()
+            assert state_entropy.shape == (N, T - 1)
+            return (observation_loglik_mean, constraint_total / self.num_observations,
+                    state_entropy.sum() / self.num_observations, initial_state_kl / self.num_observations)
+        if self.row_shard is not None:
+            raise RuntimeError("row sharding needs the fused shooting step (rk4, affine decoder, frozen constraint "
+                               "scale, D <= 8)")
         # one launch: S*N*T independent one-interval IVPs sharing one GP function draw
         predicted_xs = self.flow(x0=stack_segments(ss_samples), ts=ts[:2])  # (S*N*T, 2, D)
         predicted_xs = unstack_segments(predicted_xs[:, -1], (S, N, T, D))

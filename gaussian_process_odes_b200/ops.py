@@ -11,7 +11,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import GpodeCache, check, f32, ptr, stream_ptr
+from ._lib import GpodeCache, GpodeShoot, check, f32, ptr, stream_ptr
 
 
 def _cache_struct(D, M, S, omega, phase, w, Z, nu, ell, var):
@@ -333,6 +333,97 @@ def state_entropy(L_packed, D, jitter=1e-5):
 def loglik_mean(pred, ys, W, bias, var):
     """pred ``(S?, ..., D)``, ys ``(..., D_obs)``: mean Gaussian log-density of ``ys`` under ``pred @ W + bias``."""
     return _LoglikMean.apply(pred, ys, W, bias, var)
+
+
+class _ShootStep(torch.autograd.Function):
+    """The integrator launch of the multiple-shooting ELBO with its two end-point terms fused in (``gpode_shoot_fwd`` /
+    ``gpode_shoot_bwd``; reference ``src/gpode_shooting/models.py:119-135``): -> (log-likelihood SUM, constraint SUM,
+    end points or None) over the rows ``[row_lo, row_hi)`` of the ``(S_mc, N, T)`` segment batch."""
+
+    @staticmethod
+    def forward(ctx, ss, t2, Z, ell, var, nu, omega, phase, w, ys, W, bias, lik_var, cons_scale, laplace, row_lo,
+                row_hi, want_grad, want_pred):
+        lib = _lib.load()
+        pc = PackedCache(Z, ell, var, nu, omega, phase, w)
+        sc, tc = f32(ss, "ss"), f32(t2, "ts[:2]")
+        if sc.ndim != 4 or sc.shape[3] != pc.D:
+            raise _lib.GpodeError("ss must be (S_mc,N,T,%d), got %s" % (pc.D, tuple(sc.shape)))
+        if tc.numel() != 2:
+            raise _lib.GpodeError("the fused shooting step integrates one interval: ts[:2], got %d points" % tc.numel())
+        S_mc, N, T, D = sc.shape
+        yc, Wc, vc, kc = f32(ys, "ys"), f32(W, "W"), f32(lik_var, "likelihood variance"), f32(cons_scale, "scale")
+        bc = f32(bias, "bias") if bias is not None else None
+        Dobs = Wc.shape[1]
+        if tuple(yc.shape) != (N, T, Dobs) or Wc.shape[0] != D or vc.numel() != Dobs or kc.numel() != 1 \
+                or (bc is not None and bc.numel() != Dobs):
+            raise _lib.GpodeError("inconsistent shooting shapes: ss %s ys %s W %s var %s scale %s" % (
+                tuple(sc.shape), tuple(yc.shape), tuple(Wc.shape), tuple(vc.shape), tuple(kc.shape)))
+        if ctx.needs_input_grad[13]:
+            raise _lib.GpodeError("the fused shooting step treats the constraint scale as a constant")
+        n_total = S_mc * N * T
+        row_lo, row_hi = int(row_lo), int(n_total if row_hi is None else row_hi)
+        B = row_hi - row_lo
+        sh = GpodeShoot()
+        sh.S_mc, sh.N, sh.T, sh.D_obs, sh.laplace = S_mc, N, T, Dobs, int(bool(laplace))
+        sh.ys, sh.W, sh.bias = ptr(yc).value, ptr(Wc).value, (ptr(bc).value if bc is not None else None)
+        sh.lik_var, sh.cons_scale = ptr(vc).value, ptr(kc).value
+        sh.row_lo, sh.row_hi = row_lo, row_hi
+        need_grad = want_grad and any(ctx.needs_input_grad)
+        dev = sc.device
+        kst = torch.empty(1, 4, B, D, dtype=torch.float32, device=dev) if need_grad else None
+        seeds = torch.empty(2, B, D, dtype=torch.float32, device=dev) if need_grad else None
+        pred = torch.empty(B, D, dtype=torch.float32, device=dev) if want_pred else None
+        sums = torch.empty(2, dtype=torch.float64, device=dev)
+        gvar = torch.empty(Dobs, dtype=torch.float32, device=dev) if need_grad else None
+        work = torch.empty(lib.gpode_shoot_work_doubles(), dtype=torch.float64, device=dev)
+        _lib.call("gpode_shoot_fwd", ptr(pc.packed), pc.D, pc.M, pc.S, ctypes.byref(sh), ptr(sc), ptr(tc), ptr(kst),
+                  ptr(pred), ptr(seeds), ptr(sums), ptr(gvar), ptr(work), stream_ptr())
+        ctx.pc, ctx.nu_shape, ctx.sh, ctx.keep = pc, nu.shape, sh, (yc, Wc, bc, vc, kc)
+        ctx.full = (row_lo == 0 and row_hi == n_total)
+        ctx.var_shape = lik_var.shape
+        if need_grad:
+            ctx.save_for_backward(sc, tc, kst, seeds, gvar)
+        out32 = sums.to(torch.float32)
+        if pred is not None:
+            ctx.mark_non_differentiable(pred)
+        return out32[0], out32[1], pred
+
+    @staticmethod
+    def backward(ctx, g_ll, g_cons, _g_pred):
+        pc, sh = ctx.pc, ctx.sh
+        sc, tc, kst, seeds, gvar = ctx.saved_tensors
+        lib = _lib.load()
+        B, D = seeds.shape[1], seeds.shape[2]
+        dev = sc.device
+        zero = lambda: torch.zeros((), dtype=torch.float32, device=dev)
+        g_ll = f32(g_ll, "grad") if g_ll is not None else zero()
+        g_cons = f32(g_cons, "grad") if g_cons is not None else zero()
+        g_ss = torch.empty_like(sc) if ctx.full else torch.zeros_like(sc)
+        acc = pc.new_acc()
+        vrows = torch.empty(lib.gpode_vrow_floats(D, 4 * B), dtype=torch.float32, device=dev)
+        _lib.call("gpode_shoot_bwd", ptr(pc.packed), pc.D, pc.M, pc.S, ctypes.byref(sh), ptr(sc), ptr(tc), ptr(kst),
+                  ptr(seeds), ptr(g_ll), ptr(g_cons), ptr(g_ss), ptr(vrows), ptr(acc), stream_ptr())
+        if B:
+            _lib.call("gpode_param_grad", ptr(pc.packed), pc.D, pc.M, pc.S, ptr(vrows), ptr(vrows[4 * B * D:]), 4 * B,
+                      ptr(acc), stream_ptr())
+        g_Z, g_ell, g_var, g_nu = pc.finalize(acc)
+        g_lik = (gvar * g_ll).reshape(ctx.var_shape)
+        return (g_ss, None, g_Z, g_ell, g_var, g_nu.reshape(ctx.nu_shape), None, None, None, None, None, None, g_lik,
+                None, None, None, None, None, None)
+
+
+def shooting_step(ss, t2, Z, ell, var, nu, omega, phase, w, ys, W, bias, lik_var, cons_scale, laplace=False,
+                  rows=None, want_pred=False):
+    """One RK4 interval for every row of the sampled-state batch ``ss (S_mc,N,T,D)`` with the observation
+    log-likelihood and the shooting constraint evaluated inside the integrator kernel. Returns
+    ``(loglik_sum, constraint_sum, pred)``: sums over the rows ``rows = (lo, hi)`` of the flattened batch (all rows by
+    default) -- ``loglik_sum`` over ``(row, d)`` of ``log N(ys[n,t,d] | (pred W + bias)_d, lik_var_d)`` and
+    ``constraint_sum`` over ``(row with t < T-1, d)`` of ``log p(ss[s,n,t+1,d] | pred_d, cons_scale)`` -- and the end
+    points ``pred (hi-lo, D)`` when ``want_pred`` (no gradient flows through them). Differentiable in ``ss``, ``Z``,
+    ``ell``, ``var``, ``nu`` and ``lik_var``."""
+    lo, hi = (0, None) if rows is None else rows
+    return _ShootStep.apply(ss, t2, Z, ell, var, nu, omega, phase, w, ys, W, bias, lik_var, cons_scale, laplace, lo, hi,
+                            torch.is_grad_enabled(), want_pred)
 
 
 MAX_D_REGISTER = 8    # GPODE_MAX_D: differentiable register-resident kernels

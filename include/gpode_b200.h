@@ -228,6 +228,40 @@ int64_t gpode_side_work_doubles(void);
 int gpode_constraint_sum(const float* ss, const float* pred, const float* scale, int64_t SN, int T, int D, int laplace,
                          double* sum_out, float* grad_ss, float* grad_pred, double* work, void* stream);
 
+/* Fused multiple-shooting ELBO step. Every row (s, n, t) of the (S_mc, N, T) batch of
+ * sampled states `ss` is integrated over ONE interval t2[0] -> t2[1] with the 3/8-rule RK4 step (as gpode_rk4_fwd with
+ * Tg = 2) and the two ELBO terms that use the end point are evaluated inside the integrator kernel, on the end point
+ * while it is in registers (UniformSequenceModel.build_lowerbound_terms, src/gpode_shooting/models.py:119-135):
+ *   sums_out[0] = sum_rows sum_d log N(ys[n,t,d] | (pred W + bias)_d, lik_var_d)    (src/core/likelihoods.py:27-45)
+ *   sums_out[1] = sum_{rows, t < T-1} log p(ss[s,n,t+1] | loc = pred, scale)        (src/core/constraints.py:26-66)
+ * for the rows [row_lo, row_hi) of the batch (row = (s N + n) T + t): a rank of a multi-GPU job passes its own range
+ * and the FULL `ss`, so the constraint's neighbour state is local (the "halo" of the shard is one extra row of `ss`).
+ * Outputs besides the two sums: grad_lik_var [D_obs] (d sums_out[0] / d lik_var, may be NULL), kstages [1,4,B,D] and
+ * seeds [2,B,D] (d sums_out[0] / d pred | d sums_out[1] / d pred; both NULL for a forward without gradients),
+ * pred_out [B,D] (may be NULL). work: gpode_shoot_work_doubles() float64 of scratch. Sums are taken in a fixed order
+ * (bitwise reproducible). */
+typedef struct {
+    int32_t S_mc, N, T, D_obs, laplace;
+    const float* ys;         /* [N, T, D_obs] */
+    const float* W;          /* [D, D_obs] decoder (identity for the plain Gaussian likelihood) */
+    const float* bias;       /* [D_obs] or NULL */
+    const float* lik_var;    /* [D_obs] */
+    const float* cons_scale; /* 1 float */
+    int64_t row_lo, row_hi;
+} gpode_shoot_t;
+int64_t gpode_shoot_work_doubles(void);
+int gpode_shoot_fwd(const float* packed, int D, int M, int S, const gpode_shoot_t* sh, const float* ss, const float* t2,
+                    float* kstages, float* pred_out, float* seeds, double* sums_out, float* grad_lik_var, double* work,
+                    void* stream);
+/* Its adjoint: starts from lambda = g_ll seeds[0] + g_cons seeds[1] (g_ll, g_cons: upstream gradients of the two sums,
+ * device scalars), writes grad_ss [S_mc,N,T,D] for rows [row_lo, row_hi) -- dynamics plus the constraint's pull on the
+ * next state -- and for row row_hi when the range ends inside a sequence (the caller zeroes grad_ss first when the
+ * range is not the whole batch); lengthscale / variance partial sums and virtual rows as gpode_rk4_bwd
+ * (vrows: gpode_vrow_floats(D, 4 B) floats). Follow with gpode_param_grad over 4 B rows and gpode_grads_finalize. */
+int gpode_shoot_bwd(const float* packed, int D, int M, int S, const gpode_shoot_t* sh, const float* ss, const float* t2,
+                    const float* kstages, const float* seeds, const float* g_ll, const float* g_cons, float* grad_ss,
+                    float* vrows, float* acc, void* stream);
+
 /* EXPERIMENTAL (2 <= D <= 7): gpode_vf_fwd with the Fourier-feature projection on the 5th-generation tensor cores
  * (tcgen05.mma kind::tf32, 3xTF32 error compensation, accumulators in TMEM); same arguments and results. */
 int gpode_vf_fwd_umma(const float* packed, int D, int M, int S, const float* x, float* f, int64_t B, void* stream);
