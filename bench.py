@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """bench.py -- GP vector-field evals/s of the multiple-shooting ELBO forward+backward step (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--rows-scale F]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scaling weak|strong]
+                    [--rows-scale F] [--no-parity-check] [--no-cpu-baseline]
 
 Workload (``config.workload``): BASELINE.json configs[3], "MoCap GPODE shooting variant on long synthetic
 MoCap-shaped trajectories": latent D=5 -> D_obs=50 through a fixed orthonormal decoder, M=100 inducing points, S=256
@@ -13,6 +14,11 @@ One "step" = one ELBO forward + backward (``build_lowerbound_terms`` + ``build_i
 plus the shared-gradient all-reduce when N > 1) through the reference-facing API: GP cache build (whitening kernel),
 fused RK4 forward kernel over all segments, the ELBO side terms, the discrete-adjoint kernel, the per-inducing-point
 gradient kernel, whitening backward. The optimiser step is not part of the metric.
+
+``--scaling strong`` keeps the TOTAL at 16 sequences = 10^6 segments and splits them over the GPUs (16 / N sequences
+each) instead of giving every GPU 16 sequences of its own. Before anything is timed, rank 0 checks the ELBO loss and
+every parameter gradient of a 60 000-segment problem of the same shape -- the same kernels -- against the oracle port
+(``tests/util.py::elbo_errors``; the oracle is the checker, never the thing measured).
 
 value = segments x 4 vector-field evaluations (the reference's own NFE count for this step) / step time, aggregated
 over all GPUs. ``e2e`` repeats the measurement with the observations copied from pinned host memory and the loss
@@ -59,10 +65,15 @@ def synthetic_sequences(N, T, D, D_obs, seed):
     return lat.astype(np.float32), ys.astype(np.float32), comp
 
 
-def build_ours(w, rank, world, rows_scale):
+def build_ours(w, rank, world, rows_scale, strong=False):
     from gaussian_process_odes_b200 import builders, distributed
     T = max(3, int(round(w["T"] * rows_scale)))
-    N_loc, N_glob = w["N_per_gpu"], w["N_per_gpu"] * world
+    if strong:
+        if w["N_per_gpu"] % world:
+            raise SystemExit("--scaling strong needs the GPU count to divide %d sequences" % w["N_per_gpu"])
+        N_loc, N_glob = w["N_per_gpu"] // world, w["N_per_gpu"]
+    else:
+        N_loc, N_glob = w["N_per_gpu"], w["N_per_gpu"] * world
     lat, ys, comp = synthetic_sequences(N_loc, T, w["D"], w["D_obs"], seed=121 + rank)
     from gaussian_process_odes_b200.misc.mocap_utils import LinearProjection
     projection = LinearProjection(comp)
@@ -215,6 +226,41 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def pin_to_gpu_numa_node(index):
+    """Bind this process to the CPU cores next to its GPU (NVML's ideal affinity) BEFORE any pinned buffer is allocated,
+    so the staging memory of the end-to-end copies is first-touched on the GPU's own NUMA node (round 1: all ranks sat on
+    cores 0-31 and shared one node's memory controller for 8 x 40 MB per step)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index))
+        return sorted(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
+def parity_precheck():
+    """ELBO loss + every parameter gradient of a 60 000-segment MoCap-shaped shooting problem (whitened nu; the
+    tensor-core forward / adjoint kernels and the row-per-thread gradient contraction -- the kernels timed below)
+    against the oracle port in float32, arbitrated by float64. Raises on a mismatch."""
+    for pth in (os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+        if pth not in sys.path:
+            sys.path.insert(0, pth)
+    from util import elbo_errors
+    kw = dict(D=5, M=100, S=256, N=4, T=3000, S_mc=5, D_obs=50, dt=0.01, ell0=1.25)
+    rows = elbo_errors("shooting", kw, "rk4", {}, 11)
+    worst, bad = 0.0, []
+    for k, (e_cuda64, e_ref64, e_cuda32) in rows.items():
+        ok = e_cuda32 <= 1e-4 or e_cuda64 <= max(1e-4, 1.5 * e_ref64)
+        worst = max(worst, min(e_cuda32, e_cuda64))
+        if not ok:
+            bad.append((k, e_cuda64, e_ref64, e_cuda32))
+    if bad:
+        raise SystemExit("parity pre-check FAILED against the oracle: %r" % (bad,))
+    return {"segments": kw["S_mc"] * kw["N"] * kw["T"], "tensors": len(rows), "worst_rel_err": worst,
+            "rule": "<= 1e-4 vs the float32 oracle port, or no further from float64 than 1.5x the port's own float32 error"}
+
+
 def run_ours(args):
     from gaussian_process_odes_b200 import _lib, distributed
     rank, world, local_rank = distributed.init_from_env()
@@ -224,14 +270,20 @@ def run_ours(args):
             print("warning: --gpus %d but WORLD_SIZE=%d" % (args.gpus, world), file=sys.stderr)
     w = WORKLOAD
     dev = torch.device("cuda", local_rank)
+    cpus = pin_to_gpu_numa_node(local_rank)
     _lib.load()
+    parity = None
+    if rank == 0 and not args.no_parity_check:
+        parity = parity_precheck()
+    strong = args.scaling == "strong"
     distributed.seed_ranks(121, rank)
-    model, ys_host, ts_host, N_glob, T = build_ours(w, rank, world, args.rows_scale)
+    model, ys_host, ts_host, N_glob, T = build_ours(w, rank, world, args.rows_scale, strong)
+    N_loc = ys_host.shape[0]
     ys_pinned = ys_host.pin_memory()
     ts_dev = ts_host.to(dev)
     ys_dev = ys_pinned.to(dev, non_blocking=True)
-    rows_local = w["S_mc"] * w["N_per_gpu"] * T
-    rows_total = rows_local * world
+    rows_local = w["S_mc"] * N_loc * T
+    rows_total = w["S_mc"] * N_glob * T
     evals_per_step = rows_total * 4
 
     def step(ys):
@@ -325,17 +377,23 @@ def run_ours(args):
     ms_e2e = e2e_run(args.steps) / args.steps
     e2e = {"value": evals_per_step / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
            "h2d_bytes_per_step": int((ys_pinned.numel() + ts_host.numel()) * 4 * world), "d2h_bytes_per_step": 4 * world,
-           "h2d": "pinned host -> device every step, double-buffered on a copy stream (step i+1's copy overlaps step i)",
+           "h2d": "pinned host -> device every step, double-buffered on a copy stream (step i+1's copy overlaps step i); "
+                  "every rank is bound to the CPU cores of its GPU's NUMA node before the pinned buffers are allocated",
            "d2h": "every step's loss -> pinned host (async copy after the step), read by the host one step later; the "
-                  "last one is awaited inside the timed region"}
+                  "last one is awaited inside the timed region", "cpu_affinity_rank0": cpus}
 
-    # ---- per-kernel breakdown (separate pass, CUDA events around every C-ABI call) and the roofline ----
+    # ---- per-kernel breakdown (separate pass: CUDA events around every C-ABI call, MEDIAN over n_prof steps) ----
+    n_prof = max(10, args.steps)
     _lib.profile_start()
-    n_prof = 3
     for _ in range(n_prof):
         step(ys_dev)
-    prof = _lib.profile_stop()
-    kern = {k: {"calls_per_step": c / n_prof, "ms_per_step": ms / n_prof} for k, (c, ms) in prof.items()}
+    raw = _lib.profile_stop(raw=True)
+    kern = {}
+    for k, v in raw.items():
+        per = max(1, len(v) // n_prof)                       # calls of this entry point per step
+        per_step = [sum(v[i * per:(i + 1) * per]) for i in range(n_prof)]
+        kern[k] = {"calls_per_step": len(v) / n_prof, "ms_per_step": float(np.median(per_step)),
+                   "ms_min": float(min(per_step)), "ms_max": float(max(per_step))}
     ours_ms = sum(v["ms_per_step"] for v in kern.values())
 
     roof = None
@@ -346,8 +404,17 @@ def run_ours(args):
         _lib.check(_lib.load().gpode_probe_fp32_fma(ctypes.byref(tf), ctypes.byref(ms_probe),
                                                     _lib.ptr(scratch), _lib.stream_ptr()))
         fv = f_vf(w["D"], w["S"], w["M"])
-        flops = {"gpode_rk4_fwd": rows_local * (4 * fv + 14 * w["D"]),   # 4 F_vf + 14 D per row-step
-                 "gpode_rk4_bwd": rows_local * 8 * fv}                     # 4 VJPs ~ 2 F_vf each; nothing is recomputed
+        FWD, BWD, PG = "gpode_shoot_fwd", "gpode_shoot_bwd", "gpode_param_grad"
+        flops = {FWD: rows_local * (4 * fv + 14 * w["D"]),   # 4 F_vf + 14 D per row-step
+                 BWD: rows_local * 8 * fv}                     # 4 VJPs ~ 2 F_vf each; nothing is recomputed
+        # transcendentals (MUFU: cos / sin / ex2) per launch: D S + D M per evaluation or VJP, four of them per row
+        mufu_ops = rows_local * 4 * w["D"] * (w["S"] + w["M"])
+        sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
+        try:
+            n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+        except Exception:
+            n_sm = 148
+        mufu_peak = 16.0 * n_sm * sm_clock * 1e6             # 16 MUFU results / clk / SM (4 per sub-partition)
         dom = max(flops, key=lambda k: kern.get(k, {"ms_per_step": 0})["ms_per_step"])
         ms_dom = kern[dom]["ms_per_step"] / max(kern[dom]["calls_per_step"], 1)
         achieved = flops[dom] / (ms_dom * 1e-3) / 1e12
@@ -358,20 +425,36 @@ def run_ours(args):
                 traffic = json.load(open(tpath)).get(dom)
             except Exception:
                 traffic = None
-        other = "gpode_rk4_fwd" if dom == "gpode_rk4_bwd" else "gpode_rk4_bwd"
+        other = FWD if dom == BWD else BWD
+
+        def entry(k):
+            ms = kern[k]["ms_per_step"]
+            return {"achieved": flops[k] / (ms * 1e-3) / 1e12, "frac": flops[k] / (ms * 1e-3) / 1e12 / tf.value,
+                    "kernel_ms": ms,
+                    "mufu": {"transcendentals_per_launch": mufu_ops, "floor_ms": mufu_ops / mufu_peak * 1e3,
+                             "frac": (mufu_ops / mufu_peak * 1e3) / ms,
+                             "peak": "16 / clk / SM x %d SMs x %.0f MHz (median SM clock of the timed region)" % (
+                                 n_sm, sm_clock)}}
+        comb_ms = kern[BWD]["ms_per_step"] + kern.get(PG, {"ms_per_step": 0.0})["ms_per_step"]
         roof = {"bound": "fp32_fma", "kernel": dom, "achieved": achieved, "peak": tf.value, "unit": "TFLOP/s",
                 "frac": achieved / tf.value, "traffic": traffic,
                 "peak_source": "measured here: gpode_probe_fp32_fma (register-only FMA loop, best of 5); "
                                "MEASURED_PEAKS.json has no FP32 entry",
                 "algorithmic_flops_per_launch": flops[dom], "kernel_ms": ms_dom,
-                "pipes": "at 4 <= D <= 5 gpode_rk4_bwd runs the two Fourier projections of every VJP (theta = x Omega, "
-                         "G = g Omega^T: 10 of the 14 algorithmic FMAs per feature-output) and gpode_rk4_fwd the projection "
+                "mufu": entry(dom)["mufu"],
+                "combined_adjoint": {"kernels": [BWD, PG], "ms": comb_ms,
+                                     "achieved": flops[BWD] / (comb_ms * 1e-3) / 1e12,
+                                     "frac": flops[BWD] / (comb_ms * 1e-3) / 1e12 / tf.value,
+                                     "note": "the Z / nu half of every VJP runs in the second kernel; same 8 F_vf credit "
+                                             "over both durations"},
+                "pipes": "at 4 <= D <= 5 the adjoint runs the two Fourier projections of every VJP (theta = x Omega, "
+                         "G = g Omega^T: 10 of the 14 algorithmic FMAs per feature-output) and the forward the projection "
                          "theta as split-fp16 mma.sync on the tensor cores (csrc/vjp_mma.cuh); the flop count stays the "
                          "algorithmic FP32 one and the peak stays the FP32 FMA peak, so frac measures the whole kernel "
-                         "against the CUDA-core roofline",
-                "also": {other: {"achieved": flops[other] / (kern[other]["ms_per_step"] * 1e-3) / 1e12,
-                                 "frac": flops[other] / (kern[other]["ms_per_step"] * 1e-3) / 1e12 / tf.value,
-                                 "kernel_ms": kern[other]["ms_per_step"]}},
+                         "against the CUDA-core roofline; 'mufu' is the transcendental (cos/sin/ex2) floor of the same "
+                         "launch, which binds the forward kernel. Both kernels now include the fused ELBO epilogue "
+                         "(likelihood + constraint on the end point; csrc/shoot.cuh) at no extra credit",
+                "also": {other: entry(other)},
                 "hbm_note": "FMA-bound path: algorithmic HBM bytes are %d per row forward (arithmetic intensity > 1e3 "
                             "flop/byte), so the HBM roofline (MEASURED_PEAKS.json hbm_gbs) is not the binding one" % (
                                 4 * w["D"] * 3)}
@@ -379,21 +462,28 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_elbo_timing(w, steps=8, warmup=2)
+        sat = {}
+        for Ts in (1000, 3000):   # saturation: the port's throughput no longer depends on the sample size
+            c2 = cpu_elbo_timing(w, steps=3, warmup=1, T_sample=Ts)
+            sat["%d_segments" % c2["rows"]] = c2["value"]
+        sat["%d_segments" % cpu["rows"]] = cpu["value"]
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cpu["saturation_evals_per_s"] = sat
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": w["name"], "D": w["D"], "D_obs": w["D_obs"], "M": w["M"], "S": w["S"],
-                           "S_mc": w["S_mc"], "N_sequences_per_gpu": w["N_per_gpu"], "T": T, "solver": w["solver"],
-                           "segments_per_gpu": rows_local, "segments_total": rows_total,
+                           "S_mc": w["S_mc"], "N_sequences_per_gpu": N_loc, "N_sequences_total": N_glob, "T": T,
+                           "solver": w["solver"], "segments_per_gpu": rows_local, "segments_total": rows_total,
                            "evals_per_step": evals_per_step, "parallelism": "sequences sharded x%d" % world,
-                           "l2": "working set per step (>= 0.6 GB of segment states, stage checkpoints and decoded "
-                                 "predictions) exceeds the 126 MB L2; no explicit flush"},
+                           "l2": "working set per step (>= 0.4 GB of sampled states, stage checkpoints, adjoint seeds "
+                                 "and virtual rows per 10^6 segments) exceeds the 126 MB L2; no explicit flush"},
                 "elbo_fwd_bwd_ms": ms_per_step, "e2e": e2e, "gpu_launches": launches * world,
                 "kernels_ms_per_step": kern, "own_kernels_share_of_step": ours_ms / ms_per_step,
-                "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "loss": getattr(e2e_body, "last", None)}
+                "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "parity_precheck": parity,
+                "loss": getattr(e2e_body, "last", None)}
         print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()
@@ -406,7 +496,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows-scale", type=float, default=1.0, help="scale T (segments per GPU) for quick runs")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: 16 sequences (10^6 segments) per GPU; strong: 16 sequences in total")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true", help="skip the oracle check before timing (profiling)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

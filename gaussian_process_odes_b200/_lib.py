@@ -160,11 +160,13 @@ def profile_start():
     _PROFILE = {}
 
 
-def profile_stop():
-    """-> {name: (calls, total_ms)}; synchronises the device."""
+def profile_stop(raw=False):
+    """-> {name: (calls, total_ms)} (``raw``: {name: [ms of every call, in call order]}); synchronises the device."""
     global _PROFILE
     rec, _PROFILE = _PROFILE, None
     torch.cuda.synchronize()
+    if raw:
+        return {k: [a.elapsed_time(b) for a, b in v] for k, v in (rec or {}).items()}
     return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in (rec or {}).items()}
 
 

@@ -17,7 +17,7 @@ def _run(p, ys, ts, draws, proj, kw, fuse, row_shard=None, world=1, constraint=N
     model = build_product_model("shooting", p, ys, kw['S'], "rk4", proj=None if proj is None else proj.components)
     if constraint is not None:
         from gaussian_process_odes_b200.core import constraints
-        model.constraint = constraints.Laplace(d=1, scale=constraint, requires_grad=False).to(ys.device)
+        model.constraint = constraints.Laplace(d=1, scale=constraint, requires_grad=False).cuda()
     model.fuse_elbo = fuse
     model.row_shard = row_shard
     with injected_draws(draws, mvn_order=("eps_x0", "eps_states")):
