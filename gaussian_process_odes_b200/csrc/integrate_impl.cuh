@@ -1094,7 +1094,7 @@ int launch_rk4_fwd(const float* packed, int M, int S, const float* x0, const flo
     constexpr int RW = RowsFwd<D>::value;
     if constexpr (kMmaBwd<D>) {
         const HParams hp = h_params<D>(L);
-        const size_t hs0 = (h_smem<D>(hp, false, kHFWarps) + 7) & ~(size_t)7;
+        const size_t hs0 = (h_smem<D>(hp, false, kHFWarps) + 15) & ~(size_t)15;
         const size_t hs = hs0 + shoot_bytes(kHFWarps);
         if (use_mma_fwd(B) && hs <= 227 * 1024) {
             int grid = 0;

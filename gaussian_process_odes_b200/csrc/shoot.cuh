@@ -32,9 +32,12 @@ struct ShootArgs {
     double* work;             // [gridDim.x][2 + Dobs]
 };
 
-// shared-memory region of the epilogue: floats [W D*Dobs | bias Dobs | 1/var Dobs | log(2 pi var) Dobs] (padded to an
-// even count), then float64 [nwarps][2 + Dobs] accumulators (loglik, constraint, d loglik / d var_d)
-__host__ __device__ inline size_t shoot_smem_floats(int D, int Dobs) { return ((size_t)(D + 3) * Dobs + 1) & ~(size_t)1; }
+// shared-memory region of the epilogue (16-byte aligned): floats [W D x DP | bias DP | 1/var DP | log(2 pi var) DP] with
+// the observed dimension padded to DP = roundup4(Dobs) (zero padding: a padded dimension contributes exactly 0), so that
+// four observed dimensions are one LDS.128 per operand; then float64 [nwarps][2 + Dobs] accumulators (loglik,
+// constraint, d loglik / d var_d)
+__host__ __device__ inline int shoot_dp(int Dobs) { return (Dobs + 3) & ~3; }
+__host__ __device__ inline size_t shoot_smem_floats(int D, int Dobs) { return (size_t)(D + 3) * shoot_dp(Dobs); }
 __host__ __device__ inline size_t shoot_smem_bytes(int D, int Dobs, int nwarps) {
     return shoot_smem_floats(D, Dobs) * 4 + (size_t)nwarps * (2 + Dobs) * 8;
 }
@@ -53,17 +56,21 @@ struct ShootSmem {
     // all threads of the CTA; `base` is 8-byte aligned. Ends with a __syncthreads().
     __device__ __forceinline__ void init(unsigned char* base, const ShootArgs& a) {
         float* f = reinterpret_cast<float*>(base);
-        const int Dobs = a.Dobs;
+        const int Dobs = a.Dobs, DP = shoot_dp(Dobs);
         float* sW = f;
-        float* sb = f + D * Dobs;
-        float* siv = sb + Dobs;
-        float* slv = siv + Dobs;
-        for (int i = threadIdx.x; i < D * Dobs; i += blockDim.x) sW[i] = a.W[i];
-        for (int d = threadIdx.x; d < Dobs; d += blockDim.x) {
-            const float v = a.lik_var[d];
-            sb[d] = a.bias ? a.bias[d] : 0.f;
-            siv[d] = 1.0f / v;
-            slv[d] = 1.8378770664093453f + logf(v);  // log(2 pi) + log var
+        float* sb = f + D * DP;
+        float* siv = sb + DP;
+        float* slv = siv + DP;
+        for (int i = threadIdx.x; i < D * DP; i += blockDim.x) {
+            const int l = i / DP, d = i - l * DP;
+            sW[i] = d < Dobs ? a.W[l * Dobs + d] : 0.f;
+        }
+        for (int d = threadIdx.x; d < DP; d += blockDim.x) {
+            const bool ok = d < Dobs;
+            const float v = ok ? a.lik_var[d] : 1.f;
+            sb[d] = (ok && a.bias) ? a.bias[d] : 0.f;
+            siv[d] = ok ? 1.0f / v : 0.f;
+            slv[d] = ok ? 1.8378770664093453f + logf(v) : 0.f;  // log(2 pi) + log var
         }
         double* acc = reinterpret_cast<double*>(base + shoot_smem_floats(D, Dobs) * 4);
         const int nwarps = (blockDim.x + 31) >> 5;
@@ -93,22 +100,46 @@ __device__ __forceinline__ void shoot_epilogue(const ShootArgs& a, const ShootSm
 #pragma unroll
     for (int l = 0; l < D; ++l) sl[l] = 0.f;
     float lsum = 0.f;
-    for (int d = 0; d < Dobs; ++d) {
-        float f = sm.bias[d];
+    const int DP = shoot_dp(Dobs);
+    // four observed dimensions per trip (one LDS.128 per operand); the four observations are fetched before anything
+    // depends on them and the loop is unrolled twice, so eight global loads are in flight per lane (the first version
+    // went dimension by dimension and spent its time waiting on one 4-byte load at a time: ncu, stall_long_sb)
+#pragma unroll 2
+    for (int d0 = 0; d0 < DP; d0 += 4) {
+        float yv[4];
 #pragma unroll
-        for (int l = 0; l < D; ++l) f = fmaf(pred[l], sm.W[l * Dobs + d], f);
-        const float diff = valid ? f - __ldg(y + d) : 0.f;
-        const float q = diff * sm.iv[d];
-        lsum += -0.5f * (sm.lv[d] + diff * q);
-        float gvd = valid ? -0.5f * (sm.iv[d] - q * q) : 0.f;
-        if constexpr (kLanes) {
-            gvd = gpode_warp_sum(gvd);
-            if ((threadIdx.x & 31) == 0) sm.wacc[2 + d] += (double)gvd;
-        } else {
-            sm.wacc[2 + d] += (double)gvd;
+        for (int u = 0; u < 4; ++u) yv[u] = (valid && d0 + u < Dobs) ? __ldg(y + d0 + u) : 0.f;
+        const float4 b4 = *reinterpret_cast<const float4*>(sm.bias + d0);
+        const float4 i4 = *reinterpret_cast<const float4*>(sm.iv + d0);
+        const float4 l4 = *reinterpret_cast<const float4*>(sm.lv + d0);
+        float f[4] = {b4.x, b4.y, b4.z, b4.w};
+        const float iv[4] = {i4.x, i4.y, i4.z, i4.w}, lv[4] = {l4.x, l4.y, l4.z, l4.w};
+        float4 w4[D];
+#pragma unroll
+        for (int l = 0; l < D; ++l) {
+            w4[l] = *reinterpret_cast<const float4*>(sm.W + l * DP + d0);
+            f[0] = fmaf(pred[l], w4[l].x, f[0]);
+            f[1] = fmaf(pred[l], w4[l].y, f[1]);
+            f[2] = fmaf(pred[l], w4[l].z, f[2]);
+            f[3] = fmaf(pred[l], w4[l].w, f[3]);
+        }
+        float q[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float diff = valid ? f[u] - yv[u] : 0.f;   // a padded dimension has f = y = 0
+            q[u] = diff * iv[u];
+            lsum += -0.5f * (lv[u] + diff * q[u]);
+            float gvd = valid ? -0.5f * (iv[u] - q[u] * q[u]) : 0.f;
+            if constexpr (kLanes) {
+                gvd = gpode_warp_sum(gvd);
+                if ((threadIdx.x & 31) == 0 && d0 + u < Dobs) sm.wacc[2 + d0 + u] += (double)gvd;
+            } else {
+                if (d0 + u < Dobs) sm.wacc[2 + d0 + u] += (double)gvd;
+            }
         }
 #pragma unroll
-        for (int l = 0; l < D; ++l) sl[l] = fmaf(-q, sm.W[l * Dobs + d], sl[l]);
+        for (int l = 0; l < D; ++l)
+            sl[l] = fmaf(-q[0], w4[l].x, fmaf(-q[1], w4[l].y, fmaf(-q[2], w4[l].z, fmaf(-q[3], w4[l].w, sl[l]))));
     }
     // shooting constraint: this row's end point against the NEXT sampled state of the same sequence
     float sc[D];
