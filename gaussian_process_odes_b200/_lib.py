@@ -59,6 +59,13 @@ SIGNATURES = {
     "gpode_constraint_sum": (_I, [_P, _P, _P, _L, _I, _I, _I, _P, _P, _P, _P, _P]),
     "gpode_side_work_doubles": (_L, []),
     "gpode_shoot_work_doubles": (_L, []),
+    "gpode_packed_large_bwd_floats": (_L, [_I, _I, _I]),
+    "gpode_acc_large_floats": (_L, [_I, _I]),
+    "gpode_pack_cache_large_bwd": (_I, [_CP, _P, _P]),
+    "gpode_vf_bwd_large": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _L, _P]),
+    "gpode_grads_finalize_large": (_I, [_CP, _P, _L, _P, _P, _P, _P, _P]),
+    "gpode_rk4_fwd_large_dev": (_I, [_P, _CP, _P, _P, _I, _L, _P, _P, _P, _P]),
+    "gpode_rk4_bwd_large": (_I, [_P, _CP, _P, _I, _L, _P, _P, _P, _P, _P, _P, _P]),
     "gpode_shoot_fwd": (_I, [_P, _I, _I, _I, ctypes.POINTER(GpodeShoot), _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gpode_shoot_bwd": (_I, [_P, _I, _I, _I, ctypes.POINTER(GpodeShoot), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gpode_acc_header_floats": (_L, []),
@@ -148,6 +155,9 @@ KERNELS_PER_CALL = {
     "gpode_vf_fwd_large_add_rbf": 1, "gpode_dopri5_bwd_dev": 1, "gpode_param_grad_dev": 1, "gpode_vf_fwd_umma": 1,
     "gpode_pack_cache_sets": 1, "gpode_whiten_fwd_sets": 2, "gpode_vf_fwd_sets": 1, "gpode_rk4_fwd_sets": 1,
     "gpode_dopri5_fwd_sets": 1, "gpode_shoot_fwd": 2, "gpode_shoot_bwd": 1,
+    "gpode_pack_cache_large_bwd": 1, "gpode_vf_bwd_large": 1, "gpode_grads_finalize_large": 1,
+    # per RK4 step: forward 4 evaluations x 2 kernels + 4 stage kernels; adjoint 4 VJPs + 8 element-wise kernels
+    "gpode_rk4_fwd_large_dev": 12, "gpode_rk4_bwd_large": 12,
 }
 assert all(isinstance(v, int) for v in KERNELS_PER_CALL.values()), "KERNELS_PER_CALL holds launch counts"
 assert set(KERNELS_PER_CALL) <= set(SIGNATURES), sorted(set(KERNELS_PER_CALL) - set(SIGNATURES))

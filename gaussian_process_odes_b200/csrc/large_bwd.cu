@@ -1,0 +1,587 @@
+// Backward (vector-Jacobian product) and device-side fixed-grid RK4 for 8 < D <= 64 -- the upper half of BASELINE.json
+// configs[4] (state dimension 2-64). Round 1 had a forward-only tensor-core vector field driven by eager PyTorch host
+// loops; this file adds
+//   * vjp_large_kernel<DP>: xb = J(x)^T kb plus every shared-parameter partial sum (lengthscales, variances, nu, Z) of
+//     one batch of (point, cotangent) rows -- what autograd does through DSVGP_Layer.forward (reference
+//     src/core/dsvgp.py:172-197, rff_forward :124-137, RBF.K src/core/kernels.py:53-99); formulas: SURVEY.md 8(a) A7;
+//   * gpode_rk4_fwd_large_dev / gpode_rk4_bwd_large: torchdiffeq's 3/8-rule RK4 (same operation order as
+//     integrate_impl.cuh) and its discrete adjoint as a stream-ordered sequence of launches -- the tcgen05 vector-field
+//     kernels of large_umma.cu for the forward evaluations, this VJP kernel for the adjoint, small element-wise kernels
+//     for the stage algebra; step sizes are read from the device-side grid, nothing returns to the host;
+//   * gpode_grads_finalize_large: per-CTA partial rows -> parameter gradients in float64, fixed order (no atomics).
+//
+// VJP mapping (FP32 CUDA cores). CTA = 128 threads = one tile of 128 rows, THREAD = ROW for everything that is per row:
+//   RFF part, per output k: theta_s = phase_sk + sum_j x_j Omega_jsk, g_s = a_sk sin(theta_s), G_j = sum_s g_s Omega_jsk
+//     with x, G in registers and the (k, 64-feature) chunk of Omega -- 16 KB, j contiguous -- staged in shared memory by
+//     the bulk-copy engine (cp.async.bulk + mbarrier, double-buffered one chunk ahead) and read by broadcast LDS.128:
+//     4 features per trip = 4 independent FMA chains;  xb_j -= kb_k G_j;  A[k][j] -= sum_rows kb_k x_j G_j.
+//   RBF part, per inducing point m (CTA-uniform loop): dd_j = (x_j - Z_mj)^2 in registers; per k: e = sum_j dd_j w_kj,
+//     K = 2^-e, p = kb_k K, t_j += 2 ln2 c_km p w_kj;  xb_j -= d_j t_j.
+//   The sums over ROWS -- T[k][m] = sum_r p, A2[k][j] = sum_r p dd_j, Zb[m][j] = sum_r d_j t_j -- are taken by
+//     re-mapping the CTA to (k, j-slice) / (j) over the staged [128 x D] tiles of p, dd and d t (no atomics, fixed
+//     order), accumulated per CTA: A in shared memory, T and Zb in the CTA's own rows of a global scratch block.
+#include "common.cuh"
+#include "../../include/gpode_b200.h"
+
+int gpode_vf_large_eval(const float* packed_large, const gpode_cache_t* c, const float* x, float* tmp, float* f,
+                        int64_t B, cudaStream_t st);  // large_umma.cu: f = vf(x) on the tcgen05 tensor cores
+
+namespace {
+
+constexpr int kLbRows = 128, kLbThreads = 128, kLbSC = 64;  // tile rows, threads, features per staged Omega chunk
+constexpr int kLbMaxCtas = 148 * 2;
+
+__host__ __device__ inline int lb_dp(int D) { return D <= 16 ? 16 : (D <= 32 ? 32 : 64); }
+
+struct LbLayout {
+    int D, DP, M, S, SU, NCH;
+    int64_t off_om, off_ph, off_aw, off_w, off_z, off_c, total;  // floats
+};
+__host__ __device__ inline LbLayout lb_layout(int D, int M, int S) {
+    LbLayout L;
+    L.D = D; L.DP = lb_dp(D); L.M = M; L.S = S;
+    L.SU = (S + kLbSC - 1) / kLbSC * kLbSC;
+    L.NCH = L.SU / kLbSC;
+    L.off_om = 0;                                     // [k < D][chunk][feature in chunk][DP]  Omega_jsk, j contiguous
+    L.off_ph = L.off_om + (int64_t)D * L.SU * L.DP;   // [k][SU] phase
+    L.off_aw = L.off_ph + (int64_t)D * L.SU;          // [k][SU] a_sk = w_sk sqrt(var_k / S)  (0 for padded features)
+    L.off_w = L.off_aw + (int64_t)D * L.SU;           // [DP][DP] w_kj = 0.5 log2(e) / ell_kj^2
+    L.off_z = L.off_w + (int64_t)L.DP * L.DP;         // [M][DP] Z
+    L.off_c = L.off_z + (int64_t)M * L.DP;            // [M][DP] c_km = var_k nu_km, k contiguous
+    L.total = L.off_c + (int64_t)M * L.DP;
+    return L;
+}
+
+__global__ void pack_lb_kernel(const LbLayout L, const float* __restrict__ omega, const float* __restrict__ phase,
+                               const float* __restrict__ w, const float* __restrict__ Z, const float* __restrict__ nu,
+                               const float* __restrict__ ell, const float* __restrict__ var, float* __restrict__ out) {
+    const int D = L.D, DP = L.DP, S = L.S, SU = L.SU, M = L.M;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t i = i0; i < (int64_t)D * SU * DP; i += stride) {
+        const int j = (int)(i % DP), s = (int)((i / DP) % SU), k = (int)(i / ((int64_t)DP * SU));
+        out[L.off_om + i] = (s < S && j < D) ? omega[((size_t)j * S + s) * D + k] : 0.f;
+    }
+    for (int64_t i = i0; i < (int64_t)D * SU; i += stride) {
+        const int s = (int)(i % SU), k = (int)(i / SU);
+        out[L.off_ph + i] = s < S ? phase[s * D + k] : 0.f;
+        out[L.off_aw + i] = s < S ? w[s * D + k] * sqrtf(var[k] / (float)S) : 0.f;
+    }
+    for (int64_t i = i0; i < (int64_t)DP * DP; i += stride) {
+        const int j = (int)(i % DP), k = (int)(i / DP);
+        float v = 0.f;
+        if (k < D && j < D) {
+            const float l = ell[k * D + j];
+            v = GPODE_HALF_LOG2E / (l * l);
+        }
+        out[L.off_w + i] = v;
+    }
+    for (int64_t i = i0; i < (int64_t)M * DP; i += stride) {
+        const int j = (int)(i % DP), m = (int)(i / DP);
+        out[L.off_z + i] = j < D ? Z[m * D + j] : 0.f;
+        out[L.off_c + i] = j < D ? var[j] * nu[j * M + m] : 0.f;   // here j plays the role of k
+    }
+}
+
+// shared memory (floats): xs | kbs | stA | stB | xbs (each [128][DP + 4]; xbs = the running row cotangent: kept out of
+// the register file, which holds x / G resp. dd / t) | Ws [DP][DP] | As [DP][DP] | red [4][DP] | V1 [DP],
+// then two mbarriers. The two Omega chunk buffers (64 x DP floats each) alias stA and stB during the RFF part.
+template <int DP>
+struct LbSmem {
+    static constexpr int LD = DP + 4;
+    static constexpr int tile = kLbRows * LD;
+    static constexpr int floats = 5 * tile + 2 * DP * DP + 4 * DP + DP;
+    static constexpr size_t bytes = (size_t)floats * 4 + 16;
+};
+
+template <int DP>
+__global__ void __launch_bounds__(kLbThreads, 1)
+vjp_large_kernel(const float* __restrict__ pk, const LbLayout L, const float* __restrict__ x,
+                 const float* __restrict__ f, const float* __restrict__ kb, float* __restrict__ gx, const int64_t B,
+                 float* __restrict__ accA, float* __restrict__ accT, float* __restrict__ accZ) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int LD = LbSmem<DP>::LD, TILE = LbSmem<DP>::tile;
+    float* xs = reinterpret_cast<float*>(smem_raw);
+    float* kbs = xs + TILE;
+    float* stA = kbs + TILE;
+    float* stB = stA + TILE;
+    float* xbs = stB + TILE;
+    float* Ws = xbs + TILE;
+    float* As = Ws + DP * DP;
+    float* red = As + DP * DP;
+    float* V1 = red + 4 * DP;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(V1 + DP);
+    float* obuf[2] = {stA, stB};
+    const int D = L.D, M = L.M, SU = L.SU, NCH = L.NCH;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* __restrict__ om_g = pk + L.off_om;
+    const float* __restrict__ ph_g = pk + L.off_ph;
+    const float* __restrict__ aw_g = pk + L.off_aw;
+    const float* __restrict__ z_g = pk + L.off_z;
+    const float* __restrict__ c_g = pk + L.off_c;
+    constexpr uint32_t kChunkBytes = kLbSC * DP * 4;
+
+    for (int i = tid; i < DP * DP; i += kLbThreads) {
+        Ws[i] = pk[L.off_w + i];
+        As[i] = 0.f;
+    }
+    for (int i = tid; i < DP; i += kLbThreads) V1[i] = 0.f;
+    if (tid == 0) {
+        gpode_mbar_init(mbar, 1);
+        gpode_mbar_init(mbar + 1, 1);
+    }
+    __syncthreads();
+    uint32_t it = 0;  // running count of staged chunks (buffer = it & 1, parity = (it >> 1) & 1)
+    float* __restrict__ Tg = accT + (size_t)blockIdx.x * D * M;
+    float* __restrict__ Zg = accZ + (size_t)blockIdx.x * M * DP;
+
+    const int64_t n_tiles = (B + kLbRows - 1) / kLbRows;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t r0 = tile * kLbRows;
+        const int n = (int)((B - r0) < kLbRows ? (B - r0) : kLbRows);
+        // ---- tiles of x and kb (coalesced), zero padded in both directions ----
+        for (int i = tid; i < kLbRows * DP; i += kLbThreads) {
+            const int r = i / DP, j = i - r * DP;
+            const bool ok = r < n && j < D;
+            xs[r * LD + j] = ok ? __ldg(x + (r0 + r) * D + j) : 0.f;
+            kbs[r * LD + j] = ok ? __ldg(kb + (r0 + r) * D + j) : 0.f;
+        }
+        // first Omega chunk of this tile; the generic-proxy writes of the previous tile's RBF part to stA / stB are
+        // ordered before the async-proxy copy by the barrier at the end of that tile + this fence
+        if (tid == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            gpode_bulk_g2s(obuf[it & 1], om_g, kChunkBytes, mbar + (it & 1));
+        }
+        __syncthreads();
+        float xr[DP];
+        float* __restrict__ xbr = xbs + tid * LD;   // this row's cotangent (only its own thread touches it)
+#pragma unroll
+        for (int j4 = 0; j4 < DP / 4; ++j4) {
+            const float4 v = *reinterpret_cast<const float4*>(xs + tid * LD + 4 * j4);
+            xr[4 * j4] = v.x; xr[4 * j4 + 1] = v.y; xr[4 * j4 + 2] = v.z; xr[4 * j4 + 3] = v.w;
+            *reinterpret_cast<float4*>(xbr + 4 * j4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        // variance partial sum, first half: V1[k] += sum_rows kb_k f_k
+        for (int k = 0; k < D; ++k) {
+            const float fv = tid < n ? __ldg(f + (r0 + tid) * D + k) : 0.f;
+            const float v = gpode_warp_sum(kbs[tid * LD + k] * fv);
+            if (lane == 0) red[warp * DP + k] = v;
+        }
+        __syncthreads();
+        for (int k = tid; k < D; k += kLbThreads) V1[k] += (red[k] + red[DP + k]) + (red[2 * DP + k] + red[3 * DP + k]);
+
+        // ================= RFF part =================
+        for (int k = 0; k < D; ++k) {
+            float G[DP];
+#pragma unroll
+            for (int j = 0; j < DP; ++j) G[j] = 0.f;
+            for (int ch = 0; ch < NCH; ++ch, ++it) {
+                // stage the next chunk (of this k, or the first of k + 1) into the other buffer: its last readers
+                // finished before the barrier that closed the previous trip
+                const bool more = !(k == D - 1 && ch == NCH - 1);
+                if (tid == 0 && more) {
+                    const int kn = ch + 1 < NCH ? k : k + 1, cn = ch + 1 < NCH ? ch + 1 : 0;
+                    gpode_bulk_g2s(obuf[(it + 1) & 1], om_g + ((size_t)kn * NCH + cn) * kLbSC * DP, kChunkBytes,
+                                   mbar + ((it + 1) & 1));
+                }
+                gpode_mbar_wait(mbar + (it & 1), (it >> 1) & 1);
+                const float* __restrict__ ob = obuf[it & 1];
+                const float* __restrict__ php = ph_g + (size_t)k * SU + ch * kLbSC;
+                const float* __restrict__ awp = aw_g + (size_t)k * SU + ch * kLbSC;
+#pragma unroll 1
+                for (int s = 0; s < kLbSC; s += 4) {
+                    const float4 ph4 = __ldg(reinterpret_cast<const float4*>(php + s));
+                    const float4 a4 = __ldg(reinterpret_cast<const float4*>(awp + s));
+                    float th0 = ph4.x, th1 = ph4.y, th2 = ph4.z, th3 = ph4.w;
+                    const float* __restrict__ o = ob + s * DP;
+#pragma unroll
+                    for (int j4 = 0; j4 < DP / 4; ++j4) {
+                        const float4 o0 = *reinterpret_cast<const float4*>(o + 4 * j4);
+                        const float4 o1 = *reinterpret_cast<const float4*>(o + DP + 4 * j4);
+                        const float4 o2 = *reinterpret_cast<const float4*>(o + 2 * DP + 4 * j4);
+                        const float4 o3 = *reinterpret_cast<const float4*>(o + 3 * DP + 4 * j4);
+                        th0 = fmaf(xr[4 * j4], o0.x, th0); th1 = fmaf(xr[4 * j4], o1.x, th1);
+                        th2 = fmaf(xr[4 * j4], o2.x, th2); th3 = fmaf(xr[4 * j4], o3.x, th3);
+                        th0 = fmaf(xr[4 * j4 + 1], o0.y, th0); th1 = fmaf(xr[4 * j4 + 1], o1.y, th1);
+                        th2 = fmaf(xr[4 * j4 + 1], o2.y, th2); th3 = fmaf(xr[4 * j4 + 1], o3.y, th3);
+                        th0 = fmaf(xr[4 * j4 + 2], o0.z, th0); th1 = fmaf(xr[4 * j4 + 2], o1.z, th1);
+                        th2 = fmaf(xr[4 * j4 + 2], o2.z, th2); th3 = fmaf(xr[4 * j4 + 2], o3.z, th3);
+                        th0 = fmaf(xr[4 * j4 + 3], o0.w, th0); th1 = fmaf(xr[4 * j4 + 3], o1.w, th1);
+                        th2 = fmaf(xr[4 * j4 + 3], o2.w, th2); th3 = fmaf(xr[4 * j4 + 3], o3.w, th3);
+                    }
+                    const float g0 = a4.x * __sinf(th0), g1 = a4.y * __sinf(th1), g2 = a4.z * __sinf(th2),
+                                g3 = a4.w * __sinf(th3);
+#pragma unroll
+                    for (int j4 = 0; j4 < DP / 4; ++j4) {
+                        const float4 o0 = *reinterpret_cast<const float4*>(o + 4 * j4);
+                        const float4 o1 = *reinterpret_cast<const float4*>(o + DP + 4 * j4);
+                        const float4 o2 = *reinterpret_cast<const float4*>(o + 2 * DP + 4 * j4);
+                        const float4 o3 = *reinterpret_cast<const float4*>(o + 3 * DP + 4 * j4);
+                        G[4 * j4] = fmaf(g0, o0.x, fmaf(g1, o1.x, fmaf(g2, o2.x, fmaf(g3, o3.x, G[4 * j4]))));
+                        G[4 * j4 + 1] = fmaf(g0, o0.y, fmaf(g1, o1.y, fmaf(g2, o2.y, fmaf(g3, o3.y, G[4 * j4 + 1]))));
+                        G[4 * j4 + 2] = fmaf(g0, o0.z, fmaf(g1, o1.z, fmaf(g2, o2.z, fmaf(g3, o3.z, G[4 * j4 + 2]))));
+                        G[4 * j4 + 3] = fmaf(g0, o0.w, fmaf(g1, o1.w, fmaf(g2, o2.w, fmaf(g3, o3.w, G[4 * j4 + 3]))));
+                    }
+                }
+                __syncthreads();  // everyone is done with this buffer before it is refilled two trips later
+            }
+            // xb_j -= kb_k G_j;  A[k][j] -= sum_rows kb_k x_j G_j  (rows by warp shuffle, warps in warp order)
+            const float nkb = -kbs[tid * LD + k];
+#pragma unroll
+            for (int j = 0; j < DP; ++j) {
+                const float gj = nkb * G[j];
+                xbr[j] += gj;
+                const float v = gpode_warp_sum(xr[j] * gj);
+                if (lane == 0) red[warp * DP + j] = v;
+            }
+            __syncthreads();
+            for (int j = tid; j < DP; j += kLbThreads)
+                As[k * DP + j] += (red[j] + red[DP + j]) + (red[2 * DP + j] + red[3 * DP + j]);
+            __syncthreads();
+        }
+
+        // ================= RBF part =================
+        constexpr int KT = kLbThreads / DP;   // threads per output k in the row-contraction phase
+        constexpr int JT = DP / KT;           // input dimensions per such thread
+        const int ck = tid / KT, cj0 = (tid - ck * KT) * JT;
+        for (int m = 0; m < M; ++m) {
+            const float* __restrict__ zm = z_g + (size_t)m * DP;
+            const float* __restrict__ cm = c_g + (size_t)m * DP;
+            float dd[DP], tt[DP];
+#pragma unroll
+            for (int j4 = 0; j4 < DP / 4; ++j4) {
+                const float4 xv = *reinterpret_cast<const float4*>(xs + tid * LD + 4 * j4);
+                const float4 zv = __ldg(reinterpret_cast<const float4*>(zm + 4 * j4));
+                const float d0 = xv.x - zv.x, d1 = xv.y - zv.y, d2 = xv.z - zv.z, d3 = xv.w - zv.w;
+                dd[4 * j4] = d0 * d0; dd[4 * j4 + 1] = d1 * d1; dd[4 * j4 + 2] = d2 * d2; dd[4 * j4 + 3] = d3 * d3;
+                tt[4 * j4] = tt[4 * j4 + 1] = tt[4 * j4 + 2] = tt[4 * j4 + 3] = 0.f;
+                *reinterpret_cast<float4*>(stB + tid * LD + 4 * j4) =
+                    make_float4(dd[4 * j4], dd[4 * j4 + 1], dd[4 * j4 + 2], dd[4 * j4 + 3]);
+            }
+#pragma unroll 1
+            for (int k = 0; k < D; ++k) {
+                const float* __restrict__ wk = Ws + k * DP;
+                float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
+#pragma unroll
+                for (int j4 = 0; j4 < DP / 4; ++j4) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(wk + 4 * j4);
+                    e0 = fmaf(dd[4 * j4], w4.x, e0); e1 = fmaf(dd[4 * j4 + 1], w4.y, e1);
+                    e2 = fmaf(dd[4 * j4 + 2], w4.z, e2); e3 = fmaf(dd[4 * j4 + 3], w4.w, e3);
+                }
+                const float K = gpode_ex2(-((e0 + e1) + (e2 + e3)));
+                const float p = kbs[tid * LD + k] * K;
+                stA[tid * LD + k] = p;
+                const float q = -GPODE_NEG_2LN2 * __ldg(cm + k) * p;   // 2 ln2 c_km kb_k K
+#pragma unroll
+                for (int j4 = 0; j4 < DP / 4; ++j4) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(wk + 4 * j4);
+                    tt[4 * j4] = fmaf(q, w4.x, tt[4 * j4]); tt[4 * j4 + 1] = fmaf(q, w4.y, tt[4 * j4 + 1]);
+                    tt[4 * j4 + 2] = fmaf(q, w4.z, tt[4 * j4 + 2]); tt[4 * j4 + 3] = fmaf(q, w4.w, tt[4 * j4 + 3]);
+                }
+            }
+            __syncthreads();  // p and dd of all 128 rows are staged
+            // rows contracted by (k, j-slice) threads: T[k][m] = sum_r p;  A[k][j] -= 2 ln2 w_kj c_km sum_r p dd_j
+            if (ck < D) {
+                float s1 = 0.f, s2[JT];
+#pragma unroll
+                for (int j = 0; j < JT; ++j) s2[j] = 0.f;
+#pragma unroll 4
+                for (int r = 0; r < kLbRows; ++r) {
+                    const float pv = stA[r * LD + ck];
+                    s1 += pv;
+                    if constexpr (JT % 4 == 0) {
+#pragma unroll
+                        for (int j4 = 0; j4 < JT / 4; ++j4) {
+                            const float4 d4 = *reinterpret_cast<const float4*>(stB + r * LD + cj0 + 4 * j4);
+                            s2[4 * j4] = fmaf(pv, d4.x, s2[4 * j4]); s2[4 * j4 + 1] = fmaf(pv, d4.y, s2[4 * j4 + 1]);
+                            s2[4 * j4 + 2] = fmaf(pv, d4.z, s2[4 * j4 + 2]); s2[4 * j4 + 3] = fmaf(pv, d4.w, s2[4 * j4 + 3]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < JT; ++j) s2[j] = fmaf(pv, stB[r * LD + cj0 + j], s2[j]);
+                    }
+                }
+                if (cj0 == 0) Tg[(size_t)ck * M + m] += s1;
+                const float cf = GPODE_NEG_2LN2 * __ldg(cm + ck);   // -2 ln2 c_km
+#pragma unroll
+                for (int j = 0; j < JT; ++j) As[ck * DP + cj0 + j] = fmaf(cf * Ws[ck * DP + cj0 + j], s2[j], As[ck * DP + cj0 + j]);
+            }
+            __syncthreads();  // stB is free again
+            // xb_j -= d_j t_j; the same products, summed over rows, are the Z gradient
+#pragma unroll
+            for (int j4 = 0; j4 < DP / 4; ++j4) {
+                const float4 xv = *reinterpret_cast<const float4*>(xs + tid * LD + 4 * j4);
+                const float4 zv = __ldg(reinterpret_cast<const float4*>(zm + 4 * j4));
+                float4 dt;
+                dt.x = (xv.x - zv.x) * tt[4 * j4]; dt.y = (xv.y - zv.y) * tt[4 * j4 + 1];
+                dt.z = (xv.z - zv.z) * tt[4 * j4 + 2]; dt.w = (xv.w - zv.w) * tt[4 * j4 + 3];
+                float4 xv4 = *reinterpret_cast<const float4*>(xbr + 4 * j4);
+                xv4.x -= dt.x; xv4.y -= dt.y; xv4.z -= dt.z; xv4.w -= dt.w;
+                *reinterpret_cast<float4*>(xbr + 4 * j4) = xv4;
+                *reinterpret_cast<float4*>(stB + tid * LD + 4 * j4) = dt;
+            }
+            __syncthreads();
+            if (tid < D) {
+                float zs0 = 0.f, zs1 = 0.f, zs2 = 0.f, zs3 = 0.f;
+#pragma unroll 4
+                for (int r = 0; r < kLbRows; r += 4) {
+                    zs0 += stB[r * LD + tid]; zs1 += stB[(r + 1) * LD + tid];
+                    zs2 += stB[(r + 2) * LD + tid]; zs3 += stB[(r + 3) * LD + tid];
+                }
+                Zg[(size_t)m * DP + tid] += (zs0 + zs1) + (zs2 + zs3);
+            }
+            __syncthreads();  // stA / stB are rewritten by the next inducing point
+        }
+        // ---- xb out (coalesced from its shared-memory tile) ----
+        __syncthreads();
+        for (int i = tid; i < n * D; i += kLbThreads) {
+            const int r = i / D, j = i - r * D;
+            gx[(r0 + r) * D + j] = xbs[r * LD + j];
+        }
+        __syncthreads();
+    }
+    // ---- this CTA's lengthscale / variance partial sums: accumulate into its own row (sequential launches add up) ----
+    float* __restrict__ Ag = accA + (size_t)blockIdx.x * (DP * DP + DP);
+    for (int i = tid; i < DP * DP; i += kLbThreads) Ag[i] += As[i];
+    for (int i = tid; i < DP; i += kLbThreads) Ag[DP * DP + i] += V1[i];
+}
+
+// ---- parameter gradients from the per-CTA rows (float64, rows in row order) ------------------------------------------
+// grid.x covers the D*D + D + D*M + M*D outputs; acc = [accA rows | accT rows | accZ rows]
+__global__ void finalize_large_kernel(const int D, const int DP, const int M, const int n_rows,
+                                      const float* __restrict__ accA, const float* __restrict__ accT,
+                                      const float* __restrict__ accZ, const float* __restrict__ nu,
+                                      const float* __restrict__ ell, const float* __restrict__ var,
+                                      float* __restrict__ g_ell, float* __restrict__ g_var, float* __restrict__ g_Z,
+                                      float* __restrict__ g_nu) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nA = D * D, nT = D * M, nZ = M * D;
+    auto sum_rows = [&](const float* base, size_t stride, size_t off) {
+        double s = 0.0;
+        for (int r = 0; r < n_rows; ++r) s += (double)__ldcg(base + (size_t)r * stride + off);
+        return s;
+    };
+    if (i < nA) {
+        const int k = i / D, j = i - k * D;
+        g_ell[i] = (float)(-sum_rows(accA, (size_t)DP * DP + DP, (size_t)k * DP + j) / (double)ell[i]);
+    } else if (i < nA + D) {
+        // V[k] = sum_rows kb_k f_k + sum_m c_km T[k][m]
+        const int k = i - nA;
+        double v = sum_rows(accA, (size_t)DP * DP + DP, (size_t)DP * DP + k);
+        for (int m = 0; m < M; ++m)
+            v += (double)var[k] * (double)nu[k * M + m] * sum_rows(accT, (size_t)D * M, (size_t)k * M + m);
+        g_var[k] = (float)(0.5 * v / (double)var[k]);
+    } else if (i < nA + D + nT) {
+        const int e = i - nA - D, k = e / M;
+        g_nu[e] = (float)((double)var[k] * sum_rows(accT, (size_t)D * M, (size_t)e));
+    } else if (i < nA + D + nT + nZ) {
+        const int e = i - nA - D - nT, m = e / D, j = e - m * D;
+        g_Z[e] = (float)sum_rows(accZ, (size_t)M * DP, (size_t)m * DP + j);
+    }
+}
+
+// ---- element-wise stage algebra of the 3/8-rule RK4 step and of its adjoint ------------------------------------------
+#define LB_THIRD 0.3333333432674407958984375f
+// mode 2..4: stage input of stage `mode`; mode 5: the step itself (out = y + (k1 + 3 (k2 + k3) + k4) dt / 8)
+__global__ void rk4_stage_large_kernel(const int mode, const float* __restrict__ t, const int i,
+                                       const float* __restrict__ y, const float* __restrict__ k1,
+                                       const float* __restrict__ k2, const float* __restrict__ k3,
+                                       const float* __restrict__ k4, float* __restrict__ out, const int64_t n) {
+    const float dt = __fsub_rn(__ldg(t + i + 1), __ldg(t + i));
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        float v;
+        if (mode == 2) v = __fadd_rn(y[e], __fmul_rn(__fmul_rn(dt, k1[e]), LB_THIRD));
+        else if (mode == 3) v = __fadd_rn(y[e], __fmul_rn(dt, __fsub_rn(k2[e], __fmul_rn(k1[e], LB_THIRD))));
+        else if (mode == 4) v = __fadd_rn(y[e], __fmul_rn(dt, __fadd_rn(__fsub_rn(k1[e], k2[e]), k3[e])));
+        else {
+            const float sum = __fadd_rn(__fadd_rn(k1[e], __fmul_rn(3.0f, __fadd_rn(k2[e], k3[e]))), k4[e]);
+            v = __fadd_rn(y[e], __fmul_rn(__fmul_rn(sum, dt), 0.125f));
+        }
+        out[e] = v;
+    }
+}
+// cotangent of stage `st` (4..1) from lambda and the VJPs already done (recursion of integrate_impl.cuh::rk4_bwd_kernel);
+// st == 0: lambda <- grad_xs[i] + lambda + yb1 + yb2 + yb3 + yb4
+__global__ void rk4_cot_large_kernel(const int st, const float* __restrict__ t, const int i,
+                                     const float* lam, const float* __restrict__ yb4,
+                                     const float* __restrict__ yb3, const float* __restrict__ yb2,
+                                     const float* __restrict__ yb1, const float* __restrict__ gxi,
+                                     float* out, const int64_t n) {  // st == 0 runs in place: out == lam
+    const float h = __fsub_rn(__ldg(t + i + 1), __ldg(t + i));
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        float v;
+        if (st == 4) v = 0.125f * h * lam[e];
+        else if (st == 3) v = fmaf(0.375f * h, lam[e], h * yb4[e]);
+        else if (st == 2) v = fmaf(0.375f * h, lam[e], h * (yb3[e] - yb4[e]));
+        else if (st == 1) v = fmaf(0.125f * h, lam[e], fmaf(h * LB_THIRD, yb2[e] - yb3[e], h * yb4[e]));
+        else v = gxi[e] + lam[e] + ((yb4[e] + yb3[e]) + (yb2[e] + yb1[e]));
+        out[e] = v;
+    }
+}
+
+int lb_check(const gpode_cache_t* c) {
+    GPODE_CHECK_ARG(c != nullptr, "cache is NULL");
+    GPODE_CHECK_ARG(c->D > GPODE_MAX_D && c->D <= GPODE_MAX_D_LARGE, "large-D path needs %d < D <= %d, got %d",
+                    GPODE_MAX_D, GPODE_MAX_D_LARGE, c->D);
+    GPODE_CHECK_ARG(c->S >= 1 && c->M >= 1 && c->omega && c->phase && c->w && c->Z && c->var && c->ell && c->nu,
+                    "cache tensor is NULL");
+    return 0;
+}
+
+int lb_grid(int64_t B) {
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t tiles = (B + kLbRows - 1) / kLbRows;
+    int64_t g = tiles < sms ? tiles : sms;
+    if (g > kLbMaxCtas) g = kLbMaxCtas;
+    return (int)(g < 1 ? 1 : g);
+}
+
+template <int DP>
+int launch_vjp(const float* pk, const LbLayout& L, const float* x, const float* f, const float* kb, float* gx,
+               int64_t B, float* acc, cudaStream_t st) {
+    const size_t smem = LbSmem<DP>::bytes;
+    GPODE_CUDA(cudaFuncSetAttribute(vjp_large_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    float* accA = acc;
+    float* accT = accA + (size_t)kLbMaxCtas * (DP * DP + DP);
+    float* accZ = accT + (size_t)kLbMaxCtas * L.D * L.M;
+    vjp_large_kernel<DP><<<lb_grid(B), kLbThreads, smem, st>>>(pk, L, x, f, kb, gx, B, accA, accT, accZ);
+    GPODE_LAUNCH_CHECK();
+    return 0;
+}
+
+int vjp_dispatch(const float* pk, int D, int M, int S, const float* x, const float* f, const float* kb, float* gx,
+                 int64_t B, float* acc, cudaStream_t st) {
+    const LbLayout L = lb_layout(D, M, S);
+    if (L.DP == 16) return launch_vjp<16>(pk, L, x, f, kb, gx, B, acc, st);
+    if (L.DP == 32) return launch_vjp<32>(pk, L, x, f, kb, gx, B, acc, st);
+    return launch_vjp<64>(pk, L, x, f, kb, gx, B, acc, st);
+}
+
+inline unsigned ew_grid(int64_t n) {
+    const int64_t g = (n + 255) / 256;
+    return (unsigned)(g < 2368 ? (g < 1 ? 1 : g) : 2368);
+}
+
+}  // namespace
+
+extern "C" int64_t gpode_packed_large_bwd_floats(int D, int M, int S) {
+    if (D <= GPODE_MAX_D || D > GPODE_MAX_D_LARGE || S < 1 || M < 1) return -1;
+    return lb_layout(D, M, S).total;
+}
+
+extern "C" int64_t gpode_acc_large_floats(int D, int M) {
+    if (D <= GPODE_MAX_D || D > GPODE_MAX_D_LARGE || M < 1) return -1;
+    const int DP = lb_dp(D);
+    return (int64_t)kLbMaxCtas * ((int64_t)DP * DP + DP + (int64_t)D * M + (int64_t)M * DP);
+}
+
+extern "C" int gpode_pack_cache_large_bwd(const gpode_cache_t* c, float* packed_bwd, void* stream) {
+    if (int rc = lb_check(c)) return rc;
+    GPODE_CHECK_ARG(packed_bwd != nullptr, "packed_bwd is NULL");
+    pack_lb_kernel<<<592, 256, 0, (cudaStream_t)stream>>>(lb_layout(c->D, c->M, c->S), c->omega, c->phase, c->w, c->Z,
+                                                         c->nu, c->ell, c->var, packed_bwd);
+    GPODE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gpode_vf_bwd_large(const float* packed_bwd, int D, int M, int S, const float* x, const float* f,
+                                  const float* grad_f, float* grad_x, float* acc_large, int64_t B, void* stream) {
+    GPODE_CHECK_ARG(D > GPODE_MAX_D && D <= GPODE_MAX_D_LARGE && M >= 1 && S >= 1 && B >= 0, "bad sizes D=%d M=%d S=%d", D,
+                    M, S);
+    if (B == 0) return 0;
+    GPODE_CHECK_ARG(packed_bwd && x && f && grad_f && grad_x && acc_large, "NULL argument");
+    return vjp_dispatch(packed_bwd, D, M, S, x, f, grad_f, grad_x, B, acc_large, (cudaStream_t)stream);
+}
+
+extern "C" int gpode_grads_finalize_large(const gpode_cache_t* c, const float* acc_large, int64_t B, float* grad_ell,
+                                          float* grad_var, float* grad_Z, float* grad_nu, void* stream) {
+    if (int rc = lb_check(c)) return rc;
+    GPODE_CHECK_ARG(acc_large && grad_ell && grad_var && grad_Z && grad_nu, "NULL argument");
+    const int D = c->D, M = c->M, DP = lb_dp(D);
+    const float* accA = acc_large;
+    const float* accT = accA + (size_t)kLbMaxCtas * (DP * DP + DP);
+    const float* accZ = accT + (size_t)kLbMaxCtas * D * M;
+    const int n_out = D * D + D + 2 * D * M;
+    finalize_large_kernel<<<(n_out + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        D, DP, M, lb_grid(B), accA, accT, accZ, c->nu, c->ell, c->var, grad_ell, grad_var, grad_Z, grad_nu);
+    GPODE_LAUNCH_CHECK();
+    return 0;
+}
+
+// xs [Tg,B,D] (xs[0] = x0), kstages [Tg-1,4,B,D] or NULL; tmp: 2 B D floats (6 B D when kstages is NULL)
+extern "C" int gpode_rk4_fwd_large_dev(const float* packed_large, const gpode_cache_t* c, const float* x0, const float* t,
+                                       int Tg, int64_t B, float* xs, float* kstages, float* tmp, void* stream) {
+    if (int rc = lb_check(c)) return rc;
+    GPODE_CHECK_ARG(Tg >= 1 && B >= 0, "bad sizes Tg=%d B=%lld", Tg, (long long)B);
+    if (B == 0) return 0;
+    GPODE_CHECK_ARG(packed_large && x0 && t && xs && tmp, "NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = B * c->D;
+    GPODE_CUDA(cudaMemcpyAsync(xs, x0, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+    float* ys = tmp;
+    float* frff = tmp + n;
+    float* kloc = tmp + 2 * n;  // used only when the caller keeps no checkpoints
+    const unsigned g = ew_grid(n);
+    for (int i = 0; i + 1 < Tg; ++i) {
+        const float* y = xs + (int64_t)i * n;
+        float* k = kstages ? kstages + (int64_t)i * 4 * n : kloc;
+        float *k1 = k, *k2 = k + n, *k3 = k + 2 * n, *k4 = k + 3 * n;
+        if (int rc = gpode_vf_large_eval(packed_large, c, y, frff, k1, B, st)) return rc;
+        rk4_stage_large_kernel<<<g, 256, 0, st>>>(2, t, i, y, k1, k2, k3, k4, ys, n);
+        if (int rc = gpode_vf_large_eval(packed_large, c, ys, frff, k2, B, st)) return rc;
+        rk4_stage_large_kernel<<<g, 256, 0, st>>>(3, t, i, y, k1, k2, k3, k4, ys, n);
+        if (int rc = gpode_vf_large_eval(packed_large, c, ys, frff, k3, B, st)) return rc;
+        rk4_stage_large_kernel<<<g, 256, 0, st>>>(4, t, i, y, k1, k2, k3, k4, ys, n);
+        if (int rc = gpode_vf_large_eval(packed_large, c, ys, frff, k4, B, st)) return rc;
+        rk4_stage_large_kernel<<<g, 256, 0, st>>>(5, t, i, y, k1, k2, k3, k4, xs + (int64_t)(i + 1) * n, n);
+        GPODE_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+// Discrete adjoint of the above. work: 7 B D floats (lambda, stage input, cotangent, yb4, yb3, yb2, yb1).
+extern "C" int gpode_rk4_bwd_large(const float* packed_bwd, const gpode_cache_t* c, const float* t, int Tg, int64_t B,
+                                   const float* xs, const float* kstages, const float* grad_xs, float* grad_x0,
+                                   float* acc_large, float* work, void* stream) {
+    if (int rc = lb_check(c)) return rc;
+    GPODE_CHECK_ARG(Tg >= 1 && B >= 0, "bad sizes Tg=%d B=%lld", Tg, (long long)B);
+    if (B == 0) return 0;
+    GPODE_CHECK_ARG(packed_bwd && t && xs && grad_xs && grad_x0 && acc_large && work, "NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int D = c->D, M = c->M, S = c->S;
+    const int64_t n = B * D;
+    if (Tg == 1) {
+        GPODE_CUDA(cudaMemcpyAsync(grad_x0, grad_xs, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+        return 0;
+    }
+    GPODE_CHECK_ARG(kstages != nullptr, "kstages is NULL");
+    float *lam = work, *ys = work + n, *kbar = work + 2 * n, *yb4 = work + 3 * n, *yb3 = work + 4 * n,
+          *yb2 = work + 5 * n, *yb1 = work + 6 * n;
+    GPODE_CUDA(cudaMemcpyAsync(lam, grad_xs + (int64_t)(Tg - 1) * n, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+    const unsigned g = ew_grid(n);
+    for (int i = Tg - 2; i >= 0; --i) {
+        const float* y = xs + (int64_t)i * n;
+        const float* k = kstages + (int64_t)i * 4 * n;
+        const float *k1 = k, *k2 = k + n, *k3 = k + 2 * n, *k4 = k + 3 * n;
+        // stage 4
+        rk4_stage_large_kernel<<<g, 256, 0, st>>>(4, t, i, y, k1, k2, k3, k4, ys, n);
+        rk4_cot_large_kernel<<<g, 256, 0, st>>>(4, t, i, lam, yb4, yb3, yb2, yb1, nullptr, kbar, n);
+        if (int rc = vjp_dispatch(packed_bwd, D, M, S, ys, k4, kbar, yb4, B, acc_large, st)) return rc;
+        // stage 3
+        rk4_stage_large_kernel<<<g, 256, 0, st>>>(3, t, i, y, k1, k2, k3, k4, ys, n);
+        rk4_cot_large_kernel<<<g, 256, 0, st>>>(3, t, i, lam, yb4, yb3, yb2, yb1, nullptr, kbar, n);
+        if (int rc = vjp_dispatch(packed_bwd, D, M, S, ys, k3, kbar, yb3, B, acc_large, st)) return rc;
+        // stage 2
+        rk4_stage_large_kernel<<<g, 256, 0, st>>>(2, t, i, y, k1, k2, k3, k4, ys, n);
+        rk4_cot_large_kernel<<<g, 256, 0, st>>>(2, t, i, lam, yb4, yb3, yb2, yb1, nullptr, kbar, n);
+        if (int rc = vjp_dispatch(packed_bwd, D, M, S, ys, k2, kbar, yb2, B, acc_large, st)) return rc;
+        // stage 1
+        rk4_cot_large_kernel<<<g, 256, 0, st>>>(1, t, i, lam, yb4, yb3, yb2, yb1, nullptr, kbar, n);
+        if (int rc = vjp_dispatch(packed_bwd, D, M, S, y, k1, kbar, yb1, B, acc_large, st)) return rc;
+        rk4_cot_large_kernel<<<g, 256, 0, st>>>(0, t, i, lam, yb4, yb3, yb2, yb1, grad_xs + (int64_t)i * n, lam, n);
+        GPODE_LAUNCH_CHECK();
+    }
+    GPODE_CUDA(cudaMemcpyAsync(grad_x0, lam, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}

@@ -535,3 +535,14 @@ extern "C" int gpode_rbf_fwd_large(const float* packed_large, int D, int M, int 
     GPODE_LAUNCH_CHECK();
     return 0;
 }
+
+// f = vf(x) for 8 < D <= 64: Fourier-feature term, then the RBF term added to it, both on the tcgen05 tensor cores (the
+// RBF term falls back to the tiled FP32 kernel when Z does not fit its shared-memory copy). tmp: B D floats.
+int gpode_vf_large_eval(const float* packed_large, const gpode_cache_t* c, const float* x, float* tmp, float* f,
+                        int64_t B, cudaStream_t st) {
+    if (int rc = gpode_rff_fwd_large(packed_large, c->D, c->S, x, tmp, B, st)) return rc;
+    const int KD = lu_kd(c->D), ND = lu_nd(c->D);
+    const size_t smem = RbSmem::data + (size_t)(2 * ND * KD + c->M * KD + KD * kLuRows + 4 * KD * kLuRows) * 4;
+    if (smem <= 227u * 1024u) return gpode_rbf_fwd_large(packed_large, c->D, c->M, c->S, c->Z, x, tmp, f, B, st);
+    return gpode_vf_fwd_large_add_rbf(c, x, tmp, f, B, st);
+}

@@ -427,7 +427,7 @@ def shooting_step(ss, t2, Z, ell, var, nu, omega, phase, w, ys, W, bias, lik_var
 
 
 MAX_D_REGISTER = 8    # GPODE_MAX_D: differentiable register-resident kernels
-MAX_D_LARGE = 64      # GPODE_MAX_D_LARGE: forward-only tiled kernels
+MAX_D_LARGE = 64      # GPODE_MAX_D_LARGE: tcgen05 forward + FP32 VJP kernels (rk4 differentiable, dopri5 forward)
 
 
 def _large_d_call(name, x, t, Z, ell, var, nu, omega, phase, w):
@@ -456,14 +456,13 @@ LARGE_RBF_TENSOR_CORES = True   # False: RBF term in the FP32 tiled kernel (gpod
 
 
 class LargeField:
-    """One sampled GP function for 8 < D <= 64, forward only: the Fourier-feature term runs on the tcgen05 tensor cores
-    (``gpode_rff_fwd_large`` over the pre-tiled 3xTF32 operand chunks of ``gpode_pack_cache_large``), the RBF term in the
-    tiled FP32 kernel (``gpode_vf_fwd_large_add_rbf``). Pack once, evaluate many times (the host-driven integrators)."""
+    """One sampled GP function for 8 < D <= 64: the Fourier-feature term runs on the tcgen05 tensor cores
+    (``gpode_rff_fwd_large`` over the pre-tiled 3xTF32 operand chunks of ``gpode_pack_cache_large``), the RBF term as
+    well (``gpode_rbf_fwd_large``; tiled FP32 kernel ``gpode_vf_fwd_large_add_rbf`` when Z does not fit its shared-
+    memory copy). Pack once, evaluate many times. The backward operand block (``gpode_pack_cache_large_bwd``) is packed
+    on first use."""
 
     def __init__(self, Z, ell, var, nu, omega, phase, w):
-        if torch.is_grad_enabled() and any(a.requires_grad for a in (Z, ell, var, nu)):
-            raise _lib.GpodeError("state dimension %d > %d: only the forward (no_grad) path exists for large D"
-                                  % (Z.shape[1], MAX_D_REGISTER))
         lib = _lib.load()
         Zc, ec, vc, oc, wc = f32(Z, "Z"), f32(ell, "ell"), f32(var, "var"), f32(omega, "omega"), f32(w, "w")
         self.M, self.D = Zc.shape
@@ -476,12 +475,33 @@ class LargeField:
             raise _lib.GpodeError("large-D path needs %d < D <= %d, got %d" % (MAX_D_REGISTER, MAX_D_LARGE, self.D))
         self.packed = torch.empty(n, dtype=torch.float32, device=Zc.device)
         self.rbf_on_tensor_cores = True
+        self._packed_bwd = None
         _lib.call("gpode_pack_cache_large", ctypes.byref(self.struct), ptr(self.packed), stream_ptr())
 
+    @property
+    def packed_bwd(self):
+        if self._packed_bwd is None:
+            n = _lib.load().gpode_packed_large_bwd_floats(self.D, self.M, self.S)
+            self._packed_bwd = torch.empty(n, dtype=torch.float32, device=self.packed.device)
+            _lib.call("gpode_pack_cache_large_bwd", ctypes.byref(self.struct), ptr(self._packed_bwd), stream_ptr())
+        return self._packed_bwd
+
+    def new_acc(self):
+        n = _lib.load().gpode_acc_large_floats(self.D, self.M)
+        return torch.zeros(n, dtype=torch.float32, device=self.packed.device)
+
+    def finalize(self, acc, B):
+        """acc -> (grad_Z, grad_ell, grad_var, grad_nu)"""
+        dev = self.packed.device
+        g_ell = torch.empty(self.D, self.D, dtype=torch.float32, device=dev)
+        g_var = torch.empty(self.D, dtype=torch.float32, device=dev)
+        g_Z = torch.empty(self.M, self.D, dtype=torch.float32, device=dev)
+        g_nu = torch.empty(self.D, self.M, dtype=torch.float32, device=dev)
+        _lib.call("gpode_grads_finalize_large", ctypes.byref(self.struct), ptr(acc), B, ptr(g_ell), ptr(g_var),
+                  ptr(g_Z), ptr(g_nu), stream_ptr())
+        return g_Z, g_ell, g_var, g_nu
+
     def __call__(self, x):
-        if torch.is_grad_enabled() and x.requires_grad:
-            raise _lib.GpodeError("state dimension %d > %d: only the forward (no_grad) path exists for large D"
-                                  % (self.D, MAX_D_REGISTER))
         xc = f32(x, "x")
         if xc.ndim != 2 or xc.shape[1] != self.D:
             raise _lib.GpodeError("x must be (B,%d), got %s" % (self.D, tuple(xc.shape)))
@@ -503,37 +523,85 @@ class LargeField:
         return f
 
 
-def _rk4_large_d(x0, t, field):
-    """torchdiffeq's fixed-grid rk4 (3/8 rule, same operation order) around the large-D vector field, forward only."""
-    y = f32(x0, "x0")
-    tc = t.detach().to(device=y.device, dtype=torch.float32)
-    dts = (tc[1:] - tc[:-1]).tolist()
-    third = 1.0 / 3.0
-    out = [y]
-    for dt in dts:
-        k1 = field(y)
-        k2 = field(y + dt * k1 * third)
-        k3 = field(y + dt * (k2 - k1 * third))
-        k4 = field(y + dt * (k1 - k2 + k3))
-        y = y + (k1 + 3 * (k2 + k3) + k4) * dt * 0.125
-        out.append(y)
-    return torch.stack(out, 0)
+class _VectorFieldLarge(torch.autograd.Function):
+    """f = DSVGP_Layer.forward(t, x) for 8 < D <= 64: tcgen05 forward, ``gpode_vf_bwd_large`` backward."""
+
+    @staticmethod
+    def forward(ctx, x, Z, ell, var, nu, omega, phase, w):
+        field = LargeField(Z, ell, var, nu, omega, phase, w)
+        xc = f32(x, "x")
+        f = field(xc)
+        ctx.field, ctx.nu_shape = field, nu.shape
+        ctx.save_for_backward(xc, f)
+        return f
+
+    @staticmethod
+    def backward(ctx, gf):
+        field = ctx.field
+        xc, f = ctx.saved_tensors
+        gf = f32(gf, "grad_f")
+        B = xc.shape[0]
+        gx = torch.empty_like(xc)
+        acc = field.new_acc()
+        _lib.call("gpode_vf_bwd_large", ptr(field.packed_bwd), field.D, field.M, field.S, ptr(xc), ptr(f), ptr(gf),
+                  ptr(gx), ptr(acc), B, stream_ptr())
+        g_Z, g_ell, g_var, g_nu = field.finalize(acc, B)
+        return gx, g_Z, g_ell, g_var, g_nu.reshape(ctx.nu_shape), None, None, None
+
+
+class _RK4Large(torch.autograd.Function):
+    """``odeint(f, x0, t, method='rk4')`` for 8 < D <= 64 as a stream-ordered sequence of launches
+    (``gpode_rk4_fwd_large_dev`` / ``gpode_rk4_bwd_large``): no host loop, no host read of the grid."""
+
+    @staticmethod
+    def forward(ctx, x0, t, Z, ell, var, nu, omega, phase, w, want_grad):
+        field = LargeField(Z, ell, var, nu, omega, phase, w)
+        xc, tc = f32(x0, "x0"), f32(t, "t")
+        if xc.ndim != 2 or xc.shape[1] != field.D:
+            raise _lib.GpodeError("x0 must be (B,%d), got %s" % (field.D, tuple(xc.shape)))
+        B, D, Tg = xc.shape[0], field.D, tc.shape[0]
+        need_grad = want_grad and any(ctx.needs_input_grad)
+        dev = xc.device
+        xs = torch.empty(Tg, B, D, dtype=torch.float32, device=dev)
+        kst = torch.empty(max(Tg - 1, 0), 4, B, D, dtype=torch.float32, device=dev) if need_grad else None
+        tmp = torch.empty((2 if need_grad else 6) * B * D, dtype=torch.float32, device=dev)
+        _lib.call("gpode_rk4_fwd_large_dev", ptr(field.packed), ctypes.byref(field.struct), ptr(xc), ptr(tc), Tg, B,
+                  ptr(xs), ptr(kst), ptr(tmp), stream_ptr())
+        _lib.LAUNCH_COUNT["gpode_rk4_fwd_large_dev"] += 12 * max(Tg - 2, 0)   # counted once per call: add the other steps
+        ctx.field, ctx.nu_shape = field, nu.shape
+        if need_grad:
+            ctx.save_for_backward(tc, xs, kst)
+        return xs
+
+    @staticmethod
+    def backward(ctx, gxs):
+        field = ctx.field
+        tc, xs, kst = ctx.saved_tensors
+        Tg, B, D = xs.shape
+        gxs = f32(gxs, "grad_xs")
+        gx0 = torch.empty(B, D, dtype=torch.float32, device=xs.device)
+        acc = field.new_acc()
+        work = torch.empty(7 * B * D, dtype=torch.float32, device=xs.device)
+        _lib.call("gpode_rk4_bwd_large", ptr(field.packed_bwd), ctypes.byref(field.struct), ptr(tc), Tg, B, ptr(xs),
+                  ptr(kst), ptr(gxs), ptr(gx0), ptr(acc), ptr(work), stream_ptr())
+        _lib.LAUNCH_COUNT["gpode_rk4_bwd_large"] += 12 * max(Tg - 2, 0)
+        g_Z, g_ell, g_var, g_nu = field.finalize(acc, B)
+        return gx0, None, g_Z, g_ell, g_var, g_nu.reshape(ctx.nu_shape), None, None, None, None
 
 
 def vector_field(x, Z, ell, var, nu, omega, phase, w):
-    """f(x) of one sampled GP function; differentiable in x, Z, ell, var, nu (forward only for D > 8)."""
+    """f(x) of one sampled GP function; differentiable in x, Z, ell, var, nu (D <= 8: register-resident kernels;
+    8 < D <= 64: tcgen05 forward + ``gpode_vf_bwd_large``)."""
     if Z.shape[1] > MAX_D_REGISTER:
-        return LargeField(Z, ell, var, nu, omega, phase, w)(x)
+        return _VectorFieldLarge.apply(x, Z, ell, var, nu, omega, phase, w)
     return _VectorField.apply(x, Z, ell, var, nu, omega, phase, w)
 
 
 def rk4_integrate(x0, t, Z, ell, var, nu, omega, phase, w):
     """Fixed-grid RK4 (3/8 rule) over the float32 grid ``t``; returns ``(len(t), B, D)`` like torchdiffeq."""
     if Z.shape[1] > MAX_D_REGISTER:
-        if torch.is_grad_enabled() and x0.requires_grad:
-            raise _lib.GpodeError("state dimension %d > %d: only the forward (no_grad) path exists for large D"
-                                  % (Z.shape[1], MAX_D_REGISTER))
-        return _rk4_large_d(x0, t, LargeField(Z, ell, var, nu, omega, phase, w))
+        return _RK4Large.apply(x0, f32(t.to(device=x0.device, dtype=torch.float32), "t"), Z, ell, var, nu, omega, phase,
+                               w, torch.is_grad_enabled())
     return _RK4.apply(x0, t, Z, ell, var, nu, omega, phase, w, torch.is_grad_enabled())
 
 

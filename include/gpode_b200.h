@@ -228,6 +228,32 @@ int64_t gpode_side_work_doubles(void);
 int gpode_constraint_sum(const float* ss, const float* pred, const float* scale, int64_t SN, int T, int D, int laplace,
                          double* sum_out, float* grad_ss, float* grad_pred, double* work, void* stream);
 
+/* Differentiable path for 8 < D <= GPODE_MAX_D_LARGE (autograd through src/core/dsvgp.py:172-197 at the upper sweep
+ * dimensions; round 1 was forward-only there). Everything is stream-ordered on the device -- no host loop reads a value.
+ *   gpode_pack_cache_large_bwd: Omega re-tiled per (output k, 64-feature chunk) with the input dimension contiguous, plus
+ *     w_kj = 0.5 log2(e)/ell_kj^2, Z and c_km = var_k nu_km, padded to DP = 16 / 32 / 64
+ *     (gpode_packed_large_bwd_floats(D,M,S) floats).
+ *   gpode_vf_bwd_large: grad_x = J(x)^T grad_f and the partial sums of every shared-parameter gradient, ADDED to the
+ *     calling launch's per-CTA rows of acc_large (gpode_acc_large_floats(D,M) floats, zeroed by the caller before the
+ *     first launch of a backward pass; all launches of one pass must use the same B). f = the forward value at x.
+ *   gpode_grads_finalize_large: rows -> grad_ell [D,D], grad_var [D], grad_Z [M,D], grad_nu [D,M] (float64, row order).
+ *   gpode_rk4_fwd_large_dev: torchdiffeq's 3/8-rule RK4 on the float32 device grid t[Tg] as a sequence of launches (the
+ *     tcgen05 vector-field kernels + element-wise stage kernels); xs [Tg,B,D], kstages [Tg-1,4,B,D] or NULL, tmp 2 B D
+ *     floats of scratch (6 B D when kstages is NULL).
+ *   gpode_rk4_bwd_large: its discrete adjoint (four gpode_vf_bwd_large launches per step); work: 7 B D floats. */
+int64_t gpode_packed_large_bwd_floats(int D, int M, int S);
+int64_t gpode_acc_large_floats(int D, int M);
+int gpode_pack_cache_large_bwd(const gpode_cache_t* cache, float* packed_bwd, void* stream);
+int gpode_vf_bwd_large(const float* packed_bwd, int D, int M, int S, const float* x, const float* f, const float* grad_f,
+                       float* grad_x, float* acc_large, int64_t B, void* stream);
+int gpode_grads_finalize_large(const gpode_cache_t* cache, const float* acc_large, int64_t B, float* grad_ell,
+                               float* grad_var, float* grad_Z, float* grad_nu, void* stream);
+int gpode_rk4_fwd_large_dev(const float* packed_large, const gpode_cache_t* cache, const float* x0, const float* t, int Tg,
+                            int64_t B, float* xs, float* kstages, float* tmp, void* stream);
+int gpode_rk4_bwd_large(const float* packed_bwd, const gpode_cache_t* cache, const float* t, int Tg, int64_t B,
+                        const float* xs, const float* kstages, const float* grad_xs, float* grad_x0, float* acc_large,
+                        float* work, void* stream);
+
 /* Fused multiple-shooting ELBO step. Every row (s, n, t) of the (S_mc, N, T) batch of
  * sampled states `ss` is integrated over ONE interval t2[0] -> t2[1] with the 3/8-rule RK4 step (as gpode_rk4_fwd with
  * Tg = 2) and the two ELBO terms that use the end point are evaluated inside the integrator kernel, on the end point

@@ -175,7 +175,7 @@ def test_rk4_forward(D, M, S, B, Tg, h):
 @pytest.mark.parametrize("D,M,S,B", [(16, 100, 256, 1000), (32, 40, 64, 77), (64, 100, 256, 300), (9, 10, 17, 5),
                                       (24, 7, 33, 64), (64, 150, 64, 130), (41, 30, 200, 257)])
 def test_large_state_dimension_forward(D, M, S, B):
-    """8 < D <= 64 (upper half of the scaling sweep): forward-only tiled kernels, same parity bars."""
+    """8 < D <= 64 (upper half of the scaling sweep): tensor-core forward kernels, same parity bars."""
     from gaussian_process_odes_b200 import ops, _lib
     gp32, c32, gp64, c64, x = _setup(D, M, S, B, seed=D, nu_scale=0.1)
     args = _cuda_args(gp32, c32)
@@ -194,9 +194,59 @@ def test_large_state_dimension_forward(D, M, S, B):
     assert relerr(xs_fma, xs) <= TOL_TRAJ
     ref32 = O.odeint(lambda t, y: O.vf_forward(y, gp32['Z'], gp32['ell'], gp32['var'], c32), x, ts, method='rk4')
     assert relerr(xs, ref32) <= TOL_TRAJ
-    xg = x.cuda().requires_grad_(True)
-    with pytest.raises(_lib.GpodeError):
-        ops.vector_field(xg, *args)
+
+
+@pytest.mark.parametrize("D,M,S,B", [(16, 100, 256, 1000), (32, 40, 64, 77), (64, 100, 256, 300), (9, 10, 17, 5),
+                                      (24, 7, 33, 200), (64, 30, 64, 130), (41, 30, 200, 257)])
+def test_large_state_dimension_backward(D, M, S, B):
+    """8 < D <= 64: gradients of the vector field and of a 2-step RK4 solve w.r.t. x, Z, lengthscales, variances and
+    nu (gpode_vf_bwd_large / gpode_rk4_bwd_large: device-side adjoint, no host loop) against autograd through the
+    oracle (reference src/core/dsvgp.py:124-137,172-197, kernels.py:53-99), float64-arbitrated."""
+    from gaussian_process_odes_b200 import ops
+    gp32, c32, gp64, c64, x = _setup(D, M, S, B, seed=D + 1, nu_scale=0.1)
+    cot = torch.tensor(np.random.default_rng(5).normal(size=(B, D)), dtype=torch.float32)
+
+    def cuda_grads(fn):
+        args = [a.detach().clone().requires_grad_(i < 4) for i, a in enumerate(_cuda_args(gp32, c32))]
+        xc = x.cuda().requires_grad_(True)
+        out = fn(xc, args)
+        return out, dict(x=xc.grad, Z=args[0].grad, ell=args[1].grad, var=args[2].grad, nu=args[3].grad), (xc, args)
+
+    # ---- vector field
+    args = [a.detach().clone().requires_grad_(i < 4) for i, a in enumerate(_cuda_args(gp32, c32))]
+    xc = x.cuda().requires_grad_(True)
+    ops.vector_field(xc, *args).backward(cot.cuda())
+    got = dict(x=xc.grad, Z=args[0].grad, ell=args[1].grad, var=args[2].grad, nu=args[3].grad)
+    fn = lambda l, cc: O.vf_forward(l['x'], l['Z'], l['ell'], l['var'], cc)
+    out, leaves = _grads_oracle(fn, gp32, c32, x, torch.float32)
+    out.backward(cot)
+    g64 = _lazy_f64_grads(fn, gp32, c32, x, cot)
+    for k in got:
+        assert_parity("large-D vf grad " + k, got[k].cpu().reshape(leaves[k].grad.shape), leaves[k].grad,
+                      lambda k=k: g64()[k], TOL_GRAD)
+    # ---- RK4, 2 steps
+    ts = _grid(3, 0.05, 3)
+    cot3 = torch.tensor(np.random.default_rng(6).normal(size=(3, B, D)), dtype=torch.float32)
+    args = [a.detach().clone().requires_grad_(i < 4) for i, a in enumerate(_cuda_args(gp32, c32))]
+    xc = x.cuda().requires_grad_(True)
+    xs = ops.rk4_integrate(xc, ts.cuda(), *args)
+    xs.backward(cot3.cuda())
+    got = dict(x=xc.grad, Z=args[0].grad, ell=args[1].grad, var=args[2].grad, nu=args[3].grad)
+    fn = lambda l, cc: O.odeint(lambda t, y: O.vf_forward(y, l['Z'], l['ell'], l['var'], cc), l['x'],
+                                ts.to(l['x'].dtype), method='rk4')
+    out, leaves = _grads_oracle(fn, gp32, c32, x, torch.float32)
+    assert relerr(xs.detach().cpu(), out.detach()) <= TOL_TRAJ
+    out.backward(cot3)
+    g64 = _lazy_f64_grads(fn, gp32, c32, x, cot3)
+    for k in got:
+        assert_parity("large-D rk4 grad " + k, got[k].cpu().reshape(leaves[k].grad.shape), leaves[k].grad,
+                      lambda k=k: g64()[k], TOL_GRAD)
+    # bitwise reproducible
+    args2 = [a.detach().clone().requires_grad_(i < 4) for i, a in enumerate(_cuda_args(gp32, c32))]
+    xc2 = x.cuda().requires_grad_(True)
+    ops.rk4_integrate(xc2, ts.cuda(), *args2).backward(cot3.cuda())
+    assert torch.equal(xc2.grad, xc.grad) and torch.equal(args2[0].grad, args[0].grad)
+    assert torch.equal(args2[1].grad, args[1].grad) and torch.equal(args2[3].grad, args[3].grad)
 
 
 @pytest.mark.parametrize("D,M,S,B", [(16, 100, 256, 300), (33, 20, 64, 40)])
