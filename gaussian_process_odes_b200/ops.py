@@ -697,97 +697,36 @@ class _Dopri5(torch.autograd.Function):
         return gx0, None, g_Z, g_ell, g_var, g_nu.reshape(ctx.nu_shape), None, None, None, None, None, None
 
 
-# Dormand-Prince 5(4) coefficients (Shampine's tableau, as torchdiffeq 0.2.0 uses them)
-_DP_BETA = ((1 / 5,), (3 / 40, 9 / 40), (44 / 45, -56 / 15, 32 / 9),
-            (19372 / 6561, -25360 / 2187, 64448 / 6561, -212 / 729),
-            (9017 / 3168, -355 / 33, 46732 / 5247, 49 / 176, -5103 / 18656),
-            (35 / 384, 0.0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84))
-_DP_CERR = (35 / 384 - 1951 / 21600, 0.0, 500 / 1113 - 22642 / 50085, 125 / 192 - 451 / 720,
-            -2187 / 6784 + 12231 / 42400, 11 / 84 - 649 / 6300, -1 / 60)
-_DP_CMID = tuple(0.5 * c for c in (6025192743 / 30085553152, 0.0, 51252292925 / 65400821598,
-                                   -2691868925 / 45128329728, 187940372067 / 1594534317056,
-                                   -1776094331 / 19743644256, 11237099 / 235043384))
-
-
 def _dopri5_large_d(x0, t, Z, ell, var, nu, omega, phase, w, rtol, atol, max_attempts=100000):
-    """dopri5 for 8 < D <= 64, forward only: the controller of torchdiffeq 0.2.0 (whole-batch RMS norm, float64 time,
-    Hairer initial step with order 4, safety 0.9 / growth <= 10 / shrink >= 0.2, quartic dense output) driven from the
-    host -- one synchronisation per attempt, like the reference -- around the tiled large-D vector-field kernel
-    (an evaluation costs milliseconds at these sizes, so the host round trip does not matter)."""
+    """dopri5 for 8 < D <= 64, forward only: torchdiffeq 0.2.0's controller (whole-batch RMS norm, float64 time, Hairer
+    initial step with order 4, safety 0.9 / growth <= 10 / shrink >= 0.2, quartic dense output) ON THE DEVICE --
+    ``gpode_dopri5_fwd_large``: one attempt = six evaluations on the tcgen05 vector-field kernels + element-wise stage /
+    error kernels + a one-CTA controller kernel, looped by a CUDA-graph WHILE node whose condition the controller sets.
+    The host enqueues one graph launch and reads nothing back (the reference synchronises once per attempt)."""
     tensors = (x0, Z, ell, var, nu)
     if torch.is_grad_enabled() and any(a.requires_grad for a in tensors):
-        raise _lib.GpodeError("state dimension %d > %d: only the forward (no_grad) path exists for large D"
+        raise _lib.GpodeError("state dimension %d > %d: dopri5 is forward-only there (rk4 is differentiable)"
                               % (Z.shape[1], MAX_D_REGISTER))
-    t64 = t.detach().to(torch.float64).cpu()
-    sign = -1.0 if (t64.numel() > 1 and t64[-1] < t64[0]) else 1.0
-    tt = (t64 * sign).tolist()
-
+    lib = _lib.load()
     field = LargeField(Z, ell, var, nu, omega, phase, w)
-
-    def f(y):
-        out = field(y.contiguous())
-        return out if sign > 0 else -out
-
-    rms = lambda v: float(v.pow(2).mean().sqrt())
-    y0 = f32(x0, "x0").clone()
-    f0 = f(y0)
-    nfe = 1
-    # initial step (misc._select_initial_step)
-    scale = atol + y0.abs() * rtol
-    d0, d1 = rms(y0 / scale), rms(f0 / scale)
-    h0 = 1e-6 if (d0 < 1e-5 or d1 < 1e-5) else 0.01 * d0 / d1
-    f1 = f(y0 + h0 * f0)
-    nfe += 1
-    d2 = rms((f1 - f0) / scale) / h0
-    h1 = max(1e-6, h0 * 1e-3) if (d1 <= 1e-15 and d2 <= 1e-15) else (0.01 / max(d1, d2)) ** 0.2
-    dt = min(100 * h0, h1)
-    out = [y0]
-    t1, j, n_acc, n_rej = tt[0], 1, 0, 0
-    while j < len(tt):
-        if not (tt[j] > t1):
-            j += 1
-            continue
-        if n_acc + n_rej >= max_attempts or not (t1 + dt > t1):
-            raise _lib.GpodeError("dopri5 failed: attempt limit or step-size underflow")
-        k = [f0]
-        for b in _DP_BETA:
-            yi = y0 + sum(kk * (bb * dt) for kk, bb in zip(k, b) if bb != 0.0)
-            k.append(f(yi))
-        nfe += 6
-        y1 = yi
-        err = sum(kk * (c * dt) for kk, c in zip(k, _DP_CERR) if c != 0.0)
-        tol = atol + rtol * torch.maximum(y0.abs(), y1.abs())
-        ratio = rms(err / tol)
-        if ratio <= 1.0:
-            t1n = t1 + dt
-            if j < len(tt) and not (tt[j] > t1n):
-                ymid = y0 + sum(kk * (c * dt) for kk, c in zip(k, _DP_CMID) if c != 0.0)
-                fa, fb = k[0], k[6]
-                ca = 2 * dt * (fb - fa) - 8 * (y1 + y0) + 16 * ymid
-                cb = dt * (5 * fa - 3 * fb) + 18 * y0 + 14 * y1 - 32 * ymid
-                cc = dt * (fb - 4 * fa) - 11 * y0 - 5 * y1 + 16 * ymid
-                cd = dt * fa
-                while j < len(tt) and not (tt[j] > t1n):
-                    xq = (tt[j] - t1) / (t1n - t1)
-                    out.append(y0 + xq * cd + xq ** 2 * cc + xq ** 3 * cb + xq ** 4 * ca)
-                    j += 1
-            y0, f0, t1 = y1, k[6], t1n
-            n_acc += 1
-        else:
-            n_rej += 1
-        if ratio == 0.0:
-            dt *= 10.0
-        else:
-            dt *= min(10.0, max(0.9 / ratio ** 0.2, 1.0 if ratio < 1.0 else 0.2))
-    stats = torch.tensor([nfe, n_acc, n_rej, 0], dtype=torch.int32, device=y0.device)
-    return torch.stack(out, 0), stats
+    xc = f32(x0, "x0")
+    if xc.ndim != 2 or xc.shape[1] != field.D:
+        raise _lib.GpodeError("x0 must be (B,%d), got %s" % (field.D, tuple(xc.shape)))
+    B, Tg = xc.shape[0], t.shape[0]
+    t64 = t.detach().to(device=xc.device, dtype=torch.float64).contiguous()
+    xs = torch.empty(Tg, B, field.D, dtype=torch.float32, device=xc.device)
+    work = torch.empty(lib.gpode_dopri5_large_work_floats(field.D, B), dtype=torch.float32, device=xc.device)
+    stats = torch.zeros(4, dtype=torch.int32, device=xc.device)
+    _lib.call("gpode_dopri5_fwd_large", ptr(field.packed), ctypes.byref(field.struct), ptr(xc), ptr(t64), Tg, B,
+              float(rtol), float(atol), ptr(xs), ptr(work), ptr(stats), int(max_attempts), stream_ptr())
+    return xs, stats
 
 
 def dopri5_integrate(x0, t, Z, ell, var, nu, omega, phase, w, rtol=1e-6, atol=1e-6):
     """Adaptive dopri5 with torchdiffeq 0.2.0's controller in one cooperative kernel. Returns ``(xs (len(t),B,D),
     stats)`` with ``stats`` a device int32 tensor [nfe, accepted, rejected, status]. Differentiable in x0, Z, ell,
     var, nu through the discrete adjoint of the accepted steps (step sizes are constants, as in torchdiffeq).
-    For 8 < D <= 64 (forward only) the same controller runs on the host around the tiled vector-field kernel."""
+    For 8 < D <= 64 (forward only) the same controller runs on the device inside a CUDA-graph while loop."""
     if Z.shape[1] > MAX_D_REGISTER:
         return _dopri5_large_d(x0, t, Z, ell, var, nu, omega, phase, w, rtol, atol)
     return _Dopri5.apply(x0, t, Z, ell, var, nu, omega, phase, w, rtol, atol, torch.is_grad_enabled())

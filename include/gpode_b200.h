@@ -254,6 +254,18 @@ int gpode_rk4_bwd_large(const float* packed_bwd, const gpode_cache_t* cache, con
                         const float* xs, const float* kstages, const float* grad_xs, float* grad_x0, float* acc_large,
                         float* work, void* stream);
 
+/* Adaptive dopri5 for 8 < D <= GPODE_MAX_D_LARGE, forward only, controller on the device: torchdiffeq 0.2.0's
+ * odeint(method='dopri5') as called from Flow.forward (src/core/flow.py:84-90). One attempt (six tcgen05 vector-field
+ * evaluations, stage / error kernels, a one-CTA controller kernel, an accept kernel) is the body of a CUDA-graph WHILE
+ * node; the controller sets the loop condition, so the host enqueues one graph launch and never synchronises (the
+ * reference does once per attempt). t: float64 device grid (increasing or decreasing); xs [Tg,B,D]; stats_out (device,
+ * 4 int32): nfe, accepted, rejected, status (0 ok, 1 attempt limit, 2 dt underflow); work:
+ * gpode_dopri5_large_work_floats(D,B) floats. Cannot be called inside a stream capture (it builds its own graph). */
+int64_t gpode_dopri5_large_work_floats(int D, int64_t B);
+int gpode_dopri5_fwd_large(const float* packed_large, const gpode_cache_t* cache, const float* x0, const double* t, int Tg,
+                           int64_t B, double rtol, double atol, float* xs, float* work, int32_t* stats_out,
+                           int max_attempts, void* stream);
+
 /* Fused multiple-shooting ELBO step. Every row (s, n, t) of the (S_mc, N, T) batch of
  * sampled states `ss` is integrated over ONE interval t2[0] -> t2[1] with the 3/8-rule RK4 step (as gpode_rk4_fwd with
  * Tg = 2) and the two ELBO terms that use the end point are evaluated inside the integrator kernel, on the end point

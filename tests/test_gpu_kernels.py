@@ -251,7 +251,8 @@ def test_large_state_dimension_backward(D, M, S, B):
 
 @pytest.mark.parametrize("D,M,S,B", [(16, 100, 256, 300), (33, 20, 64, 40)])
 def test_large_state_dimension_dopri5(D, M, S, B):
-    """8 < D <= 64: the adaptive solver (host-driven controller around the tiled kernel) against the restated dopri5."""
+    """8 < D <= 64: the adaptive solver (device-side controller inside a CUDA-graph while loop around the tensor-core
+    vector field, gpode_dopri5_fwd_large) against the restated dopri5; repeated calls are bitwise equal."""
     from gaussian_process_odes_b200 import ops
     gp32, c32, gp64, c64, x = _setup(D, M, S, B, seed=D, nu_scale=0.1)
     args = _cuda_args(gp32, c32)
