@@ -29,7 +29,7 @@ int gpode_vf_large_eval(const float* packed_large, const gpode_cache_t* c, const
 namespace {
 
 constexpr int kLbRows = 128, kLbThreads = 128, kLbSC = 64;  // tile rows, threads, features per staged Omega chunk
-constexpr int kLbMaxCtas = 148 * 2;
+constexpr int kLbMaxCtas = 148 * 4;
 
 __host__ __device__ inline int lb_dp(int D) { return D <= 16 ? 16 : (D <= 32 ? 32 : 64); }
 
@@ -94,7 +94,7 @@ struct LbSmem {
 };
 
 template <int DP>
-__global__ void __launch_bounds__(kLbThreads, 1)
+__global__ void __launch_bounds__(kLbThreads, DP >= 64 ? 1 : 2)
 vjp_large_kernel(const float* __restrict__ pk, const LbLayout L, const float* __restrict__ x,
                  const float* __restrict__ f, const float* __restrict__ kb, float* __restrict__ gx, const int64_t B,
                  float* __restrict__ accA, float* __restrict__ accT, float* __restrict__ accZ) {
@@ -152,12 +152,18 @@ vjp_large_kernel(const float* __restrict__ pk, const LbLayout L, const float* __
             gpode_bulk_g2s(obuf[it & 1], om_g, kChunkBytes, mbar + (it & 1));
         }
         __syncthreads();
-        float xr[DP];
+        // At DP = 64 the state row stays in shared memory (one extra LDS.128 per four input dimensions): x, G and the
+        // four feature chains together exceed the register file (ptxas: 4 KB of spills, 140 ms per 1e5-row VJP).
+        constexpr bool kXReg = DP < 64;
+        float xr[kXReg ? DP : 4];
+        const float* __restrict__ xrow = xs + tid * LD;
         float* __restrict__ xbr = xbs + tid * LD;   // this row's cotangent (only its own thread touches it)
 #pragma unroll
         for (int j4 = 0; j4 < DP / 4; ++j4) {
-            const float4 v = *reinterpret_cast<const float4*>(xs + tid * LD + 4 * j4);
-            xr[4 * j4] = v.x; xr[4 * j4 + 1] = v.y; xr[4 * j4 + 2] = v.z; xr[4 * j4 + 3] = v.w;
+            if constexpr (kXReg) {
+                const float4 v = *reinterpret_cast<const float4*>(xrow + 4 * j4);
+                xr[4 * j4] = v.x; xr[4 * j4 + 1] = v.y; xr[4 * j4 + 2] = v.z; xr[4 * j4 + 3] = v.w;
+            }
             *reinterpret_cast<float4*>(xbr + 4 * j4) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         // variance partial sum, first half: V1[k] += sum_rows kb_k f_k
@@ -199,14 +205,17 @@ vjp_large_kernel(const float* __restrict__ pk, const LbLayout L, const float* __
                         const float4 o1 = *reinterpret_cast<const float4*>(o + DP + 4 * j4);
                         const float4 o2 = *reinterpret_cast<const float4*>(o + 2 * DP + 4 * j4);
                         const float4 o3 = *reinterpret_cast<const float4*>(o + 3 * DP + 4 * j4);
-                        th0 = fmaf(xr[4 * j4], o0.x, th0); th1 = fmaf(xr[4 * j4], o1.x, th1);
-                        th2 = fmaf(xr[4 * j4], o2.x, th2); th3 = fmaf(xr[4 * j4], o3.x, th3);
-                        th0 = fmaf(xr[4 * j4 + 1], o0.y, th0); th1 = fmaf(xr[4 * j4 + 1], o1.y, th1);
-                        th2 = fmaf(xr[4 * j4 + 1], o2.y, th2); th3 = fmaf(xr[4 * j4 + 1], o3.y, th3);
-                        th0 = fmaf(xr[4 * j4 + 2], o0.z, th0); th1 = fmaf(xr[4 * j4 + 2], o1.z, th1);
-                        th2 = fmaf(xr[4 * j4 + 2], o2.z, th2); th3 = fmaf(xr[4 * j4 + 2], o3.z, th3);
-                        th0 = fmaf(xr[4 * j4 + 3], o0.w, th0); th1 = fmaf(xr[4 * j4 + 3], o1.w, th1);
-                        th2 = fmaf(xr[4 * j4 + 3], o2.w, th2); th3 = fmaf(xr[4 * j4 + 3], o3.w, th3);
+                        float4 xv;
+                        if constexpr (kXReg) xv = make_float4(xr[4 * j4], xr[4 * j4 + 1], xr[4 * j4 + 2], xr[4 * j4 + 3]);
+                        else xv = *reinterpret_cast<const float4*>(xrow + 4 * j4);
+                        th0 = fmaf(xv.x, o0.x, th0); th1 = fmaf(xv.x, o1.x, th1);
+                        th2 = fmaf(xv.x, o2.x, th2); th3 = fmaf(xv.x, o3.x, th3);
+                        th0 = fmaf(xv.y, o0.y, th0); th1 = fmaf(xv.y, o1.y, th1);
+                        th2 = fmaf(xv.y, o2.y, th2); th3 = fmaf(xv.y, o3.y, th3);
+                        th0 = fmaf(xv.z, o0.z, th0); th1 = fmaf(xv.z, o1.z, th1);
+                        th2 = fmaf(xv.z, o2.z, th2); th3 = fmaf(xv.z, o3.z, th3);
+                        th0 = fmaf(xv.w, o0.w, th0); th1 = fmaf(xv.w, o1.w, th1);
+                        th2 = fmaf(xv.w, o2.w, th2); th3 = fmaf(xv.w, o3.w, th3);
                     }
                     const float g0 = a4.x * __sinf(th0), g1 = a4.y * __sinf(th1), g2 = a4.z * __sinf(th2),
                                 g3 = a4.w * __sinf(th3);
@@ -230,7 +239,7 @@ vjp_large_kernel(const float* __restrict__ pk, const LbLayout L, const float* __
             for (int j = 0; j < DP; ++j) {
                 const float gj = nkb * G[j];
                 xbr[j] += gj;
-                const float v = gpode_warp_sum(xr[j] * gj);
+                const float v = gpode_warp_sum((kXReg ? xr[j < (kXReg ? DP : 4) ? j : 0] : xrow[j]) * gj);
                 if (lane == 0) red[warp * DP + j] = v;
             }
             __syncthreads();
@@ -427,12 +436,28 @@ int lb_check(const gpode_cache_t* c) {
     return 0;
 }
 
-int lb_grid(int64_t B) {
+// persistent grid: SMs x resident CTAs of the VJP kernel for this DP (the accumulator rows are per CTA: every launch
+// of one backward pass and the finalize kernel must agree on this number)
+int lb_grid(int64_t B, int DP) {
+    static int occ_cache[3] = {0, 0, 0};
     int sms = 148, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int slot = DP == 16 ? 0 : (DP == 32 ? 1 : 2);
+    if (occ_cache[slot] == 0) {
+        int occ = 1;
+        if (DP == 16) {
+            cudaFuncSetAttribute(vjp_large_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LbSmem<16>::bytes);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, vjp_large_kernel<16>, kLbThreads, LbSmem<16>::bytes);
+        } else if (DP == 32) {
+            cudaFuncSetAttribute(vjp_large_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LbSmem<32>::bytes);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, vjp_large_kernel<32>, kLbThreads, LbSmem<32>::bytes);
+        }
+        occ_cache[slot] = occ < 1 ? 1 : (occ > 4 ? 4 : occ);
+    }
     const int64_t tiles = (B + kLbRows - 1) / kLbRows;
-    int64_t g = tiles < sms ? tiles : sms;
+    int64_t g = (int64_t)sms * occ_cache[slot];
+    if (g > tiles) g = tiles;
     if (g > kLbMaxCtas) g = kLbMaxCtas;
     return (int)(g < 1 ? 1 : g);
 }
@@ -445,7 +470,7 @@ int launch_vjp(const float* pk, const LbLayout& L, const float* x, const float* 
     float* accA = acc;
     float* accT = accA + (size_t)kLbMaxCtas * (DP * DP + DP);
     float* accZ = accT + (size_t)kLbMaxCtas * L.D * L.M;
-    vjp_large_kernel<DP><<<lb_grid(B), kLbThreads, smem, st>>>(pk, L, x, f, kb, gx, B, accA, accT, accZ);
+    vjp_large_kernel<DP><<<lb_grid(B, DP), kLbThreads, smem, st>>>(pk, L, x, f, kb, gx, B, accA, accT, accZ);
     GPODE_LAUNCH_CHECK();
     return 0;
 }
@@ -504,7 +529,7 @@ extern "C" int gpode_grads_finalize_large(const gpode_cache_t* c, const float* a
     const float* accZ = accT + (size_t)kLbMaxCtas * D * M;
     const int n_out = D * D + D + 2 * D * M;
     finalize_large_kernel<<<(n_out + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-        D, DP, M, lb_grid(B), accA, accT, accZ, c->nu, c->ell, c->var, grad_ell, grad_var, grad_Z, grad_nu);
+        D, DP, M, lb_grid(B, DP), accA, accT, accZ, c->nu, c->ell, c->var, grad_ell, grad_var, grad_Z, grad_nu);
     GPODE_LAUNCH_CHECK();
     return 0;
 }
