@@ -225,29 +225,37 @@ __global__ void whiten_bwd_kernel(const gpode_cache_t c, const float* __restrict
         P[m * ld + n] = v;
     }
     __syncthreads();
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, ny = blockDim.x >> 5;
-    // Y = L^-T P  (rows from the bottom; right-looking elimination of the rows above)
-    for (int i = M - 1; i >= 0; --i) {
-        const Real inv = (Real)1 / L[i * ld + i];
-        for (int n = threadIdx.x; n < M; n += blockDim.x) P[i * ld + n] *= inv;
-        __syncthreads();
-        for (int r = ty; r < i; r += ny) {
-            const Real lir = L[i * ld + r];
-            for (int n = tx; n < M; n += 32) P[r * ld + n] -= lir * P[i * ld + n];
+    // Y = L^-T P, then X = Y L^-1: 2 M independent triangular solves -- every COLUMN of P in the first pass, every ROW
+    // in the second -- each done by one thread from start to end, so neither pass needs a single barrier (round 1
+    // eliminated row by row with the whole CTA: ~4 M barriers, which was most of this kernel's 0.4 ms at M = 100).
+    // All threads read the same L entry at the same time (shared-memory broadcast); the leading dimension is odd, so
+    // the per-thread columns / rows of P sit in different banks.
+    for (int n = threadIdx.x; n < M; n += blockDim.x) {          // column n:  L^T y = p  (back substitution)
+        for (int i = M - 1; i >= 0; --i) {
+            Real a0 = P[i * ld + n], a1 = (Real)0;
+            int r = i + 1;
+            for (; r + 1 < M; r += 2) {
+                a0 -= L[r * ld + i] * P[r * ld + n];
+                a1 -= L[(r + 1) * ld + i] * P[(r + 1) * ld + n];
+            }
+            if (r < M) a0 -= L[r * ld + i] * P[r * ld + n];
+            P[i * ld + n] = (a0 + a1) / L[i * ld + i];
         }
-        __syncthreads();
     }
-    // X = Y L^-1  (columns from the right)
-    for (int cidx = M - 1; cidx >= 0; --cidx) {
-        const Real inv = (Real)1 / L[cidx * ld + cidx];
-        for (int r = threadIdx.x; r < M; r += blockDim.x) P[r * ld + cidx] *= inv;
-        __syncthreads();
-        for (int r = ty; r < M; r += ny) {
-            const Real xrc = P[r * ld + cidx];
-            for (int n = tx; n < cidx; n += 32) P[r * ld + n] -= xrc * L[cidx * ld + n];
+    __syncthreads();
+    for (int r = threadIdx.x; r < M; r += blockDim.x) {          // row r:  x L = y  (from the last column down)
+        for (int cidx = M - 1; cidx >= 0; --cidx) {
+            Real a0 = P[r * ld + cidx], a1 = (Real)0;
+            int q = cidx + 1;
+            for (; q + 1 < M; q += 2) {
+                a0 -= P[r * ld + q] * L[q * ld + cidx];
+                a1 -= P[r * ld + q + 1] * L[(q + 1) * ld + cidx];
+            }
+            if (q < M) a0 -= P[r * ld + q] * L[q * ld + cidx];
+            P[r * ld + cidx] = (a0 + a1) / L[cidx * ld + cidx];
         }
-        __syncthreads();
     }
+    __syncthreads();
     // No floating-point atomics below: every sum is taken in a fixed order, so repeated calls are bitwise identical.
     // RBF backward with Kb = (X + X^T)/2: thread = (inducing point m, slice of the partner points n)
     double gvar = 0.0;           // this thread's share of the variance / lengthscale gradients (both parts)
