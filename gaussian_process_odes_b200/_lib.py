@@ -58,6 +58,8 @@ SIGNATURES = {
     "gpode_loglik_sum": (_I, [_P, _P, _P, _P, _P, _I, _L, _I, _I, _P, _P, _P, _P, _P]),
     "gpode_constraint_sum": (_I, [_P, _P, _P, _L, _I, _I, _I, _P, _P, _P, _P, _P]),
     "gpode_side_work_doubles": (_L, []),
+    "gpode_set_option": (_I, [ctypes.c_char_p, _I]),
+    "gpode_get_option": (_I, [ctypes.c_char_p]),
     "gpode_shoot_work_doubles": (_L, []),
     "gpode_packed_large_bwd_floats": (_L, [_I, _I, _I]),
     "gpode_acc_large_floats": (_L, [_I, _I]),
@@ -114,6 +116,15 @@ def load():
         raise GpodeError("libgpode_b200.so ABI version %d, expected 1" % lib.gpode_abi_version())
     _lib = lib
     return lib
+
+
+def set_option(name, value):
+    """Process-wide kernel-selection option (``gpode_set_option``): bwd_mma, fwd_mma, mma_parts, force_narrow, use_mma."""
+    check(load().gpode_set_option(name.encode(), int(value)))
+
+
+def get_option(name):
+    return load().gpode_get_option(name.encode())
 
 
 def check(rc):

@@ -994,7 +994,7 @@ inline int warp_shape_for(K kernel, int64_t B, size_t smem, LaunchShape* out) {
 
 template <int D, int R>
 inline bool use_wide(int64_t B) {
-    static const bool force_narrow = getenv("GPODE_FORCE_NARROW") != nullptr;  // tuning knob: one row per thread
+    const bool force_narrow = gpode_option(GPODE_OPT_FORCE_NARROW) != 0;  // tuning knob: one row per thread
     return !force_narrow && R > 1 && B >= (int64_t)num_sms() * 2 * kThreads * R;
 }
 
@@ -1004,13 +1004,11 @@ inline bool use_wide(int64_t B) {
 template <int D>
 constexpr bool kMmaBwd = (D >= 4 && D <= GPODE_MMAH_MAX_D);  // D = 3: measured slower than FFMA2 (1.77 vs 1.56 ms)
 inline bool use_mma_bwd(int64_t B) {
-    const char* e = getenv("GPODE_BWD_MMA");  // read per call: the parity tests run both adjoints in one process
-    if (e != nullptr && e[0] == '0') return false;
+    if (gpode_option(GPODE_OPT_BWD_MMA) == 0) return false;  // the parity tests run both adjoints in one process
     return B >= (int64_t)num_sms() * kHThreads;
 }
 inline bool use_mma_fwd(int64_t B) {
-    const char* e = getenv("GPODE_FWD_MMA");  // =0 keeps the FFMA2 forward kernels
-    if (e != nullptr && e[0] == '0') return false;
+    if (gpode_option(GPODE_OPT_FWD_MMA) == 0) return false;  // 0 keeps the FFMA2 forward kernels
     return B >= (int64_t)num_sms() * kHFThreads;
 }
 template <int D>
@@ -1019,8 +1017,7 @@ inline HParams h_params(const GpodeLayout& L) {
     p.M = L.M; p.S8P = L.S8P;
     p.off_kern = L.off_kern; p.n_small = L.total - L.off_kern;
     p.off_mmah = L.off_mmag; p.n_mmah = D * L.S8P * GPODE_MMAH_REC;
-    const char* e = getenv("GPODE_MMA_PARTS");
-    p.parts = e ? atoi(e) : 3;
+    p.parts = gpode_option(GPODE_OPT_MMA_PARTS);
     return p;
 }
 template <int D>
@@ -1046,7 +1043,7 @@ int launch_vf_fwd(const float* packed, int M, int S, const float* x, float* f, i
     const size_t smem = 16 + (size_t)L.total * 4;
     LaunchShape ls;
     constexpr int RW = RowsFwd<D>::value;
-    static const bool use_mma = getenv("GPODE_USE_MMA") != nullptr;
+    const bool use_mma = gpode_option(GPODE_OPT_USE_MMA) != 0;
     if constexpr (kMmaBwd<D>) {
         const HParams hp = h_params<D>(L);
         const size_t hs = h_smem<D>(hp, false, kHFWarps);

@@ -178,3 +178,46 @@ extern "C" int gpode_pack_cache(const gpode_cache_t* c, float* packed, void* str
 extern "C" int gpode_pack_cache_sets(const gpode_cache_t* c, int n_sets, float* packed, void* stream) {
     return pack_sets(c, n_sets, packed, stream);
 }
+
+// ---- process-wide kernel-selection options (see common.cuh) ---------------------------------------------------------
+#include <atomic>
+#include <mutex>
+#include <stdlib.h>
+#include <string.h>
+namespace {
+std::atomic<int> g_opt[GPODE_OPT_COUNT];
+std::once_flag g_opt_once;
+const char* const kOptNames[GPODE_OPT_COUNT] = {"bwd_mma", "fwd_mma", "mma_parts", "force_narrow", "use_mma"};
+void opt_init() {
+    auto env_int = [](const char* n, int dflt) {
+        const char* e = getenv(n);
+        return e ? atoi(e) : dflt;
+    };
+    g_opt[GPODE_OPT_BWD_MMA] = env_int("GPODE_BWD_MMA", 1);
+    g_opt[GPODE_OPT_FWD_MMA] = env_int("GPODE_FWD_MMA", 1);
+    g_opt[GPODE_OPT_MMA_PARTS] = env_int("GPODE_MMA_PARTS", 3);
+    g_opt[GPODE_OPT_FORCE_NARROW] = getenv("GPODE_FORCE_NARROW") != nullptr;
+    g_opt[GPODE_OPT_USE_MMA] = getenv("GPODE_USE_MMA") != nullptr;
+}
+}  // namespace
+int gpode_option(int which) {
+    std::call_once(g_opt_once, opt_init);
+    return g_opt[which].load(std::memory_order_relaxed);
+}
+extern "C" int gpode_set_option(const char* name, int value) {
+    std::call_once(g_opt_once, opt_init);
+    GPODE_CHECK_ARG(name != nullptr, "option name is NULL");
+    for (int i = 0; i < GPODE_OPT_COUNT; ++i)
+        if (strcmp(name, kOptNames[i]) == 0) {
+            g_opt[i].store(value, std::memory_order_relaxed);
+            return 0;
+        }
+    gpode_set_error("unknown option %s (bwd_mma, fwd_mma, mma_parts, force_narrow, use_mma)", name);
+    return -1;
+}
+extern "C" int gpode_get_option(const char* name) {
+    if (name == nullptr) return -1;
+    for (int i = 0; i < GPODE_OPT_COUNT; ++i)
+        if (strcmp(name, kOptNames[i]) == 0) return gpode_option(i);
+    return -1;
+}

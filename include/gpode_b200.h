@@ -300,6 +300,16 @@ int gpode_shoot_bwd(const float* packed, int D, int M, int S, const gpode_shoot_
                     const float* kstages, const float* seeds, const float* g_ll, const float* g_cons, float* grad_ss,
                     float* vrows, float* acc, void* stream);
 
+/* Kernel-selection options (tuning / ablation; the library's only process-wide mutable state). Defaults are read from
+ * the environment once (GPODE_BWD_MMA, GPODE_FWD_MMA, GPODE_MMA_PARTS, GPODE_FORCE_NARROW, GPODE_USE_MMA); names:
+ *   "bwd_mma" / "fwd_mma" (1): tensor-core adjoint / forward at D = 4, 5 and B >= SMs x 384 rows; 0 = FFMA2 kernels.
+ *       Domain of the split-fp16 operands: |x_j|, |Omega| < 65504 -- beyond it the kernels return NaN (fp16 overflow),
+ *       never silently wrong numbers; a float32 angle of that size carries no phase information anyway.
+ *   "mma_parts" (3): ablation mask of the tensor-core adjoint (anything else gives wrong gradients; timing only)
+ *   "force_narrow" (0): FFMA2 kernels with one row per thread;  "use_mma" (0): the 3xTF32 forward experiment. */
+int gpode_set_option(const char* name, int value);
+int gpode_get_option(const char* name);
+
 /* EXPERIMENTAL (2 <= D <= 7): gpode_vf_fwd with the Fourier-feature projection on the 5th-generation tensor cores
  * (tcgen05.mma kind::tf32, 3xTF32 error compensation, accumulators in TMEM); same arguments and results. */
 int gpode_vf_fwd_umma(const float* packed, int D, int M, int S, const float* x, float* f, int64_t B, void* stream);

@@ -389,22 +389,26 @@ def test_errors_are_loud():
 def test_rk4_backward_tensor_core_adjoint(D, M, S, B, monkeypatch):
     """D = 4, 5 and a batch that fills the machine: the adjoint's two Fourier projections run as split-fp16 mma.sync
     (csrc/vjp_mma.cuh). Checked against the oracle's autograd and against the FFMA2 adjoint (GPODE_BWD_MMA=0)."""
-    from gaussian_process_odes_b200 import ops
+    from gaussian_process_odes_b200 import ops, _lib
     gp32, c32, gp64, c64, x = _setup(D, M, S, B, seed=D + B, nu_scale=0.3)
     Tg = 3
     ts = _grid(Tg, 0.1, Tg)
     cot = torch.tensor(np.random.default_rng(9).normal(size=(Tg, B, D)), dtype=torch.float32)
 
     def run(mode):
-        monkeypatch.setenv("GPODE_BWD_MMA", mode)
-        monkeypatch.setenv("GPODE_FWD_MMA", mode)
+        _lib.set_option("bwd_mma", int(mode))
+        _lib.set_option("fwd_mma", int(mode))
         args = [a.detach().clone().requires_grad_(i < 4) for i, a in enumerate(_cuda_args(gp32, c32))]
         xc = x.cuda().requires_grad_(True)
         xs = ops.rk4_integrate(xc, ts.cuda(), *args)
         xs.backward(cot.cuda())
         return dict(x=xc.grad, Z=args[0].grad, ell=args[1].grad, var=args[2].grad, nu=args[3].grad)
 
-    got, base = run("1"), run("0")
+    try:
+        got, base = run("1"), run("0")
+    finally:
+        _lib.set_option("bwd_mma", 1)
+        _lib.set_option("fwd_mma", 1)
     out, leaves = _grads_oracle(
         lambda l, cc: O.odeint(lambda t, y: O.vf_forward(y, l['Z'], l['ell'], l['var'], cc), l['x'],
                                ts.to(l['x'].dtype), method='rk4'), gp32, c32, x, torch.float32)
@@ -420,18 +424,22 @@ def test_rk4_backward_tensor_core_adjoint(D, M, S, B, monkeypatch):
 
 @pytest.mark.parametrize("D,M,S,B", [(5, 100, 256, 58000), (4, 16, 40, 57011)])
 def test_vf_backward_tensor_core_adjoint(D, M, S, B, monkeypatch):
-    from gaussian_process_odes_b200 import ops
+    from gaussian_process_odes_b200 import ops, _lib
     gp32, c32, gp64, c64, x = _setup(D, M, S, B, seed=D * 7 + B, nu_scale=0.3)
     cot = torch.tensor(np.random.default_rng(5).normal(size=(B, D)), dtype=torch.float32)
 
     def run(mode):
-        monkeypatch.setenv("GPODE_BWD_MMA", mode)
+        _lib.set_option("bwd_mma", int(mode))
         args = [a.detach().clone().requires_grad_(i < 4) for i, a in enumerate(_cuda_args(gp32, c32))]
         xc = x.cuda().requires_grad_(True)
         ops.vector_field(xc, *args).backward(cot.cuda())
         return dict(x=xc.grad, Z=args[0].grad, ell=args[1].grad, var=args[2].grad, nu=args[3].grad)
 
-    got, base = run("1"), run("0")
+    try:
+        got, base = run("1"), run("0")
+    finally:
+        _lib.set_option("bwd_mma", 1)
+        _lib.set_option("fwd_mma", 1)
     out, leaves = _grads_oracle(lambda l, cc: O.vf_forward(l['x'], l['Z'], l['ell'], l['var'], cc), gp32, c32, x,
                                 torch.float32)
     out.backward(cot)
@@ -447,19 +455,29 @@ def test_forward_tensor_core_path(D, M, S, B, monkeypatch):
     """D = 4, 5 and a batch that fills the machine: theta = x Omega of the forward pass as split-fp16 mma.sync
     (vf_eval_h). Vector field and a 3-step RK4 trajectory against the oracle and against the FFMA2 kernels
     (GPODE_FWD_MMA=0)."""
-    from gaussian_process_odes_b200 import ops
+    from gaussian_process_odes_b200 import ops, _lib
     gp32, c32, gp64, c64, x = _setup(D, M, S, B, seed=D + B, nu_scale=0.3)
     ts = _grid(4, 0.1, 4)
 
     def run(mode):
-        monkeypatch.setenv("GPODE_FWD_MMA", mode)
+        _lib.set_option("fwd_mma", int(mode))
         with torch.no_grad():
             args = _cuda_args(gp32, c32)
             return ops.vector_field(x.cuda(), *args).cpu(), ops.rk4_integrate(x.cuda(), ts.cuda(), *args).cpu()
 
-    (f1, xs1), (f0, xs0) = run("1"), run("0")
+    try:
+        (f1, xs1), (f0, xs0) = run("1"), run("0")
+    finally:
+        _lib.set_option("fwd_mma", 1)
     f32 = O.vf_forward(x, gp32['Z'], gp32['ell'], gp32['var'], c32)
     out = O.odeint(lambda t, y: O.vf_forward(y, gp32['Z'], gp32['ell'], gp32['var'], c32), x, ts, method='rk4')
     assert relerr(f1, f0) <= TOL_VF and relerr(f1, f32) <= TOL_VF
     assert relerr(xs1, xs0) <= TOL_TRAJ and relerr(xs1, out) <= TOL_TRAJ
     assert torch.equal(xs1[0], x)
+    # outside the split-fp16 domain (|x| >= 65504) the tensor-core kernels answer NaN, never a wrong finite number
+    if D == 5 and B == 60000:
+        xbad = x.clone()
+        xbad[7, 2] = 1.0e5
+        with torch.no_grad():
+            fbad = ops.vector_field(xbad.cuda(), *_cuda_args(gp32, c32)).cpu()
+        assert torch.isnan(fbad[7]).any() and torch.isfinite(fbad[:7]).all() and torch.isfinite(fbad[8:]).all()

@@ -12,7 +12,7 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 import gpode_oracle as O  # noqa: E402
-from gaussian_process_odes_b200 import ops  # noqa: E402
+from gaussian_process_odes_b200 import ops, _lib  # noqa: E402
 
 shapes = [(5, 100), (4, 100), (7, 100), (3, 24), (6, 100)] if len(sys.argv) < 2 else [(int(sys.argv[1]), int(sys.argv[2]))]
 B = int(os.environ.get("TB_ROWS", 1000000))
@@ -29,7 +29,7 @@ for D, M in shapes:
     tg = torch.tensor([0.0, 0.01], device="cuda")
     out = {}
     for mode in ("0", "1"):
-        os.environ["GPODE_BWD_MMA"] = mode
+        _lib.set_option("bwd_mma", int(mode))
         args = [a.detach().clone().requires_grad_(i < 4) for i, a in enumerate(base)]
         xc = x.clone().requires_grad_(True)
         xs = ops.rk4_integrate(xc, tg, *args)

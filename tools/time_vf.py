@@ -11,7 +11,7 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 import gpode_oracle as O  # noqa: E402
-from gaussian_process_odes_b200 import ops  # noqa: E402
+from gaussian_process_odes_b200 import ops, _lib  # noqa: E402
 
 shapes = [(5, 100), (2, 16), (8, 100), (4, 100)] if len(sys.argv) < 2 else [(int(sys.argv[1]), int(sys.argv[2]))]
 for D, M in shapes:
@@ -25,7 +25,7 @@ for D, M in shapes:
     B = 1000000
     x = torch.randn(B, D, device="cuda")
     for fmode in ("0", "1"):
-        os.environ["GPODE_FWD_MMA"] = fmode
+        _lib.set_option("fwd_mma", int(fmode))
         tg = torch.tensor([0.0, 0.01], device="cuda")
         with torch.no_grad():
             for _ in range(3):

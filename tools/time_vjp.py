@@ -29,8 +29,8 @@ gx = torch.empty_like(x)
 ptr = ops.ptr
 VARIANTS = [v.split(":") for v in os.environ.get("TV_VARIANTS", "0:3,1:3,1:1,1:2,1:0").split(",")]
 for mode, parts in VARIANTS:
-    os.environ["GPODE_BWD_MMA"] = mode
-    os.environ["GPODE_MMA_PARTS"] = parts
+    _lib.set_option("bwd_mma", int(mode))
+    _lib.set_option("mma_parts", int(parts))
     acc = pc.new_acc()
     def run():
         _lib.call("gpode_vf_bwd", ptr(pc.packed), pc.D, pc.M, pc.S, ptr(x), ptr(f), ptr(gf), ptr(gx), ptr(acc),
