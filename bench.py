@@ -286,10 +286,36 @@ def run_ours(args):
     rows_total = w["S_mc"] * N_glob * T
     evals_per_step = rows_total * 4
 
-    def step(ys):
+    def eager_step(ys):
         model.zero_grad(set_to_none=True)
         loss = distributed.sharded_shooting_loss(model, ys, ts_dev, w["S_mc"], N_glob, world)
         loss.backward()
+        distributed.allreduce_shared_grads(model)
+        return loss
+
+    # The step is ~110 launches, and the host needs about as long to issue them (8.1 ms of CPU time per step, torch
+    # profiler) as the GPU needs to run them, so the GPU idles ~0.4 ms per step behind the host. The library's own
+    # answer for launch-bound steps is graphs.GraphedStep: ELBO forward + backward captured once into a CUDA graph and
+    # replayed; per step the host only draws the GP function's random numbers (numpy, reference order) into static
+    # buffers. The observations enter through a static device buffer; the gradient all-reduce stays outside the graph.
+    gstep, ys_static = None, None
+    if not args.no_graph:
+        try:
+            from gaussian_process_odes_b200 import graphs
+            ys_static = ys_dev.clone()
+            gstep = graphs.GraphedStep(
+                model, lambda: distributed.sharded_shooting_loss(model, ys_static, ts_dev, w["S_mc"], N_glob, world))
+        except Exception as e:  # capture is an optimisation: report and fall back to eager launches
+            if rank == 0:
+                print("warning: CUDA-graph capture failed (%r); timing eager launches" % (e,), file=sys.stderr)
+            gstep = None
+
+    def step(ys):
+        if gstep is None:
+            return eager_step(ys)
+        if ys is not ys_static:
+            ys_static.copy_(ys, non_blocking=True)   # device -> device, 40 MB, on the compute stream
+        loss = gstep()
         distributed.allreduce_shared_grads(model)
         return loss
 
@@ -311,15 +337,18 @@ def run_ours(args):
             torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
         return float(ms.item())
 
+    resident = ys_static if gstep is not None else ys_dev   # device-resident input of the `value` measurement
     for _ in range(args.warmup):
-        step(ys_dev)
+        step(resident)
 
     # ---- device-resident measurement ----
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    ms_total = timed(args.steps, lambda: step(resident))
     _lib.reset_launch_count()
-    ms_total = timed(args.steps, lambda: step(ys_dev))
+    for _ in range(args.steps):   # the kernels a step launches are counted on eager launches (a graph replay runs the same)
+        eager_step(ys_dev)
     launches = _lib.total_launches()
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ms_total / args.steps
@@ -349,13 +378,21 @@ def run_ours(args):
             prefetch(i)  # first step of a timed region: its own copy, not overlapped with anything
         torch.cuda.current_stream().wait_event(ready[i % 2])
         y, t = y_bufs[i % 2], t_bufs[i % 2]
-        model.zero_grad(set_to_none=True)
-        loss = distributed.sharded_shooting_loss(model, y, t, w["S_mc"], N_glob, world)
         state["left"] -= 1
-        if state["left"] > 0:
-            prefetch(i + 1)  # next step's inputs: in flight during this step's backward
-        loss.backward()
-        distributed.allreduce_shared_grads(model)
+        if gstep is None:
+            model.zero_grad(set_to_none=True)
+            loss = distributed.sharded_shooting_loss(model, y, t, w["S_mc"], N_glob, world)
+            if state["left"] > 0:
+                prefetch(i + 1)  # next step's inputs: in flight during this step's backward
+            loss.backward()
+            distributed.allreduce_shared_grads(model)
+        else:
+            ys_static.copy_(y, non_blocking=True)   # staging buffer -> the graph's static input (device to device)
+            ts_dev.copy_(t, non_blocking=True)
+            loss = gstep()
+            if state["left"] > 0:
+                prefetch(i + 1)  # next step's inputs travel while this step's graph runs
+            distributed.allreduce_shared_grads(model)
         # device -> host read of every step's loss: copied to pinned host memory on the compute stream right after the
         # step, consumed one step later (so the host keeps issuing the next step instead of idling the GPU behind a
         # blocking .item()); the last step's value is awaited inside the timed region
@@ -386,7 +423,7 @@ def run_ours(args):
     n_prof = max(10, args.steps)
     _lib.profile_start()
     for _ in range(n_prof):
-        step(ys_dev)
+        eager_step(ys_dev)   # eager launches: the events bracket the individual C-ABI calls
     raw = _lib.profile_stop(raw=True)
     kern = {}
     for k, v in raw.items():
@@ -478,6 +515,7 @@ def run_ours(args):
                            "S_mc": w["S_mc"], "N_sequences_per_gpu": N_loc, "N_sequences_total": N_glob, "T": T,
                            "solver": w["solver"], "segments_per_gpu": rows_local, "segments_total": rows_total,
                            "evals_per_step": evals_per_step, "parallelism": "sequences sharded x%d" % world,
+                           "cuda_graph": gstep is not None,
                            "l2": "working set per step (>= 0.4 GB of sampled states, stage checkpoints, adjoint seeds "
                                  "and virtual rows per 10^6 segments) exceeds the 126 MB L2; no explicit flush"},
                 "elbo_fwd_bwd_ms": ms_per_step, "e2e": e2e, "gpu_launches": launches * world,
@@ -499,6 +537,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: 16 sequences (10^6 segments) per GPU; strong: 16 sequences in total")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of the captured CUDA graph")
     ap.add_argument("--no-parity-check", action="store_true", help="skip the oracle check before timing (profiling)")
     args = ap.parse_args()
     if args.impl == "reference":
