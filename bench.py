@@ -389,9 +389,9 @@ def run_ours(args):
         else:
             ys_static.copy_(y, non_blocking=True)   # staging buffer -> the graph's static input (device to device)
             ts_dev.copy_(t, non_blocking=True)
-            loss = gstep()
             if state["left"] > 0:
-                prefetch(i + 1)  # next step's inputs travel while this step's graph runs
+                prefetch(i + 1)  # enqueued BEFORE the replay: the next step's inputs travel while this step's graph runs
+            loss = gstep()
             distributed.allreduce_shared_grads(model)
         # device -> host read of every step's loss: copied to pinned host memory on the compute stream right after the
         # step, consumed one step later (so the host keeps issuing the next step instead of idling the GPU behind a
