@@ -13,7 +13,7 @@ GPODE_DECL(1) GPODE_DECL(2) GPODE_DECL(3) GPODE_DECL(4) GPODE_DECL(5) GPODE_DECL
 
 extern "C" int64_t gpode_dopri5_work_floats(int D, int64_t B) {
     const int64_t plane = B * (int64_t)D;
-    return 5 * plane + 1 + 8;  // five [B,D] state planes + alignment + four float64 accumulators
+    return 5 * plane + 1 + 2 * 3 * 2048;  // five [B,D] state planes + alignment + 3 x 2048 float64 per-CTA partial sums
 }
 
 // checkpoint block: y [cap][B][D] | k [cap][7][B][D] | dt [cap] | out_x [Tg] | out_step [Tg] (int32)

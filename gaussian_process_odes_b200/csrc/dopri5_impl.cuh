@@ -17,6 +17,7 @@ namespace cg = cooperative_groups;
 namespace {
 
 constexpr int kDpThreads = 128;
+constexpr int kDpMaxGrid = 2048;  // cooperative grid cap: 3 rotating error sums x one float64 slot per CTA
 constexpr int kDpSetThreads = 256;  // sets mode: one CTA per parameter set, up to 8 warps = 8 rows in flight
 
 // Dormand-Prince / Shampine tableau (float32 copies, like torchdiffeq's tableau cast to the state dtype)
@@ -48,7 +49,7 @@ struct Dopri5Args {
     double rtol, atol;
     float* xs;        // [Tg,B,D]
     float* work;      // y | f | y1 | f1 | ymid  (5 x [B,D])
-    double* red;      // 4 accumulators (3 rotating for the error norm + 1 spare), zeroed by the host
+    double* red;      // [3][kDpMaxGrid] per-CTA partial sums of the three rotating error norms
     int32_t* stats;   // nfe, accepted, rejected, status  (sets mode: 4 per set)
     // sets mode (batched Monte-Carlo prediction): CTA q integrates rows [q set_rows, (q+1) set_rows) with the packed
     // block at packed + q set_stride and ITS OWN controller (error norm over the set's rows, as if called per set)
@@ -121,13 +122,15 @@ __global__ void __launch_bounds__(kSets ? kDpSetThreads : kDpThreads) dopri5_ker
     const int64_t row_end = kSets ? row_begin + a.set_rows : B;
     int32_t* const stats = a.stats + (kSets ? 4 * blockIdx.x : 0);
     const bool writer = !kWarp || (threadIdx.x & 31) == 0;
-    // the only cross-thread quantities: three sums of squares. Grid mode: float64 atomics + grid barrier; sets mode:
-    // the CTA is the whole "batch", so shared memory + __syncthreads.
+    // the only cross-thread quantities: three sums of squares. Grid mode: every CTA writes its float64 partial sum to a
+    // slot of its own and, after the grid barrier, warp 0 of every CTA adds the slots in a FIXED order (no atomics: the
+    // norm, hence every accept / reject decision and step size, is bitwise reproducible); sets mode: the CTA is the
+    // whole "batch", so shared memory + __syncthreads.
     auto publish = [&](double v, int slot) {
         const double b = block_sum_to(v, sred);
         if (threadIdx.x == 0) {
             if constexpr (kSets) sset[slot] = b;
-            else atomicAdd(a.red + slot, b);
+            else a.red[(size_t)slot * kDpMaxGrid + blockIdx.x] = b;
         }
     };
     auto barrier = [&]() {
@@ -135,8 +138,20 @@ __global__ void __launch_bounds__(kSets ? kDpSetThreads : kDpThreads) dopri5_ker
         else grid.sync();
     };
     auto total_of = [&](int slot) -> double {
-        if constexpr (kSets) return sset[slot];
-        else return a.red[slot];
+        if constexpr (kSets) {
+            return sset[slot];
+        } else {
+            __syncthreads();   // sset[3] may still be read from the previous call
+            if (threadIdx.x < 32) {
+                const double* __restrict__ p = a.red + (size_t)slot * kDpMaxGrid;
+                double v = 0.0;
+                for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) v += __ldcg(p + i);
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (threadIdx.x == 0) sset[3] = v;
+            }
+            __syncthreads();
+            return sset[3];
+        }
     };
     float* Y = a.work;
     float* F = a.work + plane;
@@ -200,11 +215,7 @@ __global__ void __launch_bounds__(kSets ? kDpSetThreads : kDpThreads) dopri5_ker
         else h1 = powf(0.01f / fmaxf(d1, d2), 1.0f / 5.0f);
         dt = (double)fminf(100.f * h0, h1);
     }
-    barrier();  // everyone has read the three sums before their slots are recycled as the rotating error accumulators
-    if constexpr (!kSets) {
-        if (gtid == 0) a.red[0] = a.red[1] = a.red[2] = 0.0;
-    }
-    barrier();
+    barrier();  // everyone has read the three sums before their slots are recycled as the rotating error sums
 
     // ---- main loop: controller state replicated in every thread ----
     double t0 = dir * a.t[0], t1 = dir * a.t[0];
@@ -269,9 +280,6 @@ __global__ void __launch_bounds__(kSets ? kDpSetThreads : kDpThreads) dopri5_ker
         publish(se, attempt % 3);
         barrier();
         const float ratio = (float)sqrt(total_of(attempt % 3) / n_elem);
-        if constexpr (!kSets) {
-            if (gtid == 0) a.red[(attempt + 2) % 3] = 0.0;
-        }
         const bool accept = ratio <= 1.0f;
         nfe += 6;
         if (accept) {
@@ -400,7 +408,8 @@ int launch_dopri5(const float* packed, int M, int S, const float* x0, const doub
     const int64_t rows_per_cta = warp_mode ? kDpThreads / 32 : kDpThreads;
     const int64_t want = (B + rows_per_cta - 1) / rows_per_cta;
     const int64_t grid_cap = (int64_t)sms * occ;
-    const int grid = (int)(want < grid_cap ? want : grid_cap);
+    int grid = (int)(want < grid_cap ? want : grid_cap);
+    if (grid > kDpMaxGrid) grid = kDpMaxGrid;   // one float64 slot per CTA and rotating sum
     Dopri5Args a;
     a.packed = packed; a.M = M; a.S = S; a.total = L.total; a.x0 = x0; a.t = t; a.Tg = Tg; a.B = B;
     a.rtol = rtol; a.atol = atol; a.xs = xs;
@@ -412,7 +421,6 @@ int launch_dopri5(const float* packed, int M, int S, const float* x0, const doub
     a.set_stride = 0;
     a.max_attempts = 1 << 20;
     dopri5_set_ckpt(a, ckpt, cap, plane, Tg);
-    GPODE_CUDA(cudaMemsetAsync(a.red, 0, 4 * sizeof(double), st));
     void* params[] = {(void*)&a};
     GPODE_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kDpThreads), params, smem, st));
     return 0;
