@@ -61,6 +61,9 @@ SIGNATURES = {
     "gpode_set_option": (_I, [ctypes.c_char_p, _I]),
     "gpode_get_option": (_I, [ctypes.c_char_p]),
     "gpode_shoot_work_doubles": (_L, []),
+    "gpode_packed_ubwd_floats": (_L, [_I, _I]),
+    "gpode_pack_cache_ubwd": (_I, [_CP, _P, _P]),
+    "gpode_vf_bwd_umma": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _L, _P]),
     "gpode_packed_large_bwd_floats": (_L, [_I, _I, _I]),
     "gpode_acc_large_floats": (_L, [_I, _I]),
     "gpode_pack_cache_large_bwd": (_I, [_CP, _P, _P]),
@@ -168,6 +171,7 @@ KERNELS_PER_CALL = {
     "gpode_vf_fwd_large_add_rbf": 1, "gpode_dopri5_bwd_dev": 1, "gpode_param_grad_dev": 1, "gpode_vf_fwd_umma": 1,
     "gpode_pack_cache_sets": 1, "gpode_whiten_fwd_sets": 2, "gpode_vf_fwd_sets": 1, "gpode_rk4_fwd_sets": 1,
     "gpode_dopri5_fwd_sets": 1, "gpode_shoot_fwd": 2, "gpode_shoot_bwd": 1,
+    "gpode_pack_cache_ubwd": 1, "gpode_vf_bwd_umma": 1,
     "gpode_pack_cache_large_bwd": 1, "gpode_vf_bwd_large": 1, "gpode_grads_finalize_large": 1,
     # per RK4 step: forward 4 evaluations x 2 kernels + 4 stage kernels; adjoint 4 VJPs + 8 element-wise kernels
     "gpode_rk4_fwd_large_dev": 12, "gpode_rk4_bwd_large": 12,

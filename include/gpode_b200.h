@@ -310,6 +310,15 @@ int gpode_shoot_bwd(const float* packed, int D, int M, int S, const gpode_shoot_
 int gpode_set_option(const char* name, int value);
 int gpode_get_option(const char* name);
 
+/* gpode_vf_bwd with both Fourier projections of the VJP on the tcgen05 tensor cores (D = 4, 5): theta as a kind::f16
+ * split GEMM from shared memory, sin(theta) written back to tensor memory as the A operand of the second GEMM
+ * (G = sin(theta) (a Omega)^T, kind::tf32, TS form); csrc/vjp_umma.cu. packed_ubwd: its operand block
+ * (gpode_packed_ubwd_floats(D,S) floats, gpode_pack_cache_ubwd). Same outputs as gpode_vf_bwd. */
+int64_t gpode_packed_ubwd_floats(int D, int S);
+int gpode_pack_cache_ubwd(const gpode_cache_t* cache, float* packed_ubwd, void* stream);
+int gpode_vf_bwd_umma(const float* packed, const float* packed_ubwd, int D, int M, int S, const float* x, const float* f,
+                      const float* grad_f, float* grad_x, float* acc, int64_t B, void* stream);
+
 /* EXPERIMENTAL (2 <= D <= 7): gpode_vf_fwd with the Fourier-feature projection on the 5th-generation tensor cores
  * (tcgen05.mma kind::tf32, 3xTF32 error compensation, accumulators in TMEM); same arguments and results. */
 int gpode_vf_fwd_umma(const float* packed, int D, int M, int S, const float* x, float* f, int64_t B, void* stream);
