@@ -181,27 +181,51 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------------
 # CPU baseline: the oracle port (reference algorithm restated op-for-op on torch CPU) on a bounded sample
 # ----------------------------------------------------------------------------------------------------------------------
-def cpu_elbo_timing(w, steps, warmup, T_sample=6000, N_sample=1):
+def cpu_elbo_timing(w, steps, warmup, T_sample=6000, N_sample=1, prefer_reference=True):
+    """One ELBO forward+backward per step on the host cores. With the staged archive (or the checkout) present this is the
+    UNMODIFIED reference -- its own DSVGP_Layer / Flow / UniformSequenceModel classes (oracle/reference_harness.py, the
+    restated torchdiffeq 0.2.0 underneath, random draws injected so that every step sees the same numbers) --
+    `kind: "reference"`; otherwise the oracle port (`kind: "port"`)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import gpode_oracle as O
+    import reference_harness as H
     torch.set_num_threads(os.cpu_count())
     p, ys, ts, draws, proj = O.make_problem(D=w["D"], M=w["M"], S=w["S"], N=N_sample, T=T_sample, S_mc=w["S_mc"],
                                             D_obs=w["D_obs"], dt=w["dt"], ell0=1.25, seed=121)
     rows = w["S_mc"] * N_sample * T_sample
+    use_ref = prefer_reference and H.available()
     times = []
-    for i in range(warmup + steps):
-        pp = {k: v.detach().clone().requires_grad_(True) for k, v in p.items()}
-        t0 = time.perf_counter()
-        r = O.elbo_shooting(pp, ys, ts, draws, method=w["solver"], project=proj)
-        r["loss"].backward()
-        t1 = time.perf_counter()
-        if i >= warmup:
-            times.append(t1 - t0)
+    if use_ref:
+        mods = H._import_reference()
+        model = H.build_reference_shooting(mods, p, ys, w["S"], solver=w["solver"], project=proj)
+        params = [q for q in model.parameters() if q.requires_grad]
+        for i in range(warmup + steps):
+            for q in params:
+                q.grad = None
+            t0 = time.perf_counter()
+            with H.injected_draws(mods, draws, n_caches=1, mvn_order=("eps_x0", "eps_states")):
+                loss, _ = H.reference_shooting_loss(model, ys, ts, num_samples=w["S_mc"])
+            loss.backward()
+            t1 = time.perf_counter()
+            if i >= warmup:
+                times.append(t1 - t0)
+        what = "the UNMODIFIED reference modules (%s; restated torchdiffeq 0.2.0 rk4)" % (
+            "/root/reference" if H.source() == "tree" else "oracle/_ref archive")
+    else:
+        for i in range(warmup + steps):
+            pp = {k: v.detach().clone().requires_grad_(True) for k, v in p.items()}
+            t0 = time.perf_counter()
+            r = O.elbo_shooting(pp, ys, ts, draws, method=w["solver"], project=proj)
+            r["loss"].backward()
+            t1 = time.perf_counter()
+            if i >= warmup:
+                times.append(t1 - t0)
+        what = "the oracle port"
     sec = float(np.median(times))
-    return dict(value=rows * 4 / sec, unit=UNIT, cores=torch.get_num_threads(), kind="port",
+    return dict(value=rows * 4 / sec, unit=UNIT, cores=torch.get_num_threads(), kind="reference" if use_ref else "port",
                 sample="%d segments (S_mc=%d x N=%d x T=%d) of the same D=%d,M=%d,S=%d,D_obs=%d workload, median of %d "
-                       "ELBO fwd+bwd steps of the oracle port (torch CPU float32, %d threads)" % (
-                           rows, w["S_mc"], N_sample, T_sample, w["D"], w["M"], w["S"], w["D_obs"], steps,
+                       "ELBO fwd+bwd steps of %s (torch CPU float32, %d threads)" % (
+                           rows, w["S_mc"], N_sample, T_sample, w["D"], w["M"], w["S"], w["D_obs"], steps, what,
                            torch.get_num_threads()),
                 ms_per_step=sec * 1e3, rows=rows)
 
@@ -218,8 +242,10 @@ def run_reference(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": w["name"], "D": w["D"], "D_obs": w["D_obs"], "M": w["M"], "S": w["S"],
                        "S_mc": w["S_mc"], "solver": w["solver"], "segments_per_step": cb["rows"],
-                       "note": "reference algorithm (oracle port; the Python reference and torchdiffeq cannot travel "
-                               "to the GPU box) on the host cores, bounded sample of the workload"},
+                       "note": ("the unmodified reference modules (archive staged by build(), restated torchdiffeq "
+                                "underneath) on the host cores, bounded sample of the workload" if cb["kind"] == "reference"
+                                else "reference algorithm (oracle port: no staged reference archive found) on the host "
+                                     "cores, bounded sample of the workload")},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}

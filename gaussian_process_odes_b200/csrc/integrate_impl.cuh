@@ -644,13 +644,16 @@ vf_fwd_mma_kernel(const float* __restrict__ packed, const int M, const int S, co
 // One CTA of kHWarps warps per SM (the f16 operand records take ~92 KB at D = 5, S = 256, so they are staged once per
 // SM); a warp owns 32 rows, lane = row.
 // dynamic shared memory: [0,16) mbarrier | [kern | il] | mmah records | (D*D + D) block-reduction floats | per-warp stage
-constexpr int kHWarps = 12;
+#ifndef GPODE_HWARPS
+#define GPODE_HWARPS 12
+#endif
+constexpr int kHWarps = GPODE_HWARPS;
 constexpr int kHThreads = kHWarps * 32;
 
 struct HParams {
     int M, S8P, off_kern, n_small, off_mmah, n_mmah;
-    int parts;  // tuning (GPODE_MMA_PARTS): bit 0 = RFF part, bit 1 = RBF part of the adjoint; bit 2 = forward without
-                // the staggered part order (default 3)
+    int parts;  // tuning (GPODE_MMA_PARTS): bit 0 = RFF part, bit 1 = RBF part of the adjoint; bits 2-3 = schedule of the
+                // forward evaluation (0 fused stream, 1 two parts, 2 two parts staggered across warps); default 3
 };
 
 template <int D>
@@ -717,7 +720,7 @@ vf_fwd_h_kernel(const float* __restrict__ packed, const HParams p, const float* 
         const int64_t row = blk * 32 + lane;
         float xr[1][D], fr[1][D];
         load_rows<D, 1>(xr, x, row, B, 0);
-        vf_eval_h<D>(sm.small, sm.mmah, sm.stage, p.M, p.S8P, xr, fr, lane, (p.parts & 4) == 0);
+        vf_eval_h<D>(sm.small, sm.mmah, sm.stage, p.M, p.S8P, xr, fr, lane, (p.parts >> 2) & 3);
         store_rows<D, 1>(fr, f, row, B, 0);
     }
 }
@@ -753,7 +756,7 @@ rk4_fwd_h_kernel(const float* __restrict__ packed, const HParams p, const float*
             }
 #pragma unroll 1
             for (int st = 1; st <= 4; ++st) {
-                vf_eval_h<D>(sm.small, sm.mmah, sm.stage, p.M, p.S8P, ys, kk, lane, (p.parts & 4) == 0);
+                vf_eval_h<D>(sm.small, sm.mmah, sm.stage, p.M, p.S8P, ys, kk, lane, (p.parts >> 2) & 3);
                 if (kst != nullptr) store_rows<D, R>(kk, kst + ((int64_t)i * 4 + (st - 1)) * plane, row0, B, 0);
                 if (st == 1) {
 #pragma unroll

@@ -130,112 +130,104 @@ __device__ __forceinline__ void vf_vjp_h(const float* __restrict__ small, const 
     float xbp[D];
 #pragma unroll
     for (int j = 0; j < D; ++j) xbp[j] = 0.f;
-#pragma unroll 1
-    for (int part = 0; part < 2; ++part) {
-        if ((part == 0) != rbf_first) {
-    // ---------------- RFF part on the tensor cores (quad layout) ----------------
-        if (parts & 1) {
-            uint32_t ax[2][4];
-            auto slotA = [&](const int row, const int s) -> float {  // x_hi | x_hi | x_lo | 0
-                const int kind = s / D, j = s - kind * D;
-                const float v = kind < 3 ? sx[row * SXS + j] : 0.f;
-                const float hi = gpode_trunc11(v);
-                return kind == 2 ? v - hi : hi;
-            };
+
+    // ---- RFF part on the tensor cores (quad layout): state of one VJP ----
+    uint32_t ax[2][4];
+    float xsel[4][2], xbq[4][2];  // rows g + 8 r, input dimensions j = 2t, 2t+1
+    auto rff_begin = [&]() {
+        auto slotA = [&](const int row, const int s) -> float {  // x_hi | x_hi | x_lo | 0
+            const int kind = s / D, j = s - kind * D;
+            const float v = kind < 3 ? sx[row * SXS + j] : 0.f;
+            const float hi = gpode_trunc11(v);
+            return kind == 2 ? v - hi : hi;
+        };
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            const int r0 = 16 * mt + g, r1 = r0 + 8;
+            ax[mt][0] = gpode_pack_h2(slotA(r0, 2 * t), slotA(r0, 2 * t + 1));
+            ax[mt][1] = gpode_pack_h2(slotA(r1, 2 * t), slotA(r1, 2 * t + 1));
+            ax[mt][2] = gpode_pack_h2(slotA(r0, 2 * t + 8), slotA(r0, 2 * t + 9));
+            ax[mt][3] = gpode_pack_h2(slotA(r1, 2 * t + 8), slotA(r1, 2 * t + 9));
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+                xsel[r][jj] = (2 * t + jj < D) ? sx[(g + 8 * r) * SXS + 2 * t + jj] : 0.f;
+                xbq[r][jj] = 0.f;
+            }
+    };
+    // one feature-tile PAIR of output k: theta, sine, split, and the three G MMAs. The G MMAs contract over the 16
+    // features of the pair (slots 0..7 = even tile, 8..15 = odd tile), so every A fragment is written in place by the
+    // conversions and every B pair is one LDS.64.
+    auto rff_pair = [&](const uint32_t* __restrict__ rec, float (&Ga)[2][4], float (&Gb)[2][4], float (&Gl)[2][4]) {
+        uint32_t ah[2][4], al[2][4];  // [row tile][row g: even tile | row g+8: even | row g: odd | row g+8: odd]
+        const uint2 bh = *reinterpret_cast<const uint2*>(rec + 80 + lane * 2);
+        const uint2 bl = *reinterpret_cast<const uint2*>(rec + GPODE_MMAH_REC + 80 + lane * 2);
+#pragma unroll
+        for (int tl = 0; tl < 2; ++tl) {
+            const uint32_t* __restrict__ rc = rec + tl * GPODE_MMAH_REC;
+            const uint2 b = *reinterpret_cast<const uint2*>(rc + lane * 2);
+            const float4 ph = *reinterpret_cast<const float4*>(rc + 64 + t * 4);
+            float c[2][4];
+            gpode_mma_f16(c[0], ax[0], b.x, b.y, ph);
+            gpode_mma_f16(c[1], ax[1], b.x, b.y, ph);
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
-                const int r0 = 16 * mt + g, r1 = r0 + 8;
-                ax[mt][0] = gpode_pack_h2(slotA(r0, 2 * t), slotA(r0, 2 * t + 1));
-                ax[mt][1] = gpode_pack_h2(slotA(r1, 2 * t), slotA(r1, 2 * t + 1));
-                ax[mt][2] = gpode_pack_h2(slotA(r0, 2 * t + 8), slotA(r0, 2 * t + 9));
-                ax[mt][3] = gpode_pack_h2(slotA(r1, 2 * t + 8), slotA(r1, 2 * t + 9));
+                float h[4], l[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float v = __sinf(c[mt][i]);
+                    h[i] = gpode_trunc11(v);
+                    l[i] = v - h[i];
+                }
+                ah[mt][2 * tl + 0] = gpode_pack_h2(h[0], h[1]);
+                ah[mt][2 * tl + 1] = gpode_pack_h2(h[2], h[3]);
+                al[mt][2 * tl + 0] = gpode_pack_h2(l[0], l[1]);
+                al[mt][2 * tl + 1] = gpode_pack_h2(l[2], l[3]);
             }
-            float xsel[4][2], xbq[4][2];  // rows g + 8 r, input dimensions j = 2t, 2t+1
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-                for (int jj = 0; jj < 2; ++jj) {
-                    xsel[r][jj] = (2 * t + jj < D) ? sx[(g + 8 * r) * SXS + 2 * t + jj] : 0.f;
-                    xbq[r][jj] = 0.f;
-                }
-
-#pragma unroll 1   // one copy of the feature loop: the instruction cache is the scarce resource with 12 warps per SM
-            for (int k = 0; k < D; ++k) {
-                // three independent accumulation chains per row tile, one per split term: g_hi Bp_hi, g_lo Bp_hi, g_hi Bp_lo
-            float Ga[2][4], Gb[2][4], Gl[2][4];
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) Ga[mt][i] = Gb[mt][i] = Gl[mt][i] = 0.f;
-
-            const uint32_t* __restrict__ rec = mmah + (size_t)k * S8P * GPODE_MMAH_REC;
-#pragma unroll 1
-            for (int ft = 0; ft < S8P; ft += 2, rec += 2 * GPODE_MMAH_REC) {
-                // The G MMAs contract over the 16 features of a tile PAIR (slots 0..7 = even tile, 8..15 = odd tile),
-                // so every A fragment is written in place by the conversions and every B pair is one LDS.64.
-                uint32_t ah[2][4], al[2][4];  // [row tile][row g: even tile | row g+8: even | row g: odd | row g+8: odd]
-                const uint2 bh = *reinterpret_cast<const uint2*>(rec + 80 + lane * 2);
-                const uint2 bl = *reinterpret_cast<const uint2*>(rec + GPODE_MMAH_REC + 80 + lane * 2);
-#pragma unroll
-                for (int tl = 0; tl < 2; ++tl) {
-                    const uint32_t* __restrict__ rc = rec + tl * GPODE_MMAH_REC;
-                    const uint2 b = *reinterpret_cast<const uint2*>(rc + lane * 2);
-                    const float4 ph = *reinterpret_cast<const float4*>(rc + 64 + t * 4);
-                    float c[2][4];
-                    gpode_mma_f16(c[0], ax[0], b.x, b.y, ph);
-                    gpode_mma_f16(c[1], ax[1], b.x, b.y, ph);
-#pragma unroll
-                    for (int mt = 0; mt < 2; ++mt) {
-                        float h[4], l[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float v = __sinf(c[mt][i]);
-                            h[i] = gpode_trunc11(v);
-                            l[i] = v - h[i];
-                        }
-                        ah[mt][2 * tl + 0] = gpode_pack_h2(h[0], h[1]);
-                        ah[mt][2 * tl + 1] = gpode_pack_h2(h[2], h[3]);
-                        al[mt][2 * tl + 0] = gpode_pack_h2(l[0], l[1]);
-                        al[mt][2 * tl + 1] = gpode_pack_h2(l[2], l[3]);
-                    }
-                }
-#pragma unroll
-                for (int mt = 0; mt < 2; ++mt) {
-                    gpode_mma_f16_acc(Ga[mt], ah[mt], bh.x, bh.y);
-                    gpode_mma_f16_acc(Gb[mt], al[mt], bh.x, bh.y);
-                    gpode_mma_f16_acc(Gl[mt], ah[mt], bl.x, bl.y);
-                }
-            }
-            // the row's factor (2 ln2 kb_k; sign and scale are folded into cG) once per output, after the feature loop
-                float aq[2] = {0.f, 0.f};
-#pragma unroll
-                for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int r = 2 * mt + (i >> 1), jj = i & 1;
-                        const float tt = ((Ga[mt][i] + Gb[mt][i]) + Gl[mt][i]) * skb[(g + 8 * r) * SXS + k];
-                        xbq[r][jj] += tt;
-                        aq[jj] = fmaf(xsel[r][jj], tt, aq[jj]);
-                    }
-#pragma unroll
-                for (int kk = 0; kk < D; ++kk) {  // k is a run-time index here: predicated scatter keeps Aq in registers
-                    acc.Aq[kk][0] += (kk == k) ? aq[0] : 0.f;
-                    acc.Aq[kk][1] += (kk == k) ? aq[1] : 0.f;
-                }
-            }
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-                *reinterpret_cast<float2*>(sxb + (g + 8 * r) * 8 + 2 * t) = make_float2(xbq[r][0], xbq[r][1]);
         }
-        } else if (parts & 2) {
-        // ---------------- RBF part: lane = row, output pairs per FFMA2 ----------------
-        // Full output pairs ride in FFMA2; the odd last output (D = 3, 5) goes through scalar FMAs instead of a
-        // half-empty pair: the FMA pipe bounds this part (ncu: math_pipe_throttle) and a half-empty FFMA2 costs it as
-        // much as a full one. (All-scalar was measured too: 0.47 ms per 1e6-row VJP against 0.43 for this split.)
-        constexpr int KF = D / 2;
-        constexpr bool kOdd = (D & 1) != 0;
-        float2 wn[D][KF > 0 ? KF : 1];
-        float wl[D];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            gpode_mma_f16_acc(Ga[mt], ah[mt], bh.x, bh.y);
+            gpode_mma_f16_acc(Gb[mt], al[mt], bh.x, bh.y);
+            gpode_mma_f16_acc(Gl[mt], ah[mt], bl.x, bl.y);
+        }
+    };
+    // the row's factor (2 ln2 kb_k; sign and scale are folded into cG) once per output, after the feature loop
+    auto rff_output_done = [&](const int k, const float (&Ga)[2][4], const float (&Gb)[2][4], const float (&Gl)[2][4]) {
+        float aq[2] = {0.f, 0.f};
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = 2 * mt + (i >> 1), jj = i & 1;
+                const float tt = ((Ga[mt][i] + Gb[mt][i]) + Gl[mt][i]) * skb[(g + 8 * r) * SXS + k];
+                xbq[r][jj] += tt;
+                aq[jj] = fmaf(xsel[r][jj], tt, aq[jj]);
+            }
+#pragma unroll
+        for (int kk = 0; kk < D; ++kk) {  // k is a run-time index here: predicated scatter keeps Aq in registers
+            acc.Aq[kk][0] += (kk == k) ? aq[0] : 0.f;
+            acc.Aq[kk][1] += (kk == k) ? aq[1] : 0.f;
+        }
+    };
+    auto rff_end = [&]() {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            *reinterpret_cast<float2*>(sxb + (g + 8 * r) * 8 + 2 * t) = make_float2(xbq[r][0], xbq[r][1]);
+    };
+
+    // ---- RBF part: lane = row, output pairs per FFMA2 ----
+    // Full output pairs ride in FFMA2; the odd last output (D = 3, 5) goes through scalar FMAs instead of a
+    // half-empty pair: the FMA pipe bounds this part (ncu: math_pipe_throttle) and a half-empty FFMA2 costs it as
+    // much as a full one. (All-scalar was measured too: 0.47 ms per 1e6-row VJP against 0.43 for this split.)
+    constexpr int KF = D / 2;
+    constexpr bool kOdd = (D & 1) != 0;
+    float2 wn[D][KF > 0 ? KF : 1];
+    float wl[D];
+    float2 kb2[KF > 0 ? KF : 1];
+    auto rbf_begin = [&]() {
 #pragma unroll
         for (int j = 0; j < D; ++j) {
             float w[WP];
@@ -244,61 +236,125 @@ __device__ __forceinline__ void vf_vjp_h(const float* __restrict__ small, const 
             for (int kp = 0; kp < KF; ++kp) wn[j][kp] = make_float2(w[2 * kp], w[2 * kp + 1]);
             wl[j] = w[D - 1];
         }
-        float2 kb2[KF > 0 ? KF : 1];
 #pragma unroll
         for (int kp = 0; kp < KF; ++kp) {
             kb2[kp] = make_float2(kbn[2 * kp], kbn[2 * kp + 1]);
             acc.Vq[kp] = ffma2(kb2[kp], make_float2(fst[0][2 * kp], fst[0][2 * kp + 1]), acc.Vq[kp]);
         }
         if constexpr (kOdd) acc.Vq[KF].x = fmaf(kbn[D - 1], fst[0][D - 1], acc.Vq[KF].x);
+    };
+    auto rbf_step = [&](const int m) {
+        float kp_[KS];
+        lds_vec<KS>(kp_, kern + m * KS);
+        float d[D], dd[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            d[j] = x[0][j] - kp_[j];
+            dd[j] = d[j] * d[j];
+        }
+        float2 tq[D];
+        float tl[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            tq[j] = make_float2(0.f, 0.f);
+            tl[j] = 0.f;
+        }
+#pragma unroll
+        for (int kp = 0; kp < KF; ++kp) {
+            float2 e = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < D; ++j) e = ffma2(dd[j], wn[j][kp], e);
+            const float2 K = make_float2(gpode_ex2(e.x), gpode_ex2(e.y));
+            const float2 cK = fmul2(make_float2(kp_[D + 2 * kp], kp_[D + 2 * kp + 1]), K);
+            const float2 q = fmul2(kb2[kp], cK);   // q' = 2 ln2 kb c K
+            acc.Vq[kp] = fadd2(acc.Vq[kp], q);
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                tq[j] = ffma2(q, wn[j][kp], tq[j]);
+                acc.A2[kp][j] = ffma2(dd[j], q, acc.A2[kp][j]);
+            }
+        }
+        if constexpr (kOdd) {
+            float e = 0.f;
+#pragma unroll
+            for (int j = 0; j < D; ++j) e = fmaf(dd[j], wl[j], e);
+            const float q = kbn[D - 1] * (kp_[2 * D - 1] * gpode_ex2(e));
+            acc.Vq[KF].x += q;
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                tl[j] = q * wl[j];
+                acc.A2[KF][j].x = fmaf(dd[j], q, acc.A2[KF][j].x);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < D; ++j) xbp[j] = fmaf(d[j], (tq[j].x + tq[j].y) + tl[j], xbp[j]);
+    };
+
+#ifdef GPODE_VJP_FUSED_EXPERIMENT
+    if ((parts & 16) && (parts & 3) == 3) {
+        // FUSED stream (experiment, compiled only with -DGPODE_VJP_FUSED_EXPERIMENT; mma_parts bit 4): two inducing
+        // points of the RBF part ride in every feature-tile-pair trip of the RFF loop; same sums in the same order, so
+        // the results are bit-identical. MEASURED (B200, D = 5, M = 100, 1e6 rows, tools/time_bwd_modes.py, whole
+        // backward pass): 12 warps 5.40 ms against 5.06 ms for the two-part form (168 registers, 100 bytes of spills);
+        // 8 warps / 248 registers 5.07 ms against 5.21 ms. Unlike the forward evaluation (vf_eval_h mode 2, -5 %) the
+        // adjoint gains nothing: it is bound by instruction dispatch (10 issue slots per sine), not by a pipe that the
+        // other part leaves idle.
+        rff_begin();
+        rbf_begin();
+        int m = 0;
+#pragma unroll 1
+        for (int k = 0; k < D; ++k) {
+            float Ga[2][4], Gb[2][4], Gl[2][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) Ga[mt][i] = Gb[mt][i] = Gl[mt][i] = 0.f;
+            const uint32_t* __restrict__ rec = mmah + (size_t)k * S8P * GPODE_MMAH_REC;
+            const int n_pairs = S8P >> 1;
+            const int n_fused = ((M - m) >> 1) < n_pairs ? ((M - m) >> 1) : n_pairs;
+            int fp = 0;
+#pragma unroll 1
+            for (; fp < n_fused; ++fp, rec += 2 * GPODE_MMAH_REC, m += 2) {
+                rff_pair(rec, Ga, Gb, Gl);
+                rbf_step(m);
+                rbf_step(m + 1);
+            }
+#pragma unroll 1
+            for (; fp < n_pairs; ++fp, rec += 2 * GPODE_MMAH_REC) rff_pair(rec, Ga, Gb, Gl);
+            rff_output_done(k, Ga, Gb, Gl);
+        }
+        rff_end();
+#pragma unroll 1
+        for (; m < M; ++m) rbf_step(m);
+    } else
+#endif
+    {
+#pragma unroll 1
+    for (int part = 0; part < 2; ++part) {
+        if ((part == 0) != rbf_first) {
+        if (parts & 1) {
+            rff_begin();
+#pragma unroll 1   // one copy of the feature loop: the instruction cache is the scarce resource with 12 warps per SM
+            for (int k = 0; k < D; ++k) {
+                // three independent accumulation chains per row tile, one per split term: g_hi Bp_hi, g_lo Bp_hi, g_hi Bp_lo
+                float Ga[2][4], Gb[2][4], Gl[2][4];
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) Ga[mt][i] = Gb[mt][i] = Gl[mt][i] = 0.f;
+                const uint32_t* __restrict__ rec = mmah + (size_t)k * S8P * GPODE_MMAH_REC;
+#pragma unroll 1
+                for (int ft = 0; ft < S8P; ft += 2, rec += 2 * GPODE_MMAH_REC) rff_pair(rec, Ga, Gb, Gl);
+                rff_output_done(k, Ga, Gb, Gl);
+            }
+            rff_end();
+        }
+        } else if (parts & 2) {
+            rbf_begin();
 #pragma unroll 2
-        for (int m = 0; m < M; ++m) {
-            float kp_[KS];
-            lds_vec<KS>(kp_, kern + m * KS);
-            float d[D], dd[D];
-#pragma unroll
-            for (int j = 0; j < D; ++j) {
-                d[j] = x[0][j] - kp_[j];
-                dd[j] = d[j] * d[j];
-            }
-            float2 tq[D];
-            float tl[D];
-#pragma unroll
-            for (int j = 0; j < D; ++j) {
-                tq[j] = make_float2(0.f, 0.f);
-                tl[j] = 0.f;
-            }
-#pragma unroll
-            for (int kp = 0; kp < KF; ++kp) {
-                float2 e = make_float2(0.f, 0.f);
-#pragma unroll
-                for (int j = 0; j < D; ++j) e = ffma2(dd[j], wn[j][kp], e);
-                const float2 K = make_float2(gpode_ex2(e.x), gpode_ex2(e.y));
-                const float2 cK = fmul2(make_float2(kp_[D + 2 * kp], kp_[D + 2 * kp + 1]), K);
-                const float2 q = fmul2(kb2[kp], cK);   // q' = 2 ln2 kb c K
-                acc.Vq[kp] = fadd2(acc.Vq[kp], q);
-#pragma unroll
-                for (int j = 0; j < D; ++j) {
-                    tq[j] = ffma2(q, wn[j][kp], tq[j]);
-                    acc.A2[kp][j] = ffma2(dd[j], q, acc.A2[kp][j]);
-                }
-            }
-            if constexpr (kOdd) {
-                float e = 0.f;
-#pragma unroll
-                for (int j = 0; j < D; ++j) e = fmaf(dd[j], wl[j], e);
-                const float q = kbn[D - 1] * (kp_[2 * D - 1] * gpode_ex2(e));
-                acc.Vq[KF].x += q;
-#pragma unroll
-                for (int j = 0; j < D; ++j) {
-                    tl[j] = q * wl[j];
-                    acc.A2[KF][j].x = fmaf(dd[j], q, acc.A2[KF][j].x);
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < D; ++j) xbp[j] = fmaf(d[j], (tq[j].x + tq[j].y) + tl[j], xbp[j]);
+            for (int m = 0; m < M; ++m) rbf_step(m);
         }
-        }
+    }
     }
     __syncwarp();
     const float cG = 1.f / (GPODE_NEG_2LN2 * GPODE_MMAH_SCALE);
@@ -313,7 +369,7 @@ __device__ __forceinline__ void vf_vjp_h(const float* __restrict__ small, const 
 template <int D>
 __device__ __forceinline__ void vf_eval_h(const float* __restrict__ small, const uint32_t* __restrict__ mmah,
                                           float* __restrict__ stage, const int M, const int S8P, const float (&x)[1][D],
-                                          float (&f)[1][D], const int lane, const bool stagger = true) {
+                                          float (&f)[1][D], const int lane, const int mode = 0) {
     static_assert(D <= GPODE_MMAH_MAX_D, "x_hi | x_hi | x_lo must fit the 16 contraction slots");
     constexpr int KS = VfShape<D>::KS, WP = VfShape<D>::WP, SXS = HShape<D>::SXS;
     const float* __restrict__ kern = small;
@@ -343,6 +399,109 @@ __device__ __forceinline__ void vf_eval_h(const float* __restrict__ small, const
     for (int kp = 0; kp < KF; ++kp) fu[kp] = make_float2(0.f, 0.f);
     // The RFF part is bound by the MUFU pipe (cos), the RBF part by FMA dispatch: half of the warps of every scheduler
     // take them in the opposite order so that the two kinds of work meet on the SM at the same time.
+    // mode 0 (default): FUSED -- one inducing point of the RBF term rides in every feature-tile trip of the RFF loop;
+    // mode 1: the two parts one after the other; mode 2: one after the other, half of the warps in the opposite order
+    // (the round-1 / early round-2 form). Why fused: the RFF loop alone saturates the MUFU pipe (ncu source view: 16
+    // cosines per 129.7 cycles of a sub-partition = 99 %), the RBF loop alone needs the FP32 pipe and the MUFU pipe for
+    // 40 cycles each per inducing point and reaches 65 % of either, and a warp issues in order -- only a stream that
+    // carries MUFU work everywhere keeps that pipe fed (tools/pipe_probe.cu: FFMA2 and MUFU do overlap when both are on
+    // offer). Measured, D = 5, M = 100, 1e6 rows: evaluation 0.528 -> 0.516 ms, RK4 step 2.123 -> 2.021 ms, bit-identical
+    // results (the sums run in the same order); XU pipe 83 % of the active cycles (profiles/r02_summary.md).
+    const bool stagger = mode == 2;
+    auto rbf_compute = [&](const float (&kp_)[KS]) {
+        float dd[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            const float d = x[0][j] - kp_[j];
+            dd[j] = d * d;
+        }
+#pragma unroll
+        for (int kp = 0; kp < KF; ++kp) {
+            float2 e = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < D; ++j) e = ffma2(dd[j], wn[j][kp], e);
+            const float2 K = make_float2(gpode_ex2(e.x), gpode_ex2(e.y));
+            fu[kp] = ffma2(make_float2(kp_[D + 2 * kp], kp_[D + 2 * kp + 1]), K, fu[kp]);
+        }
+        if constexpr (kOdd) {
+            float e = 0.f;
+#pragma unroll
+            for (int j = 0; j < D; ++j) e = fmaf(dd[j], wl[j], e);
+            fl = fmaf(kp_[2 * D - 1], gpode_ex2(e), fl);
+        }
+    };
+    auto rbf_step = [&](const int m) {
+        float kp_[KS];
+        lds_vec<KS>(kp_, kern + m * KS);
+        rbf_compute(kp_);
+    };
+    if (mode == 0) {
+        uint32_t ax[2][4];
+        auto slotA = [&](const int row, const int s) -> float {  // x_hi | x_hi | x_lo | 0
+            const int kind = s / D, j = s - kind * D;
+            const float v = kind < 3 ? sx[row * SXS + j] : 0.f;
+            const float hi = gpode_trunc11(v);
+            return kind == 2 ? v - hi : hi;
+        };
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            const int r0 = 16 * mt + g, r1 = r0 + 8;
+            ax[mt][0] = gpode_pack_h2(slotA(r0, 2 * t), slotA(r0, 2 * t + 1));
+            ax[mt][1] = gpode_pack_h2(slotA(r1, 2 * t), slotA(r1, 2 * t + 1));
+            ax[mt][2] = gpode_pack_h2(slotA(r0, 2 * t + 8), slotA(r0, 2 * t + 9));
+            ax[mt][3] = gpode_pack_h2(slotA(r1, 2 * t + 8), slotA(r1, 2 * t + 9));
+        }
+        int m = 0;
+#pragma unroll 1
+        for (int k = 0; k < D; ++k) {
+            float fk[4] = {0.f, 0.f, 0.f, 0.f};
+            const uint32_t* __restrict__ rc = mmah + (size_t)k * S8P * GPODE_MMAH_REC;
+            const int n_fused = M - m < S8P ? M - m : S8P;   // tiles of this output that carry an inducing point
+            int ft = 0;
+#pragma unroll 2
+            for (; ft < n_fused; ++ft, rc += GPODE_MMAH_REC, ++m) {   // branch-free body: one scheduling region
+                const uint2 b = *reinterpret_cast<const uint2*>(rc + lane * 2);
+                const float4 ph = *reinterpret_cast<const float4*>(rc + 64 + t * 4);
+                const float2 a2 = *reinterpret_cast<const float2*>(rc + 144 + t * 2);
+                float c[2][4];
+                gpode_mma_f16(c[0], ax[0], b.x, b.y, ph);
+                gpode_mma_f16(c[1], ax[1], b.x, b.y, ph);
+                rbf_step(m);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    fk[2 * mt] = fmaf(a2.x, __cosf(c[mt][0]), fk[2 * mt]);
+                    fk[2 * mt] = fmaf(a2.y, __cosf(c[mt][1]), fk[2 * mt]);
+                    fk[2 * mt + 1] = fmaf(a2.x, __cosf(c[mt][2]), fk[2 * mt + 1]);
+                    fk[2 * mt + 1] = fmaf(a2.y, __cosf(c[mt][3]), fk[2 * mt + 1]);
+                }
+            }
+#pragma unroll 2
+            for (; ft < S8P; ++ft, rc += GPODE_MMAH_REC) {
+                const uint2 b = *reinterpret_cast<const uint2*>(rc + lane * 2);
+                const float4 ph = *reinterpret_cast<const float4*>(rc + 64 + t * 4);
+                const float2 a2 = *reinterpret_cast<const float2*>(rc + 144 + t * 2);
+                float c[2][4];
+                gpode_mma_f16(c[0], ax[0], b.x, b.y, ph);
+                gpode_mma_f16(c[1], ax[1], b.x, b.y, ph);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    fk[2 * mt] = fmaf(a2.x, __cosf(c[mt][0]), fk[2 * mt]);
+                    fk[2 * mt] = fmaf(a2.y, __cosf(c[mt][1]), fk[2 * mt]);
+                    fk[2 * mt + 1] = fmaf(a2.x, __cosf(c[mt][2]), fk[2 * mt + 1]);
+                    fk[2 * mt + 1] = fmaf(a2.y, __cosf(c[mt][3]), fk[2 * mt + 1]);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                float v = fk[r];
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                if (r == t) sxb[(g + 8 * r) * 8 + k] = v;
+            }
+        }
+#pragma unroll 1
+        for (; m < M; ++m) rbf_step(m);   // more inducing points than feature tiles
+    } else {
     const int warp_id = threadIdx.x >> 5;
     const bool rbf_first = stagger && ((warp_id ^ (warp_id >> 2)) & 1) != 0;
 #pragma unroll 1
@@ -394,32 +553,12 @@ __device__ __forceinline__ void vf_eval_h(const float* __restrict__ small, const
             }
         }
         } else {
+        {
 #pragma unroll 2
-        for (int m = 0; m < M; ++m) {
-            float kp_[KS];
-            lds_vec<KS>(kp_, kern + m * KS);
-            float dd[D];
-#pragma unroll
-            for (int j = 0; j < D; ++j) {
-                const float d = x[0][j] - kp_[j];
-                dd[j] = d * d;
-            }
-#pragma unroll
-            for (int kp = 0; kp < KF; ++kp) {
-                float2 e = make_float2(0.f, 0.f);
-#pragma unroll
-                for (int j = 0; j < D; ++j) e = ffma2(dd[j], wn[j][kp], e);
-                const float2 K = make_float2(gpode_ex2(e.x), gpode_ex2(e.y));
-                fu[kp] = ffma2(make_float2(kp_[D + 2 * kp], kp_[D + 2 * kp + 1]), K, fu[kp]);
-            }
-            if constexpr (kOdd) {
-                float e = 0.f;
-#pragma unroll
-                for (int j = 0; j < D; ++j) e = fmaf(dd[j], wl[j], e);
-                fl = fmaf(kp_[2 * D - 1], gpode_ex2(e), fl);
-            }
+        for (int m = 0; m < M; ++m) rbf_step(m);
         }
         }
+    }
     }
     __syncwarp();
 #pragma unroll

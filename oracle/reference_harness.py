@@ -1,6 +1,5 @@
-"""TEST INFRASTRUCTURE ONLY -- runs the UNMODIFIED reference modules from ``/root/reference`` on CPU.
-
-Usable only where ``/root/reference`` exists (the build container, NOT the GPU box). It
+"""TEST INFRASTRUCTURE ONLY -- runs the UNMODIFIED reference modules on CPU: from ``/root/reference`` in the build
+container, from the archive ``oracle/_ref/gpode_reference_src.zip`` (``oracle/stage_reference.py``) on the GPU box. It
 * puts ``oracle/torchdiffeq_shim`` on ``sys.path`` so reference ``src/core/flow.py:3-4`` imports unchanged,
 * replaces the reference's three numpy RNG helpers (``src/core/dsvgp.py:11-26``, ``src/core/kernels.py:13-15`` --
   the latter builds an UNSEEDED ``RandomState()``, so omega is irreproducible without this) and torch's
@@ -15,17 +14,29 @@ import warnings
 import numpy as np
 import torch
 
-REFERENCE_ROOT = os.environ.get("GPODE_REFERENCE_ROOT", "/root/reference")
 _HERE = os.path.dirname(os.path.abspath(__file__))
+# the reference tree itself (build container), else the byte-for-byte archive of its src/ staged by
+# oracle/stage_reference.py (git-ignored; travels to the GPU box): either way the UNMODIFIED modules are imported
+STAGED_ARCHIVE = os.path.join(_HERE, "_ref", "gpode_reference_src.zip")
+REFERENCE_ROOT = os.environ.get("GPODE_REFERENCE_ROOT", "/root/reference")
+if not os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "core")) and os.path.isfile(STAGED_ARCHIVE):
+    REFERENCE_ROOT = STAGED_ARCHIVE
 
 
 def available():
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "core"))
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "core")) or os.path.isfile(REFERENCE_ROOT)
+
+
+def source():
+    """'tree' (the reference checkout), 'archive' (oracle/_ref) or None."""
+    if os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "core")):
+        return "tree"
+    return "archive" if os.path.isfile(REFERENCE_ROOT) else None
 
 
 def _import_reference():
     if not available():
-        raise RuntimeError("reference tree not found at %s" % REFERENCE_ROOT)
+        raise RuntimeError("reference not found: neither %s nor %s" % (REFERENCE_ROOT, STAGED_ARCHIVE))
     shim = os.path.join(_HERE, "torchdiffeq_shim")
     for p in (shim, REFERENCE_ROOT):
         if p not in sys.path:

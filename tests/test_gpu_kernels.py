@@ -474,6 +474,15 @@ def test_forward_tensor_core_path(D, M, S, B, monkeypatch):
     assert relerr(f1, f0) <= TOL_VF and relerr(f1, f32) <= TOL_VF
     assert relerr(xs1, xs0) <= TOL_TRAJ and relerr(xs1, out) <= TOL_TRAJ
     assert torch.equal(xs1[0], x)
+    # the schedule variants of the tensor-core evaluation (mma_parts bits 2-3: fused stream = default, two parts, two
+    # parts staggered across warps) run the same sums in the same order: bit-identical results
+    try:
+        for parts in (7, 11):
+            _lib.set_option("mma_parts", parts)
+            fv, xsv = run("1")
+            assert torch.equal(fv, f1) and torch.equal(xsv, xs1), parts
+    finally:
+        _lib.set_option("mma_parts", 3)
     # outside the split-fp16 domain (|x| >= 65504) the tensor-core kernels answer NaN, never a wrong finite number
     if D == 5 and B == 60000:
         xbad = x.clone()
