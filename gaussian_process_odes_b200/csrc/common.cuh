@@ -41,10 +41,10 @@ void gpode_set_error(const char* fmt, ...);
 // ------------------------------------------------------------------------------------------------------------------
 // process-wide kernel-selection options (gpode_set_option / gpode_get_option, include/gpode_b200.h): the library's only
 // mutable global state. Defaults come from the environment ONCE, when the first option is read (GPODE_BWD_MMA,
-// GPODE_FWD_MMA, GPODE_MMA_PARTS, GPODE_FORCE_NARROW, GPODE_USE_MMA); after that only gpode_set_option changes them.
+// GPODE_FWD_MMA, GPODE_MMA_PARTS, GPODE_FORCE_NARROW, GPODE_USE_MMA, GPODE_LARGE_BWD_UMMA); after that only gpode_set_option changes them.
 // ------------------------------------------------------------------------------------------------------------------
 enum { GPODE_OPT_BWD_MMA = 0, GPODE_OPT_FWD_MMA, GPODE_OPT_MMA_PARTS, GPODE_OPT_FORCE_NARROW, GPODE_OPT_USE_MMA,
-       GPODE_OPT_COUNT };
+       GPODE_OPT_LARGE_BWD_UMMA, GPODE_OPT_COUNT };
 int gpode_option(int which);  // pack.cu
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -25,6 +25,15 @@
 
 int gpode_vf_large_eval(const float* packed_large, const gpode_cache_t* c, const float* x, float* tmp, float* f,
                         int64_t B, cudaStream_t st);  // large_umma.cu: f = vf(x) on the tcgen05 tensor cores
+// large_rffb.cu: the RFF part of the VJP on the tcgen05 tensor cores (both projections as 3xTF32 GEMMs)
+int64_t gpode_rv_packed_floats(int D, int S);
+int64_t gpode_rv_acc_floats(int D);
+bool gpode_rv_supported(int D);
+int gpode_rv_grid(int64_t B);
+int gpode_rv_dn(int D);
+int gpode_rv_pack(const gpode_cache_t* c, float* out, cudaStream_t st);
+int gpode_rv_launch(const float* packed, int D, int S, const float* x, const float* kb, float* gx, int64_t B, float* acc,
+                    cudaStream_t st);
 
 namespace {
 
@@ -97,7 +106,9 @@ template <int DP>
 __global__ void __launch_bounds__(kLbThreads, DP >= 64 ? 1 : 2)
 vjp_large_kernel(const float* __restrict__ pk, const LbLayout L, const float* __restrict__ x,
                  const float* __restrict__ f, const float* __restrict__ kb, float* __restrict__ gx, const int64_t B,
-                 float* __restrict__ accA, float* __restrict__ accT, float* __restrict__ accZ) {
+                 float* __restrict__ accA, float* __restrict__ accT, float* __restrict__ accZ, const int rff_done) {
+    // rff_done != 0: the tensor-core kernel of large_rffb.cu has already written the RFF part of the row cotangent to gx
+    // (and its lengthscale partial sums to its own rows): this kernel adds the RBF part and the variance sums.
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int LD = LbSmem<DP>::LD, TILE = LbSmem<DP>::tile;
     float* xs = reinterpret_cast<float*>(smem_raw);
@@ -147,7 +158,7 @@ vjp_large_kernel(const float* __restrict__ pk, const LbLayout L, const float* __
         }
         // first Omega chunk of this tile; the generic-proxy writes of the previous tile's RBF part to stA / stB are
         // ordered before the async-proxy copy by the barrier at the end of that tile + this fence
-        if (tid == 0) {
+        if (tid == 0 && !rff_done) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             gpode_bulk_g2s(obuf[it & 1], om_g, kChunkBytes, mbar + (it & 1));
         }
@@ -164,7 +175,15 @@ vjp_large_kernel(const float* __restrict__ pk, const LbLayout L, const float* __
                 const float4 v = *reinterpret_cast<const float4*>(xrow + 4 * j4);
                 xr[4 * j4] = v.x; xr[4 * j4 + 1] = v.y; xr[4 * j4 + 2] = v.z; xr[4 * j4 + 3] = v.w;
             }
-            *reinterpret_cast<float4*>(xbr + 4 * j4) = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 init = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rff_done && tid < n) {
+                const float* __restrict__ gr = gx + (r0 + tid) * D;
+                init.x = 4 * j4 < D ? gr[4 * j4] : 0.f;
+                init.y = 4 * j4 + 1 < D ? gr[4 * j4 + 1] : 0.f;
+                init.z = 4 * j4 + 2 < D ? gr[4 * j4 + 2] : 0.f;
+                init.w = 4 * j4 + 3 < D ? gr[4 * j4 + 3] : 0.f;
+            }
+            *reinterpret_cast<float4*>(xbr + 4 * j4) = init;
         }
         // variance partial sum, first half: V1[k] += sum_rows kb_k f_k
         for (int k = 0; k < D; ++k) {
@@ -176,7 +195,7 @@ vjp_large_kernel(const float* __restrict__ pk, const LbLayout L, const float* __
         for (int k = tid; k < D; k += kLbThreads) V1[k] += (red[k] + red[DP + k]) + (red[2 * DP + k] + red[3 * DP + k]);
 
         // ================= RFF part =================
-        for (int k = 0; k < D; ++k) {
+        for (int k = 0; k < (rff_done ? 0 : D); ++k) {
             float G[DP];
 #pragma unroll
             for (int j = 0; j < DP; ++j) G[j] = 0.f;
@@ -358,7 +377,8 @@ vjp_large_kernel(const float* __restrict__ pk, const LbLayout L, const float* __
 // grid.x covers the D*D + D + D*M + M*D outputs; acc = [accA rows | accT rows | accZ rows]
 __global__ void finalize_large_kernel(const int D, const int DP, const int M, const int n_rows,
                                       const float* __restrict__ accA, const float* __restrict__ accT,
-                                      const float* __restrict__ accZ, const float* __restrict__ nu,
+                                      const float* __restrict__ accZ, const float* __restrict__ accR, const int n_rows_r,
+                                      const int DN, const float* __restrict__ nu,
                                       const float* __restrict__ ell, const float* __restrict__ var,
                                       float* __restrict__ g_ell, float* __restrict__ g_var, float* __restrict__ g_Z,
                                       float* __restrict__ g_nu) {
@@ -371,7 +391,10 @@ __global__ void finalize_large_kernel(const int D, const int DP, const int M, co
     };
     if (i < nA) {
         const int k = i / D, j = i - k * D;
-        g_ell[i] = (float)(-sum_rows(accA, (size_t)DP * DP + DP, (size_t)k * DP + j) / (double)ell[i]);
+        double a = sum_rows(accA, (size_t)DP * DP + DP, (size_t)k * DP + j);
+        // rows of the tensor-core RFF kernel (one per CTA and row warp), in row order
+        for (int r = 0; r < n_rows_r; ++r) a += (double)__ldcg(accR + (size_t)r * DN * DN + (size_t)k * DN + j);
+        g_ell[i] = (float)(-a / (double)ell[i]);
     } else if (i < nA + D) {
         // V[k] = sum_rows kb_k f_k + sum_m c_km T[k][m]
         const int k = i - nA;
@@ -464,23 +487,36 @@ int lb_grid(int64_t B, int DP) {
 
 template <int DP>
 int launch_vjp(const float* pk, const LbLayout& L, const float* x, const float* f, const float* kb, float* gx,
-               int64_t B, float* acc, cudaStream_t st) {
+               int64_t B, float* acc, cudaStream_t st, int rff_done) {
     const size_t smem = LbSmem<DP>::bytes;
     GPODE_CUDA(cudaFuncSetAttribute(vjp_large_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     float* accA = acc;
     float* accT = accA + (size_t)kLbMaxCtas * (DP * DP + DP);
     float* accZ = accT + (size_t)kLbMaxCtas * L.D * L.M;
-    vjp_large_kernel<DP><<<lb_grid(B, DP), kLbThreads, smem, st>>>(pk, L, x, f, kb, gx, B, accA, accT, accZ);
+    vjp_large_kernel<DP><<<lb_grid(B, DP), kLbThreads, smem, st>>>(pk, L, x, f, kb, gx, B, accA, accT, accZ, rff_done);
     GPODE_LAUNCH_CHECK();
     return 0;
 }
 
+// floats of the FP32 kernel's accumulator rows (the tensor-core RFF rows follow them in acc_large)
+int64_t lb_acc_floats(int D, int M) {
+    const int DP = lb_dp(D);
+    return (int64_t)kLbMaxCtas * ((int64_t)DP * DP + DP + (int64_t)D * M + (int64_t)M * DP);
+}
+// the RFF part on the tcgen05 kernel of large_rffb.cu unless the option large_bwd_umma is 0 (or it does not fit)
+bool use_rv(int D) { return gpode_option(GPODE_OPT_LARGE_BWD_UMMA) != 0 && gpode_rv_supported(D); }
+
 int vjp_dispatch(const float* pk, int D, int M, int S, const float* x, const float* f, const float* kb, float* gx,
                  int64_t B, float* acc, cudaStream_t st) {
     const LbLayout L = lb_layout(D, M, S);
-    if (L.DP == 16) return launch_vjp<16>(pk, L, x, f, kb, gx, B, acc, st);
-    if (L.DP == 32) return launch_vjp<32>(pk, L, x, f, kb, gx, B, acc, st);
-    return launch_vjp<64>(pk, L, x, f, kb, gx, B, acc, st);
+    int rff_done = 0;
+    if (use_rv(D)) {
+        if (int rc = gpode_rv_launch(pk + L.total, D, S, x, kb, gx, B, acc + lb_acc_floats(D, M), st)) return rc;
+        rff_done = 1;
+    }
+    if (L.DP == 16) return launch_vjp<16>(pk, L, x, f, kb, gx, B, acc, st, rff_done);
+    if (L.DP == 32) return launch_vjp<32>(pk, L, x, f, kb, gx, B, acc, st, rff_done);
+    return launch_vjp<64>(pk, L, x, f, kb, gx, B, acc, st, rff_done);
 }
 
 inline unsigned ew_grid(int64_t n) {
@@ -492,22 +528,22 @@ inline unsigned ew_grid(int64_t n) {
 
 extern "C" int64_t gpode_packed_large_bwd_floats(int D, int M, int S) {
     if (D <= GPODE_MAX_D || D > GPODE_MAX_D_LARGE || S < 1 || M < 1) return -1;
-    return lb_layout(D, M, S).total;
+    return lb_layout(D, M, S).total + gpode_rv_packed_floats(D, S);   // FP32 kernel's block | tensor-core RFF operands
 }
 
 extern "C" int64_t gpode_acc_large_floats(int D, int M) {
     if (D <= GPODE_MAX_D || D > GPODE_MAX_D_LARGE || M < 1) return -1;
-    const int DP = lb_dp(D);
-    return (int64_t)kLbMaxCtas * ((int64_t)DP * DP + DP + (int64_t)D * M + (int64_t)M * DP);
+    return lb_acc_floats(D, M) + gpode_rv_acc_floats(D);
 }
 
 extern "C" int gpode_pack_cache_large_bwd(const gpode_cache_t* c, float* packed_bwd, void* stream) {
     if (int rc = lb_check(c)) return rc;
     GPODE_CHECK_ARG(packed_bwd != nullptr, "packed_bwd is NULL");
-    pack_lb_kernel<<<592, 256, 0, (cudaStream_t)stream>>>(lb_layout(c->D, c->M, c->S), c->omega, c->phase, c->w, c->Z,
-                                                         c->nu, c->ell, c->var, packed_bwd);
+    const LbLayout L = lb_layout(c->D, c->M, c->S);
+    pack_lb_kernel<<<592, 256, 0, (cudaStream_t)stream>>>(L, c->omega, c->phase, c->w, c->Z, c->nu, c->ell, c->var,
+                                                         packed_bwd);
     GPODE_LAUNCH_CHECK();
-    return 0;
+    return gpode_rv_pack(c, packed_bwd + L.total, (cudaStream_t)stream);
 }
 
 extern "C" int gpode_vf_bwd_large(const float* packed_bwd, int D, int M, int S, const float* x, const float* f,
@@ -528,8 +564,11 @@ extern "C" int gpode_grads_finalize_large(const gpode_cache_t* c, const float* a
     const float* accT = accA + (size_t)kLbMaxCtas * (DP * DP + DP);
     const float* accZ = accT + (size_t)kLbMaxCtas * D * M;
     const int n_out = D * D + D + 2 * D * M;
+    const float* accR = acc_large + lb_acc_floats(D, M);
+    const int n_rows_r = use_rv(D) ? gpode_rv_grid(B) * 4 : 0;
     finalize_large_kernel<<<(n_out + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-        D, DP, M, lb_grid(B, DP), accA, accT, accZ, c->nu, c->ell, c->var, grad_ell, grad_var, grad_Z, grad_nu);
+        D, DP, M, lb_grid(B, DP), accA, accT, accZ, accR, n_rows_r, gpode_rv_dn(D), c->nu, c->ell, c->var, grad_ell,
+        grad_var, grad_Z, grad_nu);
     GPODE_LAUNCH_CHECK();
     return 0;
 }

@@ -187,7 +187,8 @@ extern "C" int gpode_pack_cache_sets(const gpode_cache_t* c, int n_sets, float* 
 namespace {
 std::atomic<int> g_opt[GPODE_OPT_COUNT];
 std::once_flag g_opt_once;
-const char* const kOptNames[GPODE_OPT_COUNT] = {"bwd_mma", "fwd_mma", "mma_parts", "force_narrow", "use_mma"};
+const char* const kOptNames[GPODE_OPT_COUNT] = {"bwd_mma", "fwd_mma", "mma_parts", "force_narrow", "use_mma",
+                                                  "large_bwd_umma"};
 void opt_init() {
     auto env_int = [](const char* n, int dflt) {
         const char* e = getenv(n);
@@ -198,6 +199,7 @@ void opt_init() {
     g_opt[GPODE_OPT_MMA_PARTS] = env_int("GPODE_MMA_PARTS", 3);
     g_opt[GPODE_OPT_FORCE_NARROW] = getenv("GPODE_FORCE_NARROW") != nullptr;
     g_opt[GPODE_OPT_USE_MMA] = getenv("GPODE_USE_MMA") != nullptr;
+    g_opt[GPODE_OPT_LARGE_BWD_UMMA] = env_int("GPODE_LARGE_BWD_UMMA", 1);
 }
 }  // namespace
 int gpode_option(int which) {
@@ -212,7 +214,7 @@ extern "C" int gpode_set_option(const char* name, int value) {
             g_opt[i].store(value, std::memory_order_relaxed);
             return 0;
         }
-    gpode_set_error("unknown option %s (bwd_mma, fwd_mma, mma_parts, force_narrow, use_mma)", name);
+    gpode_set_error("unknown option %s (bwd_mma, fwd_mma, mma_parts, force_narrow, use_mma, large_bwd_umma)", name);
     return -1;
 }
 extern "C" int gpode_get_option(const char* name) {

@@ -66,8 +66,11 @@ if __name__ == "__main__":
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
     res = []
-    for D, M, S, B in [(16, 100, 256, 100000), (32, 100, 256, 100000), (64, 100, 256, 100000), (16, 100, 256, 1000000),
-                       (32, 100, 256, 1000000), (64, 100, 256, 1000000)]:
+    shapes = [(16, 100, 256, 100000), (32, 100, 256, 100000), (64, 100, 256, 100000), (16, 100, 256, 1000000),
+              (32, 100, 256, 1000000), (64, 100, 256, 1000000)]
+    if os.environ.get("TL_SMALL"):   # quick A/B of the kernel-selection options: 1e5 rows only
+        shapes = shapes[:3]
+    for D, M, S, B in shapes:
         r = run(D, M, S, B)
         print(json.dumps(r), flush=True)
         res.append(r)
