@@ -172,9 +172,9 @@ KERNELS_PER_CALL = {
     "gpode_pack_cache_sets": 1, "gpode_whiten_fwd_sets": 2, "gpode_vf_fwd_sets": 1, "gpode_rk4_fwd_sets": 1,
     "gpode_dopri5_fwd_sets": 1, "gpode_shoot_fwd": 2, "gpode_shoot_bwd": 1,
     "gpode_pack_cache_ubwd": 1, "gpode_vf_bwd_umma": 1,
-    "gpode_pack_cache_large_bwd": 1, "gpode_vf_bwd_large": 1, "gpode_grads_finalize_large": 1,
+    "gpode_pack_cache_large_bwd": 2, "gpode_vf_bwd_large": 2, "gpode_grads_finalize_large": 2,
     # per RK4 step: forward 4 evaluations x 2 kernels + 4 stage kernels; adjoint 4 VJPs + 8 element-wise kernels
-    "gpode_rk4_fwd_large_dev": 12, "gpode_rk4_bwd_large": 12,
+    "gpode_rk4_fwd_large_dev": 12, "gpode_rk4_bwd_large": 16,
     # start: 2 evaluations (2 kernels each) + 6 small kernels; every attempt of the device-side loop launches 21 more
     "gpode_dopri5_fwd_large": 10 + 21,
 }
