@@ -187,6 +187,17 @@ __device__ __forceinline__ float gpode_sin_cw(const float x) {
     return (n & 2) ? -v : v;         // quadrants 0..3: sin, cos, -sin, -cos
 }
 
+// MUFU cosine / sine behind a two-piece Cody-Waite reduction by 2 pi (round-to-nearest by the 1.5 * 2^23 trick: four
+// FP32-pipe operations, no conversion instruction). cos.approx first multiplies its argument by 1 / 2 pi in float32, so
+// its absolute error grows like 1.2e-7 |theta|; with theta of tens of radians (large state dimensions: a sum over up to
+// 64 inputs) that was the leading error of long solves. Reduced to [-pi, pi] it stays below ~5e-7 at any angle.
+__device__ __forceinline__ float gpode_reduce_2pi(const float x) {
+    const float q = fmaf(x, 0.15915494309189535f, 12582912.f) - 12582912.f;
+    return fmaf(q, 1.7484555e-07f, fmaf(q, -6.2831854820251465f, x));   // 2 pi = 6.2831854820251465 - 1.7484555e-07
+}
+__device__ __forceinline__ float gpode_cos_red(const float x) { return __cosf(gpode_reduce_2pi(x)); }
+__device__ __forceinline__ float gpode_sin_red(const float x) { return __sinf(gpode_reduce_2pi(x)); }
+
 // ---- packed dual-FP32 arithmetic (sm_100: one issue slot, two FMAs) ---------------------------------------------
 __device__ __forceinline__ unsigned long long gpode_pack2(float lo, float hi) {
     unsigned long long r;

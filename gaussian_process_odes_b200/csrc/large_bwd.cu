@@ -236,8 +236,8 @@ vjp_large_kernel(const float* __restrict__ pk, const LbLayout L, const float* __
                         th0 = fmaf(xv.w, o0.w, th0); th1 = fmaf(xv.w, o1.w, th1);
                         th2 = fmaf(xv.w, o2.w, th2); th3 = fmaf(xv.w, o3.w, th3);
                     }
-                    const float g0 = a4.x * __sinf(th0), g1 = a4.y * __sinf(th1), g2 = a4.z * __sinf(th2),
-                                g3 = a4.w * __sinf(th3);
+                    const float g0 = a4.x * gpode_sin_red(th0), g1 = a4.y * gpode_sin_red(th1), g2 = a4.z * gpode_sin_red(th2),
+                                g3 = a4.w * gpode_sin_red(th3);
 #pragma unroll
                     for (int j4 = 0; j4 < DP / 4; ++j4) {
                         const float4 o0 = *reinterpret_cast<const float4*>(o + 4 * j4);

@@ -221,7 +221,7 @@ rff_vjp_large_kernel(const float* __restrict__ packed, const int D, const int S,
                             const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
-                                const float p = (wv[u] * __sinf(__uint_as_float(r[i + u]))) * nkb;
+                                const float p = (wv[u] * gpode_sin_red(__uint_as_float(r[i + u]))) * nkb;
                                 float h, l;
                                 gpode_split_tf32_rn(p, h, l);
                                 r[i + u] = __float_as_uint(h);
@@ -355,6 +355,7 @@ rff_vjp_large_kernel(const float* __restrict__ packed, const int D, const int S,
                     umma_tf32_ss(d, ah, bhd, idesc1, ks > 0 ? 1u : 0u);
                     umma_tf32_ss(d, al, bhd, idesc1, 1u);
                     umma_tf32_ss(d, ah, bld, idesc1, 1u);
+                    umma_tf32_ss(d, al, bld, idesc1, 1u);   // lo lo: see large_umma.cu (theta reaches tens of radians)
                 }
                 umma_commit(&bar->th_full[slot]);
                 umma_commit(&bar->b1_free[slot]);

@@ -184,10 +184,10 @@ rff_large_umma_kernel(const float* __restrict__ packed, const int D, const int S
 #pragma unroll
                         for (int i = 0; i < 32; i += 4) {
                             const float4 w4 = __ldg(reinterpret_cast<const float4*>(wgt + i));
-                            acc0 = fmaf(w4.x, __cosf(__uint_as_float(r[i])), acc0);
-                            acc1 = fmaf(w4.y, __cosf(__uint_as_float(r[i + 1])), acc1);
-                            acc0 = fmaf(w4.z, __cosf(__uint_as_float(r[i + 2])), acc0);
-                            acc1 = fmaf(w4.w, __cosf(__uint_as_float(r[i + 3])), acc1);
+                            acc0 = fmaf(w4.x, gpode_cos_red(__uint_as_float(r[i])), acc0);
+                            acc1 = fmaf(w4.y, gpode_cos_red(__uint_as_float(r[i + 1])), acc1);
+                            acc0 = fmaf(w4.z, gpode_cos_red(__uint_as_float(r[i + 2])), acc0);
+                            acc1 = fmaf(w4.w, gpode_cos_red(__uint_as_float(r[i + 3])), acc1);
                         }
                     };
                     // 32-column blocks, the next block's TMEM load in flight while the current one is on the MUFU
@@ -257,14 +257,20 @@ rff_large_umma_kernel(const float* __restrict__ packed, const int D, const int S
                 uint64_t ah = desc_a_hi, al = desc_a_lo;
                 uint64_t bhd = umma_smem_desc(gpode_smem_u32(bh), lbo_b, 128);
                 uint64_t bld = umma_smem_desc(gpode_smem_u32(bl), lbo_b, 128);
+                // all FOUR products of the split (hi hi, lo hi, hi lo, lo lo): the angle theta reaches tens of radians, and
+                // without the lo lo term (2^-22 of |x||Omega|) the gradients of a 30-step solve with whitened nu were
+                // 3.3x further from float64 than the reference's own float32 run; the tensor pipe has the slack (the
+                // kernel is bound by the L2 operand stream / the row threads)
                 umma_tf32_ss(d, ah, bhd, idesc, 0u);
                 umma_tf32_ss(d, al, bhd, idesc, 1u);
                 umma_tf32_ss(d, ah, bld, idesc, 1u);
+                umma_tf32_ss(d, al, bld, idesc, 1u);
                 for (int ks = 1; ks < KP / 8; ++ks) {
                     ah += step_a; al += step_a; bhd += step_b; bld += step_b;
                     umma_tf32_ss(d, ah, bhd, idesc, 1u);
                     umma_tf32_ss(d, al, bhd, idesc, 1u);
                     umma_tf32_ss(d, ah, bld, idesc, 1u);
+                    umma_tf32_ss(d, al, bld, idesc, 1u);
                 }
                 umma_commit(bar_full + tb);     // theta of this chunk is complete -> rows
                 umma_commit(bar_bfree + slot);  // ... and the ring slot has been read -> a later copy

@@ -732,8 +732,34 @@ def dopri5_integrate(x0, t, Z, ell, var, nu, omega, phase, w, rtol=1e-6, atol=1e
     return _Dopri5.apply(x0, t, Z, ell, var, nu, omega, phase, w, rtol, atol, torch.is_grad_enabled())
 
 
+def _whiten_large(Z, ell, var, u, omega, phase, w, jitter):
+    """The same whitening for 8 < D <= 64, where the in-shared-memory Cholesky kernels (one CTA per output dimension, a
+    cluster of D <= 8 CTAs in the backward) do not apply: D batched M x M factorisations and triangular solves through
+    torch.linalg (cuSOLVER / cuBLAS -- library calls, once per ELBO step) in float64 like the kernels, squared distance in
+    the direct form, differentiated by autograd. At these state dimensions the step time is in the integrator kernels
+    (tcgen05 vector field and VJP); this keeps ``DSVGP_Layer.build_cache`` -- and with it ``Flow`` and the model classes --
+    usable up to D = 64 (reference src/core/dsvgp.py:92-122 has no dimension limit)."""
+    D, M = ell.shape[0], Z.shape[0]
+    S = w.shape[0]
+    Zd, ed, vd = Z.double(), ell.double(), var.double()
+    d = (Zd[None, :, None, :] - Zd[None, None, :, :]) / ed[:, None, None, :]          # (D, M, M, J)
+    K = vd[:, None, None] * torch.exp(-0.5 * (d * d).sum(-1))
+    L = torch.linalg.cholesky(K + jitter * torch.eye(M, dtype=torch.float64, device=Z.device))
+    theta = torch.einsum('mj,jsk->msk', Zd, omega.double()) + phase.double().reshape(1, S, D)
+    prior = (torch.cos(theta) * (w.double() * torch.sqrt(vd / S)).unsqueeze(0)).sum(1)  # rff_forward(Z): (M, D)
+    a = torch.linalg.solve_triangular(L, prior.t().unsqueeze(2), upper=False)
+    nu = torch.linalg.solve_triangular(L.transpose(1, 2), u.double().t().unsqueeze(2) - a, upper=True)
+    return nu.squeeze(2).float()
+
+
 def whiten(Z, ell, var, u, omega, phase, w, jitter=1e-5):
     """nu (D,M) = L^-T (u - L^-1 rff_forward(Z)), L = chol(K(Z,Z) + jitter I), per output dimension."""
+    if Z.shape[1] > MAX_D_REGISTER:
+        if not Z.is_cuda:
+            raise _lib.GpodeError("gpode_b200 has no CPU path: Z is on %s" % Z.device)
+        if Z.shape[1] > MAX_D_LARGE:
+            raise _lib.GpodeError("state dimension D=%d above %d" % (Z.shape[1], MAX_D_LARGE))
+        return _whiten_large(Z, ell, var, u, omega, phase, w, jitter)
     return _Whiten.apply(Z, ell, var, u, omega, phase, w, jitter)
 
 

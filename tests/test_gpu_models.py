@@ -135,3 +135,18 @@ def test_host_draws_reach_the_device_intact_through_the_pinned_ring():
     for h, d in zip(host, dev):
         assert d.device.type == "cuda" and torch.equal(d.cpu(), h)
     assert host_to_device(dev[0], "cuda") is dev[0] or torch.equal(host_to_device(dev[0], "cuda"), dev[0])
+
+
+@pytest.mark.parametrize("kind,kw", [
+    ("gpode", dict(D=12, M=20, S=64, N=2, T=8, D_obs=12)),
+    ("shooting", dict(D=17, M=24, S=96, N=2, T=6, S_mc=3, D_obs=17)),
+])
+def test_models_above_eight_state_dimensions(kind, kw):
+    """8 < D <= 64 through the model classes (SequenceModel / UniformSequenceModel, rk4): whitening by the float64
+    torch.linalg branch of ops.whiten, vector field on the tcgen05 kernels, adjoint on the large-D VJP kernels -- ELBO
+    loss and every parameter gradient against the oracle port (reference src/core/dsvgp.py:92-122,172-197 have no
+    dimension limit), float64-arbitrated."""
+    from util import elbo_errors
+    rows = elbo_errors(kind, kw, "rk4", {}, 31)
+    for name, (e_cuda64, e_ref64, e_cuda32) in rows.items():
+        assert e_cuda32 <= TOL_GRAD or e_cuda64 <= max(TOL_GRAD, 1.5 * e_ref64), (name, e_cuda64, e_ref64, e_cuda32)
