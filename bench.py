@@ -196,22 +196,27 @@ def cpu_elbo_timing(w, steps, warmup, T_sample=6000, N_sample=1, prefer_referenc
     use_ref = prefer_reference and H.available()
     times = []
     if use_ref:
-        mods = H._import_reference()
-        model = H.build_reference_shooting(mods, p, ys, w["S"], solver=w["solver"], project=proj)
-        params = [q for q in model.parameters() if q.requires_grad]
-        for i in range(warmup + steps):
-            for q in params:
-                q.grad = None
-            t0 = time.perf_counter()
-            with H.injected_draws(mods, draws, n_caches=1, mvn_order=("eps_x0", "eps_states")):
-                loss, _ = H.reference_shooting_loss(model, ys, ts, num_samples=w["S_mc"])
-            loss.backward()
-            t1 = time.perf_counter()
-            if i >= warmup:
-                times.append(t1 - t0)
-        what = "the UNMODIFIED reference modules (%s; restated torchdiffeq 0.2.0 rk4)" % (
-            "/root/reference" if H.source() == "tree" else "oracle/_ref archive")
-    else:
+        try:
+            mods = H._import_reference()
+            model = H.build_reference_shooting(mods, p, ys, w["S"], solver=w["solver"], project=proj)
+            params = [q for q in model.parameters() if q.requires_grad]
+            for i in range(warmup + steps):
+                for q in params:
+                    q.grad = None
+                t0 = time.perf_counter()
+                with H.injected_draws(mods, draws, n_caches=1, mvn_order=("eps_x0", "eps_states")):
+                    loss, _ = H.reference_shooting_loss(model, ys, ts, num_samples=w["S_mc"])
+                loss.backward()
+                t1 = time.perf_counter()
+                if i >= warmup:
+                    times.append(t1 - t0)
+            what = "the UNMODIFIED reference modules (%s; restated torchdiffeq 0.2.0 rk4)" % (
+                "/root/reference" if H.source() == "tree" else "oracle/_ref archive")
+        except Exception as exc:  # the reference arm must never take the bench line down: fall back to the port, say so
+            print("reference modules failed on this host (%s: %s); timing the oracle port instead" % (
+                type(exc).__name__, exc), file=sys.stderr)
+            use_ref, times = False, []
+    if not use_ref:
         for i in range(warmup + steps):
             pp = {k: v.detach().clone().requires_grad_(True) for k, v in p.items()}
             t0 = time.perf_counter()
@@ -524,7 +529,7 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_elbo_timing(w, steps=8, warmup=2)
+        cpu = cpu_elbo_timing(w, steps=5, warmup=1)
         sat = {}
         for Ts in (1000, 3000):   # saturation: the port's throughput no longer depends on the sample size
             c2 = cpu_elbo_timing(w, steps=3, warmup=1, T_sample=Ts)

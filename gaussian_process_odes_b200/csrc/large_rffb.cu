@@ -34,7 +34,9 @@ __host__ __device__ inline int rv_kp(int D) { return (D + 1 + 7) & ~7; }   // pa
 __host__ __device__ inline int rv_dn(int D) { return (D + 15) & ~15; }     // padded N of GEMM 2
 __host__ __device__ inline int rv_su(int S) { return (S + kRvNC - 1) / kRvNC * kRvNC; }
 __host__ __device__ inline int64_t rv_b1(int D) { return 2 * (int64_t)rv_kp(D) * kRvNC; }  // floats: hi | lo
-__host__ __device__ inline int64_t rv_b2(int D) { return 2 * (int64_t)rv_dn(D) * kRvNC; }
+// GEMM-2 record: hi | lo | the chunk's feature weights a_sk (the row threads read them from the staged record instead of
+// global memory: ncu showed the row warps -- one per scheduler -- waiting on those loads, long_scoreboard 2.8 per issue)
+__host__ __device__ inline int64_t rv_b2(int D) { return 2 * (int64_t)rv_dn(D) * kRvNC + kRvNC; }
 // canonical K-major no-swizzle tile of `rows` rows: [K/4 chunks][rows/8 groups][8 rows][4 floats]
 __host__ __device__ inline int rv_off(int rows, int r, int q) {
     return (q >> 2) * (rows * 4) + (r >> 3) * 32 + (r & 7) * 4 + (q & 3);
@@ -73,6 +75,7 @@ __global__ void rv_pack_kernel(const int D, const int S, const float* __restrict
         const int o = rv_off(DN, j, s % kRvNC);
         r[o] = hi;
         r[(int64_t)DN * kRvNC + o] = lo;
+        if (j == 0) r[2 * (int64_t)DN * kRvNC + s % kRvNC] = s < S ? w[s * D + k] * sqrtf(var[k] / (float)S) : 0.f;
     }
     for (int64_t i = i0; i < (int64_t)D * SU; i += stride) {
         const int s = (int)(i % SU), k = (int)(i / SU);
@@ -132,7 +135,6 @@ rff_vjp_large_kernel(const float* __restrict__ packed, const int D, const int S,
     float* ring2 = ring1 + 2 * b1f;          // [2][b2f]
     const float* __restrict__ g1 = packed;
     const float* __restrict__ g2 = packed + (int64_t)D * NCH * b1f;
-    const float* __restrict__ aw = g2 + (int64_t)D * NCH * b2f;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 128) {
@@ -206,7 +208,10 @@ rff_vjp_large_kernel(const float* __restrict__ packed, const int D, const int S,
                     tmem_ld_wait(rb);
                     tc_fence_before_sync();
                     mbar_arrive(&bar->th_free[buf]);
-                    const float* __restrict__ wg = aw + (int64_t)k * SU + c * kRvNC;
+                    // the chunk's feature weights ride in its GEMM-2 record (landed well before theta is ready; the slot
+                    // is recycled only after GEMM 2, which waits for this thread's p_full arrival)
+                    mbar_wait_bounded(&bar->b2_full[buf], (q >> 1) & 1);
+                    const float* __restrict__ wg = ring2 + (size_t)buf * b2f + 2 * DN * kRvNC;
                     if (q >= 2) {   // GEMM 2 of chunk q - 2 has read this p slot
                         mbar_wait_bounded(&bar->p_free[buf], ((q >> 1) - 1) & 1);
                         tc_fence_after_sync();
@@ -217,7 +222,7 @@ rff_vjp_large_kernel(const float* __restrict__ packed, const int D, const int S,
                         uint32_t lo[32];
 #pragma unroll
                         for (int i = 0; i < 32; i += 4) {
-                            const float4 w4 = __ldg(reinterpret_cast<const float4*>(wg + half * 32 + i));
+                            const float4 w4 = *reinterpret_cast<const float4*>(wg + half * 32 + i);
                             const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {

@@ -51,6 +51,11 @@ def _import_reference():
     import src.gpode.models as gpode_models
     import src.gpode_shooting.models as shooting_models
     import torch.distributions.multivariate_normal as mvn
+    # The reference's device singleton answers cuda:0 whenever a GPU is visible (src/misc/settings.py:18-19) while its
+    # RNG helpers create CPU tensors: on the GPU box that mixes devices. The CPU arm pins the property
+    # to the CPU at run time (nothing in the modules changes), as reference_in_float64 does for the dtype.
+    import src.misc.settings as _rs
+    type(_rs.settings).device = property(lambda self: torch.device('cpu'))
     return dict(dsvgp=dsvgp, kernels=kernels, flow=flow, states=states, likelihoods=likelihoods,
                 constraints=constraints, gpode_models=gpode_models, shooting_models=shooting_models, mvn=mvn)
 

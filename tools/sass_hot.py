@@ -8,7 +8,14 @@ import sys
 rows = list(csv.reader(open(sys.argv[1])))
 h = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[h]
-data = [r for r in rows[h + 1:] if len(r) >= len(hdr)]
+data, seen = [], set()
+for r in rows[h + 1:]:   # first captured launch only (an export may hold several launches of the kernel)
+    if len(r) < len(hdr):
+        continue
+    if r[0] in seen:
+        break
+    seen.add(r[0])
+    data.append(r)
 ix = {k: i for i, k in enumerate(hdr)}
 stalls = [k for k in hdr if k.startswith("stall_") and "Not Issued" not in k]
 
