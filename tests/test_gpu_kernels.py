@@ -249,6 +249,28 @@ def test_large_state_dimension_backward(D, M, S, B):
     assert torch.equal(args2[1].grad, args[1].grad) and torch.equal(args2[3].grad, args[3].grad)
 
 
+@pytest.mark.parametrize("D,M,S,B", [(16, 100, 256, 1000), (41, 30, 200, 257), (64, 30, 64, 130)])
+def test_large_state_dimension_vjp_tensor_core_vs_fp32(D, M, S, B):
+    """The Fourier half of the large-D VJP on tcgen05 (csrc/large_rffb.cu, default) against the FP32 CUDA-core form
+    (option large_bwd_umma = 0): same row cotangent and parameter gradients to float32 round-off; ragged sizes (rows not a
+    multiple of 128, S not a multiple of 64, D not a multiple of 16)."""
+    from gaussian_process_odes_b200 import ops, _lib
+    gp32, c32, gp64, c64, x = _setup(D, M, S, B, seed=D + 3, nu_scale=0.1)
+    cot = torch.tensor(np.random.default_rng(9).normal(size=(B, D)), dtype=torch.float32)
+    res = {}
+    try:
+        for u in (1, 0):
+            _lib.set_option("large_bwd_umma", u)
+            args = [a.detach().clone().requires_grad_(i < 4) for i, a in enumerate(_cuda_args(gp32, c32))]
+            xc = x.cuda().requires_grad_(True)
+            ops.vector_field(xc, *args).backward(cot.cuda())
+            res[u] = dict(x=xc.grad, Z=args[0].grad, ell=args[1].grad, var=args[2].grad, nu=args[3].grad)
+    finally:
+        _lib.set_option("large_bwd_umma", 1)
+    for k in res[1]:
+        assert relerr(res[1][k].cpu(), res[0][k].cpu()) <= 2e-6, (k, relerr(res[1][k].cpu(), res[0][k].cpu()))
+
+
 @pytest.mark.parametrize("D,M,S,B", [(16, 100, 256, 300), (33, 20, 64, 40)])
 def test_large_state_dimension_dopri5(D, M, S, B):
     """8 < D <= 64: the adaptive solver (device-side controller inside a CUDA-graph while loop around the tensor-core

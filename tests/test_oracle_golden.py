@@ -79,3 +79,44 @@ def test_rk4_is_three_eighths_rule_and_dopri5_converges():
     # decreasing grid: out[0] == y0 and the flow is reversed
     back = O.odeint(f, y0, torch.tensor([0.0, -0.5], dtype=torch.float64), method='rk4')[-1].item()
     assert back > 1.0
+
+
+def test_staged_reference_archive_reproduces_the_golden_loss(tmp_path):
+    """The CPU arm of bench.py (`--impl reference`, `cpu_baseline`) imports the UNMODIFIED reference from the archive
+    `oracle/_ref/gpode_reference_src.zip` that `__graft_entry__.build()` stages (oracle/stage_reference.py). Run in a
+    fresh interpreter with the archive as the only source of the reference: it must import (zipimport, implicit namespace
+    packages), stay on the CPU whatever torch says about CUDA, and reproduce the committed golden loss bit for bit."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    archive = os.path.join(root, "oracle", "_ref", "gpode_reference_src.zip")
+    if not os.path.isfile(archive):
+        if not os.path.isdir("/root/reference/src"):
+            pytest.skip("no staged reference archive and no reference tree on this machine")
+        sys.path.insert(0, os.path.join(root, "oracle"))
+        import stage_reference
+        assert stage_reference.stage() == archive
+    script = tmp_path / "run_ref.py"
+    script.write_text('''
+import os, sys
+root = %r
+sys.path[:0] = [os.path.join(root, "oracle"), os.path.join(root, "tests")]
+import torch
+torch.cuda.is_available = lambda: True   # what the reference's device singleton sees on the GPU box
+import reference_harness as H
+from util import load_golden
+assert H.source() == "archive", H.source()
+g = load_golden("vdp_shooting_rk4")
+mods = H._import_reference()
+assert ".zip" in mods["dsvgp"].__file__, mods["dsvgp"].__file__
+model = H.build_reference_shooting(mods, g["p"], g["ys"], 256, solver="rk4")
+with H.injected_draws(mods, g["draws"], n_caches=1, mvn_order=("eps_x0", "eps_states")):
+    loss, _ = H.reference_shooting_loss(model, g["ys"], g["ts"], num_samples=g["draws"]["eps_x0"].shape[0])
+loss.backward()
+print("LOSS %%.9e REF %%.9e" %% (float(loss), float(g["ref"]["loss"])))
+assert abs(float(loss) - float(g["ref"]["loss"])) <= 1e-6 * abs(float(g["ref"]["loss"]))
+''' % root)
+    env = dict(os.environ, GPODE_REFERENCE_ROOT=archive, CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
