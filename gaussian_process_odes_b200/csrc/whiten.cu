@@ -42,7 +42,7 @@ __device__ void rff_at_Z(const gpode_cache_t& c, int k, double* p_out) {
         for (int s = lane; s < S; s += 32) {
             float th = c.phase[s * D + k];
             for (int j = 0; j < D; ++j) th = fmaf(c.Z[m * D + j], c.omega[((size_t)j * S + s) * D + k], th);
-            acc += (double)(c.w[s * D + k] * ak) * (double)cosf(th);
+            acc += (double)(c.w[s * D + k] * ak) * (double)gpode_cos_cw(th);   // 9e-8 at any angle, no libm slow path
         }
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (lane == 0) p_out[m] = acc;
@@ -51,13 +51,17 @@ __device__ void rff_at_Z(const gpode_cache_t& c, int k, double* p_out) {
 
 // In-place right-looking Cholesky of the leading M x M block of A (row-major, leading dim ld); `rows` >= M extra
 // rows below the block are carried along, so row r >= M ends up holding (L^-1 a_r)^T.
+// dinv[c] receives 1 / L_cc: the triangular solves multiply by it instead of dividing (a float64 division is a ~40
+// instruction dependent chain, and the column loop is the critical path of the whole kernel).
 template <typename Real>
-__device__ void chol_inplace(Real* A, int M, int rows, int ld) {
+__device__ void chol_inplace(Real* A, int M, int rows, int ld, Real* dinv) {
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, ny = blockDim.x >> 5;
     for (int c = 0; c < M; ++c) {
         __syncthreads();
-        const Real dcc = sqrt(A[c * ld + c]);
-        const Real inv = (Real)1 / dcc;
+        const Real acc_ = A[c * ld + c];
+        const Real inv = rsqrt(acc_);        // one reciprocal square root instead of sqrt + division
+        const Real dcc = acc_ * inv;
+        if (threadIdx.x == 0) dinv[c] = inv;
         for (int i = c + 1 + ty; i < rows; i += ny) {
             const Real lic = A[i * ld + c] * inv;
             const int jmax = i < M ? i : M - 1;
@@ -72,12 +76,12 @@ __device__ void chol_inplace(Real* A, int M, int rows, int ld) {
 
 // v <- L^-1 v (warp 0 only; caller syncs the CTA afterwards)
 template <typename Real>
-__device__ void trsv_lower(const Real* L, int M, int ld, Real* v) {
+__device__ void trsv_lower(const Real* L, int M, int ld, Real* v, const Real* dinv) {
     if (threadIdx.x >= 32) return;
     const int lane = threadIdx.x;
     for (int c = 0; c < M; ++c) {
         __syncwarp();
-        const Real rc = v[c] / L[c * ld + c];
+        const Real rc = v[c] * dinv[c];
         __syncwarp();
         if (lane == 0) v[c] = rc;
         for (int i = c + 1 + lane; i < M; i += 32) v[i] -= L[i * ld + c] * rc;
@@ -87,12 +91,12 @@ __device__ void trsv_lower(const Real* L, int M, int ld, Real* v) {
 
 // v <- L^-T v (warp 0 only)
 template <typename Real>
-__device__ void trsv_lower_t(const Real* L, int M, int ld, Real* v) {
+__device__ void trsv_lower_t(const Real* L, int M, int ld, Real* v, const Real* dinv) {
     if (threadIdx.x >= 32) return;
     const int lane = threadIdx.x;
     for (int c = M - 1; c >= 0; --c) {
         __syncwarp();
-        const Real rc = v[c] / L[c * ld + c];
+        const Real rc = v[c] * dinv[c];
         __syncwarp();
         if (lane == 0) v[c] = rc;
         for (int i = lane; i < c; i += 32) v[i] -= L[c * ld + i] * rc;
@@ -108,6 +112,7 @@ __global__ void whiten_fwd_kernel(const gpode_cache_t c, const float* __restrict
     Real* A = reinterpret_cast<Real*>(smem_raw);  // (M+1) x ld: K then L, last row p^T -> s^T
     double* pvec = reinterpret_cast<double*>(A + (size_t)(M + 1) * ld + ((M + 1) * ld & 1));
     Real* wv = reinterpret_cast<Real*>(pvec + M);
+    __shared__ Real dinv[GPODE_MAX_M];   // 1 / L_mm
 
     const float* ellk = c.ell + k * D;
     const double vark = (double)c.var[k];
@@ -120,7 +125,7 @@ __global__ void whiten_fwd_kernel(const gpode_cache_t c, const float* __restrict
     rff_at_Z(c, k, pvec);
     __syncthreads();
     for (int m = threadIdx.x; m < M; m += blockDim.x) A[M * ld + m] = (Real)pvec[m];
-    chol_inplace<Real>(A, M, M + 1, ld);
+    chol_inplace<Real>(A, M, M + 1, ld, dinv);
     // w = u_k - s ; nu = L^-T w
     for (int m = threadIdx.x; m < M; m += blockDim.x) {
         wv[m] = (Real)u[m * D + k] - A[M * ld + m];
@@ -132,7 +137,7 @@ __global__ void whiten_fwd_kernel(const gpode_cache_t c, const float* __restrict
         L_out[(size_t)k * M * M + i] = n <= m ? (double)A[m * ld + n] : 0.0;
     }
     __syncthreads();
-    trsv_lower_t<Real>(A, M, ld, wv);
+    trsv_lower_t<Real>(A, M, ld, wv, dinv);
     __syncthreads();
     for (int m = threadIdx.x; m < M; m += blockDim.x) nu_out[k * M + m] = (float)wv[m];
 }
@@ -156,19 +161,21 @@ __global__ void whiten_solve_sets_kernel(gpode_cache_t c, const float* __restric
     Real* L = reinterpret_cast<Real*>(smem_raw);
     double* pvec = reinterpret_cast<double*>(L + (size_t)M * ld + ((M * ld) & 1));
     Real* sv = reinterpret_cast<Real*>(pvec + M);
+    __shared__ Real dinv[GPODE_MAX_M];
     for (int i = threadIdx.x; i < M * M; i += blockDim.x) {
         const int m = i / M, n = i - m * M;
         L[m * ld + n] = (Real)L_in[(size_t)k * M * M + i];
     }
+    for (int m = threadIdx.x; m < M; m += blockDim.x) dinv[m] = (Real)(1.0 / L_in[(size_t)k * M * M + (size_t)m * M + m]);
     rff_at_Z(c, k, pvec);
     __syncthreads();
     for (int m = threadIdx.x; m < M; m += blockDim.x) sv[m] = (Real)pvec[m];
     __syncthreads();
-    trsv_lower<Real>(L, M, ld, sv);
+    trsv_lower<Real>(L, M, ld, sv, dinv);
     __syncthreads();
     for (int m = threadIdx.x; m < M; m += blockDim.x) sv[m] = (Real)u[m * D + k] - sv[m];
     __syncthreads();
-    trsv_lower_t<Real>(L, M, ld, sv);
+    trsv_lower_t<Real>(L, M, ld, sv, dinv);
     __syncthreads();
     for (int m = threadIdx.x; m < M; m += blockDim.x) nu_out[k * M + m] = (float)sv[m];
 }
@@ -199,21 +206,23 @@ __global__ void whiten_bwd_kernel(const gpode_cache_t c, const float* __restrict
         const int m = i / M, n = i - m * M;
         L[m * ld + n] = (Real)L_in[(size_t)k * M * M + i];
     }
+    __shared__ Real dinv[GPODE_MAX_M];
     for (int m = threadIdx.x; m < M; m += blockDim.x) {
+        dinv[m] = (Real)(1.0 / L_in[(size_t)k * M * M + (size_t)m * M + m]);
         const Real s = (Real)sp_in[((size_t)k * 2 + 0) * M + m];
         sv[m] = s;
         wv[m] = (Real)u[m * D + k] - s;
         rb[m] = (Real)gnu[k * M + m];
     }
     __syncthreads();
-    trsv_lower<Real>(L, M, ld, rb);  // rb = L^-1 nub  (= grad wrt u_k)
+    trsv_lower<Real>(L, M, ld, rb, dinv);  // rb = L^-1 nub  (= grad wrt u_k)
     __syncthreads();
     for (int m = threadIdx.x; m < M; m += blockDim.x) {
         pb[m] = -rb[m];
         g_u[m * D + k] = (float)rb[m];
     }
     __syncthreads();
-    trsv_lower_t<Real>(L, M, ld, pb);  // pb = -L^-T rb
+    trsv_lower_t<Real>(L, M, ld, pb, dinv);  // pb = -L^-T rb
     // P = -Phi(w rb^T - rb s^T)
     for (int i = threadIdx.x; i < M * M; i += blockDim.x) {
         const int m = i / M, n = i - m * M;
@@ -230,6 +239,9 @@ __global__ void whiten_bwd_kernel(const gpode_cache_t c, const float* __restrict
     // eliminated row by row with the whole CTA: ~4 M barriers, which was most of this kernel's 0.4 ms at M = 100).
     // All threads read the same L entry at the same time (shared-memory broadcast); the leading dimension is odd, so
     // the per-thread columns / rows of P sit in different banks.
+    // (Splitting every solve over four lanes of a warp -- 4 M busy threads, two xor shuffles and a __syncwarp per
+    // substitution step -- was measured: 0.305 ms against 0.288 ms; the fixed cost per step outweighs the shorter dot
+    // products at M = 100.)
     for (int n = threadIdx.x; n < M; n += blockDim.x) {          // column n:  L^T y = p  (back substitution)
         for (int i = M - 1; i >= 0; --i) {
             Real a0 = P[i * ld + n], a1 = (Real)0;
@@ -239,7 +251,7 @@ __global__ void whiten_bwd_kernel(const gpode_cache_t c, const float* __restrict
                 a1 -= L[(r + 1) * ld + i] * P[(r + 1) * ld + n];
             }
             if (r < M) a0 -= L[r * ld + i] * P[r * ld + n];
-            P[i * ld + n] = (a0 + a1) / L[i * ld + i];
+            P[i * ld + n] = (a0 + a1) * dinv[i];
         }
     }
     __syncthreads();
@@ -252,7 +264,7 @@ __global__ void whiten_bwd_kernel(const gpode_cache_t c, const float* __restrict
                 a1 -= P[r * ld + q + 1] * L[(q + 1) * ld + cidx];
             }
             if (q < M) a0 -= P[r * ld + q] * L[q * ld + cidx];
-            P[r * ld + cidx] = (a0 + a1) / L[cidx * ld + cidx];
+            P[r * ld + cidx] = (a0 + a1) * dinv[cidx];
         }
     }
     __syncthreads();
@@ -296,7 +308,7 @@ __global__ void whiten_bwd_kernel(const gpode_cache_t c, const float* __restrict
             for (int s = lane; s < S; s += 32) {
                 float th = c.phase[s * D + k];
                 for (int j = 0; j < D; ++j) th = fmaf(c.Z[m * D + j], c.omega[((size_t)j * S + s) * D + k], th);
-                const double g = -pbm * (double)(c.w[s * D + k] * ak) * (double)sinf(th);
+                const double g = -pbm * (double)(c.w[s * D + k] * ak) * (double)gpode_sin_cw(th);
                 for (int j = 0; j < D; ++j) G[j] += g * (double)c.omega[((size_t)j * S + s) * D + k];
             }
             for (int j = 0; j < D; ++j) {

@@ -742,8 +742,11 @@ def _whiten_large(Z, ell, var, u, omega, phase, w, jitter):
     D, M = ell.shape[0], Z.shape[0]
     S = w.shape[0]
     Zd, ed, vd = Z.double(), ell.double(), var.double()
-    d = (Zd[None, :, None, :] - Zd[None, None, :, :]) / ed[:, None, None, :]          # (D, M, M, J)
-    K = vd[:, None, None] * torch.exp(-0.5 * (d * d).sum(-1))
+    Ks = []
+    for k0 in range(0, D, 8):   # direct-form squared distance, eight output dimensions at a time ((8, M, M, J) temporary)
+        d = (Zd[None, :, None, :] - Zd[None, None, :, :]) / ed[k0:k0 + 8, None, None, :]
+        Ks.append(vd[k0:k0 + 8, None, None] * torch.exp(-0.5 * (d * d).sum(-1)))
+    K = torch.cat(Ks, 0)
     L = torch.linalg.cholesky(K + jitter * torch.eye(M, dtype=torch.float64, device=Z.device))
     theta = torch.einsum('mj,jsk->msk', Zd, omega.double()) + phase.double().reshape(1, S, D)
     prior = (torch.cos(theta) * (w.double() * torch.sqrt(vd / S)).unsqueeze(0)).sum(1)  # rff_forward(Z): (M, D)
