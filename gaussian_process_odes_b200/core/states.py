@@ -55,9 +55,11 @@ class _FullRankGaussian:
             self._scale_tril = torch.linalg.cholesky(cov)
         return self._scale_tril
 
-    def rsample(self, sample_shape):
-        shape = tuple(sample_shape) + tuple(self.loc.shape)
-        eps = _standard_normal(shape, self.loc.dtype, self.loc.device)
+    def rsample(self, sample_shape, eps=None):
+        """``eps``: the reparameterisation noise, if the caller has already drawn it (time sharding slices one draw)."""
+        if eps is None:
+            shape = tuple(sample_shape) + tuple(self.loc.shape)
+            eps = _standard_normal(shape, self.loc.dtype, self.loc.device)
         if self._fused:
             return ops.state_sample(self.loc, self._packed, eps, jitter)
         return self.loc + (self.scale_tril @ eps.unsqueeze(-1)).squeeze(-1)
@@ -200,6 +202,36 @@ class StateSequenceVariationalFactorizedGaussian(StateSequenceVariationalDistrib
 
     def entropy(self):
         return self.distribution().entropy()  # (N,T)
+
+    # ---- time sharding (distributed.enable_time_sharding): only a slice of the time axis on this process ----------
+    def _slice_distribution(self, a, b):
+        """q over the shooting states a..b-1 (views of the parameters: gradients flow to those rows only)."""
+        lchol_fn = self.lchol
+        return _FullRankGaussian(self.mean()[:, a:b].contiguous(), lambda: lchol_fn()[:, a:b],
+                                 self.param_lchol.optvar[:, a:b].contiguous())
+
+    def sample_time_slice(self, num_samples, lo, hi):
+        """Time indices ``lo..hi-1`` of :meth:`sample` (index 0 = the x0 sample, index t >= 1 = shooting state t - 1):
+        the SAME numbers -- the full reparameterisation noise is drawn in the same order and then sliced -- but only this
+        slice's Cholesky factors and matrix-vector products are computed. -> ``(S, N, hi - lo, D)``."""
+        S, N, T, D = num_samples, self.dim_n, self.dim_t, self.dim_d
+        ref = self.param_mean.optvar
+        eps0 = _standard_normal((S, N, D), ref.dtype, ref.device)
+        eps = _standard_normal((S, N, T, D), ref.dtype, ref.device)
+        parts = []
+        if lo == 0:
+            parts.append(self.x0.distribution().rsample((S,), eps=eps0).unsqueeze(2))
+        a, b = max(lo, 1) - 1, hi - 1
+        if b > a:
+            parts.append(self._slice_distribution(a, b).rsample((S,), eps=eps[:, :, a:b].contiguous()))
+        return torch.cat(parts, 2) if len(parts) > 1 else parts[0]
+
+    def entropy_time_slice(self, lo, hi):
+        """Entropy of the shooting states with time indices ``lo..hi-1`` (index 0, the initial state, has none)."""
+        a, b = max(lo, 1) - 1, hi - 1
+        if b <= a:
+            return torch.zeros((self.dim_n, 0), dtype=self.param_mean.optvar.dtype, device=self.param_mean.optvar.device)
+        return self._slice_distribution(a, b).entropy()
 
     def log_prob(self, x):
         return self.distribution().log_prob(x)

@@ -216,7 +216,7 @@ extern "C" int gpode_shoot_fwd(const float* packed, int D, int M, int S, const g
     }
     ShootArgs a;
     a.ys = sh->ys; a.W = sh->W; a.bias = sh->bias; a.lik_var = sh->lik_var; a.cons_scale = sh->cons_scale; a.ss = ss;
-    a.N = sh->N; a.T = sh->T; a.Dobs = sh->D_obs; a.laplace = sh->laplace; a.row_lo = sh->row_lo;
+    a.N = sh->N; a.T = sh->T; a.Dobs = sh->D_obs; a.laplace = sh->laplace & 1; a.halo = (sh->laplace >> 1) & 1; a.row_lo = sh->row_lo;
     a.n_total = (int64_t)sh->S_mc * sh->N * sh->T;
     a.pred_out = pred_out; a.seeds = seeds; a.work = work;
     int grid = 0;

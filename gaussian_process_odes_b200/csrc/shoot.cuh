@@ -24,7 +24,9 @@ struct ShootArgs {
     const float* lik_var;     // [Dobs]
     const float* cons_scale;  // 1 float
     const float* ss;          // [S_mc, N, T, D] all sampled states (rows of the segment batch)
-    int N, T, Dobs, laplace;
+    int N, T, Dobs, laplace;  // laplace: constraint family
+    int halo;                 // 1: the LAST time index of every sequence is a neighbour state only (time sharding): no
+                              // observation term for it (its seeds are zero, so its adjoint contributes nothing)
     int64_t row_lo;           // first row of this launch in the (S_mc, N, T) batch
     int64_t n_total;          // S_mc * N * T
     float* pred_out;          // [B_local, D] or NULL
@@ -96,6 +98,8 @@ __device__ __forceinline__ void shoot_epilogue(const ShootArgs& a, const ShootSm
     const int64_t g = a.row_lo + (valid ? row_local : 0);
     const int64_t NT = (int64_t)a.N * a.T;
     const float* __restrict__ y = a.ys + (g % NT) * Dobs;
+    const int t = (int)(g % a.T);
+    const bool obs = valid && !(a.halo && t == a.T - 1);   // this row carries an observation
     float sl[D];
 #pragma unroll
     for (int l = 0; l < D; ++l) sl[l] = 0.f;
@@ -108,7 +112,7 @@ __device__ __forceinline__ void shoot_epilogue(const ShootArgs& a, const ShootSm
     for (int d0 = 0; d0 < DP; d0 += 4) {
         float yv[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) yv[u] = (valid && d0 + u < Dobs) ? __ldg(y + d0 + u) : 0.f;
+        for (int u = 0; u < 4; ++u) yv[u] = (obs && d0 + u < Dobs) ? __ldg(y + d0 + u) : 0.f;
         const float4 b4 = *reinterpret_cast<const float4*>(sm.bias + d0);
         const float4 i4 = *reinterpret_cast<const float4*>(sm.iv + d0);
         const float4 l4 = *reinterpret_cast<const float4*>(sm.lv + d0);
@@ -126,10 +130,10 @@ __device__ __forceinline__ void shoot_epilogue(const ShootArgs& a, const ShootSm
         float q[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const float diff = valid ? f[u] - yv[u] : 0.f;   // a padded dimension has f = y = 0
+            const float diff = obs ? f[u] - yv[u] : 0.f;   // a padded dimension has f = y = 0
             q[u] = diff * iv[u];
             lsum += -0.5f * (lv[u] + diff * q[u]);
-            float gvd = valid ? -0.5f * (iv[u] - q[u] * q[u]) : 0.f;
+            float gvd = obs ? -0.5f * (iv[u] - q[u] * q[u]) : 0.f;
             if constexpr (kLanes) {
                 gvd = gpode_warp_sum(gvd);
                 if ((threadIdx.x & 31) == 0 && d0 + u < Dobs) sm.wacc[2 + d0 + u] += (double)gvd;
@@ -144,7 +148,6 @@ __device__ __forceinline__ void shoot_epilogue(const ShootArgs& a, const ShootSm
     // shooting constraint: this row's end point against the NEXT sampled state of the same sequence
     float sc[D];
     float csum = 0.f;
-    const int t = (int)(g % a.T);
     const bool has_next = valid && t < a.T - 1;
     const float* __restrict__ nxt = a.ss + (g + (has_next ? 1 : 0)) * D;
 #pragma unroll
@@ -159,7 +162,7 @@ __device__ __forceinline__ void shoot_epilogue(const ShootArgs& a, const ShootSm
         }
     }
     if (valid) {
-        ll += (double)lsum;
+        ll += obs ? (double)lsum : 0.0;
         cs += (double)csum;
         if (a.seeds != nullptr) {
 #pragma unroll

@@ -136,6 +136,35 @@ def row_sharded_shooting_loss(model, ys, ts, num_samples, world=None):
     return -(ll + cons + (ent - k0 - kl) / float(world))
 
 
+# ---- time sharding: ONE (or few) long sequence(s) -- VDP shooting, BASELINE configs[1] --------------------------------
+# Row sharding keeps the whole variational state distribution on every rank: its Cholesky factors, samples, entropy and
+# their backward (2e5 matrices for a 1e6-segment VDP problem) are replicated, and measured on 8 GPUs that is 2.5 of the
+# 4 ms of a step -- no scaling. Time sharding gives each rank a contiguous slice [lo, hi) of the TIME axis of every
+# sequence (all Monte-Carlo samples): it factorises / samples only the states of its slice plus one halo state (the
+# next slice's first state, the constraint's neighbour), integrates the slice's segments, and owns their gradient rows.
+# The halo state's gradient (the constraint's pull) lands on a parameter row owned by the next rank: the same single
+# all-reduce(sum) of all gradients delivers it. Every rank draws the same noise (full shape, same order, then sliced),
+# so the result equals the unsharded one.
+def enable_time_sharding(model, rank=None, world=None):
+    """Make ``model.build_lowerbound_terms`` evaluate only this rank's slice of the time axis (fused shooting step)."""
+    if rank is None:
+        rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    model.time_shard = (int(rank), int(world)) if world > 1 else None
+    model.row_shard = None
+    return model
+
+
+def time_sharded_shooting_loss(model, ys, ts, num_samples, world=None):
+    """Rank-local loss whose SUM over ranks is the global negative ELBO: observation, constraint and entropy terms are
+    this rank's share; the replicated terms (initial-state KL, inducing KL) are counted ``1/world`` times each."""
+    if world is None:
+        world = model.time_shard[1] if model.time_shard is not None else 1
+    ll, cons, ent, k0 = model.build_lowerbound_terms(ys, ts, num_samples=num_samples)
+    kl = model.build_inducing_kl()
+    return -(ll + cons + ent - (k0 + kl) / float(world))
+
+
 def allreduce_all_grads(model):
     """ONE all-reduce(sum) over the flattened gradients of EVERY parameter (row sharding: all parameters are replicated)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:

@@ -58,9 +58,12 @@ class UniformSequenceModel(BaseSequenceModel):
     # rows of the (S,N,T) segment batch this process integrates: None = all, or (rank, world) set by
     # ``distributed.enable_row_sharding`` (contiguous row blocks; every rank samples the same states)
     row_shard = None
+    # a contiguous slice of the TIME axis per process, set by ``distributed.enable_time_sharding``: the state-distribution
+    # work (Cholesky, sampling, entropy and their backward) shards together with the segment rows
+    time_shard = None
     fuse_elbo = True   # False: the unfused path (separate integrator / likelihood / constraint launches)
 
-    def _fused_terms(self, ss_samples, ys, ts):
+    def _fused_terms(self, ss_samples, ys, ts, halo=False, T_global=None):
         """Observation log-likelihood mean and constraint total through ONE integrator launch with the two terms
         evaluated on the segment end points inside the kernel (``ops.shooting_step``), or None when the configuration
         has no fused kernel (solver other than rk4, D > 8, non-affine decoder, trainable constraint scale, CPU)."""
@@ -86,19 +89,51 @@ class UniformSequenceModel(BaseSequenceModel):
         if var.numel() != Dobs:
             var = var.expand(Dobs)
         rows = None
-        if self.row_shard is not None:
+        if self.row_shard is not None and T_global is None:
             from ..distributed import shard_range
             rows = shard_range(S * N * T, *self.row_shard)
         flow.odefunc.before_odeint(return_divergence=False, rebuild_cache=True)
         ll_sum, cons_sum, _ = ops.shooting_step(ss_samples, ts[:2], *layer.cache_tensors(), ys, W, b, var,
-                                                cons.scale.detach(), laplace=cons._laplace, rows=rows)
+                                                cons.scale.detach(), laplace=cons._laplace, rows=rows, halo=halo)
         flow.odefunc.count_evals(4)
-        return ll_sum / float(S * N * T * Dobs), cons_sum / S
+        return ll_sum / float(S * N * (T if T_global is None else T_global) * Dobs), cons_sum / S
+
+    def _time_sharded_terms(self, ys, ts, num_samples):
+        """This process's share of the four ELBO terms under time sharding: segments with time index in its slice
+        ``[lo, hi)`` of the ``T`` indices of every sequence, for all Monte-Carlo samples. The sampled states of the slice
+        plus ONE halo index (the next slice's first state: the constraint's neighbour, reference ``models.py:134-135``)
+        are computed locally from the parameter rows of the slice, so sampling, entropy and their backward shard with the
+        rows; the halo's gradient reaches its owner through the all-reduce. Observation and constraint terms and the
+        entropy add up over the processes; the initial-state KL is replicated (weighted ``1/world`` by
+        ``distributed.time_sharded_shooting_loss``)."""
+        from ..distributed import shard_range
+        sd = self.state_distribution
+        rank, world = self.time_shard
+        T = sd.dim_t + 1
+        lo, hi = shard_range(T, rank, world)
+        halo = hi < T
+        zero = ys.new_zeros(())
+        initial_state_kl = sd.x0.kl()
+        if hi <= lo:   # more processes than time indices
+            sd.sample_time_slice(num_samples, 0, 1)   # keep the random streams of all processes aligned
+            self.flow.odefunc.before_odeint(return_divergence=False, rebuild_cache=True)
+            return zero, zero, zero, initial_state_kl / self.num_observations
+        ss_loc = sd.sample_time_slice(num_samples, lo, hi + int(halo))          # (S, N, hi - lo (+1), D)
+        fused = self._fused_terms(ss_loc, ys[:, lo:hi + int(halo)].contiguous(), ts, halo=halo, T_global=T)
+        if fused is None:
+            raise RuntimeError("time sharding needs the fused shooting step (rk4, affine decoder, frozen constraint "
+                               "scale, D <= 8)")
+        observation_loglik_mean, constraint_total = fused
+        entropy = sd.entropy_time_slice(lo, hi).sum()
+        return (observation_loglik_mean, constraint_total / self.num_observations, entropy / self.num_observations,
+                initial_state_kl / self.num_observations)
 
     def build_lowerbound_terms(self, ys, ts, num_samples=1, **kwargs):
         """-> (observation log-lik mean, constraint log-lik, state entropy, initial-state KL), the last three scaled
         by ``1/num_observations`` (reference ``models.py:108-146``). With ``row_shard`` set the first two are this
         process's share (sums over its rows with the global normalisation): they add up over the ranks."""
+        if self.time_shard is not None:
+            return self._time_sharded_terms(ys, ts, num_samples)
         ss_samples = self.state_distribution.sample(num_samples=num_samples)  # (S,N,T,D)
         (S, N, T, D) = ss_samples.shape
         fused = self._fused_terms(ss_samples, ys, ts)

@@ -364,7 +364,7 @@ class _ShootStep(torch.autograd.Function):
         row_lo, row_hi = int(row_lo), int(n_total if row_hi is None else row_hi)
         B = row_hi - row_lo
         sh = GpodeShoot()
-        sh.S_mc, sh.N, sh.T, sh.D_obs, sh.laplace = S_mc, N, T, Dobs, int(bool(laplace))
+        sh.S_mc, sh.N, sh.T, sh.D_obs, sh.laplace = S_mc, N, T, Dobs, int(laplace)   # bit 0 Laplace, bit 1 halo
         sh.ys, sh.W, sh.bias = ptr(yc).value, ptr(Wc).value, (ptr(bc).value if bc is not None else None)
         sh.lik_var, sh.cons_scale = ptr(vc).value, ptr(kc).value
         sh.row_lo, sh.row_hi = row_lo, row_hi
@@ -413,7 +413,7 @@ class _ShootStep(torch.autograd.Function):
 
 
 def shooting_step(ss, t2, Z, ell, var, nu, omega, phase, w, ys, W, bias, lik_var, cons_scale, laplace=False,
-                  rows=None, want_pred=False):
+                  rows=None, want_pred=False, halo=False):
     """One RK4 interval for every row of the sampled-state batch ``ss (S_mc,N,T,D)`` with the observation
     log-likelihood and the shooting constraint evaluated inside the integrator kernel. Returns
     ``(loglik_sum, constraint_sum, pred)``: sums over the rows ``rows = (lo, hi)`` of the flattened batch (all rows by
@@ -422,7 +422,10 @@ def shooting_step(ss, t2, Z, ell, var, nu, omega, phase, w, ys, W, bias, lik_var
     points ``pred (hi-lo, D)`` when ``want_pred`` (no gradient flows through them). Differentiable in ``ss``, ``Z``,
     ``ell``, ``var``, ``nu`` and ``lik_var``."""
     lo, hi = (0, None) if rows is None else rows
-    return _ShootStep.apply(ss, t2, Z, ell, var, nu, omega, phase, w, ys, W, bias, lik_var, cons_scale, laplace, lo, hi,
+    # ``halo``: the last time index of every sequence of this (time-sharded) batch is the next rank's first state --
+    # the constraint's neighbour only, no observation term (flag bit 1 of gpode_shoot_t.laplace)
+    flags = int(bool(laplace)) | (2 if halo else 0)
+    return _ShootStep.apply(ss, t2, Z, ell, var, nu, omega, phase, w, ys, W, bias, lik_var, cons_scale, flags, lo, hi,
                             torch.is_grad_enabled(), want_pred)
 
 

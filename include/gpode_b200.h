@@ -277,7 +277,11 @@ int gpode_dopri5_fwd_large(const float* packed_large, const gpode_cache_t* cache
  * Outputs besides the two sums: grad_lik_var [D_obs] (d sums_out[0] / d lik_var, may be NULL), kstages [1,4,B,D] and
  * seeds [2,B,D] (d sums_out[0] / d pred | d sums_out[1] / d pred; both NULL for a forward without gradients),
  * pred_out [B,D] (may be NULL). work: gpode_shoot_work_doubles() float64 of scratch. Sums are taken in a fixed order
- * (bitwise reproducible). */
+ * (bitwise reproducible).
+ * `laplace` is a flag word: bit 0 = Laplace instead of Gaussian constraint density; bit 1 = TIME-SHARDED batch: `ss` /
+ * `ys` hold a contiguous slice of the time axis plus ONE trailing halo index per sequence (the next rank's first state),
+ * which is only the constraint's neighbour -- it gets no observation term and contributes nothing to any gradient except
+ * the constraint's pull on it (distributed.enable_time_sharding: the state-distribution work shards with the rows). */
 typedef struct {
     int32_t S_mc, N, T, D_obs, laplace;
     const float* ys;         /* [N, T, D_obs] */

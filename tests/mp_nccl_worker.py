@@ -3,6 +3,8 @@ its own GPU through the CUDA path, then the sharded one with the other ranks, an
 
   A. segment-ROW sharding (distributed.enable_row_sharding): VDP shooting, N = 1 sequence -- the (S_mc, N, T) batch is
      cut into contiguous row blocks across samples and time; all parameters replicated; one all-reduce of every gradient.
+  A2. TIME sharding (distributed.enable_time_sharding): the same problem, each rank owns a slice of the time axis -- the
+     state-distribution work shards too; the halo state's gradient crosses ranks through the all-reduce.
   B. SEQUENCE sharding (bench.py's mode): MoCap-shaped problem, each rank owns N / world sequences and their variational
      states; one all-reduce of the shared-parameter gradient.
 """
@@ -56,6 +58,28 @@ def main():
         assert e <= 2e-5, ("row-sharded grad", k, e)
     if rank == 0:
         print("A row sharding ok: %d gradient floats all-reduced, worst gradient deviation %.2e" % (n, worst))
+
+    # ---- A2: time sharding -----------------------------------------------------------------------------------------
+    for kw2, seed in ((dict(D=2, M=16, S=256, N=1, T=25, S_mc=5), 21), (dict(D=3, M=24, S=64, N=2, T=41, S_mc=2, D_obs=7), 23)):
+        p, ys, ts, draws, proj = O.make_problem(seed=seed, **kw2)
+        l_full, g_full = unsharded(p, ys, ts, draws, proj, kw2)
+        model = build_product_model("shooting", p, ys, kw2['S'], "rk4", proj=None if proj is None else proj.components)
+        distributed.enable_time_sharding(model)
+        assert model.time_shard == (rank, world) and model.row_shard is None
+        with injected_draws(draws, mvn_order=("eps_x0", "eps_states")):
+            loss = distributed.time_sharded_shooting_loss(model, ys.cuda(), ts.cuda(), kw2['S_mc'])
+        loss.backward()
+        distributed.allreduce_all_grads(model)
+        tot = loss.detach().clone()
+        dist.all_reduce(tot)
+        assert relerr(tot, l_full) <= 1e-6, ("time-sharded loss", float(tot), float(l_full))
+        worst = 0.0
+        for k, v in product_grads(model, "shooting").items():
+            e = relerr(v, g_full[k])
+            worst = max(worst, e)
+            assert e <= 2e-5, ("time-sharded grad", k, e)
+        if rank == 0:
+            print("A2 time sharding ok (N=%d, T=%d): worst gradient deviation %.2e" % (kw2['N'], kw2['T'], worst))
 
     # ---- B: sequence sharding ----------------------------------------------------------------------------------------
     kw = dict(D=5, M=100, S=256, N=2 * world, T=40, S_mc=3, D_obs=50, dt=0.01, ell0=1.25)

@@ -13,19 +13,23 @@ from util import TOL_GRAD, build_product_model, elbo_errors, injected_draws, pro
 pytestmark = pytest.mark.gpu
 
 
-def _run(p, ys, ts, draws, proj, kw, fuse, row_shard=None, world=1, constraint=None):
+def _run(p, ys, ts, draws, proj, kw, fuse, row_shard=None, world=1, constraint=None, time_shard=None):
     model = build_product_model("shooting", p, ys, kw['S'], "rk4", proj=None if proj is None else proj.components)
     if constraint is not None:
         from gaussian_process_odes_b200.core import constraints
         model.constraint = constraints.Laplace(d=1, scale=constraint, requires_grad=False).cuda()
     model.fuse_elbo = fuse
     model.row_shard = row_shard
+    model.time_shard = time_shard
     with injected_draws(draws, mvn_order=("eps_x0", "eps_states")):
         ll, c, e, k0 = model.build_lowerbound_terms(ys.cuda(), ts.cuda(), num_samples=kw['S_mc'])
         kl = model.build_inducing_kl()
-        loss = -(ll + c + (e - k0 - kl) / float(world))
+        if time_shard is not None:   # the entropy is this rank's share, only the two KL terms are replicated
+            loss = -(ll + c + e - (k0 + kl) / float(world))
+        else:
+            loss = -(ll + c + (e - k0 - kl) / float(world))
     loss.backward()
-    g = {k: v.detach().clone() for k, v in product_grads(model, "shooting").items()}
+    g = {k: (None if v is None else v.detach().clone()) for k, v in product_grads(model, "shooting").items()}
     return loss.detach(), dict(ll=ll.detach(), c=c.detach()), g, model
 
 
@@ -77,6 +81,26 @@ def test_row_sharded_terms_and_gradients_add_up(kw, world):
     for r in range(world):
         l, _, g, _ = _run(p, ys, ts, draws, proj, kw, fuse=True, row_shard=(r, world), world=world)
         l_sum = l_sum + l.double()
+        g_sum = {k: v.double() for k, v in g.items()} if g_sum is None else {k: g_sum[k] + g[k].double() for k in g}
+    assert relerr(l_sum, l_all) <= 1e-6
+    for k in g_all:
+        assert relerr(g_sum[k], g_all[k]) <= 2e-5, (k, relerr(g_sum[k], g_all[k]))
+
+
+@pytest.mark.parametrize("kw,world", [(CASES[0], 3), (CASES[0], 8), (CASES[1], 4), (CASES[3], 2), (CASES[2], 16)],
+                         ids=["vdp_w3", "vdp_w8", "mocap09_w4", "rows18000_w2", "more_ranks_than_times"])
+def test_time_sharded_terms_and_gradients_add_up(kw, world):
+    """Time sharding (distributed.enable_time_sharding): every rank -- run one after the other here -- samples and
+    integrates only its slice of the time axis plus one halo state; losses and gradients add up to the unsharded ones
+    (the halo state's gradient, the constraint's pull, lands on the neighbour's parameter rows). Includes slices of one
+    index and more ranks than time indices."""
+    p, ys, ts, draws, proj = O.make_problem(seed=7, **kw)
+    l_all, _, g_all, _ = _run(p, ys, ts, draws, proj, kw, fuse=True)
+    l_sum, g_sum = 0.0, None
+    for r in range(world):
+        l, _, g, _ = _run(p, ys, ts, draws, proj, kw, fuse=True, time_shard=(r, world), world=world)
+        l_sum = l_sum + l.double()
+        g = {k: (v if v is not None else torch.zeros_like(g_all[k])) for k, v in g.items()}
         g_sum = {k: v.double() for k, v in g.items()} if g_sum is None else {k: g_sum[k] + g[k].double() for k in g}
     assert relerr(l_sum, l_all) <= 1e-6
     for k in g_all:

@@ -5,7 +5,8 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/bench_scaling.py
 
 * config 2, VDP shooting (train_vdp_gpode_shooting.py defaults: D=2, M=16, S=256, N=1, T=25, S_mc=5 -> 125 segments):
-  ONE sequence, so the segment ROWS are sharded (distributed.enable_row_sharding; the constraint's neighbour state is
+  ONE sequence, so the TIME axis is sharded (distributed.enable_time_sharding: each rank samples and integrates its
+  slice plus one halo state) -- or, for comparison, the segment ROWS (distributed.enable_row_sharding; the constraint's neighbour state is
   the halo row of the replicated sample tensor) and the flattened gradient of every parameter is all-reduced once.
   ELBO fwd+bwd step ms; also a long variant (T = 200 000 -> 10^6 segments) of the same model.
 * config 5, scaling sweep: D in {2, 5, 16, 64}, 10^6 rows in total (strong scaling: 10^6 / N per GPU), S=256, M=16 (D=2)
@@ -50,24 +51,35 @@ def timed(fn, world, dev, warm=3, reps=10):
     return float(np.median(out))
 
 
-def vdp_shooting(rank, world, dev, T):
+def vdp_shooting(rank, world, dev, T, mode="time"):
     from gaussian_process_odes_b200 import distributed
     kw = dict(D=2, M=16, S=256, N=1, T=T, S_mc=5)
     p, ys, ts, draws, _ = O.make_problem(seed=121, **kw)
     model = build_product_model("shooting", p, ys, kw['S'], "rk4")
-    distributed.enable_row_sharding(model, rank, world)
+    # mode "time": every rank owns a slice of the time axis (state-distribution work shards too); "rows": contiguous row
+    # blocks with the whole state distribution replicated (round 2, first version: flat from 1 to 8 GPUs)
+    if mode == "time":
+        distributed.enable_time_sharding(model, rank, world)
+    else:
+        distributed.enable_row_sharding(model, rank, world)
     ys, ts = ys.to(dev), ts.to(dev)
 
     def step():
         distributed.seed_ranks(7, rank, same_states=True)   # every rank draws the same states and the same GP function
         model.zero_grad(set_to_none=True)
-        loss = distributed.row_sharded_shooting_loss(model, ys, ts, kw['S_mc'], world)
+        if mode == "time":
+            loss = distributed.time_sharded_shooting_loss(model, ys, ts, kw['S_mc'], world)
+        else:
+            loss = distributed.row_sharded_shooting_loss(model, ys, ts, kw['S_mc'], world)
         loss.backward()
         distributed.allreduce_all_grads(model)
     ms = timed(step, world, dev)
     rows = kw['S_mc'] * kw['N'] * T
-    return dict(config="vdp_shooting" if T == 25 else "vdp_shooting_long", n_gpus=world, segments_total=rows,
-                parallelism="segment rows sharded x%d (replicated parameters, one all-reduce of all gradients)" % world,
+    name = ("vdp_shooting" if T == 25 else "vdp_shooting_long") + ("" if mode == "time" else "_row_sharded")
+    return dict(config=name, n_gpus=world, segments_total=rows,
+                parallelism=("time axis sharded x%d (each rank samples and integrates its slice + one halo state; one "
+                             "all-reduce of all gradients)" if mode == "time" else
+                             "segment rows sharded x%d (replicated parameters, one all-reduce of all gradients)") % world,
                 elbo_fwd_bwd_ms=ms, evals_per_s=4 * rows / (ms * 1e-3))
 
 
@@ -121,6 +133,7 @@ def main():
     if not only or "vdp" in only:
         emit(vdp_shooting(rank, world, dev, 25))
         emit(vdp_shooting(rank, world, dev, 200000))
+        emit(vdp_shooting(rank, world, dev, 200000, mode="rows"))
     if not only or "sweep" in only:
         for D, M in ((2, 16), (5, 100), (16, 100), (64, 100)):
             emit(sweep(rank, world, dev, D, M, 1000000 if D < 64 else 200000))
