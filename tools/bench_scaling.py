@@ -64,23 +64,45 @@ def vdp_shooting(rank, world, dev, T, mode="time"):
         distributed.enable_row_sharding(model, rank, world)
     ys, ts = ys.to(dev), ts.to(dev)
 
-    def step():
+    def loss_fn():
+        if mode == "time":
+            return distributed.time_sharded_shooting_loss(model, ys, ts, kw['S_mc'], world)
+        return distributed.row_sharded_shooting_loss(model, ys, ts, kw['S_mc'], world)
+
+    def eager_step():
         distributed.seed_ranks(7, rank, same_states=True)   # every rank draws the same states and the same GP function
         model.zero_grad(set_to_none=True)
-        if mode == "time":
-            loss = distributed.time_sharded_shooting_loss(model, ys, ts, kw['S_mc'], world)
-        else:
-            loss = distributed.row_sharded_shooting_loss(model, ys, ts, kw['S_mc'], world)
-        loss.backward()
+        loss_fn().backward()
         distributed.allreduce_all_grads(model)
-    ms = timed(step, world, dev)
+    ms_eager = timed(eager_step, world, dev)
+    # An eager step is ~150 host-issued launches: 3-4 ms of HOST time whatever the segment count, so it cannot scale.
+    # The library's form for such steps is the CUDA-graph replay (graphs.GraphedStep, as bench.py uses): ELBO forward +
+    # backward captured once, the gradient all-reduce outside the graph. Every rank's generators are seeded identically
+    # before the capture and consume the same number of draws per step, so the ranks keep drawing the same noise.
+    ms = ms_eager
+    graphed = False
+    try:
+        from gaussian_process_odes_b200 import graphs
+        distributed.seed_ranks(7, rank, same_states=True)
+        model.zero_grad(set_to_none=True)
+        gstep = graphs.GraphedStep(model, loss_fn)
+
+        def graph_step():
+            gstep()
+            distributed.allreduce_all_grads(model)
+        ms = timed(graph_step, world, dev)
+        graphed = True
+    except Exception as exc:   # capture is an optimisation: report the eager number
+        if rank == 0:
+            print("CUDA-graph capture failed (%r): eager timing reported" % (exc,), file=sys.stderr)
     rows = kw['S_mc'] * kw['N'] * T
     name = ("vdp_shooting" if T == 25 else "vdp_shooting_long") + ("" if mode == "time" else "_row_sharded")
     return dict(config=name, n_gpus=world, segments_total=rows,
                 parallelism=("time axis sharded x%d (each rank samples and integrates its slice + one halo state; one "
                              "all-reduce of all gradients)" if mode == "time" else
                              "segment rows sharded x%d (replicated parameters, one all-reduce of all gradients)") % world,
-                elbo_fwd_bwd_ms=ms, evals_per_s=4 * rows / (ms * 1e-3))
+                cuda_graph=graphed, elbo_fwd_bwd_ms=ms, elbo_fwd_bwd_ms_eager=ms_eager,
+                evals_per_s=4 * rows / (ms * 1e-3))
 
 
 def sweep(rank, world, dev, D, M, B_total):
