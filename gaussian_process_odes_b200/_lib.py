@@ -50,6 +50,8 @@ SIGNATURES = {
     "gpode_whiten_bwd": (_I, [_CP, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gpode_kl_fwd": (_I, [_P, _P, _I, _I, _P, _P]),
     "gpode_kl_bwd": (_I, [_P, _P, _I, _I, _P, _P, _P, _P]),
+    "gpode_inducing_sample_fwd": (_I, [_P, _P, _P, _I, _I, _P, _P]),
+    "gpode_inducing_sample_bwd": (_I, [_P, _P, _I, _I, _P, _P]),
     "gpode_dopri5_work_floats": (_L, [_I, _L]),
     "gpode_vf_fwd_large": (_I, [_CP, _P, _P, _L, _P]),
     "gpode_rk4_fwd_large": (_I, [_CP, _P, _P, _I, _L, _P, _P]),
@@ -165,7 +167,7 @@ def f32(t, name="tensor"):
 KERNELS_PER_CALL = {
     "gpode_pack_cache": 1, "gpode_vf_fwd": 1, "gpode_vf_bwd": 1, "gpode_rk4_fwd": 1, "gpode_rk4_bwd": 1,
     "gpode_param_grad": 1, "gpode_grads_finalize": 1, "gpode_whiten_fwd": 1, "gpode_whiten_bwd": 1,
-    "gpode_kl_fwd": 1, "gpode_kl_bwd": 1, "gpode_dopri5_fwd": 1, "gpode_dopri5_bwd": 1, "gpode_state_fwd": 1,
+    "gpode_kl_fwd": 1, "gpode_kl_bwd": 1, "gpode_inducing_sample_fwd": 1, "gpode_inducing_sample_bwd": 1, "gpode_dopri5_fwd": 1, "gpode_dopri5_bwd": 1, "gpode_state_fwd": 1,
     "gpode_state_bwd": 1, "gpode_loglik_sum": 2, "gpode_constraint_sum": 2, "gpode_vf_fwd_large": 1,
     "gpode_rk4_fwd_large": 1, "gpode_pack_cache_large": 1, "gpode_rbf_fwd_large": 1, "gpode_rff_fwd_large": 1,
     "gpode_vf_fwd_large_add_rbf": 1, "gpode_dopri5_bwd_dev": 1, "gpode_param_grad_dev": 1, "gpode_vf_fwd_umma": 1,

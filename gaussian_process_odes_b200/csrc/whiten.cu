@@ -392,6 +392,39 @@ __global__ void kl_bwd_kernel(const float* __restrict__ Um, const float* __restr
     }
 }
 
+// ---- inducing sample u = Um + Us_sqrt eps (dsvgp.py:78-90, full-rank branch) straight from the PACKED factor --------
+// u[n][d] = Um[n][d] + sum_{m <= n} L_d[n][m] eps[m][d]; one thread per (n, d). Replaces the tril scatter of the
+// (D, M, M) factor + a batched matrix product (and their backward: two products + an index-put) of the eager mirror.
+__global__ void inducing_sample_fwd_kernel(const float* __restrict__ Um, const float* __restrict__ Ls,
+                                           const float* __restrict__ eps, int D, int M, float* __restrict__ u) {
+    const int npk = M * (M + 1) / 2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M * D; i += gridDim.x * blockDim.x) {
+        const int n = i / D, d = i - n * D;
+        const float* __restrict__ row = Ls + (size_t)d * npk + (size_t)n * (n + 1) / 2;
+        float a0 = 0.f, a1 = 0.f;
+        int m = 0;
+        for (; m + 1 <= n; m += 2) {
+            a0 = fmaf(row[m], eps[m * D + d], a0);
+            a1 = fmaf(row[m + 1], eps[(m + 1) * D + d], a1);
+        }
+        if (m <= n) a0 = fmaf(row[m], eps[m * D + d], a0);
+        u[i] = Um[i] + (a0 + a1);
+    }
+}
+// grad_Ls[d][n][m] = g_u[n][d] eps[m][d]  (m <= n);  grad_Um = g_u is the caller's (identity)
+__global__ void inducing_sample_bwd_kernel(const float* __restrict__ eps, const float* __restrict__ gu, int D, int M,
+                                           float* __restrict__ gLs) {
+    const int npk = M * (M + 1) / 2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < D * npk; i += gridDim.x * blockDim.x) {
+        const int d = i / npk, p = i - d * npk;
+        int n = (int)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
+        while ((n + 1) * (n + 2) / 2 <= p) ++n;
+        while (n * (n + 1) / 2 > p) --n;
+        const int m = p - n * (n + 1) / 2;
+        gLs[i] = gu[n * D + d] * eps[m * D + d];
+    }
+}
+
 template <typename Real>
 size_t fwd_smem(int M) {
     const int ld = (M & 1) ? M : M + 1;
@@ -510,6 +543,29 @@ extern "C" int gpode_kl_bwd(const float* Um, const float* Ls_packed, int D, int 
     int grid = (n + 255) / 256;
     if (grid > 296) grid = 296;
     kl_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(Um, Ls_packed, D, M, grad_kl, grad_Um, grad_Ls_packed);
+    GPODE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gpode_inducing_sample_fwd(const float* Um, const float* Ls_packed, const float* eps, int D, int M,
+                                         float* u_out, void* stream) {
+    GPODE_CHECK_ARG(Um && Ls_packed && eps && u_out, "NULL argument");
+    GPODE_CHECK_ARG(D >= 1 && M >= 1, "D=%d, M=%d must be positive", D, M);
+    int grid = (M * D + 127) / 128;
+    if (grid > 296) grid = 296;
+    inducing_sample_fwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(Um, Ls_packed, eps, D, M, u_out);
+    GPODE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gpode_inducing_sample_bwd(const float* eps, const float* grad_u, int D, int M, float* grad_Ls_packed,
+                                         void* stream) {
+    GPODE_CHECK_ARG(eps && grad_u && grad_Ls_packed, "NULL argument");
+    GPODE_CHECK_ARG(D >= 1 && M >= 1, "D=%d, M=%d must be positive", D, M);
+    const int n = D * (M * (M + 1) / 2);
+    int grid = (n + 255) / 256;
+    if (grid > 296) grid = 296;
+    inducing_sample_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(eps, grad_u, D, M, grad_Ls_packed);
     GPODE_LAUNCH_CHECK();
     return 0;
 }

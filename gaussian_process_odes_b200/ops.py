@@ -196,6 +196,37 @@ class _WhitenedKL(torch.autograd.Function):
         return gU, gL
 
 
+class _InducingSample(torch.autograd.Function):
+    """u = Um + Us_sqrt eps from the PACKED factor (gpode_inducing_sample_fwd/_bwd; reference dsvgp.py:78-90)."""
+
+    @staticmethod
+    def forward(ctx, Um, Ls_packed, eps):
+        Uc, Lc, ec = f32(Um, "Um"), f32(Ls_packed, "Us_sqrt optvar"), f32(eps, "epsilon")
+        M, D = Uc.shape
+        if tuple(Lc.shape) != (D, M * (M + 1) // 2) or tuple(ec.shape) != (M, D):
+            raise _lib.GpodeError("inducing sample: Us_sqrt optvar %s / epsilon %s do not match Um %s" % (
+                tuple(Lc.shape), tuple(ec.shape), tuple(Uc.shape)))
+        u = torch.empty_like(Uc)
+        _lib.call("gpode_inducing_sample_fwd", ptr(Uc), ptr(Lc), ptr(ec), D, M, ptr(u), stream_ptr())
+        ctx.save_for_backward(ec)
+        ctx.dims = (D, M, Lc.shape)
+        return u
+
+    @staticmethod
+    def backward(ctx, g):
+        (ec,) = ctx.saved_tensors
+        D, M, lshape = ctx.dims
+        gc = f32(g, "grad_u")
+        gL = torch.empty(lshape, dtype=torch.float32, device=ec.device)
+        _lib.call("gpode_inducing_sample_bwd", ptr(ec), ptr(gc), D, M, ptr(gL), stream_ptr())
+        return gc, gL, None
+
+
+def inducing_sample(Um, Ls_packed, eps):
+    """``Um (M,D) + einsum('dnm,md->nd', tril(Ls), eps)`` with ``Ls`` packed ``(D, M(M+1)/2)``."""
+    return _InducingSample.apply(Um, Ls_packed, eps)
+
+
 class _StateSample(torch.autograd.Function):
     """mean + chol(L L^T + jitter I) eps for a batch of packed lower-triangular factors (gpode_state_fwd/_bwd)."""
 

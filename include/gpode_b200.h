@@ -120,6 +120,13 @@ int gpode_whiten_bwd(const gpode_cache_t* cache_with_nu, const float* u, const d
 int gpode_kl_fwd(const float* Um, const float* Ls_packed, int D, int M, float* kl_out, void* stream);
 int gpode_kl_bwd(const float* Um, const float* Ls_packed, int D, int M, const float* grad_kl, float* grad_Um,
                  float* grad_Ls_packed, void* stream);
+/* Inducing sample in whitened coordinates, u = Um + Us_sqrt eps (DSVGP_Layer.sample_inducing, src/core/dsvgp.py:78-90,
+ * full-rank branch `einsum('dnm,md->nd', Us_sqrt, eps)`), straight from the packed lower-triangular factor Ls_packed
+ * [D, M(M+1)/2] (row-major tril packing): u_out [M,D]. Backward: grad_Ls_packed = grad_u eps^T restricted to the lower
+ * triangle (grad_Um = grad_u). */
+int gpode_inducing_sample_fwd(const float* Um, const float* Ls_packed, const float* eps, int D, int M, float* u_out,
+                              void* stream);
+int gpode_inducing_sample_bwd(const float* eps, const float* grad_u, int D, int M, float* grad_Ls_packed, void* stream);
 
 /* Adaptive Dormand-Prince 5(4) with torchdiffeq 0.2.0's controller (rtol/atol, whole-batch RMS norm, float64 time,
  * 4th-order dense output) -- odeint(..., method='dopri5'), the reference's default solver (src/core/flow.py:41).

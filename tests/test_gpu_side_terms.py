@@ -125,3 +125,45 @@ def test_laplace_constraint_model_matches_tensor_path():
         out.append((loss.detach().cpu(), m.state_distribution.param_mean.optvar.grad.cpu()))
     assert relerr(out[0][0], out[1][0]) <= 1e-5
     assert relerr(out[0][1], out[1][1]) <= 1e-4
+
+
+@pytest.mark.parametrize("D,M", [(2, 16), (5, 100), (3, 1), (1, 7)])
+def test_inducing_sample_from_the_packed_factor(D, M):
+    """u = Um + Us_sqrt eps (reference src/core/dsvgp.py:78-90, full-rank branch) through gpode_inducing_sample_fwd/_bwd
+    straight from the packed lower-triangular parameter, against the reference's einsum over the scattered factor, and
+    the x0 KL through the fused KL kernels against its spelled-out form."""
+    from gaussian_process_odes_b200 import ops
+    from gaussian_process_odes_b200.misc import transforms
+    rng = np.random.default_rng(D * 100 + M)
+    tr = transforms.LowerTriangular(M, D)
+    packed = torch.tensor(rng.normal(size=(D, M * (M + 1) // 2)), dtype=torch.float32, device="cuda", requires_grad=True)
+    Um = torch.tensor(rng.normal(size=(M, D)), dtype=torch.float32, device="cuda", requires_grad=True)
+    eps = torch.tensor(rng.normal(size=(M, D)), dtype=torch.float32, device="cuda")
+    cot = torch.tensor(rng.normal(size=(M, D)), dtype=torch.float32, device="cuda")
+    u = ops.inducing_sample(Um, packed, eps)
+    u.backward(cot)
+    got = (u.detach().clone(), Um.grad.clone(), packed.grad.clone())
+    Um.grad = packed.grad = None
+    ref = torch.einsum('dnm, md->nd', tr.forward_tensor(packed), eps) + Um
+    ref.backward(cot)
+    assert relerr(got[0], ref.detach()) <= 1e-6
+    assert relerr(got[1], Um.grad) <= 1e-6 and relerr(got[2], packed.grad) <= 1e-6
+
+
+def test_initial_state_kl_through_the_fused_kernels():
+    from gaussian_process_odes_b200.core import states
+    torch.manual_seed(3)
+    x0 = states.StateInitialVariationalGaussian(dim_n=6, dim_d=5).cuda()
+    with torch.no_grad():
+        x0.param_mean.optvar.normal_()
+        x0.param_lchol.optvar.add_(0.05 * torch.randn_like(x0.param_lchol.optvar))
+    kl = x0.kl()
+    kl.backward()
+    g = (x0.param_mean.optvar.grad.clone(), x0.param_lchol.optvar.grad.clone())
+    x0.param_mean.optvar.grad = x0.param_lchol.optvar.grad = None
+    alpha, Lq = x0.mean(), torch.tril(x0.lchol())
+    d = torch.diagonal(Lq, dim1=1, dim2=2)
+    ref = 0.5 * (-torch.log(d.pow(2)).sum(1) + alpha.pow(2).sum(1) + Lq.pow(2).sum(dim=(1, 2)) - 5.0).sum()
+    ref.backward()
+    assert relerr(kl.detach(), ref.detach()) <= 1e-6
+    assert relerr(g[0], x0.param_mean.optvar.grad) <= 1e-6 and relerr(g[1], x0.param_lchol.optvar.grad) <= 1e-6
