@@ -83,12 +83,18 @@ class DSVGP_Layer(torch.nn.Module):
         form (reference ``dsvgp.py:92-122``). Draw order on the host RNG is the reference's: weights, omega, phase,
         epsilon."""
         dev = self._device
+        # the constrained hyper-parameters are evaluated ONCE per cache build and belong to the
+        # cache (``cache_tensors`` hands the same tensors to the integrator): one softplus + one backward per parameter
+        # and step instead of one per access (ncu launch list of a VDP shooting step: 12 softplus launches)
+        ell = self.kern.lengthscales
+        self._ell_dimwise = ell if self.dimwise else ell.unsqueeze(0).expand(self.D_out, self.D_in)
+        self._var_dimwise = self.kern.variance_dimwise()
         self.rff_weights = host_to_device(sample_normal((self.S, self.D_out)), dev)
-        self.rff_omega = self.kern.sample_freq(self.S)
+        self.rff_omega = self.kern.sample_freq(self.S, lengthscales=ell)
         phase_shape = (1, self.S, self.D_out) if self.dimwise else (1, self.S)
         self.rff_phase = host_to_device(sample_uniform(phase_shape), dev) * 2 * np.pi
         inducing_val = self.sample_inducing()
-        nu = ops.whiten(self.inducing_loc(), self.kern.lengthscales_dimwise(), self.kern.variance_dimwise(),
+        nu = ops.whiten(self.inducing_loc(), self._ell_dimwise, self._var_dimwise,
                         inducing_val, self._omega_dimwise(), self._phase_dimwise(), self.rff_weights, jitter)
         # reference shapes: (D,M,1) dimwise, (M,D) otherwise
         self.nu = nu.unsqueeze(2) if self.dimwise else nu.t()
@@ -148,9 +154,13 @@ class DSVGP_Layer(torch.nn.Module):
                                 self.rff_weights)
 
     def cache_tensors(self):
-        """(Z, ell, var, nu, omega, phase, w) in the dimwise layout the integrator kernels take."""
-        return (self.inducing_loc(), self.kern.lengthscales_dimwise(), self.kern.variance_dimwise(),
-                self._nu_dimwise(), self._omega_dimwise(), self._phase_dimwise(), self.rff_weights)
+        """(Z, ell, var, nu, omega, phase, w) in the dimwise layout the integrator kernels take: the tensors of the
+        last ``build_cache`` (nu and omega were computed from exactly these Z / lengthscales / variances)."""
+        if getattr(self, "_ell_dimwise", None) is None:
+            return (self.inducing_loc(), self.kern.lengthscales_dimwise(), self.kern.variance_dimwise(),
+                    self._nu_dimwise(), self._omega_dimwise(), self._phase_dimwise(), self.rff_weights)
+        return (self.inducing_loc(), self._ell_dimwise, self._var_dimwise, self._nu_dimwise(), self._omega_dimwise(),
+                self._phase_dimwise(), self.rff_weights)
 
     def forward(self, t, x):
         """f(x) for the cached function draw; ``t`` is ignored (autonomous ODE) (reference ``dsvgp.py:172-197``)."""

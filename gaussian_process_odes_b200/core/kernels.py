@@ -71,9 +71,11 @@ class RBF(nn.Module):
             return self.variance[:, None, None] * torch.exp(-0.5 * self.square_dist_dimwise(X, X2))
         return self.variance * torch.exp(-0.5 * self.square_dist(X, X2))
 
-    def sample_freq(self, S, seed=None):
-        """omega = eps / lengthscale, ``(D_in, S, D_out)`` if dimwise else ``(D_in, S)`` (``kernels.py:101-112``)."""
+    def sample_freq(self, S, seed=None, lengthscales=None):
+        """omega = eps / lengthscale, ``(D_in, S, D_out)`` if dimwise else ``(D_in, S)`` (``kernels.py:101-112``).
+        ``lengthscales``: the already constrained parameter, if the caller holds it (one softplus per cache build)."""
         shape = (self.D_in, S, self.D_out) if self.dimwise else (self.D_in, S)
         eps = host_to_device(sample_normal(shape, seed), self.unconstrained_lengthscales.device)
-        ls = self.lengthscales.T.unsqueeze(1) if self.dimwise else self.lengthscales.unsqueeze(1)
+        ell = self.lengthscales if lengthscales is None else lengthscales
+        ls = ell.T.unsqueeze(1) if self.dimwise else ell.unsqueeze(1)
         return eps / ls

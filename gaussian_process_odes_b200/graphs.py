@@ -95,7 +95,7 @@ class GraphedStep:
         # nodes, bound to the eager stream -- alive, which would break capture on the graph's side stream
         for mod in model.modules():
             if isinstance(mod, _dsvgp.DSVGP_Layer):
-                for attr in ("nu", "rff_omega", "rff_phase", "rff_weights"):
+                for attr in ("nu", "rff_omega", "rff_phase", "rff_weights", "_ell_dimwise", "_var_dimwise"):
                     if isinstance(getattr(mod, attr, None), torch.Tensor):
                         setattr(mod, attr, getattr(mod, attr).detach())
         self.draws = _StaticDraws(params[0].device)
