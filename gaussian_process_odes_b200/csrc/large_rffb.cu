@@ -14,7 +14,9 @@
 //           the same chunk of Omega_k re-tiled with the input dimension as N and the feature as K; the accumulator G_k
 //           collects all chunks of output k.
 // The FP32 CUDA-core kernel this replaces (large_bwd.cu, RFF part of vjp_large_kernel) spends 4 S D^2 FMAs per row on
-// the two projections: 80 ms per 1e5 rows at D = 64 (register spills), against ~2.5 ms of L2 operand stream here.
+// the two projections: the whole VJP took 80 ms per 1e5 rows at D = 64 (register spills); this kernel 5.7 ms (ncu: tensor
+// pipe 26 % busy, bound by the L2 operand stream -- 14 GB per 1e5 rows, two tilings of Omega -- and by the single row
+// warp per scheduler), the whole VJP 21.5 ms (profiles/r02_summary.md section 4).
 //
 // CTA = 160 threads, one 128-row tile at a time: warps 0-3 own the rows (thread = row = TMEM lane), warp 4 lane 0 streams
 // the operand chunks from L2 (cp.async.bulk + mbarrier; separate two-slot rings for the GEMM-1 and GEMM-2 operands,
