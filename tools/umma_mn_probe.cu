@@ -13,11 +13,11 @@ static char g_err[256];
 void gpode_set_error(const char* fmt, ...) { (void)fmt; }
 const char* gpode_last_error(void) { return g_err; }
 
-constexpr int M = 128, N = 16, K = 16;   // two K-steps of 8
+constexpr int M = 128, N = 32, K = 16;   // two K-steps of 8
 
 __global__ void __launch_bounds__(160) probe(const float* A, const float* B, float* D, int variant) {
     __shared__ __align__(128) float sa[M * K];
-    __shared__ __align__(128) float sb[N * K * 2];
+    __shared__ __align__(1024) float sb[N * K * 2];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_ptr;
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -32,7 +32,12 @@ __global__ void __launch_bounds__(160) probe(const float* A, const float* B, flo
         const int n = i / K, k = i % K;
         int o;
         if (variant == 0) o = (k >> 2) * (N * 4) + (n >> 3) * 32 + (n & 7) * 4 + (k & 3);             // K-major
-        else o = (n >> 2) * 32 + (k >> 3) * (N / 4 * 32) + (k & 7) * 4 + (n & 3);                      // MN-major
+        else if (variant < 3) o = (n >> 2) * 32 + (k >> 3) * (N / 4 * 32) + (k & 7) * 4 + (n & 3);      // MN-major
+        else {   // MN-major, 128-byte swizzle: 32 consecutive n (128 bytes) per k row, 8 k rows per 1 KB atom
+            uint32_t byte = (uint32_t)((k >> 3) * 1024 + (k & 7) * 128 + n * 4);
+            byte ^= ((byte >> 7) & 7u) << 4;
+            o = (int)(byte >> 2);
+        }
         sb[o] = B[i];
     }
     if (tid == 128) gpode_mbar_init(&bar, 1);
@@ -51,9 +56,13 @@ __global__ void __launch_bounds__(160) probe(const float* A, const float* B, flo
         if (variant == 0) { bd = umma_smem_desc(gpode_smem_u32(sb), N * 16, 128); step_b = (2u * N * 16) >> 4; }
         else {
             idesc |= 1u << 16;
-            if (variant == 1) bd = umma_smem_desc(gpode_smem_u32(sb), k_stride, mn_stride);   // LBO = K-block stride
-            else bd = umma_smem_desc(gpode_smem_u32(sb), mn_stride, k_stride);               // LBO = MN-block stride
-            step_b = k_stride >> 4;
+            if (variant == 1) { bd = umma_smem_desc(gpode_smem_u32(sb), k_stride, mn_stride); step_b = k_stride >> 4; }  // LBO = K-block stride
+            else if (variant == 2) { bd = umma_smem_desc(gpode_smem_u32(sb), mn_stride, k_stride); step_b = k_stride >> 4; }
+            else {   // SWIZZLE_128B (layout type 2, bits 61-63): LBO = stride between 32-n groups, SBO = stride between 8-k groups
+                bd = umma_smem_desc(gpode_smem_u32(sb), variant == 3 ? 1024 : 2048, variant == 3 ? 1024 : 1024) | ((uint64_t)2 << 61);
+                if (variant == 5) bd = umma_smem_desc(gpode_smem_u32(sb), 1024, 2048) | ((uint64_t)2 << 61);
+                step_b = 1024 >> 4;
+            }
         }
         const uint64_t step_a = (2u * M * 16) >> 4;
         umma_tf32_ss(tb, ad, bd, idesc, 0u);
@@ -86,7 +95,7 @@ int main() {
     cudaMalloc(&dA, sizeof(hA)); cudaMalloc(&dB, sizeof(hB)); cudaMalloc(&dD, sizeof(hD));
     cudaMemcpy(dA, hA, sizeof(hA), cudaMemcpyHostToDevice);
     cudaMemcpy(dB, hB, sizeof(hB), cudaMemcpyHostToDevice);
-    for (int v = 0; v < 3; ++v) {
+    for (int v = 0; v < 6; ++v) {
         cudaMemset(dD, 0, sizeof(hD));
         probe<<<1, 160>>>(dA, dB, dD, v);
         cudaError_t e = cudaDeviceSynchronize();
@@ -95,7 +104,7 @@ int main() {
         int nz = 0;
         for (int i = 0; i < M * N; ++i) { double d = fabs((double)hD[i] - ref[i]); if (d > worst) worst = d; if (fabs(ref[i]) > mag) mag = fabs(ref[i]); if (hD[i] != 0.f) ++nz; }
         printf("{\"variant\": %d, \"what\": \"%s\", \"cuda\": \"%s\", \"max_abs_err\": %.4g, \"max_abs_ref\": %.4g, \"nonzero\": %d, \"D00\": %.3f, \"ref00\": %.3f, \"D[5][3]\": %.3f, \"ref[5][3]\": %.3f}\n", v,
-               v == 0 ? "B K-major (baseline)" : (v == 1 ? "B MN-major, LBO = K-block stride, SBO = MN-block stride" : "B MN-major, LBO = MN-block stride, SBO = K-block stride"),
+               v == 0 ? "B K-major (baseline)" : (v == 1 ? "B MN-major, LBO = K-block stride, SBO = MN-block stride" : (v == 2 ? "B MN-major, LBO = MN-block stride, SBO = K-block stride" : "B MN-major SWIZZLE_128B")),
                cudaGetErrorString(e), worst, mag, nz, hD[0], ref[0], hD[5 * N + 3], ref[5 * N + 3]);
     }
     return 0;
