@@ -18,17 +18,18 @@
 // pipe 26 % busy, bound by the L2 operand stream -- 14 GB per 1e5 rows, two tilings of Omega -- and by the single row
 // warp per scheduler), the whole VJP 21.5 ms (profiles/r02_summary.md section 4).
 //
-// CTA = 160 threads, one 128-row tile at a time: warps 0-3 own the rows (thread = row = TMEM lane), warp 4 lane 0 streams
-// the operand chunks from L2 (cp.async.bulk + mbarrier; separate two-slot rings for the GEMM-1 and GEMM-2 operands,
-// because a GEMM-1 slot is free one GEMM earlier) and issues the MMAs. GEMM 2 of chunk q is issued AFTER GEMM 1 of
-// chunk q + 1, so the tensor pipe always has work queued while the rows take the sines of chunk q.
+// CTA = 192 threads, one 128-row tile at a time: warps 0-3 own the rows (thread = row = TMEM lane); lane 0 of warp 4
+// streams the GEMM-1 operand chunks from L2 (cp.async.bulk + mbarrier, two-slot ring) and issues GEMM 1, lane 0 of warp 5
+// does the same for GEMM 2 (its own two-slot ring: a GEMM-1 slot is free one GEMM earlier). The two issuers run
+// independently -- GEMM 1 up to two chunks ahead of the rows, GEMM 2 right behind them -- so the tensor pipe always has
+// work queued while the rows take the sines.
 // TMEM (512 columns): theta 2 x 64 | p: 2 slots x (hi 64 | lo 64) | G 2 x 64.
 #include "umma.cuh"
 #include "../../include/gpode_b200.h"
 
 namespace {
 
-constexpr int kRvThreads = 160, kRvRows = 128, kRvNC = 64;
+constexpr int kRvThreads = 192, kRvRows = 128, kRvNC = 64;
 constexpr int kRvMaxCtas = 160;      // >= SM count: one accumulator row per (CTA, row warp)
 constexpr int C_TH = 0, C_P = 128, C_G = 384;
 
@@ -288,7 +289,13 @@ rff_vjp_large_kernel(const float* __restrict__ packed, const int D, const int S,
                     if (j < D) gx[row * D + j] = xb[j];
             }
         }
-    } else if (tid == 128) {
+    } else if (tid == 128 || tid == 160) {
+        // TWO issuing threads: A (warp 4) streams the GEMM-1 operands and issues GEMM 1, B (warp 5) streams the GEMM-2
+        // operands and issues GEMM 2. A single issuer was the bound at small D: 36-60 K = 8 MMAs per chunk at ~75 cycles of
+        // issue each (ncu at D = 64: tensor pipe 26 % busy, row warps waiting). tcgen05.commit tracks the MMAs of the
+        // committing thread only, which is exactly what each barrier needs; the two GEMMs write different accumulators,
+        // so their relative order in the tensor pipe does not matter.
+        const bool is_a = tid == 128;
         const uint32_t idesc1 = umma_idesc_tf32(kRvRows, kRvNC);
         const uint32_t idesc2 = umma_idesc_tf32(kRvRows, DN);
         const uint32_t lbo_a = kRvRows * 16, lbo_b1 = kRvNC * 16, lbo_b2 = DN * 16;
@@ -305,77 +312,82 @@ rff_vjp_large_kernel(const float* __restrict__ packed, const int D, const int S,
             c = (int)(local - (int64_t)kk * NCH);
             k = kk + k_rot < D ? kk + k_rot : kk + k_rot - D;
         };
-        auto load1 = [&](const int64_t gq) {
-            const int slot = (int)(gq & 1);
-            if (gq >= 2) mbar_wait_bounded(&bar->b1_free[slot], (uint32_t)(((gq >> 1) - 1) & 1));
-            int k, c;
-            chunk_src(gq, k, c);
-            gpode_bulk_g2s(ring1 + (size_t)slot * b1f, g1 + ((int64_t)k * NCH + c) * b1f, bytes1, &bar->b1_full[slot]);
-        };
-        auto load2 = [&](const int64_t gq) {
-            const int slot = (int)(gq & 1);
-            if (gq >= 2) mbar_wait_bounded(&bar->b2_free[slot], (uint32_t)(((gq >> 1) - 1) & 1));
-            int k, c;
-            chunk_src(gq, k, c);
-            gpode_bulk_g2s(ring2 + (size_t)slot * b2f, g2 + ((int64_t)k * NCH + c) * b2f, bytes2, &bar->b2_full[slot]);
-        };
-        auto gemm2 = [&](const int64_t gq, const uint32_t kcq, const int c) {   // G[kcq & 1] (+)= p(gq) Omega^T chunk
-            const int slot = (int)(gq & 1), kbuf = (int)(kcq & 1);
-            mbar_wait_bounded(&bar->b2_full[slot], (uint32_t)((gq >> 1) & 1));
-            if (c == 0 && kcq >= 2) mbar_wait_bounded(&bar->g_free[kbuf], ((kcq >> 1) - 1) & 1);
-            mbar_wait_bounded(&bar->p_full[slot], (uint32_t)((gq >> 1) & 1));
-            tc_fence_after_sync();
-            const uint32_t dG = tmem_base + (uint32_t)(C_G + kbuf * 64);
-            const uint32_t pH = tmem_base + (uint32_t)(C_P + slot * 2 * kRvNC), pL = pH + kRvNC;
-            const float* bh = ring2 + (size_t)slot * b2f;
-            uint64_t bhd = umma_smem_desc(gpode_smem_u32(bh), lbo_b2, 128);
-            uint64_t bld = umma_smem_desc(gpode_smem_u32(bh + DN * kRvNC), lbo_b2, 128);
-#pragma unroll 1
-            for (int ks = 0; ks < kRvNC / 8; ++ks, bhd += step_b2, bld += step_b2) {
-                rv_mma_ts(dG, pH + (uint32_t)(ks * 8), bhd, idesc2, (c > 0 || ks > 0) ? 1u : 0u);
-                rv_mma_ts(dG, pL + (uint32_t)(ks * 8), bhd, idesc2, 1u);
-                rv_mma_ts(dG, pH + (uint32_t)(ks * 8), bld, idesc2, 1u);
-            }
-            umma_commit(&bar->p_free[slot]);
-            umma_commit(&bar->b2_free[slot]);
-            if (c == NCH - 1) umma_commit(&bar->g_full[kbuf]);
-        };
-        int64_t gq = 0;
-        uint32_t kc = 0, tile_it = 0;
-        if (total > 0) load1(0);
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
-            mbar_wait_bounded(&bar->a_full, tile_it & 1);
-            tc_fence_after_sync();
-            for (int ci = 0; ci < chunks_per_tile; ++ci, ++gq) {
+        if (is_a) {
+            auto load1 = [&](const int64_t gq) {
                 const int slot = (int)(gq & 1);
-                if (gq + 1 < total) load1(gq + 1);
-                mbar_wait_bounded(&bar->b1_full[slot], (uint32_t)((gq >> 1) & 1));
-                if (gq >= 2) mbar_wait_bounded(&bar->th_free[slot], (uint32_t)(((gq >> 1) - 1) & 1));
+                if (gq >= 2) mbar_wait_bounded(&bar->b1_free[slot], (uint32_t)(((gq >> 1) - 1) & 1));
+                int k, c;
+                chunk_src(gq, k, c);
+                gpode_bulk_g2s(ring1 + (size_t)slot * b1f, g1 + ((int64_t)k * NCH + c) * b1f, bytes1,
+                               &bar->b1_full[slot]);
+            };
+            int64_t gq = 0;
+            uint32_t tile_it = 0;
+            if (total > 0) load1(0);
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
+                mbar_wait_bounded(&bar->a_full, tile_it & 1);
                 tc_fence_after_sync();
-                // ---- GEMM 1: theta[slot] = [x | 1] [Omega_k ; phase_k] chunk ----
-                const uint32_t d = tmem_base + (uint32_t)(C_TH + slot * kRvNC);
-                const float* bh = ring1 + (size_t)slot * b1f;
-                uint64_t ah = desc_a_hi, al = desc_a_lo;
-                uint64_t bhd = umma_smem_desc(gpode_smem_u32(bh), lbo_b1, 128);
-                uint64_t bld = umma_smem_desc(gpode_smem_u32(bh + KP * kRvNC), lbo_b1, 128);
-                for (int ks = 0; ks < KP / 8; ++ks, ah += step_a, al += step_a, bhd += step_b1, bld += step_b1) {
-                    umma_tf32_ss(d, ah, bhd, idesc1, ks > 0 ? 1u : 0u);
-                    umma_tf32_ss(d, al, bhd, idesc1, 1u);
-                    umma_tf32_ss(d, ah, bld, idesc1, 1u);
-                    umma_tf32_ss(d, al, bld, idesc1, 1u);   // lo lo: see large_umma.cu (theta reaches tens of radians)
-                }
-                umma_commit(&bar->th_full[slot]);
-                umma_commit(&bar->b1_free[slot]);
-                // ---- the GEMM-2 operands of this chunk (needed one trip later), then GEMM 2 of the previous chunk ----
-                load2(gq);
-                if (ci > 0) {
-                    const int cp = (ci - 1) % NCH;
-                    gemm2(gq - 1, kc, cp);
-                    if (cp == NCH - 1) ++kc;
+                for (int ci = 0; ci < chunks_per_tile; ++ci, ++gq) {
+                    const int slot = (int)(gq & 1);
+                    if (gq + 1 < total) load1(gq + 1);
+                    mbar_wait_bounded(&bar->b1_full[slot], (uint32_t)((gq >> 1) & 1));
+                    if (gq >= 2) mbar_wait_bounded(&bar->th_free[slot], (uint32_t)(((gq >> 1) - 1) & 1));
+                    tc_fence_after_sync();
+                    // ---- GEMM 1: theta[slot] = [x | 1] [Omega_k ; phase_k] chunk ----
+                    const uint32_t d = tmem_base + (uint32_t)(C_TH + slot * kRvNC);
+                    const float* bh = ring1 + (size_t)slot * b1f;
+                    uint64_t ah = desc_a_hi, al = desc_a_lo;
+                    uint64_t bhd = umma_smem_desc(gpode_smem_u32(bh), lbo_b1, 128);
+                    uint64_t bld = umma_smem_desc(gpode_smem_u32(bh + KP * kRvNC), lbo_b1, 128);
+                    for (int ks = 0; ks < KP / 8; ++ks, ah += step_a, al += step_a, bhd += step_b1, bld += step_b1) {
+                        umma_tf32_ss(d, ah, bhd, idesc1, ks > 0 ? 1u : 0u);
+                        umma_tf32_ss(d, al, bhd, idesc1, 1u);
+                        umma_tf32_ss(d, ah, bld, idesc1, 1u);
+                        umma_tf32_ss(d, al, bld, idesc1, 1u);   // lo lo: see large_umma.cu (theta reaches tens of radians)
+                    }
+                    umma_commit(&bar->th_full[slot]);
+                    umma_commit(&bar->b1_free[slot]);
                 }
             }
-            gemm2(gq - 1, kc, NCH - 1);   // last chunk of the tile: the rows need its G before they refill the A tile
-            ++kc;
+        } else {
+            auto load2 = [&](const int64_t gq) {
+                const int slot = (int)(gq & 1);
+                if (gq >= 2) mbar_wait_bounded(&bar->b2_free[slot], (uint32_t)(((gq >> 1) - 1) & 1));
+                int k, c;
+                chunk_src(gq, k, c);
+                gpode_bulk_g2s(ring2 + (size_t)slot * b2f, g2 + ((int64_t)k * NCH + c) * b2f, bytes2,
+                               &bar->b2_full[slot]);
+            };
+            uint32_t kc = 0;
+            if (total > 0) load2(0);
+            for (int64_t gq = 0; gq < total; ++gq) {
+                const int c = (int)(gq % NCH);
+                // the next chunk's operands (its feature weights are read by the rows as soon as its theta is ready)
+                if (gq + 1 < total) load2(gq + 1);
+                // ---- GEMM 2: G[kc & 1] (+)= p(gq) Omega^T chunk ----
+                const int slot = (int)(gq & 1), kbuf = (int)(kc & 1);
+                mbar_wait_bounded(&bar->b2_full[slot], (uint32_t)((gq >> 1) & 1));
+                if (c == 0 && kc >= 2) mbar_wait_bounded(&bar->g_free[kbuf], ((kc >> 1) - 1) & 1);
+                mbar_wait_bounded(&bar->p_full[slot], (uint32_t)((gq >> 1) & 1));
+                tc_fence_after_sync();
+                const uint32_t dG = tmem_base + (uint32_t)(C_G + kbuf * 64);
+                const uint32_t pH = tmem_base + (uint32_t)(C_P + slot * 2 * kRvNC), pL = pH + kRvNC;
+                const float* bh = ring2 + (size_t)slot * b2f;
+                uint64_t bhd = umma_smem_desc(gpode_smem_u32(bh), lbo_b2, 128);
+                uint64_t bld = umma_smem_desc(gpode_smem_u32(bh + DN * kRvNC), lbo_b2, 128);
+#pragma unroll 1
+                for (int ks = 0; ks < kRvNC / 8; ++ks, bhd += step_b2, bld += step_b2) {
+                    rv_mma_ts(dG, pH + (uint32_t)(ks * 8), bhd, idesc2, (c > 0 || ks > 0) ? 1u : 0u);
+                    rv_mma_ts(dG, pL + (uint32_t)(ks * 8), bhd, idesc2, 1u);
+                    rv_mma_ts(dG, pH + (uint32_t)(ks * 8), bld, idesc2, 1u);
+                }
+                umma_commit(&bar->p_free[slot]);
+                umma_commit(&bar->b2_free[slot]);
+                if (c == NCH - 1) {
+                    umma_commit(&bar->g_full[kbuf]);
+                    ++kc;
+                }
+            }
         }
     }
     tc_fence_before_sync();
