@@ -299,7 +299,8 @@ struct RbSmem {
     static constexpr int data = 128;
 };
 
-__global__ void __launch_bounds__(kRbThreads)
+template <int NDT>   // NDT = lu_nd(D): sizes the per-row accumulators, so small D keeps several CTAs resident per SM
+__global__ void __launch_bounds__(kRbThreads, NDT <= 16 ? 3 : (NDT <= 32 ? 2 : 1))
 rbf_large_umma_kernel(const float* __restrict__ packed, const int D, const int S, const int M,
                       const float* __restrict__ Z, const float* __restrict__ x, const float* __restrict__ f_rff,
                       float* __restrict__ f_out, const int64_t B) {
@@ -309,7 +310,8 @@ rbf_large_umma_kernel(const float* __restrict__ packed, const int D, const int S
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + RbSmem::bar_full);    // [2] commit
     uint64_t* bar_empty = reinterpret_cast<uint64_t*>(smem + RbSmem::bar_empty);  // [2] 128 consumer arrivals
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + RbSmem::tmem_ptr);
-    const int KD = lu_kd(D), ND = lu_nd(D), K4 = KD / 4;
+    const int KD = lu_kd(D), K4 = KD / 4;
+    constexpr int ND = NDT;
     const int SU = lu_su(D, S), NCH = SU / lu_nc(D);
     const float* __restrict__ wt_g = packed + (int64_t)D * NCH * lu_rec(D) + (int64_t)D * SU;
     const float* __restrict__ cp_g = wt_g + 2 * ND * KD;
@@ -348,20 +350,20 @@ rbf_large_umma_kernel(const float* __restrict__ packed, const int D, const int S
         // ---- consumers: exponent -> 2^e -> weighted sum over the inducing points ----
         uint32_t g = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            float f[64];
+            float f[ND];
 #pragma unroll
-            for (int k = 0; k < 64; ++k) f[k] = 0.f;
+            for (int k = 0; k < ND; ++k) f[k] = 0.f;
             for (int m = 0; m < M; ++m, ++g) {
                 const int buf = g & 1;
                 mbar_wait_bounded(bar_full + buf, (g >> 1) & 1);
                 tc_fence_after_sync();
                 const uint32_t t0 = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * 64);
                 const float* __restrict__ cm = cp_g + (int64_t)m * ND;
-                uint32_t ra[32], rb[32];
+                uint32_t ra[32], rb[ND > 32 ? 32 : 1];
                 tmem_ld32_issue(t0, ra);
-                if (ND > 32) tmem_ld32_issue(t0 + 32, rb);
+                if constexpr (ND > 32) tmem_ld32_issue(t0 + 32, rb);
                 tmem_ld_wait(ra);
-                if (ND > 32) tmem_ld_wait(rb);  // (one wait covers both loads; this pins rb's readers behind it)
+                if constexpr (ND > 32) tmem_ld_wait(rb);  // (one wait covers both loads; this pins rb's readers behind it)
                 tc_fence_before_sync();
                 mbar_arrive(bar_empty + buf);
 #pragma unroll
@@ -377,6 +379,7 @@ rbf_large_umma_kernel(const float* __restrict__ packed, const int D, const int S
                         }
                     }
                 }
+                if constexpr (ND > 32) {
 #pragma unroll
                 for (int q = 2; q < 4; ++q) {
                     if (q * 16 < ND) {
@@ -391,11 +394,12 @@ rbf_large_umma_kernel(const float* __restrict__ packed, const int D, const int S
                         }
                     }
                 }
+                }
             }
             const int64_t row = tile * kLuRows + tid;
             if (row < B) {
 #pragma unroll
-                for (int k = 0; k < 64; ++k)
+                for (int k = 0; k < ND; ++k)
                     if (k < D) f_out[row * D + k] = __ldg(f_rff + row * D + k) + f[k];
             }
         }
@@ -527,16 +531,25 @@ extern "C" int gpode_rbf_fwd_large(const float* packed_large, int D, int M, int 
     const int KD = lu_kd(D), ND = lu_nd(D);
     const size_t smem = RbSmem::data + (size_t)(2 * ND * KD + M * KD + KD * kLuRows + 4 * KD * kLuRows) * 4;
     GPODE_CHECK_ARG(smem <= 227u * 1024u, "M=%d too large for the shared-memory copy of Z (needs %zu bytes)", M, smem);
-    GPODE_CUDA(cudaFuncSetAttribute(rbf_large_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void (*kern)(const float*, int, int, int, const float*, const float*, const float*, float*, int64_t) =
+        ND == 16 ? rbf_large_umma_kernel<16> : ND == 32 ? rbf_large_umma_kernel<32>
+        : ND == 48 ? rbf_large_umma_kernel<48> : rbf_large_umma_kernel<64>;
+    GPODE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int sms = 148, dev = 0;
     GPODE_CUDA(cudaGetDevice(&dev));
     GPODE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     int occ = (int)((227u * 1024u) / (smem + 1024u));
     if (occ > 512 / kRbTmemCols) occ = 512 / kRbTmemCols;
     if (occ * kRbThreads > 2048) occ = 2048 / kRbThreads;
+    // registers bound the residency below shared memory and TMEM for ND >= 32 (allocation: 8-register granules per thread)
+    cudaFuncAttributes fa;
+    GPODE_CUDA(cudaFuncGetAttributes(&fa, kern));
+    GPODE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    const int reg_occ = 65536 / (((fa.numRegs + 7) & ~7) * kRbThreads);
+    if (occ > reg_occ) occ = reg_occ;
     if (occ < 1) occ = 1;
     const int64_t tiles = (B + kLuRows - 1) / kLuRows, cap = (int64_t)sms * occ;
-    rbf_large_umma_kernel<<<(unsigned)(tiles < cap ? tiles : cap), kRbThreads, smem, (cudaStream_t)stream>>>(
+    kern<<<(unsigned)(tiles < cap ? tiles : cap), kRbThreads, smem, (cudaStream_t)stream>>>(
         packed_large, D, S, M, Z, x, f_rff, f, B);
     GPODE_LAUNCH_CHECK();
     return 0;
