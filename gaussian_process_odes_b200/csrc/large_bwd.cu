@@ -268,70 +268,116 @@ vjp_large_kernel(const float* __restrict__ pk, const LbLayout L, const float* __
         }
 
         // ================= RBF part =================
-        constexpr int KT = kLbThreads / DP;   // threads per output k in the row-contraction phase
-        constexpr int JT = DP / KT;           // input dimensions per such thread
-        const int ck = tid / KT, cj0 = (tid - ck * KT) * JT;
+        constexpr int TK = DP / 16, TJ = DP / 8;   // row-contraction tile per thread: 16 x 8 tiles cover [DP][DP]
+        static_assert(kLbThreads == 128 && (DP == 16 || DP == 32 || DP == 64), "tile mapping assumes 128 threads");
+        const int ck0 = (tid >> 3) * TK, cj0 = (tid & 7) * TJ;
         for (int m = 0; m < M; ++m) {
             const float* __restrict__ zm = z_g + (size_t)m * DP;
             const float* __restrict__ cm = c_g + (size_t)m * DP;
-            float dd[DP], tt[DP];
+            // dd / t as register pairs: every FMA below is the packed dual-FP32 form (SASS FFMA2), two outputs k per trip
+            // (eight independent exponent chains, two MUFU exponentials in flight); summation order as the scalar form
+            float2 dd[DP / 2], tt[DP / 2];
 #pragma unroll
             for (int j4 = 0; j4 < DP / 4; ++j4) {
                 const float4 xv = *reinterpret_cast<const float4*>(xs + tid * LD + 4 * j4);
                 const float4 zv = __ldg(reinterpret_cast<const float4*>(zm + 4 * j4));
                 const float d0 = xv.x - zv.x, d1 = xv.y - zv.y, d2 = xv.z - zv.z, d3 = xv.w - zv.w;
-                dd[4 * j4] = d0 * d0; dd[4 * j4 + 1] = d1 * d1; dd[4 * j4 + 2] = d2 * d2; dd[4 * j4 + 3] = d3 * d3;
-                tt[4 * j4] = tt[4 * j4 + 1] = tt[4 * j4 + 2] = tt[4 * j4 + 3] = 0.f;
+                dd[2 * j4] = make_float2(d0 * d0, d1 * d1);
+                dd[2 * j4 + 1] = make_float2(d2 * d2, d3 * d3);
+                tt[2 * j4] = tt[2 * j4 + 1] = make_float2(0.f, 0.f);
                 *reinterpret_cast<float4*>(stB + tid * LD + 4 * j4) =
-                    make_float4(dd[4 * j4], dd[4 * j4 + 1], dd[4 * j4 + 2], dd[4 * j4 + 3]);
+                    make_float4(dd[2 * j4].x, dd[2 * j4].y, dd[2 * j4 + 1].x, dd[2 * j4 + 1].y);
             }
 #pragma unroll 1
-            for (int k = 0; k < D; ++k) {
-                const float* __restrict__ wk = Ws + k * DP;
-                float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
+            for (int k = 0; k < D; k += 2) {   // rows D .. DP-1 of Ws are zero padding; an odd D's last partner has q = 0
+                const float* __restrict__ wa = Ws + k * DP;
+                const float* __restrict__ wb = wa + DP;
+                float2 ea0 = make_float2(0.f, 0.f), ea1 = ea0, eb0 = ea0, eb1 = ea0;
 #pragma unroll
                 for (int j4 = 0; j4 < DP / 4; ++j4) {
-                    const float4 w4 = *reinterpret_cast<const float4*>(wk + 4 * j4);
-                    e0 = fmaf(dd[4 * j4], w4.x, e0); e1 = fmaf(dd[4 * j4 + 1], w4.y, e1);
-                    e2 = fmaf(dd[4 * j4 + 2], w4.z, e2); e3 = fmaf(dd[4 * j4 + 3], w4.w, e3);
+                    const float4 a4 = *reinterpret_cast<const float4*>(wa + 4 * j4);
+                    const float4 b4 = *reinterpret_cast<const float4*>(wb + 4 * j4);
+                    ea0 = ffma2(dd[2 * j4], make_float2(a4.x, a4.y), ea0);
+                    ea1 = ffma2(dd[2 * j4 + 1], make_float2(a4.z, a4.w), ea1);
+                    eb0 = ffma2(dd[2 * j4], make_float2(b4.x, b4.y), eb0);
+                    eb1 = ffma2(dd[2 * j4 + 1], make_float2(b4.z, b4.w), eb1);
                 }
-                const float K = gpode_ex2(-((e0 + e1) + (e2 + e3)));
-                const float p = kbs[tid * LD + k] * K;
-                stA[tid * LD + k] = p;
-                const float q = -GPODE_NEG_2LN2 * __ldg(cm + k) * p;   // 2 ln2 c_km kb_k K
+                const bool two = k + 1 < D;
+                const float Ka = gpode_ex2(-((ea0.x + ea0.y) + (ea1.x + ea1.y)));
+                const float Kb = gpode_ex2(-((eb0.x + eb0.y) + (eb1.x + eb1.y)));
+                const float pa = kbs[tid * LD + k] * Ka;
+                const float pb = two ? kbs[tid * LD + k + 1] * Kb : 0.f;
+                stA[tid * LD + k] = pa;
+                if (two) stA[tid * LD + k + 1] = pb;
+                const float qa = -GPODE_NEG_2LN2 * __ldg(cm + k) * pa;   // 2 ln2 c_km kb_k K
+                const float qb = two ? -GPODE_NEG_2LN2 * __ldg(cm + k + 1) * pb : 0.f;
 #pragma unroll
                 for (int j4 = 0; j4 < DP / 4; ++j4) {
-                    const float4 w4 = *reinterpret_cast<const float4*>(wk + 4 * j4);
-                    tt[4 * j4] = fmaf(q, w4.x, tt[4 * j4]); tt[4 * j4 + 1] = fmaf(q, w4.y, tt[4 * j4 + 1]);
-                    tt[4 * j4 + 2] = fmaf(q, w4.z, tt[4 * j4 + 2]); tt[4 * j4 + 3] = fmaf(q, w4.w, tt[4 * j4 + 3]);
+                    const float4 a4 = *reinterpret_cast<const float4*>(wa + 4 * j4);
+                    const float4 b4 = *reinterpret_cast<const float4*>(wb + 4 * j4);
+                    tt[2 * j4] = ffma2(qb, make_float2(b4.x, b4.y), ffma2(qa, make_float2(a4.x, a4.y), tt[2 * j4]));
+                    tt[2 * j4 + 1] = ffma2(qb, make_float2(b4.z, b4.w), ffma2(qa, make_float2(a4.z, a4.w), tt[2 * j4 + 1]));
                 }
             }
             __syncthreads();  // p and dd of all 128 rows are staged
-            // rows contracted by (k, j-slice) threads: T[k][m] = sum_r p;  A[k][j] -= 2 ln2 w_kj c_km sum_r p dd_j
-            if (ck < D) {
-                float s1 = 0.f, s2[JT];
+            // rows contracted by a (TK outputs k) x (TJ inputs j) register tile per thread: T[k][m] = sum_r p;
+            // A[k][j] -= 2 ln2 w_kj c_km sum_r p dd_j. Per row one vector load of p and one or two of dd feed TK*TJ/2
+            // packed FMAs (a broadcast LDS.128 costs four shared-memory wavefronts whatever its address pattern: the
+            // first mapping, one k x DP/2 inputs per thread, spent 8 loads on 16 FMAs and ran at the wavefront peak).
+            // Columns k >= D of the p tile are never written (stale bytes): their sums are computed and dropped.
+            {
+                float2 acc[TK][TJ / 2];
+                float s1[TK];
 #pragma unroll
-                for (int j = 0; j < JT; ++j) s2[j] = 0.f;
+                for (int a = 0; a < TK; ++a) {
+                    s1[a] = 0.f;
+#pragma unroll
+                    for (int c = 0; c < TJ / 2; ++c) acc[a][c] = make_float2(0.f, 0.f);
+                }
 #pragma unroll 4
                 for (int r = 0; r < kLbRows; ++r) {
-                    const float pv = stA[r * LD + ck];
-                    s1 += pv;
-                    if constexpr (JT % 4 == 0) {
+                    float pv[TK];
+                    float2 dv[TJ / 2];
+                    if constexpr (TK == 4) {
+                        const float4 p4 = *reinterpret_cast<const float4*>(stA + r * LD + ck0);
+                        pv[0] = p4.x; pv[1] = p4.y; pv[2] = p4.z; pv[3] = p4.w;
+                    } else if constexpr (TK == 2) {
+                        const float2 p2 = *reinterpret_cast<const float2*>(stA + r * LD + ck0);
+                        pv[0] = p2.x; pv[1] = p2.y;
+                    } else {
+                        pv[0] = stA[r * LD + ck0];
+                    }
+                    if constexpr (TJ >= 4) {
 #pragma unroll
-                        for (int j4 = 0; j4 < JT / 4; ++j4) {
-                            const float4 d4 = *reinterpret_cast<const float4*>(stB + r * LD + cj0 + 4 * j4);
-                            s2[4 * j4] = fmaf(pv, d4.x, s2[4 * j4]); s2[4 * j4 + 1] = fmaf(pv, d4.y, s2[4 * j4 + 1]);
-                            s2[4 * j4 + 2] = fmaf(pv, d4.z, s2[4 * j4 + 2]); s2[4 * j4 + 3] = fmaf(pv, d4.w, s2[4 * j4 + 3]);
+                        for (int c4 = 0; c4 < TJ / 4; ++c4) {
+                            const float4 d4 = *reinterpret_cast<const float4*>(stB + r * LD + cj0 + 4 * c4);
+                            dv[2 * c4] = make_float2(d4.x, d4.y);
+                            dv[2 * c4 + 1] = make_float2(d4.z, d4.w);
                         }
                     } else {
+                        dv[0] = *reinterpret_cast<const float2*>(stB + r * LD + cj0);
+                    }
 #pragma unroll
-                        for (int j = 0; j < JT; ++j) s2[j] = fmaf(pv, stB[r * LD + cj0 + j], s2[j]);
+                    for (int a = 0; a < TK; ++a) {
+                        s1[a] += pv[a];
+#pragma unroll
+                        for (int c = 0; c < TJ / 2; ++c) acc[a][c] = ffma2(pv[a], dv[c], acc[a][c]);
                     }
                 }
-                if (cj0 == 0) Tg[(size_t)ck * M + m] += s1;
-                const float cf = GPODE_NEG_2LN2 * __ldg(cm + ck);   // -2 ln2 c_km
 #pragma unroll
-                for (int j = 0; j < JT; ++j) As[ck * DP + cj0 + j] = fmaf(cf * Ws[ck * DP + cj0 + j], s2[j], As[ck * DP + cj0 + j]);
+                for (int a = 0; a < TK; ++a) {
+                    const int k = ck0 + a;
+                    if (k < D) {
+                        if (cj0 == 0) Tg[(size_t)k * M + m] += s1[a];
+                        const float cf = GPODE_NEG_2LN2 * __ldg(cm + k);   // -2 ln2 c_km
+#pragma unroll
+                        for (int c = 0; c < TJ / 2; ++c) {
+                            const int j = cj0 + 2 * c;
+                            As[k * DP + j] = fmaf(cf * Ws[k * DP + j], acc[a][c].x, As[k * DP + j]);
+                            As[k * DP + j + 1] = fmaf(cf * Ws[k * DP + j + 1], acc[a][c].y, As[k * DP + j + 1]);
+                        }
+                    }
+                }
             }
             __syncthreads();  // stB is free again
             // xb_j -= d_j t_j; the same products, summed over rows, are the Z gradient
@@ -340,8 +386,8 @@ vjp_large_kernel(const float* __restrict__ pk, const LbLayout L, const float* __
                 const float4 xv = *reinterpret_cast<const float4*>(xs + tid * LD + 4 * j4);
                 const float4 zv = __ldg(reinterpret_cast<const float4*>(zm + 4 * j4));
                 float4 dt;
-                dt.x = (xv.x - zv.x) * tt[4 * j4]; dt.y = (xv.y - zv.y) * tt[4 * j4 + 1];
-                dt.z = (xv.z - zv.z) * tt[4 * j4 + 2]; dt.w = (xv.w - zv.w) * tt[4 * j4 + 3];
+                dt.x = (xv.x - zv.x) * tt[2 * j4].x; dt.y = (xv.y - zv.y) * tt[2 * j4].y;
+                dt.z = (xv.z - zv.z) * tt[2 * j4 + 1].x; dt.w = (xv.w - zv.w) * tt[2 * j4 + 1].y;
                 float4 xv4 = *reinterpret_cast<const float4*>(xbr + 4 * j4);
                 xv4.x -= dt.x; xv4.y -= dt.y; xv4.z -= dt.z; xv4.w -= dt.w;
                 *reinterpret_cast<float4*>(xbr + 4 * j4) = xv4;
