@@ -271,52 +271,125 @@ vjp_large_kernel(const float* __restrict__ pk, const LbLayout L, const float* __
         constexpr int TK = DP / 16, TJ = DP / 8;   // row-contraction tile per thread: 16 x 8 tiles cover [DP][DP]
         static_assert(kLbThreads == 128 && (DP == 16 || DP == 32 || DP == 64), "tile mapping assumes 128 threads");
         const int ck0 = (tid >> 3) * TK, cj0 = (tid & 7) * TJ;
+        constexpr bool kTwoRows = DP >= 32;   // two rows x half the inputs per thread in the exponent / t phases
+        constexpr int NC2 = DP / 8;           // float4 chunks of a lane's half row
+        const int h2 = tid & 1, rA = tid >> 1, rB = rA + kLbRows / 2;
+        auto off2 = [&](const int c) { return h2 * (DP / 2) + 4 * ((c + (DP == 64 ? h2 * (NC2 / 2) : 0)) & (NC2 - 1)); };
         for (int m = 0; m < M; ++m) {
             const float* __restrict__ zm = z_g + (size_t)m * DP;
             const float* __restrict__ cm = c_g + (size_t)m * DP;
-            // dd / t as register pairs: every FMA below is the packed dual-FP32 form (SASS FFMA2), two outputs k per trip
-            // (eight independent exponent chains, two MUFU exponentials in flight); summation order as the scalar form
-            float2 dd[DP / 2], tt[DP / 2];
+            float2 dd[DP / 2], tt[DP / 2];   // one row x DP inputs, or two rows x DP / 2 inputs (kTwoRows)
+            if constexpr (kTwoRows) {
+            // Register tile: a thread owns TWO rows (rA, rB = rA + 64) x HALF of the input dimensions, so every W element
+            // fetched from shared memory feeds both rows -- the one-row form below issues two broadcast LDS.128 (four
+            // wavefronts each) per four packed FMAs and is bound by shared-memory wavefronts at DP >= 32. Chunk c of a
+            // lane is floats off(c) .. off(c)+3 of the row: the upper-half lane walks its chunks rotated by half a
+            // turn at DP = 64 so that the two lanes of a row pair never hit the same banks. The exponent halves of the
+            // two lanes are added by one shuffle (a + b in both lanes: bitwise the same value).
 #pragma unroll
-            for (int j4 = 0; j4 < DP / 4; ++j4) {
-                const float4 xv = *reinterpret_cast<const float4*>(xs + tid * LD + 4 * j4);
-                const float4 zv = __ldg(reinterpret_cast<const float4*>(zm + 4 * j4));
-                const float d0 = xv.x - zv.x, d1 = xv.y - zv.y, d2 = xv.z - zv.z, d3 = xv.w - zv.w;
-                dd[2 * j4] = make_float2(d0 * d0, d1 * d1);
-                dd[2 * j4 + 1] = make_float2(d2 * d2, d3 * d3);
-                tt[2 * j4] = tt[2 * j4 + 1] = make_float2(0.f, 0.f);
-                *reinterpret_cast<float4*>(stB + tid * LD + 4 * j4) =
-                    make_float4(dd[2 * j4].x, dd[2 * j4].y, dd[2 * j4 + 1].x, dd[2 * j4 + 1].y);
+            for (int c = 0; c < NC2; ++c) {
+                const int o = off2(c);
+                const float4 zv = __ldg(reinterpret_cast<const float4*>(zm + o));
+                const float4 xa = *reinterpret_cast<const float4*>(xs + rA * LD + o);
+                const float4 xb4 = *reinterpret_cast<const float4*>(xs + rB * LD + o);
+                const float a0 = xa.x - zv.x, a1 = xa.y - zv.y, a2 = xa.z - zv.z, a3 = xa.w - zv.w;
+                const float b0 = xb4.x - zv.x, b1 = xb4.y - zv.y, b2 = xb4.z - zv.z, b3 = xb4.w - zv.w;
+                dd[2 * c] = make_float2(a0 * a0, a1 * a1); dd[2 * c + 1] = make_float2(a2 * a2, a3 * a3);
+                dd[2 * NC2 + 2 * c] = make_float2(b0 * b0, b1 * b1); dd[2 * NC2 + 2 * c + 1] = make_float2(b2 * b2, b3 * b3);
+                tt[2 * c] = tt[2 * c + 1] = tt[2 * NC2 + 2 * c] = tt[2 * NC2 + 2 * c + 1] = make_float2(0.f, 0.f);
+                *reinterpret_cast<float4*>(stB + rA * LD + o) = make_float4(a0 * a0, a1 * a1, a2 * a2, a3 * a3);
+                *reinterpret_cast<float4*>(stB + rB * LD + o) = make_float4(b0 * b0, b1 * b1, b2 * b2, b3 * b3);
             }
 #pragma unroll 1
             for (int k = 0; k < D; k += 2) {   // rows D .. DP-1 of Ws are zero padding; an odd D's last partner has q = 0
                 const float* __restrict__ wa = Ws + k * DP;
                 const float* __restrict__ wb = wa + DP;
-                float2 ea0 = make_float2(0.f, 0.f), ea1 = ea0, eb0 = ea0, eb1 = ea0;
+                const float2 z2 = make_float2(0.f, 0.f);
+                float2 eAa0 = z2, eAa1 = z2, eAb0 = z2, eAb1 = z2, eBa0 = z2, eBa1 = z2, eBb0 = z2, eBb1 = z2;
 #pragma unroll
-                for (int j4 = 0; j4 < DP / 4; ++j4) {
-                    const float4 a4 = *reinterpret_cast<const float4*>(wa + 4 * j4);
-                    const float4 b4 = *reinterpret_cast<const float4*>(wb + 4 * j4);
-                    ea0 = ffma2(dd[2 * j4], make_float2(a4.x, a4.y), ea0);
-                    ea1 = ffma2(dd[2 * j4 + 1], make_float2(a4.z, a4.w), ea1);
-                    eb0 = ffma2(dd[2 * j4], make_float2(b4.x, b4.y), eb0);
-                    eb1 = ffma2(dd[2 * j4 + 1], make_float2(b4.z, b4.w), eb1);
+                for (int c = 0; c < NC2; ++c) {
+                    const float4 a4 = *reinterpret_cast<const float4*>(wa + off2(c));
+                    const float4 b4 = *reinterpret_cast<const float4*>(wb + off2(c));
+                    const float2 al = make_float2(a4.x, a4.y), ah = make_float2(a4.z, a4.w);
+                    const float2 bl = make_float2(b4.x, b4.y), bh = make_float2(b4.z, b4.w);
+                    eAa0 = ffma2(dd[2 * c], al, eAa0); eAa1 = ffma2(dd[2 * c + 1], ah, eAa1);
+                    eAb0 = ffma2(dd[2 * c], bl, eAb0); eAb1 = ffma2(dd[2 * c + 1], bh, eAb1);
+                    eBa0 = ffma2(dd[2 * NC2 + 2 * c], al, eBa0); eBa1 = ffma2(dd[2 * NC2 + 2 * c + 1], ah, eBa1);
+                    eBb0 = ffma2(dd[2 * NC2 + 2 * c], bl, eBb0); eBb1 = ffma2(dd[2 * NC2 + 2 * c + 1], bh, eBb1);
                 }
+                float sAa = (eAa0.x + eAa0.y) + (eAa1.x + eAa1.y), sAb = (eAb0.x + eAb0.y) + (eAb1.x + eAb1.y);
+                float sBa = (eBa0.x + eBa0.y) + (eBa1.x + eBa1.y), sBb = (eBb0.x + eBb0.y) + (eBb1.x + eBb1.y);
+                sAa += __shfl_xor_sync(0xffffffffu, sAa, 1); sAb += __shfl_xor_sync(0xffffffffu, sAb, 1);
+                sBa += __shfl_xor_sync(0xffffffffu, sBa, 1); sBb += __shfl_xor_sync(0xffffffffu, sBb, 1);
                 const bool two = k + 1 < D;
-                const float Ka = gpode_ex2(-((ea0.x + ea0.y) + (ea1.x + ea1.y)));
-                const float Kb = gpode_ex2(-((eb0.x + eb0.y) + (eb1.x + eb1.y)));
-                const float pa = kbs[tid * LD + k] * Ka;
-                const float pb = two ? kbs[tid * LD + k + 1] * Kb : 0.f;
-                stA[tid * LD + k] = pa;
-                if (two) stA[tid * LD + k + 1] = pb;
-                const float qa = -GPODE_NEG_2LN2 * __ldg(cm + k) * pa;   // 2 ln2 c_km kb_k K
-                const float qb = two ? -GPODE_NEG_2LN2 * __ldg(cm + k + 1) * pb : 0.f;
+                const float pAa = kbs[rA * LD + k] * gpode_ex2(-sAa);
+                const float pBa = kbs[rB * LD + k] * gpode_ex2(-sBa);
+                const float pAb = two ? kbs[rA * LD + k + 1] * gpode_ex2(-sAb) : 0.f;
+                const float pBb = two ? kbs[rB * LD + k + 1] * gpode_ex2(-sBb) : 0.f;
+                {   // each lane of the pair stages one of the two rows
+                    const int rs = h2 ? rB : rA;
+                    stA[rs * LD + k] = h2 ? pBa : pAa;
+                    if (two) stA[rs * LD + k + 1] = h2 ? pBb : pAb;
+                }
+                const float ca = -GPODE_NEG_2LN2 * __ldg(cm + k);             // q = 2 ln2 c_km kb_k K
+                const float cb = two ? -GPODE_NEG_2LN2 * __ldg(cm + k + 1) : 0.f;
+                const float qAa = ca * pAa, qAb = cb * pAb, qBa = ca * pBa, qBb = cb * pBb;
+#pragma unroll
+                for (int c = 0; c < NC2; ++c) {
+                    const float4 a4 = *reinterpret_cast<const float4*>(wa + off2(c));
+                    const float4 b4 = *reinterpret_cast<const float4*>(wb + off2(c));
+                    const float2 al = make_float2(a4.x, a4.y), ah = make_float2(a4.z, a4.w);
+                    const float2 bl = make_float2(b4.x, b4.y), bh = make_float2(b4.z, b4.w);
+                    tt[2 * c] = ffma2(qAb, bl, ffma2(qAa, al, tt[2 * c]));
+                    tt[2 * c + 1] = ffma2(qAb, bh, ffma2(qAa, ah, tt[2 * c + 1]));
+                    tt[2 * NC2 + 2 * c] = ffma2(qBb, bl, ffma2(qBa, al, tt[2 * NC2 + 2 * c]));
+                    tt[2 * NC2 + 2 * c + 1] = ffma2(qBb, bh, ffma2(qBa, ah, tt[2 * NC2 + 2 * c + 1]));
+                }
+            }
+            } else {
+                // dd / t as register pairs: every FMA below is the packed dual-FP32 form (SASS FFMA2), two outputs k per trip
+                // (eight independent exponent chains, two MUFU exponentials in flight); summation order as the scalar form
 #pragma unroll
                 for (int j4 = 0; j4 < DP / 4; ++j4) {
-                    const float4 a4 = *reinterpret_cast<const float4*>(wa + 4 * j4);
-                    const float4 b4 = *reinterpret_cast<const float4*>(wb + 4 * j4);
-                    tt[2 * j4] = ffma2(qb, make_float2(b4.x, b4.y), ffma2(qa, make_float2(a4.x, a4.y), tt[2 * j4]));
-                    tt[2 * j4 + 1] = ffma2(qb, make_float2(b4.z, b4.w), ffma2(qa, make_float2(a4.z, a4.w), tt[2 * j4 + 1]));
+                    const float4 xv = *reinterpret_cast<const float4*>(xs + tid * LD + 4 * j4);
+                    const float4 zv = __ldg(reinterpret_cast<const float4*>(zm + 4 * j4));
+                    const float d0 = xv.x - zv.x, d1 = xv.y - zv.y, d2 = xv.z - zv.z, d3 = xv.w - zv.w;
+                    dd[2 * j4] = make_float2(d0 * d0, d1 * d1);
+                    dd[2 * j4 + 1] = make_float2(d2 * d2, d3 * d3);
+                    tt[2 * j4] = tt[2 * j4 + 1] = make_float2(0.f, 0.f);
+                    *reinterpret_cast<float4*>(stB + tid * LD + 4 * j4) =
+                        make_float4(dd[2 * j4].x, dd[2 * j4].y, dd[2 * j4 + 1].x, dd[2 * j4 + 1].y);
+                }
+#pragma unroll 1
+                for (int k = 0; k < D; k += 2) {   // rows D .. DP-1 of Ws are zero padding; an odd D's last partner has q = 0
+                    const float* __restrict__ wa = Ws + k * DP;
+                    const float* __restrict__ wb = wa + DP;
+                    float2 ea0 = make_float2(0.f, 0.f), ea1 = ea0, eb0 = ea0, eb1 = ea0;
+#pragma unroll
+                    for (int j4 = 0; j4 < DP / 4; ++j4) {
+                        const float4 a4 = *reinterpret_cast<const float4*>(wa + 4 * j4);
+                        const float4 b4 = *reinterpret_cast<const float4*>(wb + 4 * j4);
+                        ea0 = ffma2(dd[2 * j4], make_float2(a4.x, a4.y), ea0);
+                        ea1 = ffma2(dd[2 * j4 + 1], make_float2(a4.z, a4.w), ea1);
+                        eb0 = ffma2(dd[2 * j4], make_float2(b4.x, b4.y), eb0);
+                        eb1 = ffma2(dd[2 * j4 + 1], make_float2(b4.z, b4.w), eb1);
+                    }
+                    const bool two = k + 1 < D;
+                    const float Ka = gpode_ex2(-((ea0.x + ea0.y) + (ea1.x + ea1.y)));
+                    const float Kb = gpode_ex2(-((eb0.x + eb0.y) + (eb1.x + eb1.y)));
+                    const float pa = kbs[tid * LD + k] * Ka;
+                    const float pb = two ? kbs[tid * LD + k + 1] * Kb : 0.f;
+                    stA[tid * LD + k] = pa;
+                    if (two) stA[tid * LD + k + 1] = pb;
+                    const float qa = -GPODE_NEG_2LN2 * __ldg(cm + k) * pa;   // 2 ln2 c_km kb_k K
+                    const float qb = two ? -GPODE_NEG_2LN2 * __ldg(cm + k + 1) * pb : 0.f;
+#pragma unroll
+                    for (int j4 = 0; j4 < DP / 4; ++j4) {
+                        const float4 a4 = *reinterpret_cast<const float4*>(wa + 4 * j4);
+                        const float4 b4 = *reinterpret_cast<const float4*>(wb + 4 * j4);
+                        tt[2 * j4] = ffma2(qb, make_float2(b4.x, b4.y), ffma2(qa, make_float2(a4.x, a4.y), tt[2 * j4]));
+                        tt[2 * j4 + 1] = ffma2(qb, make_float2(b4.z, b4.w), ffma2(qa, make_float2(a4.z, a4.w), tt[2 * j4 + 1]));
+                    }
                 }
             }
             __syncthreads();  // p and dd of all 128 rows are staged
@@ -381,17 +454,38 @@ vjp_large_kernel(const float* __restrict__ pk, const LbLayout L, const float* __
             }
             __syncthreads();  // stB is free again
             // xb_j -= d_j t_j; the same products, summed over rows, are the Z gradient
+            if constexpr (kTwoRows) {
 #pragma unroll
-            for (int j4 = 0; j4 < DP / 4; ++j4) {
-                const float4 xv = *reinterpret_cast<const float4*>(xs + tid * LD + 4 * j4);
-                const float4 zv = __ldg(reinterpret_cast<const float4*>(zm + 4 * j4));
-                float4 dt;
-                dt.x = (xv.x - zv.x) * tt[2 * j4].x; dt.y = (xv.y - zv.y) * tt[2 * j4].y;
-                dt.z = (xv.z - zv.z) * tt[2 * j4 + 1].x; dt.w = (xv.w - zv.w) * tt[2 * j4 + 1].y;
-                float4 xv4 = *reinterpret_cast<const float4*>(xbr + 4 * j4);
-                xv4.x -= dt.x; xv4.y -= dt.y; xv4.z -= dt.z; xv4.w -= dt.w;
-                *reinterpret_cast<float4*>(xbr + 4 * j4) = xv4;
-                *reinterpret_cast<float4*>(stB + tid * LD + 4 * j4) = dt;
+                for (int c = 0; c < NC2; ++c) {
+                    const int o = off2(c);
+                    const float4 zv = __ldg(reinterpret_cast<const float4*>(zm + o));
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr) {
+                        const int r = rr ? rB : rA;
+                        const float2 t0 = tt[2 * NC2 * rr + 2 * c], t1 = tt[2 * NC2 * rr + 2 * c + 1];
+                        const float4 xv = *reinterpret_cast<const float4*>(xs + r * LD + o);
+                        float4 dt;
+                        dt.x = (xv.x - zv.x) * t0.x; dt.y = (xv.y - zv.y) * t0.y;
+                        dt.z = (xv.z - zv.z) * t1.x; dt.w = (xv.w - zv.w) * t1.y;
+                        float4 xv4 = *reinterpret_cast<const float4*>(xbs + r * LD + o);
+                        xv4.x -= dt.x; xv4.y -= dt.y; xv4.z -= dt.z; xv4.w -= dt.w;
+                        *reinterpret_cast<float4*>(xbs + r * LD + o) = xv4;
+                        *reinterpret_cast<float4*>(stB + r * LD + o) = dt;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j4 = 0; j4 < DP / 4; ++j4) {
+                    const float4 xv = *reinterpret_cast<const float4*>(xs + tid * LD + 4 * j4);
+                    const float4 zv = __ldg(reinterpret_cast<const float4*>(zm + 4 * j4));
+                    float4 dt;
+                    dt.x = (xv.x - zv.x) * tt[2 * j4].x; dt.y = (xv.y - zv.y) * tt[2 * j4].y;
+                    dt.z = (xv.z - zv.z) * tt[2 * j4 + 1].x; dt.w = (xv.w - zv.w) * tt[2 * j4 + 1].y;
+                    float4 xv4 = *reinterpret_cast<const float4*>(xbr + 4 * j4);
+                    xv4.x -= dt.x; xv4.y -= dt.y; xv4.z -= dt.z; xv4.w -= dt.w;
+                    *reinterpret_cast<float4*>(xbr + 4 * j4) = xv4;
+                    *reinterpret_cast<float4*>(stB + tid * LD + 4 * j4) = dt;
+                }
             }
             __syncthreads();
             if (tid < D) {
