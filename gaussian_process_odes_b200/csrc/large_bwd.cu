@@ -518,38 +518,54 @@ vjp_large_kernel(const float* __restrict__ pk, const LbLayout L, const float* __
 // One thread per output, loads coalesced across outputs; the row loop runs eight independent partial sums (rows r,
 // r + 8, ...) that are added in a fixed order, so the result is reproducible and the loads pipeline. The variance
 // gradient needs sum_m c_km T[k][m]: it is taken from grad_nu = var_k T by a second kernel (one warp per output k) --
-// round 2's first version looped over m x rows in one thread: 2.1 ms at D = 16 (592 rows), now < 0.1 ms.
+// round 2's first version looped over m x rows in one thread: 2.1 ms at D = 16 (592 rows).
+// Block = 32 outputs x 8 row classes: thread (x, y) adds rows y, y + 8, ... of output x in row order, the eight partial
+// sums meet in shared memory and are added in the fixed order ((0+1)+(2+3))+((4+5)+(6+7)) -- bitwise what one thread
+// with eight interleaved partial sums gave (0.33-0.40 ms at 592-888 rows), at an eighth of the dependent chain.
 __device__ __forceinline__ double lb_sum_rows(const float* __restrict__ base, const size_t stride, const size_t off,
-                                              const int n_rows) {
-    double s[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    int r = 0;
-    for (; r + 8 <= n_rows; r += 8) {
-#pragma unroll
-        for (int u = 0; u < 8; ++u) s[u] += (double)__ldcg(base + (size_t)(r + u) * stride + off);
-    }
-    for (int u = 0; r < n_rows; ++r, ++u) s[u] += (double)__ldcg(base + (size_t)r * stride + off);
-    return ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+                                              const int n_rows, const int y) {
+    double s = 0.0;
+#pragma unroll 4
+    for (int r = y; r < n_rows; r += 8) s += (double)__ldcg(base + (size_t)r * stride + off);
+    return s;
 }
 
-__global__ void finalize_large_kernel(const int D, const int DP, const int M, const int n_rows,
-                                      const float* __restrict__ accA, const float* __restrict__ accT,
-                                      const float* __restrict__ accZ, const float* __restrict__ accR, const int n_rows_r,
-                                      const int DN, const float* __restrict__ ell, const float* __restrict__ var,
-                                      float* __restrict__ g_ell, float* __restrict__ g_Z, float* __restrict__ g_nu) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256)
+finalize_large_kernel(const int D, const int DP, const int M, const int n_rows,
+                      const float* __restrict__ accA, const float* __restrict__ accT,
+                      const float* __restrict__ accZ, const float* __restrict__ accR, const int n_rows_r,
+                      const int DN, const float* __restrict__ ell, const float* __restrict__ var,
+                      float* __restrict__ g_ell, float* __restrict__ g_Z, float* __restrict__ g_nu) {
+    __shared__ double part[2][8][32];
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + x;
     const int nA = D * D, nT = D * M, nZ = M * D;
+    double p0 = 0.0, p1 = 0.0;
     if (i < nA) {
         const int k = i / D, j = i - k * D;
-        double a = lb_sum_rows(accA, (size_t)DP * DP + DP, (size_t)k * DP + j, n_rows);
-        // rows of the tensor-core RFF kernel (one per CTA and row warp)
-        a += lb_sum_rows(accR, (size_t)DN * DN, (size_t)k * DN + j, n_rows_r);
-        g_ell[i] = (float)(-a / (double)ell[i]);
+        p0 = lb_sum_rows(accA, (size_t)DP * DP + DP, (size_t)k * DP + j, n_rows, y);
+        p1 = lb_sum_rows(accR, (size_t)DN * DN, (size_t)k * DN + j, n_rows_r, y);   // rows of the tensor-core RFF kernel
     } else if (i < nA + nT) {
-        const int e = i - nA, k = e / M;
-        g_nu[e] = (float)((double)var[k] * lb_sum_rows(accT, (size_t)D * M, (size_t)e, n_rows));
+        p0 = lb_sum_rows(accT, (size_t)D * M, (size_t)(i - nA), n_rows, y);
     } else if (i < nA + nT + nZ) {
         const int e = i - nA - nT, m = e / D, j = e - m * D;
-        g_Z[e] = (float)lb_sum_rows(accZ, (size_t)M * DP, (size_t)m * DP + j, n_rows);
+        p0 = lb_sum_rows(accZ, (size_t)M * DP, (size_t)m * DP + j, n_rows, y);
+    }
+    part[0][y][x] = p0;
+    part[1][y][x] = p1;
+    __syncthreads();
+    if (y != 0) return;
+    double t[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+        t[q] = ((part[q][0][x] + part[q][1][x]) + (part[q][2][x] + part[q][3][x])) +
+               ((part[q][4][x] + part[q][5][x]) + (part[q][6][x] + part[q][7][x]));
+    if (i < nA) {
+        g_ell[i] = (float)(-(t[0] + t[1]) / (double)ell[i]);
+    } else if (i < nA + nT) {
+        g_nu[i - nA] = (float)((double)var[(i - nA) / M] * t[0]);
+    } else if (i < nA + nT + nZ) {
+        g_Z[i - nA - nT] = (float)t[0];
     }
 }
 
@@ -723,7 +739,7 @@ extern "C" int gpode_grads_finalize_large(const gpode_cache_t* c, const float* a
     const int n_out = D * D + 2 * D * M;
     const float* accR = acc_large + lb_acc_floats(D, M);
     const int n_rows_r = use_rv(D) ? gpode_rv_grid(B) * 4 : 0;
-    finalize_large_kernel<<<(n_out + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+    finalize_large_kernel<<<(n_out + 31) / 32, 256, 0, (cudaStream_t)stream>>>(
         D, DP, M, lb_grid(B, DP), accA, accT, accZ, accR, n_rows_r, gpode_rv_dn(D), c->ell, c->var, grad_ell, grad_Z,
         grad_nu);
     finalize_large_var_kernel<<<(D + 3) / 4, 128, 0, (cudaStream_t)stream>>>(D, DP, M, lb_grid(B, DP), accA, c->nu,
