@@ -300,7 +300,7 @@ vjp_large_kernel(const float* __restrict__ pk, const LbLayout L, const float* __
                 *reinterpret_cast<float4*>(stB + rA * LD + o) = make_float4(a0 * a0, a1 * a1, a2 * a2, a3 * a3);
                 *reinterpret_cast<float4*>(stB + rB * LD + o) = make_float4(b0 * b0, b1 * b1, b2 * b2, b3 * b3);
             }
-#pragma unroll 1
+#pragma unroll 2
             for (int k = 0; k < D; k += 2) {   // rows D .. DP-1 of Ws are zero padding; an odd D's last partner has q = 0
                 const float* __restrict__ wa = Ws + k * DP;
                 const float* __restrict__ wb = wa + DP;
@@ -513,6 +513,268 @@ vjp_large_kernel(const float* __restrict__ pk, const LbLayout L, const float* __
     for (int i = tid; i < DP; i += kLbThreads) Ag[DP * DP + i] += V1[i];
 }
 
+// ---- RBF half of the VJP on EIGHT warps (used when the tcgen05 kernel has already done the RFF half) ---------------------
+// Same tiles, arithmetic and accumulator rows as the RBF part of vjp_large_kernel, but two warpgroups share the 128-row
+// tile, so every scheduler has two warps to interleave (ncu on the four-warp form at DP = 64: FMA pipe 24 %, issue 34 %,
+// shared-memory wavefronts 59 % -- latency with one warp per scheduler). Both warpgroups build the same dd registers
+// (thread = two rows x half the inputs); warpgroup w takes the output pairs k = 2w, 2w + 4, ... in the exponent / t
+// phases and the rows 64w .. 64w + 63 in the row contraction (its partial tile meets warpgroup 0's through a scratch
+// block), the two partial t's are applied to the cotangent tile one warpgroup after the other, and the Z column sums
+// use four row classes per column (the same four interleaved partial sums, added in the same order).
+constexpr int kRb2Threads = 256;
+template <int DP>
+struct Rb2Smem {
+    static constexpr int LD = DP + 4;
+    static constexpr int tile = kLbRows * LD;
+    static constexpr int SCR = DP * DP / 128 + DP / 16;   // contraction accumulators + p sums per thread
+    static constexpr int floats = 5 * tile + 2 * DP * DP + 4 * DP + DP + 128 * SCR;
+    static constexpr size_t bytes = (size_t)floats * 4;
+};
+
+template <int DP>
+__global__ void __launch_bounds__(kRb2Threads, 1)
+rbf_vjp_large_kernel(const float* __restrict__ pk, const LbLayout L, const float* __restrict__ x,
+                     const float* __restrict__ f, const float* __restrict__ kb, float* __restrict__ gx, const int64_t B,
+                     float* __restrict__ accA, float* __restrict__ accT, float* __restrict__ accZ) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int LD = Rb2Smem<DP>::LD, TILE = Rb2Smem<DP>::tile, SCR = Rb2Smem<DP>::SCR;
+    float* xs = reinterpret_cast<float*>(smem_raw);
+    float* kbs = xs + TILE;
+    float* stA = kbs + TILE;
+    float* stB = stA + TILE;
+    float* xbs = stB + TILE;
+    float* Ws = xbs + TILE;
+    float* As = Ws + DP * DP;
+    float* red = As + DP * DP;
+    float* V1 = red + 4 * DP;
+    float* scr = V1 + DP;
+    const int D = L.D, M = L.M;
+    const int tid = threadIdx.x, lane = tid & 31, wg = tid >> 7, t = tid & 127;
+    const float* __restrict__ z_g = pk + L.off_z;
+    const float* __restrict__ c_g = pk + L.off_c;
+    for (int i = tid; i < DP * DP; i += kRb2Threads) {
+        Ws[i] = pk[L.off_w + i];
+        As[i] = 0.f;
+    }
+    for (int i = tid; i < DP; i += kRb2Threads) V1[i] = 0.f;
+    __syncthreads();
+    float* __restrict__ Tg = accT + (size_t)blockIdx.x * D * M;
+    float* __restrict__ Zg = accZ + (size_t)blockIdx.x * M * DP;
+    constexpr int TK = DP / 16, TJ = DP / 8, NC2 = DP / 8;
+    static_assert(DP == 32 || DP == 64, "two-row mapping");
+    const int ck0 = (t >> 3) * TK, cj0 = (t & 7) * TJ;
+    const int h2 = t & 1, rA = t >> 1, rB = rA + kLbRows / 2;
+    auto off2 = [&](const int c) { return h2 * (DP / 2) + 4 * ((c + (DP == 64 ? h2 * (NC2 / 2) : 0)) & (NC2 - 1)); };
+
+    const int64_t n_tiles = (B + kLbRows - 1) / kLbRows;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t r0 = tile * kLbRows;
+        const int n = (int)((B - r0) < kLbRows ? (B - r0) : kLbRows);
+        for (int i = tid; i < kLbRows * DP; i += kRb2Threads) {
+            const int r = i / DP, j = i - r * DP;
+            const bool ok = r < n && j < D;
+            xs[r * LD + j] = ok ? __ldg(x + (r0 + r) * D + j) : 0.f;
+            kbs[r * LD + j] = ok ? __ldg(kb + (r0 + r) * D + j) : 0.f;
+            xbs[r * LD + j] = ok ? gx[(r0 + r) * D + j] : 0.f;   // the RFF half of the cotangent, written by the tensor-core kernel
+        }
+        __syncthreads();
+        // variance partial sum, first half: V1[k] += sum_rows kb_k f_k (rows by warp shuffle, warps in warp order)
+        if (wg == 0) {
+            for (int k = 0; k < D; ++k) {
+                const float fv = t < n ? __ldg(f + (r0 + t) * D + k) : 0.f;
+                const float v = gpode_warp_sum(kbs[t * LD + k] * fv);
+                if (lane == 0) red[(t >> 5) * DP + k] = v;
+            }
+        }
+        __syncthreads();
+        for (int k = tid; k < D; k += kRb2Threads) V1[k] += (red[k] + red[DP + k]) + (red[2 * DP + k] + red[3 * DP + k]);
+
+        for (int m = 0; m < M; ++m) {
+            const float* __restrict__ zm = z_g + (size_t)m * DP;
+            const float* __restrict__ cm = c_g + (size_t)m * DP;
+            float2 dd[DP / 2], tt[DP / 2];   // rows rA | rB, NC2 chunks of four inputs each
+#pragma unroll
+            for (int c = 0; c < NC2; ++c) {
+                const int o = off2(c);
+                const float4 zv = __ldg(reinterpret_cast<const float4*>(zm + o));
+                const float4 xa = *reinterpret_cast<const float4*>(xs + rA * LD + o);
+                const float4 xb4 = *reinterpret_cast<const float4*>(xs + rB * LD + o);
+                const float a0 = xa.x - zv.x, a1 = xa.y - zv.y, a2 = xa.z - zv.z, a3 = xa.w - zv.w;
+                const float b0 = xb4.x - zv.x, b1 = xb4.y - zv.y, b2 = xb4.z - zv.z, b3 = xb4.w - zv.w;
+                dd[2 * c] = make_float2(a0 * a0, a1 * a1); dd[2 * c + 1] = make_float2(a2 * a2, a3 * a3);
+                dd[2 * NC2 + 2 * c] = make_float2(b0 * b0, b1 * b1); dd[2 * NC2 + 2 * c + 1] = make_float2(b2 * b2, b3 * b3);
+                tt[2 * c] = tt[2 * c + 1] = tt[2 * NC2 + 2 * c] = tt[2 * NC2 + 2 * c + 1] = make_float2(0.f, 0.f);
+                if (wg == 0) {
+                    *reinterpret_cast<float4*>(stB + rA * LD + o) = make_float4(a0 * a0, a1 * a1, a2 * a2, a3 * a3);
+                    *reinterpret_cast<float4*>(stB + rB * LD + o) = make_float4(b0 * b0, b1 * b1, b2 * b2, b3 * b3);
+                }
+            }
+#pragma unroll 2
+            for (int k = 2 * wg; k < D; k += 4) {   // rows D .. DP-1 of Ws are zero padding; an odd D's last partner has q = 0
+                const float* __restrict__ wa = Ws + k * DP;
+                const float* __restrict__ wb = wa + DP;
+                const float2 z2 = make_float2(0.f, 0.f);
+                float2 eAa0 = z2, eAa1 = z2, eAb0 = z2, eAb1 = z2, eBa0 = z2, eBa1 = z2, eBb0 = z2, eBb1 = z2;
+#pragma unroll
+                for (int c = 0; c < NC2; ++c) {
+                    const float4 a4 = *reinterpret_cast<const float4*>(wa + off2(c));
+                    const float4 b4 = *reinterpret_cast<const float4*>(wb + off2(c));
+                    const float2 al = make_float2(a4.x, a4.y), ah = make_float2(a4.z, a4.w);
+                    const float2 bl = make_float2(b4.x, b4.y), bh = make_float2(b4.z, b4.w);
+                    eAa0 = ffma2(dd[2 * c], al, eAa0); eAa1 = ffma2(dd[2 * c + 1], ah, eAa1);
+                    eAb0 = ffma2(dd[2 * c], bl, eAb0); eAb1 = ffma2(dd[2 * c + 1], bh, eAb1);
+                    eBa0 = ffma2(dd[2 * NC2 + 2 * c], al, eBa0); eBa1 = ffma2(dd[2 * NC2 + 2 * c + 1], ah, eBa1);
+                    eBb0 = ffma2(dd[2 * NC2 + 2 * c], bl, eBb0); eBb1 = ffma2(dd[2 * NC2 + 2 * c + 1], bh, eBb1);
+                }
+                float sAa = (eAa0.x + eAa0.y) + (eAa1.x + eAa1.y), sAb = (eAb0.x + eAb0.y) + (eAb1.x + eAb1.y);
+                float sBa = (eBa0.x + eBa0.y) + (eBa1.x + eBa1.y), sBb = (eBb0.x + eBb0.y) + (eBb1.x + eBb1.y);
+                sAa += __shfl_xor_sync(0xffffffffu, sAa, 1); sAb += __shfl_xor_sync(0xffffffffu, sAb, 1);
+                sBa += __shfl_xor_sync(0xffffffffu, sBa, 1); sBb += __shfl_xor_sync(0xffffffffu, sBb, 1);
+                const bool two = k + 1 < D;
+                const float pAa = kbs[rA * LD + k] * gpode_ex2(-sAa);
+                const float pBa = kbs[rB * LD + k] * gpode_ex2(-sBa);
+                const float pAb = two ? kbs[rA * LD + k + 1] * gpode_ex2(-sAb) : 0.f;
+                const float pBb = two ? kbs[rB * LD + k + 1] * gpode_ex2(-sBb) : 0.f;
+                {   // each lane of the pair stages one of the two rows
+                    const int rs = h2 ? rB : rA;
+                    stA[rs * LD + k] = h2 ? pBa : pAa;
+                    if (two) stA[rs * LD + k + 1] = h2 ? pBb : pAb;
+                }
+                const float ca = -GPODE_NEG_2LN2 * __ldg(cm + k);             // q = 2 ln2 c_km kb_k K
+                const float cb = two ? -GPODE_NEG_2LN2 * __ldg(cm + k + 1) : 0.f;
+                const float qAa = ca * pAa, qAb = cb * pAb, qBa = ca * pBa, qBb = cb * pBb;
+#pragma unroll
+                for (int c = 0; c < NC2; ++c) {
+                    const float4 a4 = *reinterpret_cast<const float4*>(wa + off2(c));
+                    const float4 b4 = *reinterpret_cast<const float4*>(wb + off2(c));
+                    const float2 al = make_float2(a4.x, a4.y), ah = make_float2(a4.z, a4.w);
+                    const float2 bl = make_float2(b4.x, b4.y), bh = make_float2(b4.z, b4.w);
+                    tt[2 * c] = ffma2(qAb, bl, ffma2(qAa, al, tt[2 * c]));
+                    tt[2 * c + 1] = ffma2(qAb, bh, ffma2(qAa, ah, tt[2 * c + 1]));
+                    tt[2 * NC2 + 2 * c] = ffma2(qBb, bl, ffma2(qBa, al, tt[2 * NC2 + 2 * c]));
+                    tt[2 * NC2 + 2 * c + 1] = ffma2(qBb, bh, ffma2(qBa, ah, tt[2 * NC2 + 2 * c + 1]));
+                }
+            }
+            __syncthreads();  // p and dd of all 128 rows are staged
+            // rows contracted by a (TK outputs k) x (TJ inputs j) register tile per thread, 64 rows per warpgroup:
+            // T[k][m] = sum_r p;  A[k][j] -= 2 ln2 w_kj c_km sum_r p dd_j.  Columns k >= D of the p tile are never
+            // written (stale bytes): their sums are computed and dropped.
+            {
+                float2 acc[TK][TJ / 2];
+                float s1[TK];
+#pragma unroll
+                for (int a = 0; a < TK; ++a) {
+                    s1[a] = 0.f;
+#pragma unroll
+                    for (int c = 0; c < TJ / 2; ++c) acc[a][c] = make_float2(0.f, 0.f);
+                }
+#pragma unroll 4
+                for (int r = wg * (kLbRows / 2); r < (wg + 1) * (kLbRows / 2); ++r) {
+                    float pv[TK];
+                    float2 dv[TJ / 2];
+                    if constexpr (TK == 4) {
+                        const float4 p4 = *reinterpret_cast<const float4*>(stA + r * LD + ck0);
+                        pv[0] = p4.x; pv[1] = p4.y; pv[2] = p4.z; pv[3] = p4.w;
+                    } else {
+                        const float2 p2 = *reinterpret_cast<const float2*>(stA + r * LD + ck0);
+                        pv[0] = p2.x; pv[1] = p2.y;
+                    }
+#pragma unroll
+                    for (int c4 = 0; c4 < TJ / 4; ++c4) {
+                        const float4 d4 = *reinterpret_cast<const float4*>(stB + r * LD + cj0 + 4 * c4);
+                        dv[2 * c4] = make_float2(d4.x, d4.y);
+                        dv[2 * c4 + 1] = make_float2(d4.z, d4.w);
+                    }
+#pragma unroll
+                    for (int a = 0; a < TK; ++a) {
+                        s1[a] += pv[a];
+#pragma unroll
+                        for (int c = 0; c < TJ / 2; ++c) acc[a][c] = ffma2(pv[a], dv[c], acc[a][c]);
+                    }
+                }
+                float* __restrict__ mine = scr + t * SCR;
+                if (wg == 1) {
+#pragma unroll
+                    for (int a = 0; a < TK; ++a) {
+                        mine[TK * TJ + a] = s1[a];
+#pragma unroll
+                        for (int c = 0; c < TJ / 2; ++c)
+                            *reinterpret_cast<float2*>(mine + a * TJ + 2 * c) = acc[a][c];
+                    }
+                }
+                __syncthreads();
+                if (wg == 0) {
+#pragma unroll
+                    for (int a = 0; a < TK; ++a) {
+                        const int k = ck0 + a;
+                        if (k < D) {
+                            if (cj0 == 0) Tg[(size_t)k * M + m] += s1[a] + mine[TK * TJ + a];
+                            const float cf = GPODE_NEG_2LN2 * __ldg(cm + k);   // -2 ln2 c_km
+#pragma unroll
+                            for (int c = 0; c < TJ / 2; ++c) {
+                                const int j = cj0 + 2 * c;
+                                const float2 o = *reinterpret_cast<const float2*>(mine + a * TJ + 2 * c);
+                                As[k * DP + j] = fmaf(cf * Ws[k * DP + j], acc[a][c].x + o.x, As[k * DP + j]);
+                                As[k * DP + j + 1] = fmaf(cf * Ws[k * DP + j + 1], acc[a][c].y + o.y, As[k * DP + j + 1]);
+                            }
+                        }
+                    }
+                }
+            }
+            // xb_j -= d_j t_j, warpgroup 0's half of the outputs first, then warpgroup 1's; the same products, summed
+            // over rows, are the Z gradient
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+                if (wg == w) {
+#pragma unroll
+                    for (int c = 0; c < NC2; ++c) {
+                        const int o = off2(c);
+                        const float4 zv = __ldg(reinterpret_cast<const float4*>(zm + o));
+#pragma unroll
+                        for (int rr = 0; rr < 2; ++rr) {
+                            const int r = rr ? rB : rA;
+                            const float2 t0 = tt[2 * NC2 * rr + 2 * c], t1 = tt[2 * NC2 * rr + 2 * c + 1];
+                            const float4 xv = *reinterpret_cast<const float4*>(xs + r * LD + o);
+                            float4 dt;
+                            dt.x = (xv.x - zv.x) * t0.x; dt.y = (xv.y - zv.y) * t0.y;
+                            dt.z = (xv.z - zv.z) * t1.x; dt.w = (xv.w - zv.w) * t1.y;
+                            float4 xv4 = *reinterpret_cast<const float4*>(xbs + r * LD + o);
+                            xv4.x -= dt.x; xv4.y -= dt.y; xv4.z -= dt.z; xv4.w -= dt.w;
+                            *reinterpret_cast<float4*>(xbs + r * LD + o) = xv4;
+                            if (w == 1) {
+                                const float4 d0 = *reinterpret_cast<const float4*>(stB + r * LD + o);
+                                dt.x += d0.x; dt.y += d0.y; dt.z += d0.z; dt.w += d0.w;
+                            }
+                            *reinterpret_cast<float4*>(stB + r * LD + o) = dt;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+            if (tid < 4 * DP) {   // column j, row class y = r mod 4
+                const int j = tid % DP, y = tid / DP;
+                float zsum = 0.f;
+#pragma unroll 8
+                for (int r = y; r < kLbRows; r += 4) zsum += stB[r * LD + j];
+                scr[y * DP + j] = zsum;
+            }
+            __syncthreads();
+            if (tid < D)
+                Zg[(size_t)m * DP + tid] += (scr[tid] + scr[DP + tid]) + (scr[2 * DP + tid] + scr[3 * DP + tid]);
+        }
+        // ---- xb out (coalesced from its shared-memory tile) ----
+        __syncthreads();
+        for (int i = tid; i < n * D; i += kRb2Threads) {
+            const int r = i / D, j = i - r * D;
+            gx[(r0 + r) * D + j] = xbs[r * LD + j];
+        }
+        __syncthreads();
+    }
+    float* __restrict__ Ag = accA + (size_t)blockIdx.x * (DP * DP + DP);
+    for (int i = tid; i < DP * DP; i += kRb2Threads) Ag[i] += As[i];
+    for (int i = tid; i < DP; i += kRb2Threads) Ag[DP * DP + i] += V1[i];
+}
+
 // ---- parameter gradients from the per-CTA rows (float64, rows in row order) ------------------------------------------
 // grid.x covers the D*D + D*M + M*D outputs of the first kernel; acc = [accA rows | accT rows | accZ rows | accR rows].
 // One thread per output, loads coalesced across outputs; the row loop runs eight independent partial sums (rows r,
@@ -686,6 +948,17 @@ int vjp_dispatch(const float* pk, int D, int M, int S, const float* x, const flo
     if (use_rv(D)) {
         if (int rc = gpode_rv_launch(pk + L.total, D, S, x, kb, gx, B, acc + lb_acc_floats(D, M), st)) return rc;
         rff_done = 1;
+    }
+    if (rff_done && L.DP == 64 && gpode_option(GPODE_OPT_LARGE_BWD_UMMA) == 1) {   // option value 2: the four-warp RBF half
+        constexpr int DP = 64;
+        GPODE_CUDA(cudaFuncSetAttribute(rbf_vjp_large_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)Rb2Smem<DP>::bytes));
+        float* accT = acc + (size_t)kLbMaxCtas * (DP * DP + DP);
+        float* accZ = accT + (size_t)kLbMaxCtas * L.D * L.M;
+        rbf_vjp_large_kernel<DP><<<lb_grid(B, DP), kRb2Threads, Rb2Smem<DP>::bytes, st>>>(pk, L, x, f, kb, gx, B, acc, accT,
+                                                                                          accZ);
+        GPODE_LAUNCH_CHECK();
+        return 0;
     }
     if (L.DP == 16) return launch_vjp<16>(pk, L, x, f, kb, gx, B, acc, st, rff_done);
     if (L.DP == 32) return launch_vjp<32>(pk, L, x, f, kb, gx, B, acc, st, rff_done);
