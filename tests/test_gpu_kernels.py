@@ -260,7 +260,7 @@ def test_large_state_dimension_vjp_tensor_core_vs_fp32(D, M, S, B):
     cot = torch.tensor(np.random.default_rng(9).normal(size=(B, D)), dtype=torch.float32)
     res = {}
     try:
-        for u in (1, 0):
+        for u in (1, 0, 2):   # 2: tcgen05 RFF half + the four-warp form of the RBF half (1 runs it on eight warps at D > 32)
             _lib.set_option("large_bwd_umma", u)
             args = [a.detach().clone().requires_grad_(i < 4) for i, a in enumerate(_cuda_args(gp32, c32))]
             xc = x.cuda().requires_grad_(True)
@@ -270,6 +270,7 @@ def test_large_state_dimension_vjp_tensor_core_vs_fp32(D, M, S, B):
         _lib.set_option("large_bwd_umma", 1)
     for k in res[1]:
         assert relerr(res[1][k].cpu(), res[0][k].cpu()) <= 1e-5, (k, relerr(res[1][k].cpu(), res[0][k].cpu()))
+        assert relerr(res[1][k].cpu(), res[2][k].cpu()) <= 2e-6, (k, relerr(res[1][k].cpu(), res[2][k].cpu()))
 
 
 @pytest.mark.parametrize("D,M,S,B", [(16, 100, 256, 300), (33, 20, 64, 40)])
